@@ -1,0 +1,307 @@
+/* kz_bvh_build.h -- host side of the accel build (replaces Accel::build, src/kazen/accel.cpp:25-61):
+ * multi-threaded binned-SAH BVH2 over the scene triangles, collapsed to 8-wide nodes with
+ * octant-ordered child slots and quantised (outward-rounded) child boxes, emitted in the
+ * 80-byte layout of kz_scene.h.  The collapse/emit stage is also used by the on-GPU LBVH
+ * builder (kz_lbvh.cu), which only replaces the BVH2 topology step.
+ */
+#ifndef KZ_BVH_BUILD_H
+#define KZ_BVH_BUILD_H
+#include "kz_scene.h"
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace kzbvh {
+
+struct Tri { float p[3][3]; uint32_t geom, prim; };
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; ++a) { lo[a] = FLT_MAX; hi[a] = -FLT_MAX; } }
+    void grow(const float *p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    void grow(const Box &b) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+        return 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct Node2 {
+    Box box;
+    int32_t left;     /* internal: left child, right = left + 1; leaf: first ref */
+    int32_t count;    /* 0 = internal, else number of refs (<= 3) */
+};
+
+struct Ref { Box box; float c[3]; uint32_t tri; };
+
+struct Built {
+    std::vector<KzNode8> nodes;
+    std::vector<KzF4> tris;        /* 3 per triangle, leaf order */
+    float max_abs = 0.f;
+    int depth = 0;
+};
+
+static const int kMaxLeaf = 3;
+static const int kBins = 16;
+
+/* ---------------- BVH2 by binned SAH (task-parallel over subtrees) ---------------- */
+class Sah {
+public:
+    Sah(std::vector<Ref> &refs) : refs_(refs) {
+        nodes_.resize(std::max<size_t>(1, 2 * refs.size()));
+        next_.store(1);
+    }
+    std::vector<Node2> &nodes() { return nodes_; }
+    size_t nodeCount() const { return (size_t)next_.load(); }
+
+    void run(int threads) {
+        if (refs_.empty()) { nodes_[0].box.reset(); nodes_[0].left = 0; nodes_[0].count = 0; return; }
+        if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+        threads = std::max(1, std::min(threads, 64));
+        pending_ = 1;
+        queue_.push_back(Task{0, 0, refs_.size()});
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) pool.emplace_back([this]() { worker(); });
+        for (auto &th : pool) th.join();
+    }
+
+private:
+    struct Task { int node; size_t b, e; };
+    std::vector<Ref> &refs_;
+    std::vector<Node2> nodes_;
+    std::atomic<int> next_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Task> queue_;
+    size_t pending_ = 0;
+
+    void worker() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this]() { return !queue_.empty() || pending_ == 0; });
+                if (queue_.empty()) return;
+                t = queue_.front(); queue_.pop_front();
+            }
+            build(t, true);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                --pending_;
+                if (pending_ == 0) cv_.notify_all();
+            }
+        }
+    }
+    void spawn(const Task &t) {
+        std::lock_guard<std::mutex> lk(mu_);
+        ++pending_;
+        queue_.push_back(t);
+        cv_.notify_one();
+    }
+
+    /* Builds the subtree of t; big children are handed to the pool, small ones recursed here. */
+    void build(Task t, bool may_spawn) {
+        std::vector<Task> local;
+        local.push_back(t);
+        while (!local.empty()) {
+            Task j = local.back(); local.pop_back();
+            Box bb, cb; bb.reset(); cb.reset();
+            for (size_t i = j.b; i < j.e; ++i) { bb.grow(refs_[i].box); cb.grow(refs_[i].c); }
+            Node2 &nd = nodes_[j.node];
+            nd.box = bb;
+            size_t cnt = j.e - j.b;
+            if (cnt == 1) { nd.left = (int32_t)j.b; nd.count = 1; continue; }
+            /* binned SAH over the three axes */
+            float bestCost = FLT_MAX; int bestAxis = -1, bestBin = -1;
+            for (int a = 0; a < 3; ++a) {
+                float ext = cb.hi[a] - cb.lo[a];
+                if (!(ext > 0.f)) continue;
+                Box bins[kBins]; size_t cntb[kBins];
+                for (int k = 0; k < kBins; ++k) { bins[k].reset(); cntb[k] = 0; }
+                float scale = kBins / ext;
+                for (size_t i = j.b; i < j.e; ++i) {
+                    int k = std::min(kBins - 1, std::max(0, (int)((refs_[i].c[a] - cb.lo[a]) * scale)));
+                    bins[k].grow(refs_[i].box); ++cntb[k];
+                }
+                float rightArea[kBins]; Box acc; acc.reset();
+                for (int k = kBins - 1; k > 0; --k) { acc.grow(bins[k]); rightArea[k] = acc.area(); }
+                acc.reset(); size_t nl = 0;
+                for (int k = 0; k < kBins - 1; ++k) {
+                    acc.grow(bins[k]); nl += cntb[k];
+                    size_t nr = cnt - nl;
+                    if (nl == 0 || nr == 0) continue;
+                    float cost = acc.area() * (float)nl + rightArea[k + 1] * (float)nr;
+                    if (cost < bestCost) { bestCost = cost; bestAxis = a; bestBin = k; }
+                }
+            }
+            if (cnt <= (size_t)kMaxLeaf) {
+                /* leaf unless splitting is clearly cheaper (traversal cost 1, intersection cost 1) */
+                float leafCost = (float)cnt * bb.area();
+                if (bestAxis < 0 || bestCost + bb.area() >= leafCost) { nd.left = (int32_t)j.b; nd.count = (int32_t)cnt; continue; }
+            }
+            size_t mid;
+            if (bestAxis >= 0) {
+                float ext = cb.hi[bestAxis] - cb.lo[bestAxis];
+                float scale = kBins / ext; float lo = cb.lo[bestAxis]; int a = bestAxis, kb = bestBin;
+                Ref *m = std::partition(&refs_[j.b], &refs_[j.b] + cnt, [=](const Ref &r) {
+                    int k = std::min(kBins - 1, std::max(0, (int)((r.c[a] - lo) * scale)));
+                    return k <= kb;
+                });
+                mid = (size_t)(m - &refs_[0]);
+            } else {
+                mid = j.b;
+            }
+            if (mid == j.b || mid == j.e) {     /* all centroids coincide: split by count */
+                mid = (j.b + j.e) / 2;
+            }
+            int l = next_.fetch_add(2);
+            nodes_[j.node].left = l; nodes_[j.node].count = 0;
+            Task lt{l, j.b, mid}, rt{l + 1, mid, j.e};
+            const size_t kSpawn = 1u << 15;
+            if (may_spawn && (mid - j.b) > kSpawn && (j.e - mid) > kSpawn) { spawn(rt); local.push_back(lt); }
+            else { local.push_back(rt); local.push_back(lt); }
+        }
+    }
+};
+
+/* ---------------- collapse BVH2 -> 8-wide compressed nodes ---------------- */
+inline uint8_t quantExp(float ext) {
+    if (!(ext > 0.f)) return 1;
+    int ee;
+    std::frexp((double)ext / 255.0, &ee);     /* ext/255 = m * 2^ee, m in [0.5,1) -> 2^ee > ext/255 */
+    int biased = ee + 127;
+    return (uint8_t)std::min(254, std::max(1, biased));
+}
+
+/* refs[i].tri indexes `tris`; nodes2 is a BVH2 whose leaves reference contiguous ref ranges. */
+inline void collapse(const std::vector<Node2> &nodes2, const std::vector<Ref> &refs, const std::vector<Tri> &tris, Built &out) {
+    out.nodes.clear(); out.tris.clear(); out.depth = 0;
+    if (refs.empty()) return;
+    out.tris.reserve(refs.size() * 3);
+    struct Item { int n2; int wide; int depth; };
+    std::deque<Item> q;
+    out.nodes.push_back(KzNode8());
+    q.push_back(Item{0, 0, 1});
+    while (!q.empty()) {
+        Item it = q.front(); q.pop_front();
+        out.depth = std::max(out.depth, it.depth);
+        int ch[8]; int nch = 0;
+        const Node2 &r = nodes2[it.n2];
+        if (r.count > 0) { ch[nch++] = it.n2; }
+        else { ch[nch++] = r.left; ch[nch++] = r.left + 1; }
+        while (nch < 8) {
+            int best = -1; float bestA = -1.f;
+            for (int i = 0; i < nch; ++i) {
+                const Node2 &c = nodes2[ch[i]];
+                if (c.count > 0) continue;
+                float a = c.box.area();
+                if (a > bestA) { bestA = a; best = i; }
+            }
+            if (best < 0) break;
+            int c = ch[best];
+            ch[best] = nodes2[c].left;
+            ch[nch++] = nodes2[c].left + 1;
+        }
+        Box nb; nb.reset();
+        for (int i = 0; i < nch; ++i) nb.grow(nodes2[ch[i]].box);
+        /* slot assignment: greedy max of sum_a sign_s(a) * (centroid - node centre) */
+        float cen[3] = {0.5f * (nb.lo[0] + nb.hi[0]), 0.5f * (nb.lo[1] + nb.hi[1]), 0.5f * (nb.lo[2] + nb.hi[2])};
+        float cost[8][8];
+        for (int i = 0; i < nch; ++i) {
+            const Box &b = nodes2[ch[i]].box;
+            float d[3] = {0.5f * (b.lo[0] + b.hi[0]) - cen[0], 0.5f * (b.lo[1] + b.hi[1]) - cen[1], 0.5f * (b.lo[2] + b.hi[2]) - cen[2]};
+            for (int s = 0; s < 8; ++s)
+                cost[i][s] = ((s & 1) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 4) ? d[2] : -d[2]);
+        }
+        int slotOf[8]; bool slotUsed[8] = {false, false, false, false, false, false, false, false};
+        bool done[8] = {false, false, false, false, false, false, false, false};
+        for (int k = 0; k < nch; ++k) {
+            int bi = -1, bs = -1; float bc = -FLT_MAX;
+            for (int i = 0; i < nch; ++i) if (!done[i])
+                for (int s = 0; s < 8; ++s) if (!slotUsed[s] && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
+            slotOf[bi] = bs; slotUsed[bs] = true; done[bi] = true;
+        }
+        int childAt[8]; for (int s = 0; s < 8; ++s) childAt[s] = -1;
+        for (int i = 0; i < nch; ++i) childAt[slotOf[i]] = ch[i];
+
+        KzNode8 nd; memset(&nd, 0, sizeof(nd));
+        nd.px = nb.lo[0]; nd.py = nb.lo[1]; nd.pz = nb.lo[2];
+        uint8_t e[3];
+        for (int a = 0; a < 3; ++a) e[a] = quantExp(nb.hi[a] - nb.lo[a]);
+        /* make sure the far corner still fits after rounding */
+        for (int a = 0; a < 3; ++a)
+            while (e[a] < 254 && std::ceil(((double)nb.hi[a] - (double)nb.lo[a]) / std::ldexp(1.0, (int)e[a] - 127)) > 255.0) ++e[a];
+        nd.ex = e[0]; nd.ey = e[1]; nd.ez = e[2];
+        nd.child_base = (uint32_t)out.nodes.size();
+        nd.tri_base = (uint32_t)(out.tris.size() / 3);
+        uint32_t triOff = 0; uint8_t imask = 0;
+        for (int s = 0; s < 8; ++s) {
+            int c = childAt[s];
+            if (c < 0) { nd.meta[s] = 0; continue; }   /* empty: q boxes stay 0, meta 0 never sets a bit */
+            const Node2 &cn = nodes2[c];
+            double sc[3] = {std::ldexp(1.0, (int)e[0] - 127), std::ldexp(1.0, (int)e[1] - 127), std::ldexp(1.0, (int)e[2] - 127)};
+            uint8_t *qlo[3] = {nd.qlox, nd.qloy, nd.qloz}, *qhi[3] = {nd.qhix, nd.qhiy, nd.qhiz};
+            for (int a = 0; a < 3; ++a) {
+                double lo = std::floor(((double)cn.box.lo[a] - (double)nb.lo[a]) / sc[a]);
+                double hi = std::ceil(((double)cn.box.hi[a] - (double)nb.lo[a]) / sc[a]);
+                qlo[a][s] = (uint8_t)std::min(255.0, std::max(0.0, lo));
+                qhi[a][s] = (uint8_t)std::min(255.0, std::max(0.0, hi));
+            }
+            if (cn.count == 0) {
+                imask |= (uint8_t)(1u << s);
+                nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
+                int w = (int)out.nodes.size();
+                out.nodes.push_back(KzNode8());
+                q.push_back(Item{c, w, it.depth + 1});
+            } else {
+                static const uint8_t unary[4] = {0, 1, 3, 7};
+                nd.meta[s] = (uint8_t)((unary[cn.count] << 5) | triOff);
+                for (int k = 0; k < cn.count; ++k) {
+                    const Tri &t = tris[refs[cn.left + k].tri];
+                    KzF4 a, b, c4;
+                    a.x = t.p[0][0]; a.y = t.p[0][1]; a.z = t.p[0][2]; a.w = kz_u2f(t.geom);
+                    b.x = t.p[1][0]; b.y = t.p[1][1]; b.z = t.p[1][2]; b.w = kz_u2f(t.prim);
+                    c4.x = t.p[2][0]; c4.y = t.p[2][1]; c4.z = t.p[2][2]; c4.w = 0.f;
+                    out.tris.push_back(a); out.tris.push_back(b); out.tris.push_back(c4);
+                }
+                triOff += (uint32_t)cn.count;
+            }
+        }
+        nd.imask = imask;
+        out.nodes[it.wide] = nd;
+    }
+}
+
+inline void makeRefs(const std::vector<Tri> &tris, std::vector<Ref> &refs, float &max_abs) {
+    refs.resize(tris.size());
+    float m = 0.f;
+    for (size_t i = 0; i < tris.size(); ++i) {
+        Ref &r = refs[i];
+        r.box.reset();
+        for (int v = 0; v < 3; ++v) {
+            r.box.grow(tris[i].p[v]);
+            for (int a = 0; a < 3; ++a) m = std::max(m, std::fabs(tris[i].p[v][a]));
+        }
+        for (int a = 0; a < 3; ++a) r.c[a] = 0.5f * (r.box.lo[a] + r.box.hi[a]);
+        r.tri = (uint32_t)i;
+    }
+    max_abs = m;
+}
+
+inline void buildHostSah(const std::vector<Tri> &tris, int threads, Built &out) {
+    std::vector<Ref> refs;
+    makeRefs(tris, refs, out.max_abs);
+    Sah sah(refs);
+    sah.run(threads);
+    collapse(sah.nodes(), refs, tris, out);
+}
+
+}  // namespace kzbvh
+#endif

@@ -1,0 +1,315 @@
+/* kz_path.h -- the wavefront stages of PathMisIntegrator::Li as per-item routines over SoA
+ * path state.  One "item" = one path slot.  Stage order per bounce b = 0..maxDepth:
+ *
+ *   raygen  (b = 0 only)  renderer.cpp:20-33 + camera.cpp:70-91,191-223
+ *   extend                Scene::rayIntersect (closest hit) [+ the one-shot invisible-light
+ *                         re-trace of integrator.cpp:214-219 when b == 0]
+ *   shade                 integrator.cpp:224-334 for one loop iteration: light hit / miss /
+ *                         RR / NEE set-up / regularisation / BSDF sampling
+ *   shadow                integrator.cpp:259-294: closest-hit walk through invisible lights,
+ *                         then Li += pending
+ *   accumulate (end)      ImageBlock::put, block.cpp:56-85
+ *
+ * The reference's loop is   [hit] -> { light? RR NEE BSDF-sample trace -> miss? light-MIS depth++ }.
+ * Here iteration k's tail (miss / light-MIS weight / depth++) runs at the head of shade(b = k+1),
+ * so there are maxDepth+1 extend passes and the last shade only resolves the final ray.
+ */
+#ifndef KZ_PATH_H
+#define KZ_PATH_H
+#include "kz_shade.h"
+
+struct KzPathState {
+    KzF4 *ray_o;      /* o.xyz, tmin */
+    KzF4 *ray_d;      /* d.xyz, tmax */
+    KzF4 *hit;        /* t, u, v, prim(bits) */
+    uint32_t *hit_geom;
+    KzF4 *sray_o;     /* shadow ray */
+    KzF4 *sray_d;
+    KzF4 *pending;    /* rgb of the NEE contribution awaiting visibility */
+    KzF4 *thr;        /* throughput rgb, eta */
+    KzF4 *L;          /* Li rgb, bsdfWeight */
+    KzF4 *misc;       /* bsdfPdf, accumulatedRoughness, pixelSample.x, pixelSample.y */
+    uint64_t *rng_state;
+    uint64_t *rng_inc;
+    uint32_t *dim;
+    uint32_t *pix;    /* px | py << 16 */
+    uint32_t *sidx;   /* sample index */
+};
+
+struct KzCounters {
+    unsigned long long paths, rays_ext, rays_shadow, vertices;
+};
+
+#define KZ_SHADE_CONTINUE 1u   /* extension ray written, path goes to the next extend pass */
+#define KZ_SHADE_SHADOW 2u     /* shadow ray + pending contribution written               */
+
+KZ_HD float power_heuristic(float a, float b) { a *= a; b *= b; return a > 0.f ? a / (a + b) : 0.f; }
+
+KZ_HD kz3 xform_point(const float *M, kz3 p) {
+    float r0 = M[0] * p.x + M[1] * p.y + M[2] * p.z + M[3];
+    float r1 = M[4] * p.x + M[5] * p.y + M[6] * p.z + M[7];
+    float r2 = M[8] * p.x + M[9] * p.y + M[10] * p.z + M[11];
+    float r3 = M[12] * p.x + M[13] * p.y + M[14] * p.z + M[15];
+    return mk3(r0 / r3, r1 / r3, r2 / r3);
+}
+KZ_HD kz3 xform_vector(const float *M, kz3 v) {
+    return mk3(M[0] * v.x + M[1] * v.y + M[2] * v.z, M[4] * v.x + M[5] * v.y + M[6] * v.z, M[8] * v.x + M[9] * v.y + M[10] * v.z);
+}
+
+/* camera.cpp:70-91 / 191-223 */
+KZ_HD void kz_camera_ray(const kz_camera_desc &c, kz2 samplePosition, kz2 apertureSample, KzF4 &ro, KzF4 &rd) {
+    const float invW = 1.0f / (float)c.width, invH = 1.0f / (float)c.height;
+    kz3 nearP = xform_point(c.sample_to_camera, mk3(samplePosition.x * invW, samplePosition.y * invH, 0.0f));
+    kz3 o, d;
+    if (c.type == KZ_CAM_THINLENS) {
+        kz2 tmp = square_to_uniform_disk(apertureSample);
+        kz3 apertureP = mk3(tmp.x * c.aperture_radius, tmp.y * c.aperture_radius, 0.0f);
+        kz3 focusP = nearP * (c.focus_distance / nearP.z);
+        d = normalized(focusP - apertureP);
+        o = xform_point(c.camera_to_world, apertureP);
+    } else {
+        d = normalized(nearP);
+        o = xform_point(c.camera_to_world, mk3(0.f, 0.f, 0.f));
+    }
+    const float invZ = 1.0f / d.z;
+    kz3 dw = xform_vector(c.camera_to_world, d);
+    ro.x = o.x; ro.y = o.y; ro.z = o.z; ro.w = c.near_clip * invZ;
+    rd.x = dw.x; rd.y = dw.y; rd.z = dw.z; rd.w = c.far_clip * invZ;
+}
+
+KZ_HD KzF4 mkf4(float x, float y, float z, float w) { KzF4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+
+/* ---- raygen -------------------------------------------------------------------------------- */
+KZ_HD void kz_raygen_item(const KzScene &sc, const KzPathState &st, uint32_t slot, int px, int py, uint32_t sample_index) {
+    KzSampler sm;
+    kz_sampler_start(sc, sm, px, py, sample_index);
+    kz2 pix = kz_next_pixel2d(sc, sm);
+    kz2 pixelSample = mk2((float)px + pix.x, (float)py + pix.y);
+    kz2 aperture = kz_next2d(sc, sm);
+    KzF4 ro, rd;
+    kz_camera_ray(sc.camera, pixelSample, aperture, ro, rd);
+    st.ray_o[slot] = ro; st.ray_d[slot] = rd;
+    st.thr[slot] = mkf4(1.f, 1.f, 1.f, 1.f);
+    st.L[slot] = mkf4(0.f, 0.f, 0.f, 1.f);
+    st.misc[slot] = mkf4(0.f, 0.f, pixelSample.x, pixelSample.y);
+    st.rng_state[slot] = sm.state; st.rng_inc[slot] = sm.inc; st.dim[slot] = sm.dim;
+    st.pix[slot] = (uint32_t)px | ((uint32_t)py << 16);
+    st.sidx[slot] = sample_index;
+}
+
+KZ_HD int kz_classify(const KzScene &sc, uint32_t geom) {
+    if (geom == KZ_INVALID_ID) return KZ_CLASS_TERMINAL;
+    const KzMeshRec m = sc.meshes[geom];
+    if (m.flags & KZ_MESH_IS_LIGHT) return KZ_CLASS_TERMINAL;
+    const int t = sc.bsdfs[m.bsdf].type;
+    return t == KZ_BSDF_DIFFUSE ? KZ_CLASS_DIFFUSE : (t == KZ_BSDF_KISS ? KZ_CLASS_KISS : KZ_CLASS_NORMALMAP);
+}
+
+/* ---- extend -------------------------------------------------------------------------------- */
+/* Traces the path's current ray, stores the hit, returns the material class of the hit. */
+KZ_HD int kz_extend_item(const KzScene &sc, const KzStackRef &stk, const KzPathState &st, uint32_t slot, int bounce, KzCounters &cnt) {
+    const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+    KzHit h = kz_trace(sc, stk, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, false);
+    cnt.rays_ext += 1;
+    if (bounce == 0 && h.geom != KZ_INVALID_ID) {
+        const KzMeshRec m = sc.meshes[h.geom];
+        if ((m.flags & KZ_MESH_IS_LIGHT) && !(m.flags & KZ_MESH_LIGHT_VISIBLE)) {
+            /* integrator.cpp:214-219: one re-trace from its.p + eps*d; a miss keeps the light hit */
+            KzIts its; its.acc_rough = 0.f;
+            fill_intersection(sc, h, its, mk3(0.f));
+            const float eps = sc.integrator.trace_bias;
+            const kz3 d = mk3(rd.x, rd.y, rd.z);
+            const kz3 o = its.p + eps * d;
+            KzHit h2 = kz_trace(sc, stk, o.x, o.y, o.z, d.x, d.y, d.z, KZ_EPSILON, KZ_INF, false);
+            cnt.rays_ext += 1;
+            if (h2.geom != KZ_INVALID_ID) h = h2;
+        }
+    }
+    st.hit[slot] = mkf4(h.t, h.u, h.v, kz_u2f(h.prim));
+    st.hit_geom[slot] = h.geom;
+    return kz_classify(sc, h.geom);
+}
+
+/* ---- shade --------------------------------------------------------------------------------- */
+KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t slot, int bounce, KzCounters &cnt) {
+    const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+    const kz3 rayO = mk3(ro.x, ro.y, ro.z), rayD = mk3(rd.x, rd.y, rd.z);
+    const KzF4 hv = st.hit[slot];
+    KzHit h; h.t = hv.x; h.u = hv.y; h.v = hv.z; h.prim = kz_f2u(hv.w); h.geom = st.hit_geom[slot];
+    KzF4 thr4 = st.thr[slot], L4 = st.L[slot], misc = st.misc[slot];
+    kz3 throughput = mk3(thr4.x, thr4.y, thr4.z), L = mk3(L4.x, L4.y, L4.z);
+    float eta = thr4.w, bsdfWeight = L4.w;
+    const kz_integrator_desc I = sc.integrator;
+
+    if (h.geom == KZ_INVALID_ID) {
+        /* bounce 0: camera rays never see the background (integrator.cpp:210-212);
+         * later: Li += throughput * background(ray.d) (integrator.cpp:315-318) */
+        if (bounce > 0) {
+            L += throughput * kz_background(sc, rayD);
+            st.L[slot] = mkf4(L.x, L.y, L.z, bsdfWeight);
+        }
+        return 0u;
+    }
+    KzIts its; its.acc_rough = misc.y;
+    fill_intersection(sc, h, its, mk3(0.f));
+    const KzMeshRec mesh = sc.meshes[its.mesh];
+    const bool isLight = (mesh.flags & KZ_MESH_IS_LIGHT) != 0;
+    if (bounce > 0 && isLight) {   /* integrator.cpp:322-327 */
+        const kz3 wi = normalized(its.p - rayO);
+        const float lightPdf_ = light_pdf(mesh.inv_area, rayO, its.p, its.sh.n, wi);
+        bsdfWeight = power_heuristic(misc.x, lightPdf_);
+    }
+    if (bounce >= I.max_depth) return 0u;          /* depth++ ; while (depth < maxDepth) */
+    if (isLight) {       /* integrator.cpp:226-231 */
+        const kz3 wi = normalized(its.p - rayO);
+        const float cosTheta = dot(its.sh.n, -wi);
+        if (cosTheta > 0.f) {
+            const kz_light_desc l = sc.lights[mesh.light];
+            L += bsdfWeight * throughput * mk3(l.radiance[0], l.radiance[1], l.radiance[2]);
+            st.L[slot] = mkf4(L.x, L.y, L.z, bsdfWeight);
+        }
+        return 0u;
+    }
+
+    KzSampler sm;
+    sm.state = st.rng_state[slot]; sm.inc = st.rng_inc[slot]; sm.dim = st.dim[slot];
+    const uint32_t pix = st.pix[slot];
+    sm.px = (int32_t)(pix & 0xFFFFu); sm.py = (int32_t)(pix >> 16); sm.sample_index = st.sidx[slot];
+
+    if (bounce >= 3) {   /* integrator.cpp:237-244 */
+        const float probability = fminf(maxcoeff(throughput) * eta * eta, 0.95f);
+        if (probability <= kz_next1d(sc, sm)) return 0u;
+        throughput = throughput / probability;
+    }
+    cnt.vertices += 1;
+    uint32_t flags = 0u;
+    const KzBsdfCtx bc = bsdf_ctx(sc, its);
+    const kz3 wiLocal = to_local(its.sh, -rayD);
+    const float eps = I.trace_bias;
+
+    /* ---- light sampling, integrator.cpp:247-294 ---- */
+    const float rnd = kz_next1d(sc, sm);
+    if (sc.n_light_meshes > 0) {
+        const uint32_t nl = (uint32_t)sc.n_light_meshes;
+        uint32_t index = (uint32_t)floorf((float)nl * rnd);
+        if (index > nl - 1) index = nl - 1;
+        const KzMeshRec lm = sc.meshes[sc.light_meshes[index]];
+        /* Mesh::sample, mesh.cpp:108-133 */
+        const uint32_t tri = cdf_sample(sc.light_cdf + lm.cdf_offset, lm.n_triangles, kz_next1d(sc, sm));
+        const float su0 = sqrtf(kz_next1d(sc, sm));
+        const float u = 1 - su0;
+        const float v = kz_next1d(sc, sm) * su0;
+        const uint32_t *F = sc.indices + 3 * (size_t)(lm.index_offset + tri);
+        const kz3 p0 = kz_vpos(sc, lm, F[0]), p1 = kz_vpos(sc, lm, F[1]), p2 = kz_vpos(sc, lm, F[2]);
+        const kz3 lp = p0 + u * (p1 - p0) + v * (p2 - p0);
+        kz3 ln;
+        if (lm.flags & KZ_MESH_HAS_NORMALS) {
+            const kz3 n0 = kz_vnrm(sc, lm, F[0]), n1 = kz_vnrm(sc, lm, F[1]), n2 = kz_vnrm(sc, lm, F[2]);
+            ln = n0 + u * (n1 - n0) + v * (n2 - n0);          /* not normalised, mesh.cpp:128-129 */
+        } else {
+            ln = normalized(cross(p1 - p0, p2 - p0));
+        }
+        /* AreaLight::sample, light.cpp:21-34 */
+        const kz3 lwi = normalized(lp - its.p);
+        const float dist = norm(lp - its.p);
+        const float lpdf = light_pdf(lm.inv_area, its.p, lp, ln, lwi);
+        if (lpdf > 0.f && !isnan(lpdf) && !isinf(lpdf)) {
+            const kz_light_desc l = sc.lights[lm.light];
+            /* eval: cosTheta > 0 is implied by lpdf > 0 */
+            kz3 Ls = mk3(l.radiance[0], l.radiance[1], l.radiance[2]) / lpdf;
+            Ls = Ls / (1.f / (float)nl);
+            kz3 f; float bsdfPdf;
+            bsdf_eval_pdf(bc, its, wiLocal, to_local(its.sh, lwi), &f, &bsdfPdf);
+            const float lightWeight = power_heuristic(lpdf, bsdfPdf);
+            const kz3 contrib = throughput * Ls * f * lightWeight;
+            if (!iszero(contrib)) {
+                st.sray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, eps);
+                st.sray_d[slot] = mkf4(lwi.x, lwi.y, lwi.z, dist - eps);
+                st.pending[slot] = mkf4(contrib.x, contrib.y, contrib.z, 0.f);
+                flags |= KZ_SHADE_SHADOW;
+            }
+        }
+    }
+
+    /* ---- regularisation, integrator.cpp:299-301 ---- */
+    if (I.regularization) its.acc_rough += bsdf_regularize(bc) * I.accumulated_roughness;
+
+    /* ---- BSDF sampling, integrator.cpp:304-314 ---- */
+    const float s1 = kz_next1d(sc, sm);
+    const kz2 s2 = kz_next2d(sc, sm);
+    kz3 wo; float bsdfPdf; int measure;
+    const kz3 weight = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &bsdfPdf, &measure);
+    throughput *= weight;
+    st.rng_state[slot] = sm.state; st.dim[slot] = sm.dim;
+    st.thr[slot] = mkf4(throughput.x, throughput.y, throughput.z, eta);
+    st.L[slot] = mkf4(L.x, L.y, L.z, bsdfWeight);
+    if (iszero(throughput)) return flags;    /* dead path: every later term is multiplied by 0 */
+    const kz3 wow = to_world(its.sh, wo);
+    st.ray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, eps);
+    st.ray_d[slot] = mkf4(wow.x, wow.y, wow.z, KZ_INF);
+    st.misc[slot] = mkf4(bsdfPdf, its.acc_rough, misc.z, misc.w);
+    return flags | KZ_SHADE_CONTINUE;
+}
+
+/* ---- shadow -------------------------------------------------------------------------------- */
+/* integrator.cpp:259-278; returns true when occluded; *segments = closest-hit queries issued */
+KZ_HD bool kz_occluded_walk(const KzScene &sc, const KzStackRef &stk, kz3 o, kz3 d, float tmin, float tmax, float eps, int *segments) {
+    int seg = 0;
+    bool occluded = false;
+    for (;;) {
+        ++seg;
+        const KzHit h = kz_trace(sc, stk, o.x, o.y, o.z, d.x, d.y, d.z, tmin, tmax, false);
+        if (h.geom == KZ_INVALID_ID) break;
+        const uint32_t fl = sc.meshes[h.geom].flags;
+        if (!(fl & KZ_MESH_IS_LIGHT) || (fl & KZ_MESH_LIGHT_VISIBLE)) { occluded = true; break; }
+        o = o + d * (h.t + eps);
+        tmin = eps;
+        tmax = tmax - h.t;
+        if (seg > 4096) break;
+    }
+    *segments = seg;
+    return occluded;
+}
+KZ_HD void kz_shadow_item(const KzScene &sc, const KzStackRef &stk, const KzPathState &st, uint32_t slot, KzCounters &cnt) {
+    const KzF4 so = st.sray_o[slot], sd = st.sray_d[slot];
+    int seg;
+    const bool occ = kz_occluded_walk(sc, stk, mk3(so.x, so.y, so.z), mk3(sd.x, sd.y, sd.z), so.w, sd.w, sc.integrator.trace_bias, &seg);
+    cnt.rays_shadow += (unsigned long long)seg;
+    if (!occ) {
+        const KzF4 p = st.pending[slot];
+        KzF4 L = st.L[slot];
+        L.x += p.x; L.y += p.y; L.z += p.z;
+        st.L[slot] = L;
+    }
+}
+
+/* ---- accumulate ---------------------------------------------------------------------------- */
+#if KZ_DEVICE_CODE
+#define KZ_FRAME_ADD(ptr, vr, vg, vb, vw) atomicAdd(reinterpret_cast<float4 *>(ptr), make_float4(vr, vg, vb, vw))
+#else
+#define KZ_FRAME_ADD(ptr, vr, vg, vb, vw) do { (ptr)->x += (vr); (ptr)->y += (vg); (ptr)->z += (vb); (ptr)->w += (vw); } while (0)
+#endif
+/* ImageBlock::put on the whole bordered frame, block.cpp:56-85 */
+KZ_HD void kz_accumulate_item(const KzScene &sc, const KzPathState &st, uint32_t slot, KzF4 *frame) {
+    const KzF4 L = st.L[slot], misc = st.misc[slot];
+    const kz3 value = mk3(L.x, L.y, L.z);
+    if (!color_valid(value)) return;
+    const int b = sc.border, cols = sc.camera.width + 2 * b, rows = sc.camera.height + 2 * b;
+    const float radius = sc.filter.radius;
+    const float px = misc.z - 0.5f - (float)(0 - b), py = misc.w - 0.5f - (float)(0 - b);
+    const float lookup = 32 / radius;
+    int x0 = (int)ceilf(px - radius), y0 = (int)ceilf(py - radius);
+    int x1 = (int)floorf(px + radius), y1 = (int)floorf(py + radius);
+    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
+    x1 = x1 > cols - 1 ? cols - 1 : x1; y1 = y1 > rows - 1 ? rows - 1 : y1;
+    for (int y = y0; y <= y1; ++y) {
+        const float wy = sc.filter.table[(int)(fabsf((float)y - py) * lookup)];
+        for (int x = x0; x <= x1; ++x) {
+            const float wx = sc.filter.table[(int)(fabsf((float)x - px) * lookup)];
+            KzF4 *p = frame + ((size_t)y * cols + x);
+            KZ_FRAME_ADD(p, value.x * wx * wy, value.y * wx * wy, value.z * wx * wy, 1.0f * wx * wy);
+        }
+    }
+}
+
+#endif

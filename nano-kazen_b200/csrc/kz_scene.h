@@ -1,0 +1,97 @@
+/* kz_scene.h -- HBM-resident scene layout shared by the kernels (and by tests/hostemu).
+ *
+ * Accel:
+ *   nodes : 80-byte 8-wide compressed nodes (quantised child boxes, Ylitie/Karras/Laine 2017
+ *           style layout), read as 5 x 16-byte vector loads.
+ *   tris  : 48 bytes per triangle in leaf order = 3 x float4
+ *           (p0.xyz | geomID), (p1.xyz | primID), (p2.xyz | 0): raw vertices because the
+ *           parity-contracted Pluecker test works on origin-relative vertices.
+ * Shading: per-mesh vertex/normal/uv/index arrays concatenated, addressed through KzMeshRec.
+ */
+#ifndef KZ_SCENE_H
+#define KZ_SCENE_H
+#include "kz_common.h"
+#include "../../include/kzgpu.h"
+
+struct KzU4 { uint32_t x, y, z, w; };
+struct KzF4 { float x, y, z, w; };
+
+struct alignas(16) KzNode8 {
+    float    px, py, pz;          /* quantisation origin                                   */
+    uint8_t  ex, ey, ez, imask;   /* per-axis exponent (IEEE biased), internal-child mask  */
+    uint32_t child_base;          /* index of first internal child                         */
+    uint32_t tri_base;            /* index of first triangle referenced by this node       */
+    uint8_t  meta[8];             /* per slot: inner = 0x20|(24+slot); leaf = unary(ntri)<<5 | tri offset; 0 = empty */
+    uint8_t  qlox[8], qloy[8], qloz[8];
+    uint8_t  qhix[8], qhiy[8], qhiz[8];
+};
+static_assert(sizeof(KzNode8) == 80, "node must be 80 bytes");
+
+struct KzMeshRec {
+    uint32_t vertex_offset;   /* into positions/normals/uvs (in vertices) */
+    uint32_t index_offset;    /* into indices (in triangles)               */
+    uint32_t n_triangles;
+    uint32_t flags;           /* KZ_MESH_* */
+    int32_t  bsdf;
+    int32_t  light;
+    uint32_t cdf_offset;      /* into light_cdf (n_triangles+1 floats) */
+    float    inv_area;        /* DiscretePDF normalization = 1/sum(area), mesh.h pdf() */
+};
+#define KZ_MESH_HAS_NORMALS 1u
+#define KZ_MESH_HAS_UVS 2u
+#define KZ_MESH_IS_LIGHT 4u
+#define KZ_MESH_LIGHT_VISIBLE 8u
+
+/* material classes used to sort the shade queues */
+#define KZ_CLASS_TERMINAL 0   /* miss or light hit */
+#define KZ_CLASS_DIFFUSE 1
+#define KZ_CLASS_KISS 2
+#define KZ_CLASS_NORMALMAP 3
+#define KZ_NUM_CLASSES 4
+
+struct KzImageRec {
+    int32_t  width, height;
+    uint32_t texel_offset;    /* float4 index of mip level 0 */
+    int32_t  n_levels;        /* mip pyramid levels resident after level 0 (level l follows l-1) */
+};
+
+struct KzScene {
+    /* accel */
+    const KzNode8 *nodes;
+    const KzF4    *tris;
+    uint32_t       n_nodes, n_tris;
+    float          scene_max_abs;     /* max |coordinate| of any vertex: scales the traversal slack */
+    /* shading geometry */
+    const KzMeshRec *meshes;
+    uint32_t         n_meshes;
+    const float    *positions;
+    const float    *normals;
+    const float    *uvs;
+    const uint32_t *indices;
+    const float    *light_cdf;
+    const int32_t  *light_meshes;     /* scene.cpp:42-46 order */
+    int32_t         n_light_meshes;
+    /* materials */
+    const kz_bsdf_desc    *bsdfs;
+    const kz_texture_desc *textures;
+    const KzImageRec      *images;
+    const KzF4            *texels;
+    const kz_light_desc   *lights;
+    int32_t                background;
+    /* render setup */
+    kz_camera_desc     camera;
+    kz_integrator_desc integrator;
+    kz_filter_desc     filter;
+    int32_t            border;
+    /* sampler */
+    int32_t  sampler_type;
+    uint32_t sample_count;
+    uint64_t seed;
+    int32_t  res_x, res_y;
+    const uint16_t *blue_noise;
+    const uint32_t *pmj02bn;
+    const kz2      *pmj_pixel_samples;
+    int32_t         pmj_tile_size;
+};
+
+#endif

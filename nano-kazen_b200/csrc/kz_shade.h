@@ -1,0 +1,446 @@
+/* kz_shade.h -- device shading library: textures, kiss / diffuse / normalmap BSDFs, area
+ * lights, Mesh::sample, post-intersection.  References (nano-kazen):
+ *   texture.cpp:10-270, bsdf.cpp:20-92,281-417,1157-1418, ggx_brdf.h:15-170, light.cpp:7-66,
+ *   mesh.cpp:108-133, dpdf.h:99-104, accel.cpp:113-236, scene.cpp:54-79, warp.cpp:41-50,85-115.
+ * Float math here may be contracted to FMA by nvcc (image parity is statistical, SURVEY
+ * Appendix A 15a); sampler floats and hit t are produced elsewhere with exact rounding. */
+#ifndef KZ_SHADE_H
+#define KZ_SHADE_H
+#include "kz_sampler.h"
+#include "kz_traverse.h"
+
+#define KZ_MEASURE_UNKNOWN 0
+#define KZ_MEASURE_SOLID_ANGLE 1
+#define KZ_MEASURE_DISCRETE 2
+
+/* mesh.h:18-56 (subset that the hot path reads) */
+struct KzIts {
+    kz3 p;
+    kz2 uv;
+    KzFrame sh;
+    kz3 geo_n;
+    kz3 dpdu;
+    int32_t mesh;
+    float acc_rough;
+};
+
+/* ---- warps ---------------------------------------------------------------------------------- */
+KZ_HD kz2 square_to_uniform_disk(kz2 s) {
+    float r = sqrtf(s.x);
+    float a = 2.0f * KZ_PI * s.y;
+    return mk2(cosf(a) * r, sinf(a) * r);
+}
+KZ_HD kz3 square_to_cosine_hemisphere(kz2 s) {
+    float r1 = 2.0f * s.x - 1.0f, r2 = 2.0f * s.y - 1.0f;
+    float phi, r;
+    if (r1 == 0 && r2 == 0) { r = phi = 0; }
+    else if (r1 * r1 > r2 * r2) { r = r1; phi = (KZ_PI / 4.0f) * (r2 / r1); }
+    else { r = r2; phi = (KZ_PI / 2.0f) - (r1 / r2) * (KZ_PI / 4.0f); }
+    float px = r * cosf(phi), py = r * sinf(phi);
+    float z = sqrtf(1.0f - px * px - py * py);
+    if (z == 0) z = 1e-10f;
+    return mk3(px, py, z);
+}
+
+/* ---- textures -------------------------------------------------------------------------------- */
+KZ_HD int kz_wrapi(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
+KZ_HD void kz_bspline_weights(float f, float w[4]) {
+    float one_f = 1.0f - f;
+    w[0] = (one_f * one_f * one_f) / 6.0f;
+    w[1] = 2.0f / 3.0f - 0.5f * f * f * (2.0f - f);
+    w[2] = 2.0f / 3.0f - 0.5f * one_f * one_f * (2.0f - one_f);
+    w[3] = (f * f * f) / 6.0f;
+}
+/* finest mip level, periodic wrap, bicubic B-spline (OIIO default with zero derivatives) */
+KZ_HD kz3 kz_image_bicubic(const KzScene &sc, int image, float s, float t) {
+    const KzImageRec im = sc.images[image];
+    float x = s * im.width - 0.5f, y = t * im.height - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    int ix = (int)fx, iy = (int)fy;
+    float wx[4], wy[4];
+    kz_bspline_weights(x - fx, wx);
+    kz_bspline_weights(y - fy, wy);
+    kz3 acc = mk3(0.f);
+    const KzF4 *base = sc.texels + im.texel_offset;
+    for (int j = 0; j < 4; ++j) {
+        int yy = kz_wrapi(iy - 1 + j, im.height);
+        kz3 row = mk3(0.f);
+        for (int i = 0; i < 4; ++i) {
+            int xx = kz_wrapi(ix - 1 + i, im.width);
+            const KzF4 p = base[(size_t)yy * im.width + xx];
+            row += mk3(p.x, p.y, p.z) * wx[i];
+        }
+        acc += row * wy[j];
+    }
+    return acc;
+}
+
+/* Expression trees are tiny (depth <= 3 in every kazen scene); evaluated with an explicit
+ * depth bound instead of recursion so the kernels need no device call stack. */
+#define KZ_TEX_MAX_DEPTH 4
+template <int DEPTH> struct KzTexEval {
+    static KZ_HD kz3 uv(const KzScene &sc, int node, kz2 uv_) {
+        const kz_texture_desc t = sc.textures[node];
+        switch (t.type) {
+            case KZ_TEX_CONSTANT: return mk3(t.color[0], t.color[1], t.color[2]);
+            case KZ_TEX_IMAGE: {
+                kz3 c = kz_image_bicubic(sc, t.image, uv_.x * t.scale, (1.0f - uv_.y) * t.scale);
+                return t.srgb ? mk3(srgb_to_linear1(c.x), srgb_to_linear1(c.y), srgb_to_linear1(c.z)) : c;
+            }
+            case KZ_TEX_BACKGROUND:
+                return t.child[0] >= 0 ? t.a * KzTexEval<DEPTH - 1>::uv(sc, t.child[0], uv_) : mk3(0.f);
+            case KZ_TEX_COLORRAMP: {
+                if (t.child[0] < 0) return mk3(0.f);
+                kz3 c = KzTexEval<DEPTH - 1>::uv(sc, t.child[0], uv_);
+                return mk3(t.a + (t.b - t.a) * clampf(c.x, 0.f, 1.f), t.a + (t.b - t.a) * clampf(c.y, 0.f, 1.f),
+                           t.a + (t.b - t.a) * clampf(c.z, 0.f, 1.f));
+            }
+            case KZ_TEX_BLEND: {
+                kz3 mask = mk3(0.5f), in1 = mk3(0.f), in2 = mk3(1.f);
+                if (t.child[0] >= 0) mask = KzTexEval<DEPTH - 1>::uv(sc, t.child[0], uv_);
+                if (t.child[1] >= 0) in1 = KzTexEval<DEPTH - 1>::uv(sc, t.child[1], uv_);
+                if (t.child[2] >= 0) in2 = KzTexEval<DEPTH - 1>::uv(sc, t.child[2], uv_);
+                if (t.mode == KZ_BLEND_MIX) return mk3(lerpf(mask.x, in1.x, in2.x), lerpf(mask.x, in1.y, in2.y), lerpf(mask.x, in1.z, in2.z));
+                if (t.mode == KZ_BLEND_MULTIPLY) return in1 * in2;
+                return mk3(0.f);
+            }
+        }
+        return mk3(0.f);
+    }
+    static KZ_HD kz3 dir(const KzScene &sc, int node, kz3 d) {
+        const kz_texture_desc t = sc.textures[node];
+        switch (t.type) {
+            case KZ_TEX_CONSTANT: return mk3(t.color[0], t.color[1], t.color[2]);
+            case KZ_TEX_IMAGE: {
+                float s = atan2f(-d.x, d.z) / (2.0f * KZ_PI) + 0.5f;
+                float tt = 0.5f - atan2f(d.y, hypotf(d.z, -d.x)) / KZ_PI;
+                if (isnan(s)) s = 0.0f;
+                if (isnan(tt)) tt = 0.0f;
+                return kz_image_bicubic(sc, t.image, s, tt);
+            }
+            case KZ_TEX_BACKGROUND:
+                return t.child[0] >= 0 ? t.a * KzTexEval<DEPTH - 1>::dir(sc, t.child[0], d) : mk3(0.f);
+            default: return mk3(0.f);
+        }
+    }
+};
+template <> struct KzTexEval<0> {
+    static KZ_HD kz3 uv(const KzScene &, int, kz2) { return mk3(0.f); }
+    static KZ_HD kz3 dir(const KzScene &, int, kz3) { return mk3(0.f); }
+};
+KZ_HD kz3 kz_tex_uv(const KzScene &sc, int node, kz2 uv) { return KzTexEval<KZ_TEX_MAX_DEPTH>::uv(sc, node, uv); }
+KZ_HD kz3 kz_background(const KzScene &sc, kz3 d) {   /* scene.cpp:54-79 */
+    if (sc.background < 0) return mk3(0.f);
+    if (isnan3(d)) return mk3(0.f);
+    return KzTexEval<KZ_TEX_MAX_DEPTH>::dir(sc, sc.background, d);
+}
+
+/* ---- GGX helpers (ggx_brdf.h) ------------------------------------------------------------ */
+KZ_HD kz2 roughness_to_alpha(float roughness, float anisotropy) {
+    float alpha = fmaxf(0.001f, sqr(roughness));
+    return mk2(alpha * (1.0f + anisotropy), alpha * (1.0f - anisotropy));
+}
+KZ_HD float ggx_lambda(kz3 v, kz2 a) {
+    float squared = (sqr(a.x) * sqr(v.x) + sqr(a.y) * sqr(v.y)) / sqr(v.z);
+    return (-1.0f + sqrtf(1.0f + squared)) * 0.5f;
+}
+KZ_HD float smith_g1(kz3 V, kz3 H, kz2 a) { return dot(V, H) <= 0.0f ? 0.0f : 1.0f / (1.0f + ggx_lambda(V, a)); }
+KZ_HD float smith_g2(kz3 V, kz3 L, kz3 H, kz2 a) {
+    if (dot(V, H) <= 0.0f || dot(L, H) < 0.0f) return 0.0f;
+    return 1.0f / (1.0f + ggx_lambda(V, a) + ggx_lambda(L, a));
+}
+KZ_HD float ggx_ndf(kz3 H, kz2 a) {
+    float ellipse = sqr(H.x) / sqr(a.x) + sqr(H.y) / sqr(a.y) + sqr(H.z);
+    return 1.0f / (KZ_PI * a.x * a.y * sqr(ellipse));
+}
+KZ_HD float ggx_vndf(kz3 V, kz3 H, kz2 a) {
+    float VDotH = dot(V, H);
+    if (VDotH <= 0.0f) return 0.0f;
+    return ggx_ndf(H, a) * smith_g1(V, H, a) * VDotH / V.z;
+}
+KZ_HD kz3 sample_ggx_vndf(kz3 V, kz2 a, kz2 rnd) {
+    kz3 Vh = normalized(mk3(a.x * V.x, a.y * V.y, V.z));
+    float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
+    kz3 T1 = lensq > 0.0f ? mk3(-Vh.y, Vh.x, 0.0f) / sqrtf(lensq) : mk3(1.0f, 0.0f, 0.0f);
+    kz3 T2 = normalized(cross(Vh, T1));
+    float r = sqrtf(rnd.x);
+    float phi = 2.0f * KZ_PI * rnd.y;
+    float t1 = r * cosf(phi);
+    float t2 = r * sinf(phi);
+    float s = 0.5f * (1.0f + Vh.z);
+    t2 = (1.0f - s) * sqrtf(1.0f - t1 * t1) + s * t2;
+    kz3 Nh = t1 * T1 + t2 * T2 + sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
+    return normalized(mk3(a.x * Nh.x, a.y * Nh.y, fmaxf(1e-6f, Nh.z)));
+}
+KZ_HD kz3 ggx_smith_brdf(kz3 V, kz3 L, kz3 f0, float roughness, float anisotropy) {
+    if (V.z * L.z < 0.0f) return mk3(0.0f);
+    kz2 a = roughness_to_alpha(roughness, anisotropy);
+    kz3 H = normalized(V + L);
+    float D = ggx_ndf(H, a);
+    float G = smith_g2(V, L, H, a);
+    float w = powf(1.0f - dot(V, H), 5.0f);
+    kz3 F = f0 * 1.0f + (mk3(1.f) - f0) * w;
+    float denom = 4.0f * fabsf(V.z) * fabsf(L.z);
+    return (D * G) * F / denom;
+}
+
+/* ---- BSDF query record (bsdf.h:17-53), minimal ------------------------------------------- */
+struct KzBRec {
+    kz3 wi, wo;
+    kz2 uv;
+    float acc_rough;     /* bRec.its.accumulatedRoughness */
+    float eta;
+    int measure;
+};
+
+KZ_HD float schlick_weight(float x) { x = clampf(1.f - x, 0.f, 1.f); float x2 = x * x; return x2 * x2 * x; }
+KZ_HD kz3 lerp_color(kz3 c1, kz3 c2, float t) { return (1.f - t) * c1 + t * c2; }
+
+/* Texture fetches of one kiss lookup, shared by eval/pdf/sample of the same vertex. */
+struct KzKissParams { kz3 base; float metallic, roughness_raw; };
+KZ_HD KzKissParams kiss_params(const KzScene &sc, const kz_bsdf_desc &m, kz2 uv) {
+    KzKissParams p;
+    p.base = kz_tex_uv(sc, m.base_color, uv);
+    p.metallic = kz_tex_uv(sc, m.metallic, uv).x;
+    p.roughness_raw = kz_tex_uv(sc, m.roughness, uv).x;
+    return p;
+}
+KZ_HD kz3 kiss_eval(const kz_bsdf_desc &m, const KzKissParams &kp, const KzBRec &b) {   /* bsdf.cpp:1215-1267 */
+    if (b.wi.z <= 0 || b.wo.z <= 0) return mk3(0.0f);
+    kz3 V = b.wi, L = b.wo, H = normalized(V + L);
+    kz3 Cdlin = kp.base;
+    float metallic = kp.metallic;
+    float roughness = fminf(1.f, kp.roughness_raw + b.acc_rough);
+    float Cdlum = luminance(Cdlin);
+    kz3 Ctint = Cdlum > 0.f ? Cdlin / Cdlum : mk3(1.f);
+    kz3 Ctintmix = (0.08f * m.specular) * lerp_color(mk3(1.f), Ctint, m.specular_tint);
+    kz3 Cspec0 = lerp_color(Ctintmix, Cdlin, metallic);
+    float FL = schlick_weight(L.z), FV = schlick_weight(V.z), FH = schlick_weight(dot(L, H));
+    float cosThetaD = dot(V, H);
+    float Lambert = (1.f - 0.5f * FL) * (1.f - 0.5f * FV);
+    float RR = 2.f * roughness * cosThetaD * cosThetaD;
+    float retro = RR * (FL + FV + FL * FV * (RR - 1.f));
+    kz3 Csheen = lerp_color(mk3(1.f), Ctint, m.sheen_tint);
+    kz3 Fsheen = (FH * m.sheen) * Csheen;
+    kz3 specTerm = ggx_smith_brdf(V, L, Cspec0, roughness, m.anisotropy);
+    float ccR = lerpf(m.clearcoat_roughness, .01f, .3f);
+    kz3 coatTerm = m.clearcoat != 0.f ? (0.25f * m.clearcoat) * ggx_smith_brdf(V, L, mk3(0.04f), ccR, m.anisotropy) : mk3(0.f);
+    return ((1.f - metallic) * (Cdlin * KZ_INV_PI * (Lambert + retro) + Fsheen) + (specTerm + coatTerm)) * b.wo.z;
+}
+KZ_HD float kiss_pdf(const kz_bsdf_desc &m, const KzKissParams &kp, const KzBRec &b) {   /* bsdf.cpp:1269-1299 */
+    if (b.wi.z <= 0 || b.wo.z <= 0) return 0.0f;
+    float diffuse = (1.f - kp.metallic) * 0.5f;
+    float GTR2 = 1.f / (1.f + m.clearcoat);
+    kz3 H = normalized(b.wi + b.wo);
+    float jacobian = 4.0f * dot(b.wi, H);
+    float roughness = fminf(1.f, kp.roughness_raw + b.acc_rough);
+    kz2 alpha = roughness_to_alpha(roughness, m.anisotropy);
+    float specPdf = ggx_vndf(b.wi, H, alpha) / jacobian;
+    kz2 coatalpha = roughness_to_alpha(lerpf(m.clearcoat_roughness, .01f, .3f), 0.f);
+    float coatPdf = ggx_vndf(b.wi, H, coatalpha) / jacobian;
+    return diffuse * KZ_INV_PI * b.wo.z + (1.f - diffuse) * (GTR2 * specPdf + (1.f - GTR2) * coatPdf);
+}
+/* returns weight; *pdf_out = pdf(bRec) as the integrator queries it afterwards (integrator.cpp:314) */
+KZ_HD kz3 kiss_sample(const kz_bsdf_desc &m, const KzKissParams &kp, KzBRec &b, float sample1, kz2 sample2, float *pdf_out) { /* bsdf.cpp:1301-1371 */
+    *pdf_out = 0.f;
+    if (b.wi.z <= 0) return mk3(0.0f);
+    b.measure = KZ_MEASURE_SOLID_ANGLE;
+    b.eta = 1.0f;
+    float diffuse = (1.f - kp.metallic) * 0.5f;
+    if (sample1 < diffuse) {
+        b.wo = square_to_cosine_hemisphere(sample2);
+    } else {
+        float sample = (sample1 - diffuse) / (1.f - diffuse);
+        float GTR2 = 1.f / (1.f + m.clearcoat);
+        kz2 alpha = sample < GTR2 ? roughness_to_alpha(kp.roughness_raw, m.anisotropy)      /* un-biased roughness, :1323 */
+                                  : roughness_to_alpha(lerpf(m.clearcoat_roughness, 0.01f, .3f), 0.f);
+        kz3 H = sample_ggx_vndf(b.wi, alpha, sample2);     /* flip is dead code: wi.z > 0 here */
+        b.wo = normalized(reflect3(b.wi, H));
+    }
+    float pdf = kiss_pdf(m, kp, b);
+    *pdf_out = pdf;
+    if (b.wo.z <= 0 || pdf <= KZ_EPSILON || isnan3(b.wo)) return mk3(0.f);
+    return kiss_eval(m, kp, b) / pdf;
+}
+
+/* One shading vertex: the hit mesh's BSDF with its (single) optional normal-map wrapper resolved.
+ * Supported nesting (everything kazen's scenes use): diffuse | kiss | normalmap(diffuse|kiss). */
+struct KzBsdfCtx {
+    const kz_bsdf_desc *outer;     /* mesh BSDF */
+    const kz_bsdf_desc *leaf;      /* nested (== outer when not a normal map) */
+    KzKissParams kp;               /* leaf kiss parameters at uv */
+    bool is_nmap;
+    kz3 nm_n;                      /* 2*rgb-1, un-normalised */
+    KzFrame pert;                  /* perturbed frame (bsdf.cpp:366-374) */
+};
+KZ_HD KzBsdfCtx bsdf_ctx(const KzScene &sc, const KzIts &its) {
+    KzBsdfCtx c;
+    c.outer = sc.bsdfs + sc.meshes[its.mesh].bsdf;
+    c.is_nmap = c.outer->type == KZ_BSDF_NORMALMAP;
+    c.leaf = c.is_nmap ? sc.bsdfs + c.outer->nested : c.outer;
+    if (c.leaf->type == KZ_BSDF_KISS) c.kp = kiss_params(sc, *c.leaf, its.uv);
+    else { c.kp.base = mk3(0.f); c.kp.metallic = 0.f; c.kp.roughness_raw = 0.f; }
+    if (c.is_nmap) {
+        kz3 rgb = kz_tex_uv(sc, c.outer->normal_map, its.uv);
+        c.nm_n = mk3(2 * rgb.x - 1, 2 * rgb.y - 1, 2 * rgb.z - 1);
+        kz3 n = normalized(c.nm_n);
+        c.pert.n = normalized(to_world(its.sh, n));
+        c.pert.s = normalized(its.dpdu - c.pert.n * dot(c.pert.n, its.dpdu));
+        c.pert.t = normalized(cross(c.pert.n, c.pert.s));
+    } else {
+        c.nm_n = mk3(0.f, 0.f, 1.f);
+        c.pert = its.sh;
+    }
+    return c;
+}
+KZ_HD kz3 leaf_eval(const KzBsdfCtx &c, const KzBRec &b) {
+    if (c.leaf->type == KZ_BSDF_KISS) return kiss_eval(*c.leaf, c.kp, b);
+    if (b.measure != KZ_MEASURE_SOLID_ANGLE || b.wi.z <= 0 || b.wo.z <= 0) return mk3(0.0f);   /* bsdf.cpp:27-36 */
+    return mk3(c.leaf->albedo[0], c.leaf->albedo[1], c.leaf->albedo[2]) * KZ_INV_PI * b.wo.z;
+}
+KZ_HD float leaf_pdf(const KzBsdfCtx &c, const KzBRec &b) {
+    if (c.leaf->type == KZ_BSDF_KISS) return kiss_pdf(*c.leaf, c.kp, b);
+    if (b.measure != KZ_MEASURE_SOLID_ANGLE || b.wi.z <= 0 || b.wo.z <= 0) return 0.0f;        /* bsdf.cpp:39-55 */
+    return KZ_INV_PI * b.wo.z;
+}
+KZ_HD kz3 leaf_sample(const KzBsdfCtx &c, KzBRec &b, float s1, kz2 s2, float *pdf_out) {
+    if (c.leaf->type == KZ_BSDF_KISS) return kiss_sample(*c.leaf, c.kp, b, s1, s2, pdf_out);
+    *pdf_out = 0.f;                                                                            /* bsdf.cpp:58-75 */
+    if (b.wi.z <= 0) return mk3(0.0f);
+    b.measure = KZ_MEASURE_SOLID_ANGLE;
+    b.wo = square_to_cosine_hemisphere(s2);
+    b.eta = 1.0f;
+    *pdf_out = leaf_pdf(c, b);
+    return mk3(c.leaf->albedo[0], c.leaf->albedo[1], c.leaf->albedo[2]);
+}
+
+/* eval + pdf of the mesh BSDF for (wi, wo) given in the ORIGINAL shading frame (NEE, integrator.cpp:283-290) */
+KZ_HD void bsdf_eval_pdf(const KzBsdfCtx &c, const KzIts &its, kz3 wi, kz3 wo, kz3 *f, float *pdf) {
+    KzBRec b; b.wi = wi; b.wo = wo; b.uv = its.uv; b.acc_rough = its.acc_rough; b.eta = 1.f; b.measure = KZ_MEASURE_SOLID_ANGLE;
+    if (!c.is_nmap) { *f = leaf_eval(c, b); *pdf = leaf_pdf(c, b); return; }
+    /* bsdf.cpp:290-336 */
+    if (wi.z > 0 && wo.z > 0 && dot(c.nm_n, wi) <= 0) { *f = leaf_eval(c, b); *pdf = leaf_pdf(c, b); return; }
+    KzBRec pq = b;
+    pq.wi = to_local(c.pert, to_world(its.sh, wi));
+    pq.wo = to_local(c.pert, to_world(its.sh, wo));
+    pq.acc_rough = 0.f;                                  /* nested query carries a default `its` */
+    if (wo.z * pq.wo.z <= 0) { *f = mk3(0.f); *pdf = 0.f; return; }
+    *f = leaf_eval(c, pq); *pdf = leaf_pdf(c, pq);
+}
+
+/* sample() of the mesh BSDF + the integrator's follow-up pdf(bRec) query (integrator.cpp:307-314).
+ * wo is returned in the ORIGINAL shading frame. */
+KZ_HD kz3 bsdf_sample(const KzBsdfCtx &c, const KzIts &its, kz3 wi, float s1, kz2 s2, kz3 *wo, float *pdf, int *measure) {
+    KzBRec b; b.wi = wi; b.wo = mk3(0.f); b.uv = its.uv; b.acc_rough = its.acc_rough; b.eta = 1.f; b.measure = KZ_MEASURE_UNKNOWN;
+    if (!c.is_nmap || (wi.z > 0 && dot(c.nm_n, wi) <= 0)) {
+        float p;
+        kz3 w = leaf_sample(c, b, s1, s2, &p);
+        *wo = b.wo; *measure = b.measure;
+        /* integrator's pdf(bRec): for a normal map this re-enters NormalMap::pdf with the sampled wo */
+        if (c.is_nmap && !iszero(w)) { kz3 f; bsdf_eval_pdf(c, its, wi, b.wo, &f, &p); }
+        *pdf = p;
+        return w;
+    }
+    /* bsdf.cpp:343-362 */
+    KzBRec pq = b;
+    pq.wi = to_local(c.pert, to_world(its.sh, wi));
+    pq.acc_rough = 0.f;
+    float p;
+    kz3 result = leaf_sample(c, pq, s1, s2, &p);
+    *measure = KZ_MEASURE_UNKNOWN;          /* bRec.measure is never written back on this path */
+    *pdf = 0.f;
+    if (!iszero(result)) {
+        kz3 w = to_local(its.sh, to_world(c.pert, pq.wo));
+        *wo = w;
+        if (w.z * pq.wo.z <= 0) return mk3(0.f);
+        /* integrator's pdf(bRec) with measure == unknown: kiss ignores the measure, diffuse returns 0 */
+        KzBRec q = b; q.wo = w;
+        if (wi.z > 0 && w.z > 0 && dot(c.nm_n, wi) <= 0) *pdf = leaf_pdf(c, q);
+        else {
+            KzBRec pq2 = q;
+            pq2.wi = pq.wi; pq2.wo = to_local(c.pert, to_world(its.sh, w)); pq2.acc_rough = 0.f;
+            *pdf = (w.z * pq2.wo.z <= 0) ? 0.f : leaf_pdf(c, pq2);
+        }
+    }
+    return result;
+}
+KZ_HD float bsdf_regularize(const KzBsdfCtx &c) {   /* bsdf.h:125, bsdf.cpp:412,1397-1399 */
+    return c.leaf->type == KZ_BSDF_KISS ? c.kp.roughness_raw : 0.f;
+}
+
+/* ---- lights -------------------------------------------------------------------------------- */
+KZ_HD kz3 kz_vpos(const KzScene &sc, const KzMeshRec &m, uint32_t i) { const float *p = sc.positions + 3 * (size_t)(m.vertex_offset + i); return mk3(p[0], p[1], p[2]); }
+KZ_HD kz3 kz_vnrm(const KzScene &sc, const KzMeshRec &m, uint32_t i) { const float *p = sc.normals + 3 * (size_t)(m.vertex_offset + i); return mk3(p[0], p[1], p[2]); }
+KZ_HD kz2 kz_vuv(const KzScene &sc, const KzMeshRec &m, uint32_t i) { const float *p = sc.uvs + 2 * (size_t)(m.vertex_offset + i); return mk2(p[0], p[1]); }
+
+/* dpdf.h:99-104: std::lower_bound over cdf[0..n], then index = clamp(pos-1, 0, n-1) */
+KZ_HD uint32_t cdf_sample(const float *cdf, uint32_t n, float v) {
+    uint32_t lo = 0, hi = n + 1;                 /* first element >= v in [0, n+1) */
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (cdf[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    int32_t idx = (int32_t)lo - 1;
+    if (idx < 0) idx = 0;
+    return (uint32_t)idx < n - 1 ? (uint32_t)idx : n - 1;
+}
+/* light.cpp:16-19,36-51 */
+KZ_HD float light_pdf(float inv_area, kz3 ref, kz3 p, kz3 n, kz3 wi) {
+    float cosTheta = dot(n, -wi);
+    if (cosTheta > 0.f) return inv_area * sqnorm(p - ref) / cosTheta;
+    return 0.f;
+}
+
+/* ---- post-intersection (accel.cpp:113-236) ---------------------------------------------- */
+KZ_HD void fill_intersection(const KzScene &sc, const KzHit &h, KzIts &its, kz3 prev_dpdu) {
+    its.mesh = (int32_t)h.geom;
+    const KzMeshRec m = sc.meshes[h.geom];
+    const uint32_t *F = sc.indices + 3 * (size_t)(m.index_offset + h.prim);
+    const uint32_t i0 = F[0], i1 = F[1], i2 = F[2];
+    const float b0 = 1 - (h.u + h.v), b1 = h.u, b2 = h.v;
+    const bool hasN = (m.flags & KZ_MESH_HAS_NORMALS) != 0, hasUV = (m.flags & KZ_MESH_HAS_UVS) != 0;
+    const kz3 p0 = kz_vpos(sc, m, i0), p1 = kz_vpos(sc, m, i1), p2 = kz_vpos(sc, m, i2);
+    kz3 n0 = mk3(0.f), n1 = mk3(0.f), n2 = mk3(0.f);
+    if (hasN) { n0 = kz_vnrm(sc, m, i0); n1 = kz_vnrm(sc, m, i1); n2 = kz_vnrm(sc, m, i2); }
+    const kz3 orignP = b0 * p0 + b1 * p1 + b2 * p2;
+    kz3 tmpu = orignP - p0, tmpv = orignP - p1, tmpw = orignP - p2;
+    const float dotu = fminf(0.f, dot(tmpu, n0)), dotv = fminf(0.f, dot(tmpv, n1)), dotw = fminf(0.f, dot(tmpw, n2));
+    tmpu -= dotu * n0; tmpv -= dotv * n1; tmpw -= dotw * n2;
+    its.p = orignP + b0 * tmpu + b1 * tmpv + b2 * tmpw;
+    const kz3 dp0 = p1 - p0, dp1 = p2 - p0;
+    const kz3 gcross = cross(dp0, dp1);
+    its.geo_n = normalized(gcross);
+    its.uv = mk2(h.u, h.v);
+    its.dpdu = prev_dpdu;
+    kz2 uv0 = mk2(0, 0), uv1 = mk2(0, 0), uv2 = mk2(0, 0);
+    if (hasUV) {
+        uv0 = kz_vuv(sc, m, i0); uv1 = kz_vuv(sc, m, i1); uv2 = kz_vuv(sc, m, i2);
+        its.uv = mk2(b0 * uv0.x + b1 * uv1.x + b2 * uv2.x, b0 * uv0.y + b1 * uv1.y + b2 * uv2.y);
+    }
+    if (hasN && hasUV) {
+        const kz2 duv0 = mk2(uv1.x - uv0.x, uv1.y - uv0.y), duv1 = mk2(uv2.x - uv0.x, uv2.y - uv0.y);
+        const kz3 shNormal = b0 * n0 + b1 * n1 + b2 * n2;
+        const float length = norm(gcross);
+        if (length > 0.f) {
+            const float determinant = duv0.x * duv1.y - duv0.y * duv1.x;
+            if (determinant > 0.f) {
+                const float invDet = 1.0f / determinant;
+                its.dpdu = (duv1.y * dp0 - duv0.y * dp1) * invDet;
+                its.sh.n = normalized(shNormal);
+                its.sh.s = normalized(its.dpdu - shNormal * dot(shNormal, its.dpdu));
+                its.sh.t = normalized(cross(its.sh.n, its.sh.s));
+            } else {
+                its.sh = frame_from_normal(normalized(shNormal));
+                its.dpdu = its.sh.s;
+            }
+        } else {
+            its.sh = frame_from_normal(normalized(shNormal));
+        }
+    } else if (hasN) {
+        its.sh = frame_from_normal(normalized(b0 * n0 + b1 * n1 + b2 * n2));
+    } else {
+        its.sh = frame_from_normal(its.geo_n);
+    }
+}
+
+#endif

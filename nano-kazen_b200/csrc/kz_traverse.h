@@ -1,0 +1,226 @@
+/* kz_traverse.h -- closest-hit traversal of the 8-wide compressed BVH + the parity-contracted
+ * triangle test.  Replaces rtcIntersect1 as called at src/kazen/accel.cpp:98.
+ *
+ * Triangle test: Embree's robust ("Pluecker") single-ray test on origin-relative vertices with
+ * the operation shapes of its AVX2 build (fused dot/cross); every operation is an explicitly
+ * rounded intrinsic so nvcc cannot re-associate or contract differently from the oracle
+ * (oracle/kzo_accel.h): hit IDs and t are bit-identical to the oracle by construction, as long
+ * as culling is conservative.
+ *
+ * Culling is conservative by construction:
+ *   - child boxes are quantised outwards (lo rounded down, hi rounded up) at build time;
+ *   - every ray widens each slab by `slack` = 2^-18 * (max|org| + scene_max_abs) in position
+ *     space by shifting the origin used for the near / far plane (no per-child cost); this
+ *     covers the Pluecker tolerance (FLT_EPSILON*|UVW|), the rounding of p - org, and the
+ *     rounding of the slab FMAs, all of which are a few ulp of those magnitudes;
+ *   - |dir| components below 1e-18 are replaced by +-1e-18 (Embree's rcp_safe idea), so the
+ *     slab arithmetic never produces NaN.
+ *   Ties on exact t are broken by smallest (geomID, primID), independent of traversal order.
+ *
+ * Traversal: stack of (node group | triangle group) 8-byte entries, octant-ordered child
+ * visiting through the per-slot meta encoding (no distance sort), short stack in shared
+ * memory on the device with overflow to local memory.
+ */
+#ifndef KZ_TRAVERSE_H
+#define KZ_TRAVERSE_H
+#include "kz_scene.h"
+
+struct KzHit { float t, u, v; uint32_t prim, geom; };
+
+#if KZ_DEVICE_CODE
+#define KZ_LDG_U4(ptr) __ldg(reinterpret_cast<const uint4 *>(ptr))
+KZ_HD KzU4 kz_load_u4(const void *p) { uint4 v = KZ_LDG_U4(p); KzU4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+#else
+KZ_HD KzU4 kz_load_u4(const void *p) { KzU4 r; memcpy(&r, p, 16); return r; }
+#endif
+
+KZ_HD float kz_edot(float ax, float ay, float az, float bx, float by, float bz) {
+    return kz_fma(ax, bx, kz_fma(ay, by, kz_mul(az, bz)));
+}
+/* a*b - c fused */
+KZ_HD float kz_fms(float a, float b, float c) { return kz_fma(a, b, -c); }
+
+/* Returns true if the triangle is hit inside [tnear, tfar]; fills t,u,v. */
+KZ_HD bool kz_pluecker(float ox, float oy, float oz, float dx, float dy, float dz, float tnear, float tfar,
+                       KzU4 a, KzU4 b, KzU4 c, float &t_out, float &u_out, float &v_out) {
+    float v0x = kz_sub(kz_u2f(a.x), ox), v0y = kz_sub(kz_u2f(a.y), oy), v0z = kz_sub(kz_u2f(a.z), oz);
+    float v1x = kz_sub(kz_u2f(b.x), ox), v1y = kz_sub(kz_u2f(b.y), oy), v1z = kz_sub(kz_u2f(b.z), oz);
+    float v2x = kz_sub(kz_u2f(c.x), ox), v2y = kz_sub(kz_u2f(c.y), oy), v2z = kz_sub(kz_u2f(c.z), oz);
+    float e0x = kz_sub(v2x, v0x), e0y = kz_sub(v2y, v0y), e0z = kz_sub(v2z, v0z);
+    float e1x = kz_sub(v0x, v1x), e1y = kz_sub(v0y, v1y), e1z = kz_sub(v0z, v1z);
+    float e2x = kz_sub(v1x, v2x), e2y = kz_sub(v1y, v2y), e2z = kz_sub(v1z, v2z);
+    /* U = dot(cross(e0, v2+v0), D) etc. */
+    float s0x = kz_add(v2x, v0x), s0y = kz_add(v2y, v0y), s0z = kz_add(v2z, v0z);
+    float s1x = kz_add(v0x, v1x), s1y = kz_add(v0y, v1y), s1z = kz_add(v0z, v1z);
+    float s2x = kz_add(v1x, v2x), s2y = kz_add(v1y, v2y), s2z = kz_add(v1z, v2z);
+    float U = kz_edot(kz_fms(e0y, s0z, kz_mul(e0z, s0y)), kz_fms(e0z, s0x, kz_mul(e0x, s0z)), kz_fms(e0x, s0y, kz_mul(e0y, s0x)), dx, dy, dz);
+    float V = kz_edot(kz_fms(e1y, s1z, kz_mul(e1z, s1y)), kz_fms(e1z, s1x, kz_mul(e1x, s1z)), kz_fms(e1x, s1y, kz_mul(e1y, s1x)), dx, dy, dz);
+    float W = kz_edot(kz_fms(e2y, s2z, kz_mul(e2z, s2y)), kz_fms(e2z, s2x, kz_mul(e2x, s2z)), kz_fms(e2x, s2y, kz_mul(e2y, s2x)), dx, dy, dz);
+    float UVW = kz_add(kz_add(U, V), W);
+    float eps = kz_mul(1.1920928955078125e-07f, fabsf(UVW));
+    float mn = fminf(U, fminf(V, W)), mx = fmaxf(U, fmaxf(V, W));
+    if (!(mn >= -eps || mx <= eps)) return false;
+    /* stable_triangle_normal(e0, e1, e2) */
+    float ab_x = kz_mul(e0z, e1y), ab_y = kz_mul(e0x, e1z), ab_z = kz_mul(e0y, e1x);
+    float bc_x = kz_mul(e1z, e2y), bc_y = kz_mul(e1x, e2z), bc_z = kz_mul(e1y, e2x);
+    float cab_x = kz_fms(e0y, e1z, ab_x), cab_y = kz_fms(e0z, e1x, ab_y), cab_z = kz_fms(e0x, e1y, ab_z);
+    float cbc_x = kz_fms(e1y, e2z, bc_x), cbc_y = kz_fms(e1z, e2x, bc_y), cbc_z = kz_fms(e1x, e2y, bc_z);
+    float ngx = fabsf(ab_x) < fabsf(bc_x) ? cab_x : cbc_x;
+    float ngy = fabsf(ab_y) < fabsf(bc_y) ? cab_y : cbc_y;
+    float ngz = fabsf(ab_z) < fabsf(bc_z) ? cab_z : cbc_z;
+    float d = kz_edot(ngx, ngy, ngz, dx, dy, dz);
+    float den = kz_add(d, d);
+    float T0 = kz_edot(v0x, v0y, v0z, ngx, ngy, ngz);
+    float T = kz_add(T0, T0);
+    float t = kz_mul(kz_rcp(den), T);
+    if (!(tnear <= t && t <= tfar)) return false;
+    if (den == 0.0f) return false;
+    float rcpUVW = fabsf(UVW) < 1e-18f ? 0.0f : kz_rcp(UVW);
+    t_out = t;
+    u_out = fminf(kz_mul(U, rcpUVW), 1.0f);
+    v_out = fminf(kz_mul(V, rcpUVW), 1.0f);
+    return true;
+}
+
+KZ_HD float kz_rcp_safe(float d) {
+    if (fabsf(d) < 1e-18f) d = (kz_f2u(d) >> 31) ? -1e-18f : 1e-18f;
+    return 1.0f / d;
+}
+
+#ifndef KZ_SHORT_STACK
+#define KZ_SHORT_STACK 8          /* entries per thread kept in shared memory */
+#endif
+#define KZ_LOCAL_STACK 56         /* overflow entries in local memory          */
+
+struct KzStackRef {
+#if KZ_DEVICE_CODE
+    uint2 *smem;                  /* this thread's column: entry i at smem[i * stride] */
+    int stride;
+#endif
+};
+
+/* The traversal proper.  `stk` gives the shared-memory short stack on the device; on the host
+ * everything lives in the local array.  any_hit: return at the first accepted hit. */
+KZ_HD KzHit kz_trace(const KzScene &sc, const KzStackRef &stk, float ox, float oy, float oz, float dx, float dy, float dz,
+                     float tmin, float tmax, bool any_hit) {
+    KzHit best; best.t = tmax; best.u = 0.f; best.v = 0.f; best.prim = KZ_INVALID_ID; best.geom = KZ_INVALID_ID;
+    if (sc.n_nodes == 0) return best;
+
+    const float slack = (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + sc.scene_max_abs) * 3.814697265625e-06f;
+    const float rdx = kz_rcp_safe(dx), rdy = kz_rcp_safe(dy), rdz = kz_rcp_safe(dz);
+    const bool nx = rdx < 0.f, ny = rdy < 0.f, nz = rdz < 0.f;
+    /* origins used for the near / far planes (slab widened by slack in position space) */
+    const float onx = nx ? ox - slack : ox + slack, ofx = nx ? ox + slack : ox - slack;
+    const float ony = ny ? oy - slack : oy + slack, ofy = ny ? oy + slack : oy - slack;
+    const float onz = nz ? oz - slack : oz + slack, ofz = nz ? oz + slack : oz - slack;
+    const uint32_t oct_inv = ((nx ? 0u : 1u) | (ny ? 0u : 2u) | (nz ? 0u : 4u));   /* 7 - octant */
+    const uint32_t oct_inv4 = oct_inv * 0x01010101u;
+
+    uint32_t lstack_x[KZ_LOCAL_STACK], lstack_y[KZ_LOCAL_STACK];
+    int sp = 0;   /* number of stacked entries */
+
+    uint32_t ng_x = 0u, ng_y = 0x80000000u;   /* node group: (child base, hits<<24 | imask) */
+    uint32_t tg_x = 0u, tg_y = 0u;            /* triangle group: (tri base, hit bits)        */
+
+    for (;;) {
+        if (ng_y > 0x00FFFFFFu) {
+            const uint32_t hits_imask = ng_y;
+            const uint32_t bit = kz_bfind(hits_imask);
+            const uint32_t child_base = ng_x;
+            ng_y &= ~(1u << bit);
+            if (ng_y > 0x00FFFFFFu) {           /* siblings left: push the rest of the group */
+#if KZ_DEVICE_CODE
+                if (sp < KZ_SHORT_STACK) stk.smem[sp * stk.stride] = make_uint2(ng_x, ng_y);
+                else { lstack_x[sp - KZ_SHORT_STACK] = ng_x; lstack_y[sp - KZ_SHORT_STACK] = ng_y; }
+#else
+                lstack_x[sp] = ng_x; lstack_y[sp] = ng_y;
+#endif
+                ++sp;
+            }
+            const uint32_t slot = (bit - 24u) ^ oct_inv;
+            const uint32_t rel = kz_popc(hits_imask & ~(0xFFFFFFFFu << slot));
+            const KzNode8 *node = sc.nodes + (child_base + rel);
+            const KzU4 n0 = kz_load_u4(reinterpret_cast<const char *>(node));
+            const KzU4 n1 = kz_load_u4(reinterpret_cast<const char *>(node) + 16);
+            const KzU4 n2 = kz_load_u4(reinterpret_cast<const char *>(node) + 32);
+            const KzU4 n3 = kz_load_u4(reinterpret_cast<const char *>(node) + 48);
+            const KzU4 n4 = kz_load_u4(reinterpret_cast<const char *>(node) + 64);
+            const float px = kz_u2f(n0.x), py = kz_u2f(n0.y), pz = kz_u2f(n0.z);
+            const uint32_t ex = n0.w & 0xFFu, ey = (n0.w >> 8) & 0xFFu, ez = (n0.w >> 16) & 0xFFu, imask = n0.w >> 24;
+            /* t = q * (2^e * rd) + (p - o') * rd */
+            const float adx = kz_u2f(ex << 23) * rdx, ady = kz_u2f(ey << 23) * rdy, adz = kz_u2f(ez << 23) * rdz;
+            const float anx = (px - onx) * rdx, any_ = (py - ony) * rdy, anz = (pz - onz) * rdz;
+            const float afx = (px - ofx) * rdx, afy = (py - ofy) * rdy, afz = (pz - ofz) * rdz;
+            uint32_t hitmask = 0u;
+#if KZ_DEVICE_CODE
+#pragma unroll
+#endif
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t meta4 = half ? n1.w : n1.z;
+                const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const uint32_t inner_mask4 = kz_byte_perm(is_inner4 << 3, 0u, 0xBA98u);   /* sign-extend each byte */
+                const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
+                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+                const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+                const uint32_t qnx = nx ? qhix : qlox, qfx = nx ? qlox : qhix;
+                const uint32_t qny = ny ? qhiy : qloy, qfy = ny ? qloy : qhiy;
+                const uint32_t qnz = nz ? qhiz : qloz, qfz = nz ? qloz : qhiz;
+#if KZ_DEVICE_CODE
+#pragma unroll
+#endif
+                for (int j = 0; j < 4; ++j) {
+                    const int sh = 8 * j;
+                    const float tnx = fmaf((float)((qnx >> sh) & 0xFFu), adx, anx);
+                    const float tny = fmaf((float)((qny >> sh) & 0xFFu), ady, any_);
+                    const float tnz = fmaf((float)((qnz >> sh) & 0xFFu), adz, anz);
+                    const float tfx = fmaf((float)((qfx >> sh) & 0xFFu), adx, afx);
+                    const float tfy = fmaf((float)((qfy >> sh) & 0xFFu), ady, afy);
+                    const float tfz = fmaf((float)((qfz >> sh) & 0xFFu), adz, afz);
+                    const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+                    const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, best.t));
+                    if (cmin <= cmax) {
+                        const uint32_t cb = (child_bits4 >> sh) & 0xFFu;
+                        const uint32_t bi = (bit_index4 >> sh) & 0xFFu;
+                        hitmask |= cb << bi;
+                    }
+                }
+            }
+            ng_x = n1.x;
+            ng_y = (hitmask & 0xFF000000u) | imask;
+            tg_x = n1.y;
+            tg_y = hitmask & 0x00FFFFFFu;
+        } else {
+            tg_x = ng_x; tg_y = ng_y;
+            ng_x = 0u; ng_y = 0u;
+        }
+
+        while (tg_y != 0u) {
+            const uint32_t ti = kz_bfind(tg_y);
+            tg_y &= ~(1u << ti);
+            const KzF4 *tp = sc.tris + (size_t)(tg_x + ti) * 3;
+            const KzU4 a = kz_load_u4(tp), b = kz_load_u4(tp + 1), c = kz_load_u4(tp + 2);
+            float t, u, v;
+            if (kz_pluecker(ox, oy, oz, dx, dy, dz, tmin, best.t, a, b, c, t, u, v)) {
+                const uint32_t geom = a.w, prim = b.w;
+                const bool better = t < best.t || geom < best.geom || (geom == best.geom && prim < best.prim);
+                if (better) { best.t = t; best.u = u; best.v = v; best.geom = geom; best.prim = prim; }
+                if (any_hit) return best;
+            }
+        }
+
+        if (ng_y <= 0x00FFFFFFu) {
+            if (sp == 0) break;
+            --sp;
+#if KZ_DEVICE_CODE
+            if (sp < KZ_SHORT_STACK) { const uint2 e = stk.smem[sp * stk.stride]; ng_x = e.x; ng_y = e.y; }
+            else { ng_x = lstack_x[sp - KZ_SHORT_STACK]; ng_y = lstack_y[sp - KZ_SHORT_STACK]; }
+#else
+            ng_x = lstack_x[sp]; ng_y = lstack_y[sp];
+#endif
+        }
+    }
+    return best;
+}
+
+#endif

@@ -1,0 +1,187 @@
+/* tests/hostemu/emu.cpp -- DEVELOPMENT/TEST HARNESS, NOT A PRODUCT PATH.
+ *
+ * The build container has no GPU.  This file compiles the device routines of
+ * nano-kazen_b200/csrc (kz_traverse.h, kz_sampler.h, kz_shade.h, kz_path.h: the very source the
+ * CUDA kernels wrap) with g++ and runs them item by item on the CPU, so the CPU-side test suite
+ * can check the traversal / sampler / wavefront logic against the oracle before GPU time is
+ * spent.  libkzgpu.so never links this, and kzgpu_* has no CPU path: it fails with
+ * KZ_ERR_NO_DEVICE when there is no CUDA device.
+ */
+#include "../../nano-kazen_b200/csrc/kz_path.h"
+#include "../../nano-kazen_b200/csrc/kz_host_scene.h"
+#include <atomic>
+#include <thread>
+
+struct kzemu {
+    KzHostScene hs;
+    kzbvh::Built bvh;
+    KzCounters total{0, 0, 0, 0};
+};
+
+template <typename F> static void pfor(size_t n, F f) {
+    int threads = (int)std::thread::hardware_concurrency();
+    if (threads < 1) threads = 1;
+    if (n < 256) { f(0, n); return; }
+    std::atomic<size_t> next{0};
+    size_t chunk = std::max<size_t>(64, n / ((size_t)threads * 32));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&]() { for (;;) { size_t b = next.fetch_add(chunk); if (b >= n) break; f(b, std::min(n, b + chunk)); } });
+    for (auto &th : pool) th.join();
+}
+
+extern "C" {
+
+int kzemu_create(const kz_scene_desc *d, kzemu **out) {
+    kzemu *e = new kzemu();
+    if (!e->hs.flatten(d)) { fprintf(stderr, "kzemu: %s\n", e->hs.error.c_str()); delete e; return KZ_ERR_INVALID; }
+    kzbvh::buildHostSah(e->hs.tris, 0, e->bvh);
+    e->hs.sc.nodes = e->bvh.nodes.data();
+    e->hs.sc.tris = e->bvh.tris.data();
+    e->hs.sc.n_nodes = (uint32_t)e->bvh.nodes.size();
+    e->hs.sc.n_tris = (uint32_t)(e->bvh.tris.size() / 3);
+    e->hs.sc.scene_max_abs = e->bvh.max_abs;
+    *out = e;
+    return KZ_OK;
+}
+void kzemu_destroy(kzemu *e) { delete e; }
+int kzemu_bvh_info(kzemu *e, uint64_t *nodes, uint64_t *tris, int *depth) {
+    *nodes = e->bvh.nodes.size(); *tris = e->bvh.tris.size() / 3; *depth = e->bvh.depth;
+    return KZ_OK;
+}
+
+int kzemu_trace(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits) {
+    const KzScene &sc = e->hs.sc;
+    pfor(n, [&](size_t b, size_t en) {
+        KzStackRef stk;
+        for (size_t i = b; i < en; ++i) {
+            const kz_ray &r = rays[i];
+            KzHit h = kz_trace(sc, stk, r.o[0], r.o[1], r.o[2], r.d[0], r.d[1], r.d[2], r.tmin, r.tmax, false);
+            hits[i].t = h.t; hits[i].u = h.u; hits[i].v = h.v; hits[i].prim_id = h.prim; hits[i].geom_id = h.geom;
+        }
+    });
+    return KZ_OK;
+}
+
+int kzemu_occluded(kzemu *e, const kz_ray *rays, size_t n, float trace_bias, uint8_t *occ, uint8_t *segments) {
+    const KzScene &sc = e->hs.sc;
+    pfor(n, [&](size_t b, size_t en) {
+        KzStackRef stk;
+        for (size_t i = b; i < en; ++i) {
+            const kz_ray &r = rays[i];
+            int seg;
+            occ[i] = kz_occluded_walk(sc, stk, mk3(r.o[0], r.o[1], r.o[2]), mk3(r.d[0], r.d[1], r.d[2]), r.tmin, r.tmax, trace_bias, &seg) ? 1 : 0;
+            if (segments) segments[i] = (uint8_t)std::min(seg, 255);
+        }
+    });
+    return KZ_OK;
+}
+
+int kzemu_sample_dump(kzemu *e, const int32_t *triples, size_t n, const char *pattern, float *out) {
+    const KzScene &sc = e->hs.sc;
+    size_t per = 0;
+    for (const char *p = pattern; *p; ++p) per += (*p == '1') ? 1 : 2;
+    for (size_t i = 0; i < n; ++i) {
+        KzSampler sm;
+        kz_sampler_start(sc, sm, triples[3 * i], triples[3 * i + 1], (uint32_t)triples[3 * i + 2]);
+        float *o = out + i * per;
+        for (const char *p = pattern; *p; ++p) {
+            if (*p == '1') *o++ = kz_next1d(sc, sm);
+            else { kz2 v = (*p == 'P') ? kz_next_pixel2d(sc, sm) : kz_next2d(sc, sm); *o++ = v.x; *o++ = v.y; }
+        }
+    }
+    return KZ_OK;
+}
+
+int kzemu_camera_rays(kzemu *e, const float *s4, size_t n, kz_ray *out) {
+    for (size_t i = 0; i < n; ++i) {
+        KzF4 ro, rd;
+        kz_camera_ray(e->hs.sc.camera, mk2(s4[4 * i], s4[4 * i + 1]), mk2(s4[4 * i + 2], s4[4 * i + 3]), ro, rd);
+        out[i] = kz_ray{{ro.x, ro.y, ro.z}, ro.w, {rd.x, rd.y, rd.z}, rd.w};
+    }
+    return KZ_OK;
+}
+
+int kzemu_bsdf_query(kzemu *e, int mesh_bsdf, int mode, const float wi[3], const float wo[3], const float uv[2], float accR,
+                     float sample1, const float sample2[2], float out[8]) {
+    /* builds a fake intersection with an identity shading frame on a mesh slot that uses `mesh_bsdf` */
+    const KzScene &sc = e->hs.sc;
+    int mesh = -1;
+    for (uint32_t g = 0; g < sc.n_meshes; ++g) if (sc.meshes[g].bsdf == mesh_bsdf) { mesh = (int)g; break; }
+    if (mesh < 0) return KZ_ERR_INVALID;
+    KzIts its;
+    its.sh.s = mk3(1, 0, 0); its.sh.t = mk3(0, 1, 0); its.sh.n = mk3(0, 0, 1);
+    its.geo_n = its.sh.n; its.dpdu = mk3(1, 0, 0); its.uv = mk2(uv[0], uv[1]); its.mesh = mesh; its.acc_rough = accR;
+    its.p = mk3(0.f);
+    KzBsdfCtx bc = bsdf_ctx(sc, its);
+    for (int i = 0; i < 8; ++i) out[i] = 0.f;
+    if (mode == 2) {
+        kz3 w_o; float pdf; int measure;
+        kz3 w = bsdf_sample(bc, its, mk3(wi[0], wi[1], wi[2]), sample1, mk2(sample2[0], sample2[1]), &w_o, &pdf, &measure);
+        out[0] = w.x; out[1] = w.y; out[2] = w.z;
+        if (!iszero(w)) { out[3] = w_o.x; out[4] = w_o.y; out[5] = w_o.z; out[7] = pdf; }
+        out[6] = (float)measure;
+        return KZ_OK;
+    }
+    kz3 f; float pdf;
+    bsdf_eval_pdf(bc, its, mk3(wi[0], wi[1], wi[2]), mk3(wo[0], wo[1], wo[2]), &f, &pdf);
+    if (mode == 0) { out[0] = f.x; out[1] = f.y; out[2] = f.z; } else out[0] = pdf;
+    return KZ_OK;
+}
+
+/* Batch-synchronous wavefront over all requested paths, stage functions called item by item. */
+int kzemu_render(kzemu *e, const kz_render_req *req, float *frame_rgbw) {
+    const KzScene &sc = e->hs.sc;
+    const int b = sc.border, cols = sc.camera.width + 2 * b, rows = sc.camera.height + 2 * b;
+    const size_t fsz = (size_t)cols * rows;
+    KzF4 *frame = reinterpret_cast<KzF4 *>(frame_rgbw);
+    if (req->clear_frame) memset(frame, 0, fsz * sizeof(KzF4));
+    const int w = req->x1 - req->x0, hgt = req->y1 - req->y0, nS = req->spp_end - req->spp_begin;
+    const size_t B = (size_t)w * hgt * nS;
+    std::vector<KzF4> ray_o(B), ray_d(B), hit(B), sray_o(B), sray_d(B), pending(B), thr(B), L(B), misc(B);
+    std::vector<uint32_t> hit_geom(B), dim(B), pix(B), sidx(B);
+    std::vector<uint64_t> rs(B), ri(B);
+    KzPathState st{ray_o.data(), ray_d.data(), hit.data(), hit_geom.data(), sray_o.data(), sray_d.data(), pending.data(),
+                   thr.data(), L.data(), misc.data(), rs.data(), ri.data(), dim.data(), pix.data(), sidx.data()};
+    std::vector<uint32_t> q(B), qn, qs;
+    size_t slot = 0;
+    for (int y = req->y0; y < req->y1; ++y)
+        for (int x = req->x0; x < req->x1; ++x)
+            for (int s = req->spp_begin; s < req->spp_end; ++s) {
+                kz_raygen_item(sc, st, (uint32_t)slot, x, y, (uint32_t)s);
+                q[slot] = (uint32_t)slot;
+                ++slot;
+            }
+    std::mutex mu;
+    KzCounters tot{B, 0, 0, 0};
+    for (int bounce = 0; bounce <= sc.integrator.max_depth && !q.empty(); ++bounce) {
+        qn.clear(); qs.clear();
+        pfor(q.size(), [&](size_t bb, size_t ee) {
+            KzStackRef stk; KzCounters c{0, 0, 0, 0};
+            std::vector<uint32_t> ln, ls;
+            for (size_t i = bb; i < ee; ++i) {
+                kz_extend_item(sc, stk, st, q[i], bounce, c);
+                uint32_t fl = kz_shade_item(sc, st, q[i], bounce, c);
+                if (fl & KZ_SHADE_CONTINUE) ln.push_back(q[i]);
+                if (fl & KZ_SHADE_SHADOW) ls.push_back(q[i]);
+            }
+            for (uint32_t s : ls) kz_shadow_item(sc, stk, st, s, c);
+            std::lock_guard<std::mutex> lk(mu);
+            qn.insert(qn.end(), ln.begin(), ln.end());
+            tot.rays_ext += c.rays_ext; tot.rays_shadow += c.rays_shadow; tot.vertices += c.vertices;
+        });
+        q.swap(qn);
+    }
+    for (size_t i = 0; i < B; ++i) kz_accumulate_item(sc, st, (uint32_t)i, frame);
+    e->total.paths += tot.paths; e->total.rays_ext += tot.rays_ext; e->total.rays_shadow += tot.rays_shadow; e->total.vertices += tot.vertices;
+    return KZ_OK;
+}
+
+int kzemu_stats(kzemu *e, kz_stats *out) {
+    memset(out, 0, sizeof(*out));
+    out->paths = e->total.paths; out->rays_extension = e->total.rays_ext; out->rays_shadow = e->total.rays_shadow; out->vertices = e->total.vertices;
+    out->bvh_nodes = e->bvh.nodes.size(); out->bvh_bytes = e->bvh.nodes.size() * 80 + e->bvh.tris.size() * 16;
+    return KZ_OK;
+}
+
+}  // extern "C"

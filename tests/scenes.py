@@ -1,0 +1,142 @@
+"""Synthetic scenes + ray batches shared by the tests and bench.py (all seeded, numpy only)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "nano-kazen_b200"))
+import pykazen as pk  # noqa: E402
+
+
+def soup_triangles(n, seed=0x5EED):
+    """centres uniform in [-1,1]^3, three offsets uniform in [-s,s]^3, s = 2 n^(-1/3).
+    (numpy PCG64 stream instead of the PCG32 the survey suggests: same distribution, vectorised.)"""
+    rng = np.random.default_rng(seed + n)
+    c = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
+    s = np.float32(2.0 * n ** (-1.0 / 3.0))
+    off = rng.uniform(-s, s, (n, 3, 3)).astype(np.float32)
+    P = (c + off).reshape(-1, 3)
+    F = np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)
+    return P, F
+
+
+def soup_scene(n, seed=0x5EED):
+    sb = pk.SceneBuilder()
+    P, F = soup_triangles(n, seed)
+    sb.mesh(P, F, sb.bsdf_diffuse((0.5, 0.5, 0.5)))
+    sb.set_camera(64, 64, 40.0, pk.lookat((0, 0, -3), (0, 0, 0), (0, 1, 0)))
+    return sb
+
+
+def primary_rays(res, fov=40.0, origin=(0, 0, -3.0), tmin=1e-4):
+    """Pinhole at `origin` looking +z, res x res pixel centres, [tmin, inf)."""
+    ys, xs = np.mgrid[0:res, 0:res]
+    t = np.tan(np.radians(fov) / 2)
+    dx = ((xs + 0.5) / res * 2 - 1) * t
+    dy = (1 - (ys + 0.5) / res * 2) * t
+    d = np.stack([dx, dy, np.ones_like(dx)], -1).reshape(-1, 3)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = np.zeros(res * res, pk.RAY_DTYPE)
+    r["o"] = np.asarray(origin, np.float32); r["d"] = d.astype(np.float32)
+    r["tmin"] = tmin; r["tmax"] = np.inf
+    return r
+
+
+def incoherent_rays(n, seed=0xBEEF, extent=1.0):
+    """origin uniform in [-extent,extent]^3, direction uniform on the sphere, tnear 1e-3, tfar U[0.1,2]."""
+    rng = np.random.default_rng(seed)
+    r = np.zeros(n, pk.RAY_DTYPE)
+    r["o"] = rng.uniform(-extent, extent, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r["d"] = d.astype(np.float32)
+    r["tmin"] = 1e-3
+    r["tmax"] = rng.uniform(0.1, 2.0, n).astype(np.float32)
+    return r
+
+
+def quad(p0, p1, p2, p3):
+    P = np.array([p0, p1, p2, p3], np.float32)
+    F = np.array([[0, 1, 2], [3, 0, 2]], np.uint32)      # kazen's quad split (mesh.cpp:245-251)
+    return P, F
+
+
+def uv_sphere(center, radius, nu=24, nv=12):
+    """smooth-shaded sphere with normals and uvs"""
+    P, N, UV, F = [], [], [], []
+    for j in range(nv + 1):
+        th = np.pi * j / nv
+        for i in range(nu + 1):
+            ph = 2 * np.pi * i / nu
+            n = np.array([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)])
+            P.append(np.asarray(center) + radius * n); N.append(n); UV.append([i / nu, 1 - j / nv])
+    for j in range(nv):
+        for i in range(nu):
+            a = j * (nu + 1) + i; b = a + 1; c = a + nu + 1; d = c + 1
+            if j != 0:
+                F.append([a, b, c])
+            if j != nv - 1:
+                F.append([b, d, c])
+    return np.array(P, np.float32), np.array(N, np.float32), np.array(UV, np.float32), np.array(F, np.uint32)
+
+
+def cornell_scene(width=64, height=64, spp=16, sampler="stratified", with_texture=False, normalmap=False,
+                  visible_light=False, regularization=False, thinlens=None, background=None, max_depth=5):
+    """Small closed box: diffuse walls, kiss sphere (smooth normals + uvs), quad mesh light (invisible by default),
+    plus a second, flat-shaded kiss block without normals/uvs."""
+    sb = pk.SceneBuilder()
+    white = sb.bsdf_diffuse((0.73, 0.73, 0.73)); red = sb.bsdf_diffuse((0.65, 0.05, 0.05)); green = sb.bsdf_diffuse((0.12, 0.45, 0.15))
+    # floor, ceiling, back, left, right  (box [-1,1]^3, open towards -z)
+    for (a, b, c, d, m) in [
+        ((-1, -1, -1), (1, -1, -1), (1, -1, 1), (-1, -1, 1), white),
+        ((-1, 1, -1), (-1, 1, 1), (1, 1, 1), (1, 1, -1), white),
+        ((-1, -1, 1), (1, -1, 1), (1, 1, 1), (-1, 1, 1), white),
+        ((-1, -1, -1), (-1, -1, 1), (-1, 1, 1), (-1, 1, -1), red),
+        ((1, -1, -1), (1, 1, -1), (1, 1, 1), (1, -1, 1), green),
+    ]:
+        P, F = quad(a, b, c, d)
+        sb.mesh(P, F, m)
+    if with_texture:
+        rng = np.random.default_rng(7)
+        img = rng.uniform(0.1, 0.9, (32, 64, 3)).astype(np.float32)
+        base = sb.tex_image(img, scale=2.0, srgb=True)
+        rough = sb.tex_colorramp(0.2, 0.6, sb.tex_image(img[:, :, ::-1].copy(), srgb=False))
+        metal = sb.tex_blend("mix", sb.tex_constant((0.3, 0.3, 0.3)), sb.tex_constant((0, 0, 0)), sb.tex_constant((1, 1, 1)))
+    else:
+        base = sb.tex_constant((0.871, 0.376, 0.0)); rough = sb.tex_constant((0.35, 0, 1)); metal = sb.tex_constant((0.1, 0, 0))
+    kiss = sb.bsdf_kiss(base, rough, metal, specular=0.5, specular_tint=0.2, clearcoat=0.5, clearcoat_roughness=0.3, sheen=0.2, sheen_tint=0.4)
+    mat = kiss
+    if normalmap:
+        rng = np.random.default_rng(11)
+        nm = np.zeros((16, 16, 3), np.float32)
+        nm[..., 0] = 0.5 + 0.2 * rng.uniform(-1, 1, (16, 16)); nm[..., 1] = 0.5 + 0.2 * rng.uniform(-1, 1, (16, 16)); nm[..., 2] = 0.95
+        mat = sb.bsdf_normalmap(sb.tex_image(nm, scale=3.0, srgb=False), kiss)
+    P, N, UV, F = uv_sphere((-0.35, -0.55, 0.2), 0.45)
+    sb.mesh(P, F, mat, normals=N, uvs=UV)
+    # flat block without normals / uvs
+    kiss2 = sb.bsdf_kiss(sb.tex_constant((0.2, 0.3, 0.8)), sb.tex_constant((0.6, 0, 0)), sb.tex_constant((0.8, 0, 0)))
+    bx = np.array([[0.25, -1, -0.3], [0.75, -1, -0.3], [0.75, -1, 0.3], [0.25, -1, 0.3],
+                   [0.25, -0.3, -0.3], [0.75, -0.3, -0.3], [0.75, -0.3, 0.3], [0.25, -0.3, 0.3]], np.float32)
+    bf = np.array([[4, 5, 6], [7, 4, 6], [0, 1, 5], [4, 0, 5], [1, 2, 6], [5, 1, 6], [2, 3, 7], [6, 2, 7], [3, 0, 4], [7, 3, 4]], np.uint32)
+    sb.mesh(bx, bf, kiss2)
+    # ceiling light, two stacked quads so that shadow rays have an invisible light to step through
+    lt = sb.light((17.0 * 0.8, 12.0 * 0.8, 4.0 * 0.8), primary_visibility=visible_light)
+    P, F = quad((-0.3, 0.98, -0.3), (0.3, 0.98, -0.3), (0.3, 0.98, 0.3), (-0.3, 0.98, 0.3))
+    sb.mesh(P, F, white, light=lt)
+    lt2 = sb.light((2.0, 2.0, 3.0), primary_visibility=visible_light)
+    P, F = quad((-0.6, 0.9, 0.5), (-0.2, 0.9, 0.5), (-0.2, 0.9, 0.9), (-0.6, 0.9, 0.9))
+    sb.mesh(P, F, white, light=lt2)
+    if background is not None:
+        sb.background = sb.tex_background(1.0, sb.tex_constant(background))
+    sb.set_camera(width, height, 39.0, pk.lookat((0, 0, -3.4), (0, 0, 0), (0, 1, 0)), near=0.1, far=100.0, thinlens=thinlens)
+    sb.set_sampler(sampler, spp)
+    sb.set_filter("gaussian")
+    sb.set_integrator(max_depth=max_depth, regularization=regularization)
+    return sb
+
+
+def rel_mse(a, b, eps=1e-2):
+    """per-channel relative MSE of image a against reference b"""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return ((a - b) ** 2 / (b ** 2 + eps)).mean(axis=(0, 1))
