@@ -249,11 +249,19 @@ int  kzgpu_sample_dump(kzgpu_ctx *ctx, const int32_t *pixel_sample_triples, size
 /* Camera parity: rays for explicit (pixelSample, apertureSample) pairs, 4 floats each. */
 int  kzgpu_camera_rays(kzgpu_ctx *ctx, const float *samples4, size_t n, kz_ray *out);
 
+/* Shading parity probe: one BSDF query in the local shading frame on the device.
+ * mode 0 = BSDF::eval (out[0..2]), 1 = BSDF::pdf (out[0]), 2 = BSDF::sample (out[0..2] weight,
+ * out[3..5] wo, out[6] measure, out[7] pdf).  bsdf.cpp:20-92,281-417,1215-1371. */
+int  kzgpu_bsdf_query(kzgpu_ctx *ctx, int bsdf, int mode, const float wi[3], const float wo[3], const float uv[2],
+                      float accumulated_roughness, float sample1, const float sample2[2], float out[8]);
+
 /* Whole-frame render into a host frame ((H+2b)*(W+2b)*4 floats). Multi-device contexts
  * shard [spp_begin,spp_end) by sample index across their devices and sum the frames. */
 int  kzgpu_render(kzgpu_ctx *ctx, const kz_render_req *req, float *frame_rgbw);
-/* Single-device variant leaving the frame in HBM (for an NCCL reduce by the caller). */
-int  kzgpu_render_device(kzgpu_ctx *ctx, int device, const kz_render_req *req, void **d_frame_out,
+/* Single-device variant leaving the frame in HBM (for an NCCL reduce by the caller), enqueued on
+ * `stream` without synchronising.  *d_frame_inout != NULL on entry: splat into that caller-owned
+ * device buffer of (H+2b)*(W+2b) float4; NULL on entry: use the context's frame and return it. */
+int  kzgpu_render_device(kzgpu_ctx *ctx, int device, const kz_render_req *req, void **d_frame_inout,
                          void *stream);
 int  kzgpu_frame_dims(const kzgpu_ctx *ctx, int32_t *width, int32_t *height, int32_t *border);
 

@@ -1,0 +1,647 @@
+/* kz_api.cu -- the C ABI of include/kzgpu.h over the sm_100a kernels (kz_kernels.cuh).
+ *
+ * One kzgpu_ctx owns 1..N CUDA devices with the scene replicated on each.  All work of
+ * a call is enqueued on a stream without any host round trip (queue counts live in HBM, grids are
+ * persistent), so a single host thread drives all devices of a context concurrently.
+ * There is no CPU path in this file: without a usable sm_100-class device kzgpu_create fails.
+ */
+#include "kz_kernels.cuh"
+#include "kz_host_scene.h"
+#include "kz_lbvh.cuh"
+#include <cuda_runtime.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_error;
+
+enum { CAT_TRACE = 0, CAT_SHADE = 1, CAT_TOTAL = 2 };
+
+struct EvPair { cudaEvent_t a, b; int cat; };
+
+struct Device {
+    int id = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> scene_allocs, accel_allocs, pool_allocs;
+    KzScene sc;                      /* device pointers */
+    bool has_accel = false;
+    /* wavefront pool */
+    uint32_t pool_cap = 0;
+    KzPathState st;
+    KzQueues q;
+    KzControl *ctl = nullptr;
+    uint32_t *cursor = nullptr;      /* batch-trace fetch cursor */
+    KzF4 *frame = nullptr;
+    size_t frame_texels = 0;
+    /* scratch for host-pointer entry points */
+    void *scratch[3] = {nullptr, nullptr, nullptr};
+    size_t scratch_bytes[3] = {0, 0, 0};
+    /* launch geometry */
+    int grid_extend0 = 0, grid_extend = 0, grid_shadow = 0, grid_trace = 0, grid_occ = 0, grid_shade[KZ_NUM_CLASSES] = {0, 0, 0, 0};
+    /* timing */
+    std::vector<EvPair> pending;
+    std::vector<cudaEvent_t> free_events;
+    double ms[3] = {0, 0, 0};
+    uint64_t launches = 0;
+};
+
+}  // namespace
+
+struct kzgpu_ctx {
+    std::vector<Device> devs;
+    std::unique_ptr<KzHostScene> hs;
+    bool class_present[KZ_NUM_CLASSES] = {true, false, false, false};
+    bool uploaded = false, built = false;
+    uint32_t pool_cap = 1u << 22;
+    kz_stats totals{};
+    double ms_build = 0;
+    uint64_t bvh_nodes = 0, bvh_bytes = 0;
+    double last_total_ms = 0;
+    std::string error;
+};
+
+namespace {
+
+int fail(kzgpu_ctx *ctx, int code, const std::string &msg) {
+    g_error = msg;
+    if (ctx) ctx->error = msg;
+    return code;
+}
+
+#define KZ_CUDA(ctx, call)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? KZ_ERR_NOMEM : KZ_ERR_CUDA,                  \
+                        std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+template <typename T> int dev_alloc(kzgpu_ctx *ctx, std::vector<void *> &owner, size_t count, T **out) {
+    void *p = nullptr;
+    KZ_CUDA(ctx, cudaMalloc(&p, std::max<size_t>(16, count * sizeof(T))));
+    owner.push_back(p);
+    *out = reinterpret_cast<T *>(p);
+    return KZ_OK;
+}
+template <typename T> int dev_upload(kzgpu_ctx *ctx, Device &d, std::vector<void *> &owner, const T *src, size_t count, const T **out) {
+    T *p = nullptr;
+    int rc = dev_alloc(ctx, owner, count, &p);
+    if (rc) return rc;
+    if (count) KZ_CUDA(ctx, cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, d.stream));
+    *out = p;
+    return KZ_OK;
+}
+void free_all(std::vector<void *> &v) {
+    for (void *p : v) cudaFree(p);
+    v.clear();
+}
+
+int ensure_scratch(kzgpu_ctx *ctx, Device &d, int k, size_t bytes) {
+    if (d.scratch_bytes[k] >= bytes) return KZ_OK;
+    if (d.scratch[k]) { cudaFree(d.scratch[k]); d.scratch[k] = nullptr; d.scratch_bytes[k] = 0; }
+    size_t want = std::max<size_t>(bytes, 1u << 20);
+    KZ_CUDA(ctx, cudaMalloc(&d.scratch[k], want));
+    d.scratch_bytes[k] = want;
+    return KZ_OK;
+}
+
+cudaEvent_t get_event(Device &d) {
+    if (!d.free_events.empty()) { cudaEvent_t e = d.free_events.back(); d.free_events.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct Timed {   /* records an event pair around a group of launches on `s` */
+    Device &d; cudaStream_t s; EvPair p;
+    Timed(Device &dev, cudaStream_t st, int cat) : d(dev), s(st) { p.a = get_event(d); p.b = get_event(d); p.cat = cat; cudaEventRecord(p.a, s); }
+    ~Timed() { cudaEventRecord(p.b, s); d.pending.push_back(p); }
+};
+/* Folds finished event pairs into the per-category totals (synchronises on them). */
+void fold_events(Device &d) {
+    for (EvPair &p : d.pending) {
+        cudaEventSynchronize(p.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) d.ms[p.cat] += ms;
+        d.free_events.push_back(p.a); d.free_events.push_back(p.b);
+    }
+    d.pending.clear();
+}
+
+template <typename K> int persistent_grid(const Device &d, K kernel, int threads) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return d.sm_count * per_sm;
+}
+
+int select(kzgpu_ctx *ctx, int device, Device **out) {
+    if (!ctx) return fail(nullptr, KZ_ERR_INVALID, "null context");
+    if (device < 0 || device >= (int)ctx->devs.size()) return fail(ctx, KZ_ERR_INVALID, "device index out of range");
+    Device &d = ctx->devs[(size_t)device];
+    KZ_CUDA(ctx, cudaSetDevice(d.id));
+    *out = &d;
+    return KZ_OK;
+}
+
+int upload_scene(kzgpu_ctx *ctx, Device &d) {
+    const KzHostScene &h = *ctx->hs;
+    free_all(d.scene_allocs);
+    d.sc = h.sc;
+    d.sc.nodes = nullptr; d.sc.tris = nullptr; d.sc.n_nodes = 0; d.sc.n_tris = 0;
+    int rc;
+#define UP(field, vec) if ((rc = dev_upload(ctx, d, d.scene_allocs, (vec).data(), (vec).size(), &d.sc.field))) return rc
+    UP(meshes, h.meshes); UP(positions, h.positions); UP(normals, h.normals); UP(uvs, h.uvs); UP(indices, h.indices);
+    UP(light_cdf, h.light_cdf); UP(light_meshes, h.light_meshes); UP(bsdfs, h.bsdfs); UP(textures, h.textures);
+    UP(images, h.images); UP(texels, h.texels); UP(lights, h.lights); UP(blue_noise, h.blue_noise); UP(pmj02bn, h.pmj);
+    UP(pmj_pixel_samples, h.pmj_pixel_samples);
+#undef UP
+    /* frame */
+    const size_t texels = (size_t)(h.sc.camera.width + 2 * h.sc.border) * (size_t)(h.sc.camera.height + 2 * h.sc.border);
+    if ((rc = dev_alloc(ctx, d.scene_allocs, texels, &d.frame))) return rc;
+    d.frame_texels = texels;
+    KZ_CUDA(ctx, cudaMemsetAsync(d.frame, 0, texels * sizeof(KzF4), d.stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    return KZ_OK;
+}
+
+int ensure_pool(kzgpu_ctx *ctx, Device &d, uint32_t cap) {
+    if (d.pool_cap >= cap) return KZ_OK;
+    free_all(d.pool_allocs);
+    d.pool_cap = 0;
+    int rc;
+#define AL(ptr) if ((rc = dev_alloc(ctx, d.pool_allocs, (size_t)cap, &(ptr)))) return rc
+    AL(d.st.ray_o); AL(d.st.ray_d); AL(d.st.hit); AL(d.st.hit_geom); AL(d.st.sray_o); AL(d.st.sray_d); AL(d.st.pending);
+    AL(d.st.thr); AL(d.st.L); AL(d.st.misc); AL(d.st.rng_state); AL(d.st.rng_inc); AL(d.st.dim); AL(d.st.pix); AL(d.st.sidx);
+    AL(d.q.ext[0]); AL(d.q.ext[1]); AL(d.q.shadow);
+    for (int c = 0; c < KZ_NUM_CLASSES; ++c) AL(d.q.cls[c]);
+#undef AL
+    d.pool_cap = cap;
+    return KZ_OK;
+}
+
+int upload_accel(kzgpu_ctx *ctx, Device &d, const kzbvh::Built &b) {
+    free_all(d.accel_allocs);
+    int rc;
+    if ((rc = dev_upload(ctx, d, d.accel_allocs, b.nodes.data(), b.nodes.size(), &d.sc.nodes))) return rc;
+    if ((rc = dev_upload(ctx, d, d.accel_allocs, b.tris.data(), b.tris.size(), &d.sc.tris))) return rc;
+    d.sc.n_nodes = (uint32_t)b.nodes.size();
+    d.sc.n_tris = (uint32_t)(b.tris.size() / 3);
+    d.sc.scene_max_abs = b.max_abs;
+    KZ_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    d.has_accel = true;
+    return KZ_OK;
+}
+
+/* Enqueues the whole wavefront for one request on `s`; never synchronises. */
+int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStream_t s) {
+    const KzScene &sc = d.sc;
+    const int w = req.x1 - req.x0, h = req.y1 - req.y0, nS = req.spp_end - req.spp_begin;
+    if (w <= 0 || h <= 0 || nS <= 0) return KZ_OK;
+    KzChunk ch;
+    ch.x0 = req.x0; ch.y0 = req.y0; ch.x1 = req.x1; ch.y1 = req.y1;
+    ch.tiles_x = (uint32_t)(w + 7) / 8u;
+    const uint32_t tiles_y = (uint32_t)(h + 3) / 4u;
+    ch.npx_padded = ch.tiles_x * tiles_y * 32u;
+    ch.spp_begin = req.spp_begin;
+    const unsigned long long total = (unsigned long long)ch.npx_padded * (unsigned long long)nS;
+    const uint32_t cap = (uint32_t)std::min<unsigned long long>(ctx->pool_cap, (total + 31ull) & ~31ull);
+    int rc = ensure_pool(ctx, d, cap);
+    if (rc) return rc;
+    const int max_depth = sc.integrator.max_depth;
+    /* the pass after the last vertex only resolves "miss -> background" (integrator.cpp:315-318) */
+    const int last_pass = sc.background >= 0 ? max_depth : max_depth - 1;
+    Timed total_t(d, s, CAT_TOTAL);
+    for (unsigned long long first = 0; first < total; first += d.pool_cap) {
+        ch.first = first;
+        ch.count = (uint32_t)std::min<unsigned long long>(d.pool_cap, total - first);
+        {
+            Timed t(d, s, CAT_SHADE);
+            k_chunk_reset<<<1, 32, 0, s>>>(d.ctl);
+            k_raygen<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q.ext[0], ch);
+            d.launches += 2;
+        }
+        for (int b = 0; b <= last_pass; ++b) {
+            const int cur = b & 1, nxt = cur ^ 1;
+            {
+                Timed t(d, s, CAT_TRACE);
+                k_bounce_reset<<<1, 32, 0, s>>>(d.ctl, nxt);
+                if (b == 0) k_extend<true><<<d.grid_extend0, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur, b);
+                else k_extend<false><<<d.grid_extend, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur, b);
+                d.launches += 2;
+            }
+            {
+                Timed t(d, s, CAT_SHADE);
+                k_shade<KZ_CLASS_TERMINAL><<<d.grid_shade[0], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b);
+                ++d.launches;
+                if (b < max_depth) {
+                    if (ctx->class_present[KZ_CLASS_DIFFUSE]) { k_shade<KZ_CLASS_DIFFUSE><<<d.grid_shade[1], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
+                    if (ctx->class_present[KZ_CLASS_KISS]) { k_shade<KZ_CLASS_KISS><<<d.grid_shade[2], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
+                    if (ctx->class_present[KZ_CLASS_NORMALMAP]) { k_shade<KZ_CLASS_NORMALMAP><<<d.grid_shade[3], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
+                }
+            }
+            if (b < max_depth && sc.n_light_meshes > 0) {
+                Timed t(d, s, CAT_TRACE);
+                k_shadow<<<d.grid_shadow, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q);
+                ++d.launches;
+            }
+        }
+        {
+            Timed t(d, s, CAT_SHADE);
+            k_accumulate<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, d.st, ch.count, d.frame);
+            ++d.launches;
+        }
+    }
+    KZ_CUDA(ctx, cudaGetLastError());
+    return KZ_OK;
+}
+
+int check_ready(kzgpu_ctx *ctx, bool need_accel) {
+    if (!ctx) return fail(nullptr, KZ_ERR_INVALID, "null context");
+    if (!ctx->uploaded) return fail(ctx, KZ_ERR_STATE, "no scene uploaded");
+    if (need_accel && !ctx->built) return fail(ctx, KZ_ERR_STATE, "accel not built: call kzgpu_accel_build first");
+    return KZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *kzgpu_last_error(const kzgpu_ctx *ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+
+int kzgpu_create(const int *device_ids, int n_devices, kzgpu_ctx **out) {
+    if (!out) return fail(nullptr, KZ_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, KZ_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                                    " (kzgpu has no CPU fallback)");
+    std::vector<int> ids;
+    if (!device_ids || n_devices <= 0) ids.push_back(0);
+    else ids.assign(device_ids, device_ids + n_devices);
+    std::unique_ptr<kzgpu_ctx> ctx(new kzgpu_ctx());
+    if (const char *p = getenv("KZGPU_POOL_LOG2")) { int l = atoi(p); if (l >= 10 && l <= 26) ctx->pool_cap = 1u << l; }
+    for (int id : ids) {
+        if (id < 0 || id >= count) return fail(nullptr, KZ_ERR_NO_DEVICE, "device id " + std::to_string(id) + " out of range");
+        cudaDeviceProp prop;
+        KZ_CUDA(nullptr, cudaGetDeviceProperties(&prop, id));
+        if (prop.major != 10) return fail(nullptr, KZ_ERR_NO_DEVICE, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                                                       "; this library is built for sm_100a only");
+        Device d;
+        d.id = id; d.sm_count = prop.multiProcessorCount;
+        memset(&d.sc, 0, sizeof(d.sc)); memset(&d.st, 0, sizeof(d.st)); memset(&d.q, 0, sizeof(d.q));
+        KZ_CUDA(nullptr, cudaSetDevice(id));
+        KZ_CUDA(nullptr, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        KZ_CUDA(nullptr, cudaMalloc(&d.ctl, sizeof(KzControl)));
+        KZ_CUDA(nullptr, cudaMemset(d.ctl, 0, sizeof(KzControl)));
+        KZ_CUDA(nullptr, cudaMalloc(&d.cursor, 64));
+        d.grid_extend0 = persistent_grid(d, k_extend<true>, KZ_TRACE_THREADS);
+        d.grid_extend = persistent_grid(d, k_extend<false>, KZ_TRACE_THREADS);
+        d.grid_shadow = persistent_grid(d, k_shadow, KZ_TRACE_THREADS);
+        d.grid_trace = persistent_grid(d, k_trace, KZ_TRACE_THREADS);
+        d.grid_occ = persistent_grid(d, k_occluded, KZ_TRACE_THREADS);
+        d.grid_shade[0] = persistent_grid(d, k_shade<KZ_CLASS_TERMINAL>, KZ_SHADE_THREADS);
+        d.grid_shade[1] = persistent_grid(d, k_shade<KZ_CLASS_DIFFUSE>, KZ_SHADE_THREADS);
+        d.grid_shade[2] = persistent_grid(d, k_shade<KZ_CLASS_KISS>, KZ_SHADE_THREADS);
+        d.grid_shade[3] = persistent_grid(d, k_shade<KZ_CLASS_NORMALMAP>, KZ_SHADE_THREADS);
+        ctx->devs.push_back(d);
+    }
+    *out = ctx.release();
+    return KZ_OK;
+}
+
+void kzgpu_destroy(kzgpu_ctx *ctx) {
+    if (!ctx) return;
+    for (Device &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        cudaDeviceSynchronize();
+        fold_events(d);
+        for (cudaEvent_t e : d.free_events) cudaEventDestroy(e);
+        free_all(d.scene_allocs); free_all(d.accel_allocs); free_all(d.pool_allocs);
+        for (int k = 0; k < 3; ++k) if (d.scratch[k]) cudaFree(d.scratch[k]);
+        cudaFree(d.ctl); cudaFree(d.cursor);
+        cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+}
+
+int kzgpu_scene_upload(kzgpu_ctx *ctx, const kz_scene_desc *scene) {
+    if (!ctx) return fail(nullptr, KZ_ERR_INVALID, "null context");
+    std::unique_ptr<KzHostScene> hs(new KzHostScene());
+    if (!hs->flatten(scene)) {
+        const bool unsupported = hs->error.find("outside the hot-path scope") != std::string::npos || hs->error.find("unsupported") != std::string::npos;
+        return fail(ctx, unsupported ? KZ_ERR_UNSUPPORTED : KZ_ERR_INVALID, hs->error);
+    }
+    ctx->hs = std::move(hs);
+    ctx->uploaded = false; ctx->built = false;
+    for (int c = 1; c < KZ_NUM_CLASSES; ++c) ctx->class_present[c] = false;
+    for (const KzMeshRec &m : ctx->hs->meshes) {
+        if (m.flags & KZ_MESH_IS_LIGHT) continue;
+        const int t = ctx->hs->bsdfs[(size_t)m.bsdf].type;
+        ctx->class_present[t == KZ_BSDF_DIFFUSE ? KZ_CLASS_DIFFUSE : (t == KZ_BSDF_KISS ? KZ_CLASS_KISS : KZ_CLASS_NORMALMAP)] = true;
+    }
+    for (Device &d : ctx->devs) {
+        KZ_CUDA(ctx, cudaSetDevice(d.id));
+        d.has_accel = false;
+        free_all(d.accel_allocs);
+        int rc = upload_scene(ctx, d);
+        if (rc) return rc;
+    }
+    ctx->uploaded = true;
+    return KZ_OK;
+}
+
+int kzgpu_accel_build(kzgpu_ctx *ctx, int builder) {
+    int rc = check_ready(ctx, false);
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (builder == KZ_BUILD_HOST_SAH) {
+        kzbvh::Built built;
+        kzbvh::buildHostSah(ctx->hs->tris, 0, built);
+        for (Device &d : ctx->devs) {
+            KZ_CUDA(ctx, cudaSetDevice(d.id));
+            if ((rc = upload_accel(ctx, d, built))) return rc;
+        }
+        ctx->bvh_nodes = built.nodes.size();
+        ctx->bvh_bytes = built.nodes.size() * sizeof(KzNode8) + built.tris.size() * sizeof(KzF4);
+    } else if (builder == KZ_BUILD_LBVH) {
+        for (Device &d : ctx->devs) {
+            KZ_CUDA(ctx, cudaSetDevice(d.id));
+            free_all(d.accel_allocs);
+            kzlbvh::Result r;
+            std::string err;
+            rc = kzlbvh::build(ctx->hs->tris, d.stream, d.accel_allocs, r, err);
+            if (rc) return fail(ctx, rc, err);
+            d.sc.nodes = r.nodes; d.sc.tris = r.tris; d.sc.n_nodes = r.n_nodes; d.sc.n_tris = r.n_tris; d.sc.scene_max_abs = r.max_abs;
+            d.has_accel = true;
+            d.launches += r.launches;
+            ctx->bvh_nodes = r.n_nodes;
+            ctx->bvh_bytes = (uint64_t)r.n_nodes * sizeof(KzNode8) + (uint64_t)r.n_tris * 3 * sizeof(KzF4);
+        }
+    } else {
+        return fail(ctx, KZ_ERR_INVALID, "unknown builder");
+    }
+    ctx->ms_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->built = true;
+    return KZ_OK;
+}
+
+int kzgpu_trace_device(kzgpu_ctx *ctx, int device, const void *d_rays, size_t n, int shadow, void *d_hits, void *stream) {
+    (void)shadow;   /* accel.cpp:98-104: the shadow variant is the same closest-hit query */
+    int rc = check_ready(ctx, true);
+    if (rc) return rc;
+    Device *d;
+    if ((rc = select(ctx, device, &d))) return rc;
+    if (n == 0) return KZ_OK;
+    if (n > 0x7FFFFFFFull) return fail(ctx, KZ_ERR_INVALID, "batch larger than 2^31-1 rays");
+    if (!d_rays || !d_hits) return fail(ctx, KZ_ERR_INVALID, "null ray/hit buffer");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    KZ_CUDA(ctx, cudaMemsetAsync(d->cursor, 0, 4, s));
+    {
+        Timed t(*d, s, CAT_TRACE);
+        k_trace<<<d->grid_trace, KZ_TRACE_THREADS, 0, s>>>(d->sc, reinterpret_cast<const KzF4 *>(d_rays), (uint32_t)n, reinterpret_cast<float *>(d_hits), d->cursor, d->ctl);
+        ++d->launches;
+    }
+    KZ_CUDA(ctx, cudaGetLastError());
+    return KZ_OK;
+}
+
+int kzgpu_trace(kzgpu_ctx *ctx, int device, const kz_ray *rays, size_t n, int shadow, kz_hit *hits) {
+    int rc = check_ready(ctx, true);
+    if (rc) return rc;
+    Device *d;
+    if ((rc = select(ctx, device, &d))) return rc;
+    if (n == 0) return KZ_OK;
+    if (!rays || !hits) return fail(ctx, KZ_ERR_INVALID, "null ray/hit buffer");
+    if ((rc = ensure_scratch(ctx, *d, 0, n * sizeof(kz_ray)))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 1, n * sizeof(kz_hit)))) return rc;
+    Timed total_t(*d, d->stream, CAT_TOTAL);
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], rays, n * sizeof(kz_ray), cudaMemcpyHostToDevice, d->stream));
+    if ((rc = kzgpu_trace_device(ctx, device, d->scratch[0], n, shadow, d->scratch[1], d->stream))) return rc;
+    KZ_CUDA(ctx, cudaMemcpyAsync(hits, d->scratch[1], n * sizeof(kz_hit), cudaMemcpyDeviceToHost, d->stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    return KZ_OK;
+}
+
+int kzgpu_occluded(kzgpu_ctx *ctx, int device, const kz_ray *rays, size_t n, float trace_bias, uint8_t *occluded, uint8_t *segments) {
+    int rc = check_ready(ctx, true);
+    if (rc) return rc;
+    Device *d;
+    if ((rc = select(ctx, device, &d))) return rc;
+    if (n == 0) return KZ_OK;
+    if (n > 0x7FFFFFFFull) return fail(ctx, KZ_ERR_INVALID, "batch larger than 2^31-1 rays");
+    if (!rays || !occluded) return fail(ctx, KZ_ERR_INVALID, "null buffer");
+    if ((rc = ensure_scratch(ctx, *d, 0, n * sizeof(kz_ray)))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 1, 2 * n))) return rc;
+    uint8_t *d_occ = reinterpret_cast<uint8_t *>(d->scratch[1]);
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], rays, n * sizeof(kz_ray), cudaMemcpyHostToDevice, d->stream));
+    KZ_CUDA(ctx, cudaMemsetAsync(d->cursor, 0, 4, d->stream));
+    {
+        Timed t(*d, d->stream, CAT_TRACE);
+        k_occluded<<<d->grid_occ, KZ_TRACE_THREADS, 0, d->stream>>>(d->sc, reinterpret_cast<const KzF4 *>(d->scratch[0]), (uint32_t)n, trace_bias, d_occ, d_occ + n,
+                                                                    d->cursor, d->ctl);
+        ++d->launches;
+    }
+    KZ_CUDA(ctx, cudaMemcpyAsync(occluded, d_occ, n, cudaMemcpyDeviceToHost, d->stream));
+    if (segments) KZ_CUDA(ctx, cudaMemcpyAsync(segments, d_occ + n, n, cudaMemcpyDeviceToHost, d->stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    return KZ_OK;
+}
+
+int kzgpu_sample_dump(kzgpu_ctx *ctx, const int32_t *triples, size_t n, const char *pattern, float *out) {
+    int rc = check_ready(ctx, false);
+    if (rc) return rc;
+    Device *d;
+    if ((rc = select(ctx, 0, &d))) return rc;
+    if (!pattern || (!triples && n) || (!out && n)) return fail(ctx, KZ_ERR_INVALID, "null argument");
+    size_t per = 0, plen = strlen(pattern);
+    for (const char *p = pattern; *p; ++p) {
+        if (*p != '1' && *p != '2' && *p != 'P') return fail(ctx, KZ_ERR_INVALID, "pattern may only contain '1', '2', 'P'");
+        per += (*p == '1') ? 1 : 2;
+    }
+    if (n == 0 || per == 0) return KZ_OK;
+    if ((rc = ensure_scratch(ctx, *d, 0, n * 12))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 1, n * per * 4))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 2, plen + 1))) return rc;
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], triples, n * 12, cudaMemcpyHostToDevice, d->stream));
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[2], pattern, plen + 1, cudaMemcpyHostToDevice, d->stream));
+    k_sample_dump<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(d->sc, reinterpret_cast<const int32_t *>(d->scratch[0]), (uint32_t)n,
+                                                                      reinterpret_cast<const char *>(d->scratch[2]), (uint32_t)per, reinterpret_cast<float *>(d->scratch[1]));
+    ++d->launches;
+    KZ_CUDA(ctx, cudaMemcpyAsync(out, d->scratch[1], n * per * 4, cudaMemcpyDeviceToHost, d->stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    return KZ_OK;
+}
+
+int kzgpu_camera_rays(kzgpu_ctx *ctx, const float *samples4, size_t n, kz_ray *out) {
+    int rc = check_ready(ctx, false);
+    if (rc) return rc;
+    Device *d;
+    if ((rc = select(ctx, 0, &d))) return rc;
+    if (n == 0) return KZ_OK;
+    if (!samples4 || !out) return fail(ctx, KZ_ERR_INVALID, "null argument");
+    if ((rc = ensure_scratch(ctx, *d, 0, n * 16))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 1, n * 32))) return rc;
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], samples4, n * 16, cudaMemcpyHostToDevice, d->stream));
+    k_camera_rays<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(d->sc, reinterpret_cast<const KzF4 *>(d->scratch[0]), (uint32_t)n, reinterpret_cast<KzF4 *>(d->scratch[1]));
+    ++d->launches;
+    KZ_CUDA(ctx, cudaMemcpyAsync(out, d->scratch[1], n * 32, cudaMemcpyDeviceToHost, d->stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    return KZ_OK;
+}
+
+int kzgpu_bsdf_query(kzgpu_ctx *ctx, int bsdf, int mode, const float wi[3], const float wo[3], const float uv[2], float accumulated_roughness,
+                     float sample1, const float sample2[2], float out[8]) {
+    int rc = check_ready(ctx, false);
+    if (rc) return rc;
+    Device *d;
+    if ((rc = select(ctx, 0, &d))) return rc;
+    KzBsdfQuery q;
+    memset(&q, 0, sizeof(q));
+    q.mesh = -1;
+    for (size_t g = 0; g < ctx->hs->meshes.size(); ++g) if (ctx->hs->meshes[g].bsdf == bsdf) { q.mesh = (int32_t)g; break; }
+    if (q.mesh < 0) return fail(ctx, KZ_ERR_INVALID, "no mesh uses this bsdf");
+    for (int k = 0; k < 3; ++k) { q.wi[k] = wi[k]; q.wo[k] = wo ? wo[k] : 0.f; }
+    q.uv[0] = uv[0]; q.uv[1] = uv[1]; q.acc_rough = accumulated_roughness; q.s1 = sample1;
+    q.s2[0] = sample2 ? sample2[0] : 0.f; q.s2[1] = sample2 ? sample2[1] : 0.f; q.mode = mode;
+    if ((rc = ensure_scratch(ctx, *d, 0, sizeof(q)))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 1, 32))) return rc;
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], &q, sizeof(q), cudaMemcpyHostToDevice, d->stream));
+    k_bsdf_query<<<1, 32, 0, d->stream>>>(d->sc, reinterpret_cast<const KzBsdfQuery *>(d->scratch[0]), 1u, reinterpret_cast<float *>(d->scratch[1]));
+    ++d->launches;
+    KZ_CUDA(ctx, cudaMemcpyAsync(out, d->scratch[1], 32, cudaMemcpyDeviceToHost, d->stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    return KZ_OK;
+}
+
+int kzgpu_frame_dims(const kzgpu_ctx *ctx, int32_t *width, int32_t *height, int32_t *border) {
+    if (!ctx || !ctx->hs) return fail(nullptr, KZ_ERR_STATE, "no scene uploaded");
+    if (width) *width = ctx->hs->sc.camera.width;
+    if (height) *height = ctx->hs->sc.camera.height;
+    if (border) *border = ctx->hs->sc.border;
+    return KZ_OK;
+}
+
+static int check_req(kzgpu_ctx *ctx, const kz_render_req *req) {
+    if (!req) return fail(ctx, KZ_ERR_INVALID, "null request");
+    const kz_camera_desc &c = ctx->hs->sc.camera;
+    if (req->x0 < 0 || req->y0 < 0 || req->x1 > c.width || req->y1 > c.height || req->x0 > req->x1 || req->y0 > req->y1)
+        return fail(ctx, KZ_ERR_INVALID, "render rectangle outside the film");
+    if (req->spp_begin < 0 || req->spp_end < req->spp_begin) return fail(ctx, KZ_ERR_INVALID, "bad sample range");
+    return KZ_OK;
+}
+
+int kzgpu_render_device(kzgpu_ctx *ctx, int device, const kz_render_req *req, void **d_frame_inout, void *stream) {
+    int rc = check_ready(ctx, true);
+    if (rc) return rc;
+    if ((rc = check_req(ctx, req))) return rc;
+    Device *d;
+    if ((rc = select(ctx, device, &d))) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    /* caller-owned frame (e.g. a torch tensor that an NCCL reduce follows) or the context's own */
+    KzF4 *own = d->frame;
+    if (d_frame_inout && *d_frame_inout) d->frame = reinterpret_cast<KzF4 *>(*d_frame_inout);
+    if (req->clear_frame) {
+        cudaError_t e = cudaMemsetAsync(d->frame, 0, d->frame_texels * sizeof(KzF4), s);
+        if (e != cudaSuccess) { d->frame = own; return fail(ctx, KZ_ERR_CUDA, std::string("cudaMemsetAsync(frame): ") + cudaGetErrorString(e)); }
+    }
+    rc = enqueue_render(ctx, *d, *req, s);
+    if (d_frame_inout) *d_frame_inout = d->frame;
+    d->frame = own;
+    return rc;
+}
+
+int kzgpu_render(kzgpu_ctx *ctx, const kz_render_req *req, float *frame_rgbw) {
+    int rc = check_ready(ctx, true);
+    if (rc) return rc;
+    if ((rc = check_req(ctx, req))) return rc;
+    if (!frame_rgbw) return fail(ctx, KZ_ERR_INVALID, "null frame");
+    const int nd = (int)ctx->devs.size();
+    const int nS = req->spp_end - req->spp_begin;
+    const size_t texels = ctx->devs[0].frame_texels;
+    /* shard by sample index: device g takes a contiguous slice of [spp_begin, spp_end) */
+    for (int g = 0; g < nd; ++g) {
+        Device &d = ctx->devs[(size_t)g];
+        KZ_CUDA(ctx, cudaSetDevice(d.id));
+        kz_render_req r = *req;
+        r.spp_begin = req->spp_begin + (int)((long long)nS * g / nd);
+        r.spp_end = req->spp_begin + (int)((long long)nS * (g + 1) / nd);
+        KZ_CUDA(ctx, cudaMemsetAsync(d.frame, 0, texels * sizeof(KzF4), d.stream));
+        if ((rc = enqueue_render(ctx, d, r, d.stream))) return rc;
+    }
+    std::vector<float> tmp;
+    for (int g = 0; g < nd; ++g) {
+        Device &d = ctx->devs[(size_t)g];
+        KZ_CUDA(ctx, cudaSetDevice(d.id));
+        if (g == 0 && req->clear_frame) {
+            KZ_CUDA(ctx, cudaMemcpyAsync(frame_rgbw, d.frame, texels * sizeof(KzF4), cudaMemcpyDeviceToHost, d.stream));
+            KZ_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        } else {
+            tmp.resize(texels * 4);
+            KZ_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d.frame, texels * sizeof(KzF4), cudaMemcpyDeviceToHost, d.stream));
+            KZ_CUDA(ctx, cudaStreamSynchronize(d.stream));
+            for (size_t i = 0; i < texels * 4; ++i) frame_rgbw[i] += tmp[i];
+        }
+    }
+    return KZ_OK;
+}
+
+int kzgpu_resolve(kzgpu_ctx *ctx, const float *frame_rgbw, float *rgb_linear, uint8_t *srgb8) {
+    int rc = check_ready(ctx, false);
+    if (rc) return rc;
+    Device *d;
+    if ((rc = select(ctx, 0, &d))) return rc;
+    if (!frame_rgbw) return fail(ctx, KZ_ERR_INVALID, "null frame");
+    const KzScene &sc = d->sc;
+    const int W = sc.camera.width, H = sc.camera.height;
+    const size_t npx = (size_t)W * H;
+    if ((rc = ensure_scratch(ctx, *d, 0, d->frame_texels * sizeof(KzF4)))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 1, npx * 12))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 2, npx * 3))) return rc;
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], frame_rgbw, d->frame_texels * sizeof(KzF4), cudaMemcpyHostToDevice, d->stream));
+    dim3 blk(32, 8), grd((unsigned)(W + 31) / 32, (unsigned)(H + 7) / 8);
+    k_resolve<<<grd, blk, 0, d->stream>>>(reinterpret_cast<const KzF4 *>(d->scratch[0]), W, H, sc.border, rgb_linear ? reinterpret_cast<float *>(d->scratch[1]) : nullptr,
+                                          srgb8 ? reinterpret_cast<uint8_t *>(d->scratch[2]) : nullptr);
+    ++d->launches;
+    if (rgb_linear) KZ_CUDA(ctx, cudaMemcpyAsync(rgb_linear, d->scratch[1], npx * 12, cudaMemcpyDeviceToHost, d->stream));
+    if (srgb8) KZ_CUDA(ctx, cudaMemcpyAsync(srgb8, d->scratch[2], npx * 3, cudaMemcpyDeviceToHost, d->stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    return KZ_OK;
+}
+
+int kzgpu_stats(kzgpu_ctx *ctx, kz_stats *out) {
+    if (!ctx || !out) return fail(ctx, KZ_ERR_INVALID, "null argument");
+    memset(out, 0, sizeof(*out));
+    for (Device &d : ctx->devs) {
+        KZ_CUDA(ctx, cudaSetDevice(d.id));
+        KZ_CUDA(ctx, cudaDeviceSynchronize());
+        fold_events(d);
+        KzControl c;
+        KZ_CUDA(ctx, cudaMemcpy(&c, d.ctl, sizeof(c), cudaMemcpyDeviceToHost));
+        out->paths += c.paths; out->rays_extension += c.rays_ext; out->rays_shadow += c.rays_shadow; out->vertices += c.vertices;
+        out->kernel_launches += d.launches;
+        out->ms_trace = std::max(out->ms_trace, d.ms[CAT_TRACE]);
+        out->ms_shade = std::max(out->ms_shade, d.ms[CAT_SHADE]);
+        out->ms_total = std::max(out->ms_total, d.ms[CAT_TOTAL]);
+    }
+    out->bvh_nodes = ctx->bvh_nodes; out->bvh_bytes = ctx->bvh_bytes; out->ms_build = ctx->ms_build;
+    return KZ_OK;
+}
+
+int kzgpu_stats_reset(kzgpu_ctx *ctx) {
+    if (!ctx) return fail(nullptr, KZ_ERR_INVALID, "null context");
+    for (Device &d : ctx->devs) {
+        KZ_CUDA(ctx, cudaSetDevice(d.id));
+        KZ_CUDA(ctx, cudaDeviceSynchronize());
+        fold_events(d);
+        d.ms[0] = d.ms[1] = d.ms[2] = 0; d.launches = 0;
+        /* keep queue state, zero the counters */
+        KZ_CUDA(ctx, cudaMemset(reinterpret_cast<char *>(d.ctl) + offsetof(KzControl, paths), 0, 4 * sizeof(unsigned long long)));
+    }
+    return KZ_OK;
+}
+
+}  // extern "C"

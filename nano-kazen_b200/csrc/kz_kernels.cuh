@@ -1,0 +1,310 @@
+/* kz_kernels.cuh -- the sm_100a kernels of the wavefront path tracer.
+ *
+ * Pipeline per chunk of path slots (kz_api.cu drives it without any host round trip):
+ *
+ *   k_chunk_reset -> k_raygen -> for bounce b = 0..maxDepth:
+ *        k_bounce_reset -> k_extend (closest hit, sorts slots into material-class queues)
+ *                       -> k_shade<TERMINAL|DIFFUSE|KISS|NORMALMAP> (one launch per class present)
+ *                       -> k_shadow (closest-hit walk through invisible lights, adds the NEE term)
+ *   -> k_accumulate (filtered splat into the bordered frame)
+ *
+ * Queues are arrays of slot indices with device-resident counters; every kernel is launched with
+ * a persistent grid (SM count x resident CTAs) and reads its item count from HBM, so the host
+ * never waits on a count.  Traversal kernels fetch 32-ray packets per warp through an atomic
+ * cursor (rays differ wildly in cost); shading kernels use a static warp-strided assignment.
+ * Pushes are warp-aggregated: one ballot + one atomicAdd per warp per queue.
+ *
+ * No tensor-core, TMA or cluster machinery on purpose: every stage is a data-dependent gather
+ * (BVH nodes, triangles, vertex attributes) or per-item ALU work; there is no tile to stage.
+ */
+#ifndef KZ_KERNELS_CUH
+#define KZ_KERNELS_CUH
+#include "kz_path.h"
+
+#define KZ_TRACE_THREADS 128
+#define KZ_SHADE_THREADS 128
+
+struct KzControl {
+    uint32_t n_ext[2];                    /* extension-ray queue counts (ping-pong)         */
+    uint32_t n_class[KZ_NUM_CLASSES];     /* material-class queue counts                    */
+    uint32_t n_shadow;
+    uint32_t head_ext, head_shadow, head_trace;   /* persistent-fetch cursors               */
+    uint32_t pad[2];
+    unsigned long long paths, rays_ext, rays_shadow, vertices;
+};
+
+struct KzQueues {
+    uint32_t *ext[2];
+    uint32_t *cls[KZ_NUM_CLASSES];
+    uint32_t *shadow;
+};
+
+struct KzChunk {
+    int32_t x0, y0, x1, y1;          /* pixel rectangle                                     */
+    uint32_t tiles_x;                /* 8x4 pixel tiles per row                             */
+    uint32_t npx_padded;             /* tiles_x * tiles_y * 32                              */
+    int32_t spp_begin;
+    unsigned long long first;        /* first global path index of this chunk               */
+    uint32_t count;                  /* slots used by this chunk                            */
+};
+
+#define KZ_FULL 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t kz_lane() { return threadIdx.x & 31u; }
+
+/* Warp-aggregated append; must be reached by all 32 lanes of the warp. */
+__device__ __forceinline__ void kz_push(uint32_t *queue, uint32_t *counter, bool pred, uint32_t value) {
+    const uint32_t mask = __ballot_sync(KZ_FULL, pred);
+    if (mask == 0u) return;
+    const uint32_t lane = kz_lane();
+    const uint32_t leader = (uint32_t)__ffs((int)mask) - 1u;
+    uint32_t base = 0u;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(KZ_FULL, base, (int)leader);
+    if (pred) queue[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+/* Next 32-item packet of a queue for this warp (persistent threads). */
+__device__ __forceinline__ uint32_t kz_fetch32(uint32_t *cursor) {
+    uint32_t base = 0u;
+    if (kz_lane() == 0u) base = atomicAdd(cursor, 32u);
+    return __shfl_sync(KZ_FULL, base, 0);
+}
+
+__device__ __forceinline__ void kz_flush_counters(KzControl *ctl, const KzCounters &c) {
+    unsigned long long e = c.rays_ext, s = c.rays_shadow, v = c.vertices;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        e += __shfl_down_sync(KZ_FULL, e, o);
+        s += __shfl_down_sync(KZ_FULL, s, o);
+        v += __shfl_down_sync(KZ_FULL, v, o);
+    }
+    if (kz_lane() == 0u) {
+        if (e) atomicAdd(&ctl->rays_ext, e);
+        if (s) atomicAdd(&ctl->rays_shadow, s);
+        if (v) atomicAdd(&ctl->vertices, v);
+    }
+}
+
+__global__ void k_chunk_reset(KzControl *ctl) {
+    if (threadIdx.x == 0) {
+        ctl->n_ext[0] = ctl->n_ext[1] = 0u;
+        for (int c = 0; c < KZ_NUM_CLASSES; ++c) ctl->n_class[c] = 0u;
+        ctl->n_shadow = 0u; ctl->head_ext = ctl->head_shadow = ctl->head_trace = 0u;
+    }
+}
+__global__ void k_bounce_reset(KzControl *ctl, int nxt) {
+    if (threadIdx.x == 0) {
+        ctl->n_ext[nxt] = 0u;
+        for (int c = 0; c < KZ_NUM_CLASSES; ++c) ctl->n_class[c] = 0u;
+        ctl->n_shadow = 0u; ctl->head_ext = ctl->head_shadow = 0u;
+    }
+}
+
+/* ---- raygen: renderer.cpp:20-33 + camera.cpp:70-91,191-223 ------------------------------- */
+/* Slot i of the chunk = global path index first+i = (sample-major, 8x4-pixel-tile-minor), so a
+ * warp is one 8x4 pixel tile of one sample index: coherent primary rays, and the splats of a
+ * warp land on neighbouring frame texels instead of piling onto one pixel. */
+__global__ void __launch_bounds__(KZ_SHADE_THREADS) k_raygen(KzScene sc, KzPathState st, KzControl *ctl, uint32_t *q0, KzChunk ch) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < ch.count;
+    if (valid) {
+        const unsigned long long g = ch.first + i;
+        const uint32_t s_local = (uint32_t)(g / ch.npx_padded);
+        const uint32_t pix = (uint32_t)(g % ch.npx_padded);
+        const uint32_t tile = pix >> 5, in_tile = pix & 31u;
+        const int x = ch.x0 + (int)((tile % ch.tiles_x) * 8u + (in_tile & 7u));
+        const int y = ch.y0 + (int)((tile / ch.tiles_x) * 4u + (in_tile >> 3));
+        valid = x < ch.x1 && y < ch.y1;
+        if (valid) kz_raygen_item(sc, st, i, x, y, (uint32_t)(ch.spp_begin + (int)s_local));
+        else st.pix[i] = 0xFFFFFFFFu;
+    }
+    kz_push(q0, &ctl->n_ext[0], valid, i);
+    const uint32_t nvalid = (uint32_t)__popc(__ballot_sync(KZ_FULL, valid));
+    if (kz_lane() == 0u && nvalid) atomicAdd(&ctl->paths, (unsigned long long)nvalid);
+}
+
+/* ---- extend: Scene::rayIntersect for every queued path, then sort by material class ------- */
+template <bool FIRST>
+__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_extend(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int cur, int bounce) {
+    __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
+    KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
+    const uint32_t n = ctl->n_ext[cur];
+    const uint32_t *queue = q.ext[cur];
+    KzCounters cnt; cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull;
+    for (;;) {
+        const uint32_t base = kz_fetch32(&ctl->head_ext);
+        if (base >= n) break;
+        const uint32_t idx = base + kz_lane();
+        const bool active = idx < n;
+        uint32_t slot = 0u; int cls = -1;
+        if (active) {
+            slot = queue[idx];
+            cls = kz_extend_item(sc, stk, st, slot, FIRST ? 0 : bounce, cnt);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < KZ_NUM_CLASSES; ++c) kz_push(q.cls[c], &ctl->n_class[c], cls == c, slot);
+    }
+    kz_flush_counters(ctl, cnt);
+}
+
+/* ---- shade: one integrator loop iteration for every path of one material class ------------ */
+template <int CLS>
+__global__ void __launch_bounds__(KZ_SHADE_THREADS) k_shade(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int nxt, int bounce) {
+    const uint32_t n = ctl->n_class[CLS];
+    const uint32_t *queue = q.cls[CLS];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    KzCounters cnt; cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
+        const uint32_t idx = base + kz_lane();
+        uint32_t slot = 0u, flags = 0u;
+        if (idx < n) {
+            slot = queue[idx];
+            flags = kz_shade_item<CLS>(sc, st, slot, bounce, cnt);
+        }
+        __syncwarp();
+        if (CLS != KZ_CLASS_TERMINAL) {
+            kz_push(q.ext[nxt], &ctl->n_ext[nxt], (flags & KZ_SHADE_CONTINUE) != 0u, slot);
+            kz_push(q.shadow, &ctl->n_shadow, (flags & KZ_SHADE_SHADOW) != 0u, slot);
+        }
+    }
+    kz_flush_counters(ctl, cnt);
+}
+
+/* ---- shadow: integrator.cpp:259-294 ------------------------------------------------------- */
+__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_shadow(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q) {
+    __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
+    KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
+    const uint32_t n = ctl->n_shadow;
+    KzCounters cnt; cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull;
+    for (;;) {
+        const uint32_t base = kz_fetch32(&ctl->head_shadow);
+        if (base >= n) break;
+        const uint32_t idx = base + kz_lane();
+        if (idx < n) kz_shadow_item(sc, stk, st, q.shadow[idx], cnt);
+        __syncwarp();
+    }
+    kz_flush_counters(ctl, cnt);
+}
+
+/* ---- accumulate: ImageBlock::put over the whole chunk (block.cpp:56-85) ------------------- */
+__global__ void __launch_bounds__(KZ_SHADE_THREADS) k_accumulate(KzScene sc, KzPathState st, uint32_t count, KzF4 *frame) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count || st.pix[i] == 0xFFFFFFFFu) return;
+    kz_accumulate_item(sc, st, i, frame);
+}
+
+/* ---- batch entry points (parity tests + intersection microbench) -------------------------- */
+/* kzgpu_trace: rays/hits in the C-ABI's AoS layout (32 B in, 20 B out). */
+__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_trace(KzScene sc, const KzF4 *rays, uint32_t n, float *hits, uint32_t *cursor, KzControl *ctl) {
+    __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
+    KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
+    for (;;) {
+        const uint32_t base = kz_fetch32(cursor);
+        if (base >= n) break;
+        const uint32_t idx = base + kz_lane();
+        if (idx < n) {
+            const KzU4 a = kz_load_u4(rays + 2 * (size_t)idx), b = kz_load_u4(rays + 2 * (size_t)idx + 1);
+            const KzHit h = kz_trace(sc, stk, kz_u2f(a.x), kz_u2f(a.y), kz_u2f(a.z), kz_u2f(b.x), kz_u2f(b.y), kz_u2f(b.z),
+                                     kz_u2f(a.w), kz_u2f(b.w), false);
+            float *o = hits + 5 * (size_t)idx;
+            o[0] = h.t; o[1] = h.u; o[2] = h.v; o[3] = kz_u2f(h.prim); o[4] = kz_u2f(h.geom);
+        }
+        __syncwarp();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->rays_ext, (unsigned long long)n);
+}
+
+__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_occluded(KzScene sc, const KzF4 *rays, uint32_t n, float eps, uint8_t *occ, uint8_t *segments,
+                                                                uint32_t *cursor, KzControl *ctl) {
+    __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
+    KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
+    KzCounters cnt; cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull;
+    for (;;) {
+        const uint32_t base = kz_fetch32(cursor);
+        if (base >= n) break;
+        const uint32_t idx = base + kz_lane();
+        if (idx < n) {
+            const KzU4 a = kz_load_u4(rays + 2 * (size_t)idx), b = kz_load_u4(rays + 2 * (size_t)idx + 1);
+            int seg;
+            const bool o = kz_occluded_walk(sc, stk, mk3(kz_u2f(a.x), kz_u2f(a.y), kz_u2f(a.z)), mk3(kz_u2f(b.x), kz_u2f(b.y), kz_u2f(b.z)),
+                                            kz_u2f(a.w), kz_u2f(b.w), eps, &seg);
+            occ[idx] = o ? 1 : 0;
+            if (segments) segments[idx] = (uint8_t)(seg > 255 ? 255 : seg);
+            cnt.rays_shadow += (unsigned long long)seg;
+        }
+        __syncwarp();
+    }
+    kz_flush_counters(ctl, cnt);
+}
+
+/* kzgpu_sample_dump: sampler.cpp generateSample + draw pattern, one thread per (pixel, sample) */
+__global__ void k_sample_dump(KzScene sc, const int32_t *triples, uint32_t n, const char *pattern, uint32_t per, float *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    KzSampler sm;
+    kz_sampler_start(sc, sm, triples[3 * i], triples[3 * i + 1], (uint32_t)triples[3 * i + 2]);
+    float *o = out + (size_t)i * per;
+    for (const char *p = pattern; *p; ++p) {
+        if (*p == '1') *o++ = kz_next1d(sc, sm);
+        else { const kz2 v = (*p == 'P') ? kz_next_pixel2d(sc, sm) : kz_next2d(sc, sm); *o++ = v.x; *o++ = v.y; }
+    }
+}
+
+__global__ void k_camera_rays(KzScene sc, const KzF4 *samples, uint32_t n, KzF4 *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const KzF4 s = samples[i];
+    KzF4 ro, rd;
+    kz_camera_ray(sc.camera, mk2(s.x, s.y), mk2(s.z, s.w), ro, rd);
+    out[2 * (size_t)i] = ro; out[2 * (size_t)i + 1] = rd;
+}
+
+/* One BSDF query per thread in an identity shading frame (parity of the shading library). */
+struct KzBsdfQuery { float wi[3], wo[3], uv[2], acc_rough, s1, s2[2]; int32_t mesh, mode; };
+__global__ void k_bsdf_query(KzScene sc, const KzBsdfQuery *qs, uint32_t n, float *out8) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const KzBsdfQuery q = qs[i];
+    KzIts its;
+    its.sh.s = mk3(1, 0, 0); its.sh.t = mk3(0, 1, 0); its.sh.n = mk3(0, 0, 1);
+    its.geo_n = its.sh.n; its.dpdu = mk3(1, 0, 0); its.uv = mk2(q.uv[0], q.uv[1]); its.mesh = q.mesh; its.acc_rough = q.acc_rough;
+    its.p = mk3(0.f);
+    const KzBsdfCtx bc = bsdf_ctx(sc, its);
+    float *o = out8 + 8 * (size_t)i;
+    for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    const kz3 wi = mk3(q.wi[0], q.wi[1], q.wi[2]);
+    if (q.mode == 2) {
+        kz3 w_o; float pdf; int measure;
+        const kz3 w = bsdf_sample(bc, its, wi, q.s1, mk2(q.s2[0], q.s2[1]), &w_o, &pdf, &measure);
+        o[0] = w.x; o[1] = w.y; o[2] = w.z;
+        if (!iszero(w)) { o[3] = w_o.x; o[4] = w_o.y; o[5] = w_o.z; o[7] = pdf; }
+        o[6] = (float)measure;
+        return;
+    }
+    kz3 f; float pdf;
+    bsdf_eval_pdf(bc, its, wi, mk3(q.wo[0], q.wo[1], q.wo[2]), &f, &pdf);
+    if (q.mode == 0) { o[0] = f.x; o[1] = f.y; o[2] = f.z; } else o[0] = pdf;
+}
+
+/* ---- resolve: block.cpp:39-45 + common.cpp:352-366 + bitmap.cpp:46-54 --------------------- */
+__global__ void k_resolve(const KzF4 *frame, int width, int height, int border, float *rgb, uint8_t *srgb8) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const KzF4 v = frame[(size_t)(y + border) * (width + 2 * border) + (x + border)];
+    kz3 c = v.w != 0.f ? mk3(v.x / v.w, v.y / v.w, v.z / v.w) : mk3(0.f);
+    const size_t o = 3 * ((size_t)y * width + x);
+    if (rgb) { rgb[o] = c.x; rgb[o + 1] = c.y; rgb[o + 2] = c.z; }
+    if (srgb8) {
+        const float s[3] = {linear_to_srgb1(c.x), linear_to_srgb1(c.y), linear_to_srgb1(c.z)};
+        for (int k = 0; k < 3; ++k) srgb8[o + k] = (uint8_t)clampf(255.f * s[k], 0.f, 255.f);
+    }
+}
+
+__global__ void k_frame_add(KzF4 *dst, const KzF4 *src, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { KzF4 a = dst[i]; const KzF4 b = src[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; dst[i] = a; }
+}
+
+#endif

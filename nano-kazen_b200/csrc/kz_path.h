@@ -131,6 +131,8 @@ KZ_HD int kz_extend_item(const KzScene &sc, const KzStackRef &stk, const KzPathS
 }
 
 /* ---- shade --------------------------------------------------------------------------------- */
+/* CLS = material class of the queue this item was sorted into (-1: unknown, resolve at run time) */
+template <int CLS = -1>
 KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t slot, int bounce, KzCounters &cnt) {
     const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
     const kz3 rayO = mk3(ro.x, ro.y, ro.z), rayD = mk3(rd.x, rd.y, rd.z);
@@ -170,6 +172,7 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
         }
         return 0u;
     }
+    if (CLS == KZ_CLASS_TERMINAL) return 0u;      /* that queue only holds misses and light hits */
 
     KzSampler sm;
     sm.state = st.rng_state[slot]; sm.inc = st.rng_inc[slot]; sm.dim = st.dim[slot];
@@ -183,7 +186,7 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     }
     cnt.vertices += 1;
     uint32_t flags = 0u;
-    const KzBsdfCtx bc = bsdf_ctx(sc, its);
+    const KzBsdfCtx bc = bsdf_ctx<CLS>(sc, its);
     const kz3 wiLocal = to_local(its.sh, -rayD);
     const float eps = I.trace_bias;
 

@@ -52,7 +52,7 @@ KZ_HD void kz_bspline_weights(float f, float w[4]) {
     w[3] = (f * f * f) / 6.0f;
 }
 /* finest mip level, periodic wrap, bicubic B-spline (OIIO default with zero derivatives) */
-KZ_HD kz3 kz_image_bicubic(const KzScene &sc, int image, float s, float t) {
+KZ_HD_NOINLINE kz3 kz_image_bicubic(const KzScene &sc, int image, float s, float t) {
     const KzImageRec im = sc.images[image];
     float x = s * im.width - 0.5f, y = t * im.height - 0.5f;
     float fx = floorf(x), fy = floorf(y);
@@ -75,64 +75,78 @@ KZ_HD kz3 kz_image_bicubic(const KzScene &sc, int image, float s, float t) {
     return acc;
 }
 
-/* Expression trees are tiny (depth <= 3 in every kazen scene); evaluated with an explicit
- * depth bound instead of recursion so the kernels need no device call stack. */
+/* Expression trees are tiny (depth <= 3 in every kazen scene).  They are evaluated post-order
+ * with an explicit frame stack of bounded depth: no recursion (no device call stack growth) and
+ * no template expansion (a blend has three children; inlining the tree is exponential).
+ * dir_mode: Texture::eval(dir) (texture.cpp:66-81,121-126) instead of eval(uv). */
 #define KZ_TEX_MAX_DEPTH 4
-template <int DEPTH> struct KzTexEval {
-    static KZ_HD kz3 uv(const KzScene &sc, int node, kz2 uv_) {
-        const kz_texture_desc t = sc.textures[node];
-        switch (t.type) {
-            case KZ_TEX_CONSTANT: return mk3(t.color[0], t.color[1], t.color[2]);
-            case KZ_TEX_IMAGE: {
-                kz3 c = kz_image_bicubic(sc, t.image, uv_.x * t.scale, (1.0f - uv_.y) * t.scale);
-                return t.srgb ? mk3(srgb_to_linear1(c.x), srgb_to_linear1(c.y), srgb_to_linear1(c.z)) : c;
+KZ_HD_NOINLINE kz3 kz_tex_eval_tree(const KzScene &sc, int root, kz2 uv_, kz3 d, bool dir_mode) {
+    int node[KZ_TEX_MAX_DEPTH], next[KZ_TEX_MAX_DEPTH];
+    kz3 val[KZ_TEX_MAX_DEPTH][3];
+    int sp = 0;
+    node[0] = root; next[0] = 0;
+    for (;;) {
+        const kz_texture_desc t = sc.textures[node[sp]];
+        int nchild = t.type == KZ_TEX_BLEND ? 3 : ((t.type == KZ_TEX_BACKGROUND || t.type == KZ_TEX_COLORRAMP) ? 1 : 0);
+        if (dir_mode && t.type != KZ_TEX_BACKGROUND) nchild = 0;     /* only background forwards eval(dir) */
+        if (next[sp] < nchild) {
+            const int k = next[sp];
+            const int c = t.child[k];
+            if (c < 0 || sp + 1 == KZ_TEX_MAX_DEPTH) {
+                /* blend defaults, texture.cpp:215-217; a missing unary child evaluates to 0 below */
+                val[sp][k] = (t.type == KZ_TEX_BLEND && c < 0) ? (k == 0 ? mk3(0.5f) : (k == 1 ? mk3(0.f) : mk3(1.f))) : mk3(0.f);
+                next[sp] = k + 1;
+            } else {
+                ++sp; node[sp] = c; next[sp] = 0;
             }
-            case KZ_TEX_BACKGROUND:
-                return t.child[0] >= 0 ? t.a * KzTexEval<DEPTH - 1>::uv(sc, t.child[0], uv_) : mk3(0.f);
-            case KZ_TEX_COLORRAMP: {
-                if (t.child[0] < 0) return mk3(0.f);
-                kz3 c = KzTexEval<DEPTH - 1>::uv(sc, t.child[0], uv_);
-                return mk3(t.a + (t.b - t.a) * clampf(c.x, 0.f, 1.f), t.a + (t.b - t.a) * clampf(c.y, 0.f, 1.f),
-                           t.a + (t.b - t.a) * clampf(c.z, 0.f, 1.f));
-            }
-            case KZ_TEX_BLEND: {
-                kz3 mask = mk3(0.5f), in1 = mk3(0.f), in2 = mk3(1.f);
-                if (t.child[0] >= 0) mask = KzTexEval<DEPTH - 1>::uv(sc, t.child[0], uv_);
-                if (t.child[1] >= 0) in1 = KzTexEval<DEPTH - 1>::uv(sc, t.child[1], uv_);
-                if (t.child[2] >= 0) in2 = KzTexEval<DEPTH - 1>::uv(sc, t.child[2], uv_);
-                if (t.mode == KZ_BLEND_MIX) return mk3(lerpf(mask.x, in1.x, in2.x), lerpf(mask.x, in1.y, in2.y), lerpf(mask.x, in1.z, in2.z));
-                if (t.mode == KZ_BLEND_MULTIPLY) return in1 * in2;
-                return mk3(0.f);
-            }
+            continue;
         }
-        return mk3(0.f);
-    }
-    static KZ_HD kz3 dir(const KzScene &sc, int node, kz3 d) {
-        const kz_texture_desc t = sc.textures[node];
+        kz3 r = mk3(0.f);
         switch (t.type) {
-            case KZ_TEX_CONSTANT: return mk3(t.color[0], t.color[1], t.color[2]);
-            case KZ_TEX_IMAGE: {
-                float s = atan2f(-d.x, d.z) / (2.0f * KZ_PI) + 0.5f;
-                float tt = 0.5f - atan2f(d.y, hypotf(d.z, -d.x)) / KZ_PI;
-                if (isnan(s)) s = 0.0f;
-                if (isnan(tt)) tt = 0.0f;
-                return kz_image_bicubic(sc, t.image, s, tt);
-            }
-            case KZ_TEX_BACKGROUND:
-                return t.child[0] >= 0 ? t.a * KzTexEval<DEPTH - 1>::dir(sc, t.child[0], d) : mk3(0.f);
-            default: return mk3(0.f);
+            case KZ_TEX_CONSTANT: r = mk3(t.color[0], t.color[1], t.color[2]); break;
+            case KZ_TEX_IMAGE:
+                if (dir_mode) {
+                    float s = atan2f(-d.x, d.z) / (2.0f * KZ_PI) + 0.5f;
+                    float tt = 0.5f - atan2f(d.y, hypotf(d.z, -d.x)) / KZ_PI;
+                    if (isnan(s)) s = 0.0f;
+                    if (isnan(tt)) tt = 0.0f;
+                    r = kz_image_bicubic(sc, t.image, s, tt);
+                } else {
+                    r = kz_image_bicubic(sc, t.image, uv_.x * t.scale, (1.0f - uv_.y) * t.scale);
+                    if (t.srgb) r = mk3(srgb_to_linear1(r.x), srgb_to_linear1(r.y), srgb_to_linear1(r.z));
+                }
+                break;
+            case KZ_TEX_BACKGROUND: r = t.child[0] >= 0 ? t.a * val[sp][0] : mk3(0.f); break;
+            case KZ_TEX_COLORRAMP:
+                if (!dir_mode && t.child[0] >= 0) {
+                    const kz3 c = val[sp][0];
+                    r = mk3(t.a + (t.b - t.a) * clampf(c.x, 0.f, 1.f), t.a + (t.b - t.a) * clampf(c.y, 0.f, 1.f), t.a + (t.b - t.a) * clampf(c.z, 0.f, 1.f));
+                }
+                break;
+            case KZ_TEX_BLEND:
+                if (!dir_mode) {
+                    const kz3 mask = val[sp][0], in1 = val[sp][1], in2 = val[sp][2];
+                    if (t.mode == KZ_BLEND_MIX) r = mk3(lerpf(mask.x, in1.x, in2.x), lerpf(mask.x, in1.y, in2.y), lerpf(mask.x, in1.z, in2.z));
+                    else if (t.mode == KZ_BLEND_MULTIPLY) r = in1 * in2;
+                }
+                break;
+            default: break;
         }
+        if (sp == 0) return r;
+        --sp;
+        val[sp][next[sp]] = r;
+        next[sp] += 1;
     }
-};
-template <> struct KzTexEval<0> {
-    static KZ_HD kz3 uv(const KzScene &, int, kz2) { return mk3(0.f); }
-    static KZ_HD kz3 dir(const KzScene &, int, kz3) { return mk3(0.f); }
-};
-KZ_HD kz3 kz_tex_uv(const KzScene &sc, int node, kz2 uv) { return KzTexEval<KZ_TEX_MAX_DEPTH>::uv(sc, node, uv); }
+}
+KZ_HD kz3 kz_tex_uv(const KzScene &sc, int node, kz2 uv) {
+    const kz_texture_desc *t = sc.textures + node;
+    if (t->type == KZ_TEX_CONSTANT) return mk3(t->color[0], t->color[1], t->color[2]);     /* the common case */
+    return kz_tex_eval_tree(sc, node, uv, mk3(0.f), false);
+}
 KZ_HD kz3 kz_background(const KzScene &sc, kz3 d) {   /* scene.cpp:54-79 */
     if (sc.background < 0) return mk3(0.f);
     if (isnan3(d)) return mk3(0.f);
-    return KzTexEval<KZ_TEX_MAX_DEPTH>::dir(sc, sc.background, d);
+    return kz_tex_eval_tree(sc, sc.background, mk2(0.f, 0.f), d, true);
 }
 
 /* ---- GGX helpers (ggx_brdf.h) ------------------------------------------------------------ */
@@ -205,7 +219,7 @@ KZ_HD KzKissParams kiss_params(const KzScene &sc, const kz_bsdf_desc &m, kz2 uv)
     p.roughness_raw = kz_tex_uv(sc, m.roughness, uv).x;
     return p;
 }
-KZ_HD kz3 kiss_eval(const kz_bsdf_desc &m, const KzKissParams &kp, const KzBRec &b) {   /* bsdf.cpp:1215-1267 */
+KZ_HD_NOINLINE kz3 kiss_eval(const kz_bsdf_desc &m, const KzKissParams &kp, const KzBRec &b) {   /* bsdf.cpp:1215-1267 */
     if (b.wi.z <= 0 || b.wo.z <= 0) return mk3(0.0f);
     kz3 V = b.wi, L = b.wo, H = normalized(V + L);
     kz3 Cdlin = kp.base;
@@ -227,7 +241,7 @@ KZ_HD kz3 kiss_eval(const kz_bsdf_desc &m, const KzKissParams &kp, const KzBRec 
     kz3 coatTerm = m.clearcoat != 0.f ? (0.25f * m.clearcoat) * ggx_smith_brdf(V, L, mk3(0.04f), ccR, m.anisotropy) : mk3(0.f);
     return ((1.f - metallic) * (Cdlin * KZ_INV_PI * (Lambert + retro) + Fsheen) + (specTerm + coatTerm)) * b.wo.z;
 }
-KZ_HD float kiss_pdf(const kz_bsdf_desc &m, const KzKissParams &kp, const KzBRec &b) {   /* bsdf.cpp:1269-1299 */
+KZ_HD_NOINLINE float kiss_pdf(const kz_bsdf_desc &m, const KzKissParams &kp, const KzBRec &b) {   /* bsdf.cpp:1269-1299 */
     if (b.wi.z <= 0 || b.wo.z <= 0) return 0.0f;
     float diffuse = (1.f - kp.metallic) * 0.5f;
     float GTR2 = 1.f / (1.f + m.clearcoat);
@@ -241,7 +255,7 @@ KZ_HD float kiss_pdf(const kz_bsdf_desc &m, const KzKissParams &kp, const KzBRec
     return diffuse * KZ_INV_PI * b.wo.z + (1.f - diffuse) * (GTR2 * specPdf + (1.f - GTR2) * coatPdf);
 }
 /* returns weight; *pdf_out = pdf(bRec) as the integrator queries it afterwards (integrator.cpp:314) */
-KZ_HD kz3 kiss_sample(const kz_bsdf_desc &m, const KzKissParams &kp, KzBRec &b, float sample1, kz2 sample2, float *pdf_out) { /* bsdf.cpp:1301-1371 */
+KZ_HD_NOINLINE kz3 kiss_sample(const kz_bsdf_desc &m, const KzKissParams &kp, KzBRec &b, float sample1, kz2 sample2, float *pdf_out) { /* bsdf.cpp:1301-1371 */
     *pdf_out = 0.f;
     if (b.wi.z <= 0) return mk3(0.0f);
     b.measure = KZ_MEASURE_SOLID_ANGLE;
@@ -269,16 +283,21 @@ struct KzBsdfCtx {
     const kz_bsdf_desc *outer;     /* mesh BSDF */
     const kz_bsdf_desc *leaf;      /* nested (== outer when not a normal map) */
     KzKissParams kp;               /* leaf kiss parameters at uv */
+    int leaf_type;                 /* leaf->type; a literal in the class-specialised shade kernels */
     bool is_nmap;
     kz3 nm_n;                      /* 2*rgb-1, un-normalised */
     KzFrame pert;                  /* perturbed frame (bsdf.cpp:366-374) */
 };
+/* CLS: material class the caller's queue was sorted into (KZ_CLASS_*), or -1 when unknown; a known
+ * class turns the BSDF dispatch below into compile-time constants. */
+template <int CLS = -1>
 KZ_HD KzBsdfCtx bsdf_ctx(const KzScene &sc, const KzIts &its) {
     KzBsdfCtx c;
     c.outer = sc.bsdfs + sc.meshes[its.mesh].bsdf;
-    c.is_nmap = c.outer->type == KZ_BSDF_NORMALMAP;
+    c.is_nmap = CLS == KZ_CLASS_NORMALMAP ? true : (CLS >= 0 ? false : c.outer->type == KZ_BSDF_NORMALMAP);
     c.leaf = c.is_nmap ? sc.bsdfs + c.outer->nested : c.outer;
-    if (c.leaf->type == KZ_BSDF_KISS) c.kp = kiss_params(sc, *c.leaf, its.uv);
+    c.leaf_type = CLS == KZ_CLASS_DIFFUSE ? KZ_BSDF_DIFFUSE : (CLS == KZ_CLASS_KISS ? KZ_BSDF_KISS : c.leaf->type);
+    if (c.leaf_type == KZ_BSDF_KISS) c.kp = kiss_params(sc, *c.leaf, its.uv);
     else { c.kp.base = mk3(0.f); c.kp.metallic = 0.f; c.kp.roughness_raw = 0.f; }
     if (c.is_nmap) {
         kz3 rgb = kz_tex_uv(sc, c.outer->normal_map, its.uv);
@@ -294,17 +313,17 @@ KZ_HD KzBsdfCtx bsdf_ctx(const KzScene &sc, const KzIts &its) {
     return c;
 }
 KZ_HD kz3 leaf_eval(const KzBsdfCtx &c, const KzBRec &b) {
-    if (c.leaf->type == KZ_BSDF_KISS) return kiss_eval(*c.leaf, c.kp, b);
+    if (c.leaf_type == KZ_BSDF_KISS) return kiss_eval(*c.leaf, c.kp, b);
     if (b.measure != KZ_MEASURE_SOLID_ANGLE || b.wi.z <= 0 || b.wo.z <= 0) return mk3(0.0f);   /* bsdf.cpp:27-36 */
     return mk3(c.leaf->albedo[0], c.leaf->albedo[1], c.leaf->albedo[2]) * KZ_INV_PI * b.wo.z;
 }
 KZ_HD float leaf_pdf(const KzBsdfCtx &c, const KzBRec &b) {
-    if (c.leaf->type == KZ_BSDF_KISS) return kiss_pdf(*c.leaf, c.kp, b);
+    if (c.leaf_type == KZ_BSDF_KISS) return kiss_pdf(*c.leaf, c.kp, b);
     if (b.measure != KZ_MEASURE_SOLID_ANGLE || b.wi.z <= 0 || b.wo.z <= 0) return 0.0f;        /* bsdf.cpp:39-55 */
     return KZ_INV_PI * b.wo.z;
 }
 KZ_HD kz3 leaf_sample(const KzBsdfCtx &c, KzBRec &b, float s1, kz2 s2, float *pdf_out) {
-    if (c.leaf->type == KZ_BSDF_KISS) return kiss_sample(*c.leaf, c.kp, b, s1, s2, pdf_out);
+    if (c.leaf_type == KZ_BSDF_KISS) return kiss_sample(*c.leaf, c.kp, b, s1, s2, pdf_out);
     *pdf_out = 0.f;                                                                            /* bsdf.cpp:58-75 */
     if (b.wi.z <= 0) return mk3(0.0f);
     b.measure = KZ_MEASURE_SOLID_ANGLE;
@@ -365,7 +384,7 @@ KZ_HD kz3 bsdf_sample(const KzBsdfCtx &c, const KzIts &its, kz3 wi, float s1, kz
     return result;
 }
 KZ_HD float bsdf_regularize(const KzBsdfCtx &c) {   /* bsdf.h:125, bsdf.cpp:412,1397-1399 */
-    return c.leaf->type == KZ_BSDF_KISS ? c.kp.roughness_raw : 0.f;
+    return c.leaf_type == KZ_BSDF_KISS ? c.kp.roughness_raw : 0.f;
 }
 
 /* ---- lights -------------------------------------------------------------------------------- */

@@ -93,7 +93,7 @@ KZ_HD float kz_rcp_safe(float d) {
 #define KZ_LOCAL_STACK 56         /* overflow entries in local memory          */
 
 struct KzStackRef {
-#if KZ_DEVICE_CODE
+#if defined(__CUDACC__)
     uint2 *smem;                  /* this thread's column: entry i at smem[i * stride] */
     int stride;
 #endif

@@ -314,6 +314,12 @@ class _Backend:
         return rgb, srgb
 
 
+def shard_range(begin, end, rank, world):
+    """Contiguous slice of sample indices [begin, end) owned by `rank` of `world`."""
+    n = end - begin
+    return begin + n * rank // world, begin + n * (rank + 1) // world
+
+
 def _pattern_floats(pattern):
     return sum(1 if ch == "1" else 2 for ch in pattern)
 
@@ -386,13 +392,22 @@ class Gpu(_Backend):
         self._call("render", self.h, C.byref(req), frame.ctypes.data_as(c_float_p))
         return frame
 
-    def render_device(self, spp_begin, spp_end, device=0, clear=True, stream=None):
-        """Returns the device pointer of the (H+2b, W+2b, 4) float32 frame left in HBM."""
+    def render_device(self, spp_begin, spp_end, device=0, clear=True, stream=None, frame_ptr=None, rect=None):
+        """Enqueues a render on `stream`; the (H+2b, W+2b, 4) float32 frame stays in HBM (frame_ptr:
+        caller-owned device buffer, else the context's own).  Returns the frame's device pointer."""
         H, W, b = self.frame_shape()
-        req = RenderReq(0, 0, W - 2 * b, H - 2 * b, spp_begin, spp_end, int(clear))
-        ptr = C.c_void_p()
+        x0, y0, x1, y1 = rect if rect else (0, 0, W - 2 * b, H - 2 * b)
+        req = RenderReq(x0, y0, x1, y1, spp_begin, spp_end, int(clear))
+        ptr = C.c_void_p(frame_ptr or 0)
         self._call("render_device", self.h, C.c_int(device), C.byref(req), C.byref(ptr), C.c_void_p(stream or 0))
         return ptr.value
+
+    def bsdf_query(self, bsdf, mode, wi, wo=(0, 0, 1), uv=(0.5, 0.5), acc_rough=0.0, s1=0.5, s2=(0.5, 0.5)):
+        out = (C.c_float * 8)()
+        f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
+        f2 = lambda v: (C.c_float * 2)(*[float(x) for x in v])
+        self._call("bsdf_query", self.h, C.c_int(bsdf), C.c_int(mode), f3(wi), f3(wo), f2(uv), C.c_float(acc_rough), C.c_float(s1), f2(s2), out)
+        return np.array(list(out), np.float32)
 
     def stats(self, reset=False):
         s = Stats()

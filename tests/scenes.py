@@ -62,6 +62,18 @@ def quad(p0, p1, p2, p3):
     return P, F
 
 
+def orient(P, F, ref, away=True):
+    """flip triangle winding so geometric normals point away from (or towards) `ref`"""
+    P = np.asarray(P, np.float32); F = np.array(F, np.uint32)
+    for k in range(F.shape[0]):
+        a, b, c = P[F[k, 0]], P[F[k, 1]], P[F[k, 2]]
+        n = np.cross(b - a, c - a)
+        s = np.dot(n, (a + b + c) / 3 - np.asarray(ref, np.float32))
+        if (s < 0) == away:
+            F[k, 1], F[k, 2] = F[k, 2], F[k, 1]
+    return P, F
+
+
 def uv_sphere(center, radius, nu=24, nv=12):
     """smooth-shaded sphere with normals and uvs"""
     P, N, UV, F = [], [], [], []
@@ -95,7 +107,7 @@ def cornell_scene(width=64, height=64, spp=16, sampler="stratified", with_textur
         ((-1, -1, -1), (-1, -1, 1), (-1, 1, 1), (-1, 1, -1), red),
         ((1, -1, -1), (1, 1, -1), (1, 1, 1), (1, -1, 1), green),
     ]:
-        P, F = quad(a, b, c, d)
+        P, F = orient(*quad(a, b, c, d), (0, 0, 0), away=False)
         sb.mesh(P, F, m)
     if with_texture:
         rng = np.random.default_rng(7)
@@ -119,6 +131,7 @@ def cornell_scene(width=64, height=64, spp=16, sampler="stratified", with_textur
     bx = np.array([[0.25, -1, -0.3], [0.75, -1, -0.3], [0.75, -1, 0.3], [0.25, -1, 0.3],
                    [0.25, -0.3, -0.3], [0.75, -0.3, -0.3], [0.75, -0.3, 0.3], [0.25, -0.3, 0.3]], np.float32)
     bf = np.array([[4, 5, 6], [7, 4, 6], [0, 1, 5], [4, 0, 5], [1, 2, 6], [5, 1, 6], [2, 3, 7], [6, 2, 7], [3, 0, 4], [7, 3, 4]], np.uint32)
+    bx, bf = orient(bx, bf, (0.5, -0.65, 0.0), away=True)
     sb.mesh(bx, bf, kiss2)
     # ceiling light, two stacked quads so that shadow rays have an invisible light to step through
     lt = sb.light((17.0 * 0.8, 12.0 * 0.8, 4.0 * 0.8), primary_visibility=visible_light)

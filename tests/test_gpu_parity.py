@@ -1,0 +1,240 @@
+"""GPU parity: the CUDA path through the C ABI (libkzgpu.so) against the CPU oracle on identical
+inputs.  Bars (BASELINE.json north_star): hit primitive/geometry IDs bit exact, hit t within 2 ulp
+(here: bit exact, both sides use the same explicitly rounded Pluecker arithmetic), sampler
+sequences bit exact, images within a stated relative MSE at equal spp."""
+import numpy as np
+import pytest
+
+import scenes
+import pykazen as pk
+
+pytestmark = pytest.mark.gpu
+
+IMAGE_RELMSE_TOL = 2e-4      # per channel, GPU vs oracle at EQUAL samples (same sampler sequences)
+
+
+def ulp_diff(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)
+
+
+def _pair(kzo, sb, builder=pk.BUILD_HOST_SAH):
+    d = sb.desc()
+    return kzo.Oracle(d), pk.Gpu(d, builder=builder)
+
+
+@pytest.mark.parametrize("builder", [pk.BUILD_HOST_SAH, pk.BUILD_LBVH])
+def test_trace_cornell(kzo, gpu_lib, builder):
+    sb = scenes.cornell_scene(32, 32, 4)
+    O, G = _pair(kzo, sb, builder)
+    rays = np.concatenate([scenes.primary_rays(128, 39.0, (0, 0, -3.4)), scenes.incoherent_rays(100000, extent=0.95)])
+    a, b = O.trace(rays, brute=True), G.trace(rays)
+    assert np.array_equal(a["geom_id"], b["geom_id"]) and np.array_equal(a["prim_id"], b["prim_id"])
+    assert ulp_diff(a["t"], b["t"]).max() == 0
+    assert a.tobytes() == b.tobytes()
+    b2 = G.trace(rays, shadow=True)
+    assert b2.tobytes() == b.tobytes()
+    O.close(); G.close()
+
+
+@pytest.mark.parametrize("n,builder", [(1, 0), (1, 1), (2, 1), (3, 1), (4, 1), (9, 0), (9, 1), (5000, 0), (5000, 1), (200000, 0), (200000, 1)])
+def test_trace_soup(kzo, gpu_lib, n, builder):
+    sb = scenes.soup_scene(n)
+    O, G = _pair(kzo, sb, builder)
+    rays = np.concatenate([scenes.primary_rays(128), scenes.incoherent_rays(50000)])
+    a, b = O.trace(rays, brute=(n <= 5000)), G.trace(rays)
+    assert a.tobytes() == b.tobytes()
+    st = G.stats()
+    assert st["bvh_nodes"] >= 1 and st["kernel_launches"] >= 1
+    O.close(); G.close()
+
+
+def test_trace_edge_cases(kzo, gpu_lib):
+    sb = scenes.cornell_scene(8, 8, 1)
+    P = np.array([[0, 0, 0], [0.5, 0.5, 0], [1, 1, 0]], np.float32)          # zero-area triangle
+    sb.mesh(P, np.array([[0, 1, 2]], np.uint32), 0)
+    O, G = _pair(kzo, sb)
+    assert G.trace(np.zeros(0, pk.RAY_DTYPE)).shape == (0,)
+    r = np.zeros(6, pk.RAY_DTYPE)
+    r["o"] = [(0, 0, -3), (0, 0, -3), (0.25, 0.25, -0.5), (0, 0, 0), (0, 0, 0), (0.3, -1, 0.1)]
+    r["d"] = [(0, 0, 1), (0, 0, 1), (0, 0, 1), (1, 0, 0), (0, 1, 0), (0, 1, 0)]      # axis-aligned: zero direction components
+    r["tmin"] = [1e-4, 5.0, 0.0, 0, 0, 0]
+    r["tmax"] = [np.inf, 4.0, 100.0, np.inf, np.inf, np.inf]
+    assert O.trace(r, brute=True).tobytes() == G.trace(r).tobytes()
+    # 33, 31 and 1 rays: ragged last warp
+    for n in (1, 31, 33):
+        rr = scenes.incoherent_rays(n, seed=n, extent=0.9)
+        assert O.trace(rr).tobytes() == G.trace(rr).tobytes()
+    O.close(); G.close()
+
+
+def test_occluded_walk(kzo, gpu_lib):
+    sb = scenes.cornell_scene(16, 16, 4)
+    O, G = _pair(kzo, sb)
+    rays = scenes.incoherent_rays(100000, extent=0.97)
+    rays["tmax"] *= 1.5
+    (oa, sa), (ob, sb_) = O.occluded(rays, 1e-3), G.occluded(rays, 1e-3)
+    assert np.array_equal(oa, ob) and np.array_equal(sa, sb_)
+    assert sa.max() >= 2
+    O.close(); G.close()
+
+
+@pytest.mark.parametrize("kind", ["independent", "stratified", "correlated"])
+def test_sampler_bit_exact(kzo, gpu_lib, kind):
+    sb = scenes.cornell_scene(64, 64, 30, kind)
+    O, G = _pair(kzo, sb)
+    rng = np.random.default_rng(3)
+    tr = np.stack([rng.integers(0, 4000, 4000), rng.integers(0, 4000, 4000), rng.integers(0, sb.sampler.sample_count, 4000)], 1).astype(np.int32)
+    pat = "P2" + "1111" * 2 + "12" * 3 + "1"
+    a, b = O.sample_dump(tr, pat), G.sample_dump(tr, pat)
+    assert a.tobytes() == b.tobytes()
+    O.close(); G.close()
+
+
+def test_sampler_pmj02bn_synthetic_tables(kzo, gpu_lib):
+    rng = np.random.default_rng(5)
+    bn = rng.integers(0, 65536, (48, 128, 128), dtype=np.uint16)
+    pm = rng.integers(0, 2 ** 32, (5, 65536, 2), dtype=np.uint32)
+    sb = scenes.cornell_scene(16, 16, 16, "stratified")
+    sb.set_sampler("pmj02bn", 16, tables=(bn, pm))
+    O, G = _pair(kzo, sb)
+    tr = np.array([[x, y, j] for x in (0, 5, 130) for y in (1, 77) for j in (0, 3, 15)], np.int32)
+    assert O.sample_dump(tr, "P2121212121212").tobytes() == G.sample_dump(tr, "P2121212121212").tobytes()
+    O.close(); G.close()
+
+
+@pytest.mark.parametrize("thin", [None, (0.05, 3.0)])
+def test_camera_rays(kzo, gpu_lib, thin):
+    sb = scenes.cornell_scene(64, 48, 4, thinlens=thin)
+    O, G = _pair(kzo, sb)
+    rng = np.random.default_rng(2)
+    s4 = rng.uniform(0, 1, (5000, 4)).astype(np.float32) * np.array([64, 48, 1, 1], np.float32)
+    a, b = O.camera_rays(s4), G.camera_rays(s4)
+    for k in ("o", "d", "tmin", "tmax"):
+        assert np.allclose(a[k], b[k], rtol=4e-6, atol=2e-7)
+    O.close(); G.close()
+
+
+def test_bsdf_queries(kzo, gpu_lib):
+    sb = scenes.cornell_scene(8, 8, 1, with_texture=True, normalmap=True)
+    O, G = _pair(kzo, sb)
+    rng = np.random.default_rng(9)
+    for bsdf in range(len(sb.bsdfs)):
+        if not any(m.bsdf == bsdf for m in sb.meshes):
+            continue
+        for _ in range(25):
+            wi = rng.normal(size=3); wi[2] = abs(wi[2]) + 0.05; wi /= np.linalg.norm(wi)
+            wo = rng.normal(size=3); wo[2] = abs(wo[2]) * rng.choice([1, 1, 1, -1]) + 0.01; wo /= np.linalg.norm(wo)
+            uv = rng.uniform(0, 1, 2); acc = float(rng.choice([0.0, 0.3]))
+            s1 = float(rng.uniform()); s2 = rng.uniform(0, 1, 2)
+            for mode in (0, 1, 2):
+                a = O.bsdf_query(bsdf, mode, wi, wo, uv, acc, s1, s2)
+                b = G.bsdf_query(bsdf, mode, wi, wo, uv, acc, s1, s2)
+                n = 3 if mode == 0 else (1 if mode == 1 else 6)
+                assert np.allclose(a[:n], b[:n], rtol=5e-4, atol=2e-6), (bsdf, mode, a, b)
+    O.close(); G.close()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(sampler="stratified"),
+    dict(sampler="correlated", visible_light=True),
+    dict(sampler="independent", with_texture=True, normalmap=True, regularization=True),
+    dict(sampler="stratified", thinlens=(0.05, 3.2), background=(0.3, 0.4, 0.5), max_depth=3),
+])
+def test_render_matches_oracle(kzo, gpu_lib, cfg):
+    sb = scenes.cornell_scene(96, 64, 16, **cfg)
+    O, G = _pair(kzo, sb)
+    fo, fg = O.render(), G.render()
+    ro, so = O.resolve(fo); rg, sg = G.resolve(fg)
+    assert np.allclose(fo[..., 3], fg[..., 3], rtol=1e-4, atol=1e-5)         # identical splat weights: same pixel samples
+    err = scenes.rel_mse(rg, ro)
+    assert err.max() < IMAGE_RELMSE_TOL, err
+    assert np.abs(sg.astype(int) - so.astype(int)).mean() < 0.5
+    st_o, st_g = O.stats(), G.stats()
+    assert st_g["paths"] == st_o["paths"] == 96 * 64 * 16
+    assert abs(st_g["rays_extension"] - st_o["rays_extension"]) <= 2e-3 * st_o["rays_extension"]
+    assert abs(st_g["vertices"] - st_o["vertices"]) <= 2e-3 * st_o["vertices"]
+    O.close(); G.close()
+
+
+def test_render_small_pool_chunks(kzo, gpu_lib, monkeypatch):
+    """the chunked wavefront (pool smaller than the request) == one big chunk"""
+    sb = scenes.cornell_scene(50, 37, 9, "stratified")          # ragged tile edges on purpose
+    d = sb.desc()
+    G1 = pk.Gpu(d)
+    f1 = G1.render()
+    monkeypatch.setenv("KZGPU_POOL_LOG2", "12")
+    G2 = pk.Gpu(d)
+    f2 = G2.render()
+    assert np.allclose(f1, f2, rtol=1e-4, atol=1e-5)
+    O = kzo.Oracle(d)
+    ro, _ = O.resolve(O.render()); rg, _ = G2.resolve(f2)
+    assert scenes.rel_mse(rg, ro).max() < IMAGE_RELMSE_TOL
+    G1.close(); G2.close(); O.close()
+
+
+def test_render_shards_sum_to_whole(gpu_lib):
+    """sample-index shards and rectangles add up to the whole frame (the multi-GPU decomposition)"""
+    sb = scenes.cornell_scene(48, 48, 16, "stratified")
+    G = pk.Gpu(sb.desc())
+    whole = G.render()
+    parts = G.render(0, 5) + G.render(5, 16)
+    assert np.allclose(whole, parts, rtol=1e-4, atol=1e-5)
+    tiles = G.render(rect=(0, 0, 10, 48)) + G.render(rect=(10, 0, 48, 21)) + G.render(rect=(10, 21, 48, 48))
+    assert np.allclose(whole, tiles, rtol=1e-4, atol=1e-5)
+    G.close()
+
+
+def test_converged_image(kzo, gpu_lib):
+    """north_star (2): per-channel relative MSE of a GPU render against a high-spp converged
+    reference (oracle, different sampler => independent samples) is at the Monte Carlo noise level
+    of the oracle's own equal-spp render."""
+    ref_sb = scenes.cornell_scene(48, 48, 1024, "independent")
+    O = kzo.Oracle(ref_sb.desc())
+    ref, _ = O.resolve(O.render()); O.close()
+    sb = scenes.cornell_scene(48, 48, 64, "stratified")
+    O2, G = _pair(kzo, sb)
+    rg, _ = G.resolve(G.render()); ro, _ = O2.resolve(O2.render())
+    eg, eo = scenes.rel_mse(rg, ref), scenes.rel_mse(ro, ref)
+    assert eg.max() < 0.05 and np.all(eg < 1.25 * eo + 1e-4), (eg, eo)
+    O2.close(); G.close()
+
+
+def test_device_resident_api(gpu_lib):
+    """kzgpu_trace_device / kzgpu_render_device on torch-owned HBM buffers and torch's stream"""
+    import torch
+    sb = scenes.soup_scene(20000)
+    G = pk.Gpu(sb.desc(), builder=pk.BUILD_LBVH)
+    rays = scenes.incoherent_rays(1 << 16)
+    ref = G.trace(rays)
+    d_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).cuda()
+    d_hits = torch.empty((rays.shape[0], 5), dtype=torch.float32, device="cuda")
+    G.trace_device(d_rays.data_ptr(), rays.shape[0], d_hits.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_hits.cpu().numpy().reshape(-1).view(pk.HIT_DTYPE)
+    assert got.tobytes() == ref.tobytes()
+    G.close()
+
+
+def test_errors(gpu_lib):
+    import ctypes as C
+    sb = scenes.soup_scene(10)
+    d = sb.desc()
+    lib = C.CDLL(gpu_lib)
+    lib.kzgpu_last_error.restype = C.c_char_p
+    h = C.c_void_p()
+    assert lib.kzgpu_create(None, 0, C.byref(h)) == 0
+    rays = scenes.incoherent_rays(4); hits = np.zeros(4, pk.HIT_DTYPE)
+    # trace before upload / build -> KZ_ERR_STATE
+    assert lib.kzgpu_trace(h, 0, rays.ctypes.data_as(C.c_void_p), C.c_size_t(4), 0, hits.ctypes.data_as(C.c_void_p)) == -4
+    assert lib.kzgpu_scene_upload(h, C.byref(d)) == 0
+    assert lib.kzgpu_trace(h, 0, rays.ctypes.data_as(C.c_void_p), C.c_size_t(4), 0, hits.ctypes.data_as(C.c_void_p)) == -4
+    assert lib.kzgpu_accel_build(h, 7) == -1
+    assert lib.kzgpu_accel_build(h, 0) == 0
+    assert lib.kzgpu_trace(h, 3, rays.ctypes.data_as(C.c_void_p), C.c_size_t(4), 0, hits.ctypes.data_as(C.c_void_p)) == -1
+    bad = pk.RenderReq(0, 0, 9999, 9999, 0, 1, 1)
+    frame = np.zeros((68, 68, 4), np.float32)
+    assert lib.kzgpu_render(h, C.byref(bad), frame.ctypes.data_as(pk.c_float_p)) == -1
+    assert b"rectangle" in lib.kzgpu_last_error(h)
+    lib.kzgpu_destroy(h)
