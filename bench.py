@@ -230,7 +230,7 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": world * e2e_steps * rays_per_step / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": rays_per_step * 32,
            "d2h_bytes_per_step": rays_per_step * 20, "steps": e2e_steps, "api": "kzgpu_trace (pinned host buffers)"}
-    same = bool(torch.equal(batches[1]["host_hits"], batches[1]["hits"].cpu()))
+    same = bool(torch.equal(batches[1]["host_hits"].view(torch.int32), batches[1]["hits"].cpu().view(torch.int32)))   # bit compare (miss ids are NaN patterns)
 
     # ------------------------------------------------------------------ path-tracing leg (Mpaths/s)
     paths = None

@@ -36,7 +36,13 @@ KZ_HD float kz_div(float a, float b) { return __fdiv_rn(a, b); }
 KZ_HD float kz_sqrt(float a) { return __fsqrt_rn(a); }
 KZ_HD uint32_t kz_bfind(uint32_t x) { return 31u - (uint32_t)__clz((int)x); }
 KZ_HD uint32_t kz_popc(uint32_t x) { return (uint32_t)__popc(x); }
-KZ_HD uint32_t kz_byte_perm(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+/* PTX prmt in its generic mode: selector nibble bit 3 replicates the sign of the selected byte
+ * (the __byte_perm intrinsic only honours the low three selector bits, so it cannot be used). */
+KZ_HD uint32_t kz_byte_perm(uint32_t a, uint32_t b, uint32_t s) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
+}
 KZ_HD float kz_u2f(uint32_t u) { return __uint_as_float(u); }
 KZ_HD uint32_t kz_f2u(float f) { return __float_as_uint(f); }
 #else

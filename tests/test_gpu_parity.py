@@ -153,7 +153,11 @@ def test_render_matches_oracle(kzo, gpu_lib, cfg):
     assert np.abs(sg.astype(int) - so.astype(int)).mean() < 0.5
     st_o, st_g = O.stats(), G.stats()
     assert st_g["paths"] == st_o["paths"] == 96 * 64 * 16
-    assert abs(st_g["rays_extension"] - st_o["rays_extension"]) <= 2e-3 * st_o["rays_extension"]
+    # the GPU skips the extension pass after the last vertex when there is no background to look up
+    # (its result cannot reach the image), so it may trace fewer rays than the reference loop, never more
+    assert 0.95 * st_o["rays_extension"] <= st_g["rays_extension"] <= st_o["rays_extension"] * (1 + 2e-3)
+    if cfg.get("background") is not None:
+        assert abs(st_g["rays_extension"] - st_o["rays_extension"]) <= 2e-3 * st_o["rays_extension"]
     assert abs(st_g["vertices"] - st_o["vertices"]) <= 2e-3 * st_o["vertices"]
     O.close(); G.close()
 
