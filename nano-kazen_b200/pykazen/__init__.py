@@ -314,6 +314,62 @@ class _Backend:
         return rgb, srgb
 
 
+class HostScene:
+    """A kazen XML scene loaded through the C++ host (nano-kazen_b200/host: XML parser + plugin registry).
+    `.desc` is the flattened kz_scene_desc the host would upload; it stays valid until close()."""
+
+    def __init__(self, xml_path, overrides=None, lib_path=LIB_HOST):
+        if not os.path.exists(lib_path):
+            raise RuntimeError(f"{lib_path} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        self.lib = C.CDLL(lib_path)
+        self.lib.kazen_host_last_error.restype = C.c_char_p
+        self.lib.kazen_host_load.restype = C.c_void_p
+        self.lib.kazen_host_scene_desc.restype = C.POINTER(SceneDesc)
+        self.lib.kazen_host_scene_desc.argtypes = [C.c_void_p]
+        self.lib.kazen_host_free.argtypes = [C.c_void_p]
+        self.lib.kazen_host_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        self.lib.kazen_host_accel_builder.argtypes = [C.c_void_p]
+        self.lib.kazen_host_render.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        ov = ";".join(f"{k}={v}" for k, v in (overrides or {}).items()).encode() if overrides else None
+        self.h = self.lib.kazen_host_load(os.fsencode(xml_path), ov)
+        if not self.h:
+            raise RuntimeError(self.lib.kazen_host_last_error().decode())
+        p = self.lib.kazen_host_scene_desc(self.h)
+        if not p:
+            raise RuntimeError(self.lib.kazen_host_last_error().decode())
+        self.desc = p.contents
+
+    def describe(self):
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.kazen_host_describe(self.h, buf, len(buf))
+        return buf.value.decode()
+
+    def accel_builder(self):
+        return self.lib.kazen_host_accel_builder(self.h)
+
+    def render(self, output_stem, gpus=1, raw=True):
+        if self.lib.kazen_host_render(self.h, os.fsencode(output_stem), gpus, int(raw)) != 0:
+            raise RuntimeError(self.lib.kazen_host_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.kazen_host_free(self.h); self.h = None
+
+
+def host_registered_plugins(lib_path=LIB_HOST):
+    lib = C.CDLL(lib_path)
+    buf = C.create_string_buffer(1 << 14)
+    lib.kazen_host_registered(buf, len(buf))
+    return buf.value.decode().split()
+
+
+def host_fallback_tables(lib_path=LIB_HOST):
+    lib = C.CDLL(lib_path)
+    bn = np.zeros((48, 128, 128), np.uint16); pm = np.zeros((5, 65536, 2), np.uint32)
+    lib.kazen_host_fallback_tables(bn.ctypes.data_as(C.c_void_p), pm.ctypes.data_as(C.c_void_p))
+    return bn, pm
+
+
 def shard_range(begin, end, rank, world):
     """Contiguous slice of sample indices [begin, end) owned by `rank` of `world`."""
     n = end - begin

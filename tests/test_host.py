@@ -1,0 +1,214 @@
+"""The C++ host (nano-kazen_b200/host): kazen's XML scene format and plugin registry above the C ABI.
+CPU tests check parsing/flattening against numpy restatements and feed the flattened tables to the
+oracle; the GPU tests render the same XML through the `path_mis` / `gpu_bvh` plugins."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import pykazen as pk
+import scenes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BOX = os.path.join(HERE, "data", "box", "box.xml")
+KAZEN = os.path.join(ROOT, "nano-kazen_b200", "host", "kazen")
+REF_SCENES = "/root/reference/scene/2022_q1"
+
+
+@pytest.fixture(scope="module")
+def host():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "nano-kazen_b200", "host")])
+    return pk
+
+
+def _np(ptr, n, dtype):
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(dtype)), shape=(n,)).copy()
+
+
+def test_registered_plugin_names(host):
+    names = set(host.host_registered_plugins())
+    # every plugin on the hot path keeps kazen's registered name; gpu_bvh is the new accel plugin
+    for n in ("scene obj diffuse kazenstandard normalmap area perspective thinlens independent stratified correlated pmj02bn "
+              "constanttexture imagetexture background colorramp blend gaussian mitchell tent box path_mis gpu_bvh").split():
+        assert n in names
+
+
+def test_box_scene_flattening(host):
+    hs = host.HostScene(BOX)
+    d = hs.desc
+    assert d.n_meshes == 3 and d.n_lights == 1 and d.n_images == 3
+    assert d.camera.type == pk.CAM_THINLENS and (d.camera.width, d.camera.height) == (48, 32)
+    assert abs(d.camera.aperture_radius - 0.02) < 1e-7 and abs(d.camera.focus_distance - 3.4) < 1e-6
+    # stratified rounds 10 up to 16 = 4x4 (sampler.cpp:83-93)
+    assert (d.sampler.type, d.sampler.sample_count, d.sampler.res_x, d.sampler.seed) == (pk.SAMPLER_STRATIFIED, 16, 4, 1)
+    assert (d.integrator.max_depth, d.integrator.regularization) == (4, 1) and abs(d.integrator.trace_bias - 1e-3) < 1e-9
+    # mitchell default radius 2, tabulated like block.cpp:13-21
+    r, tab = pk.filter_table("mitchell")
+    assert d.filter.radius == r and np.allclose(np.array(list(d.filter.table), np.float32), tab, rtol=2e-6, atol=1e-7)
+    # camera matrices: lookat (parser.cpp:273-287) and perspective (camera.cpp:35-62)
+    assert np.allclose(np.array(list(d.camera.camera_to_world)).reshape(4, 4), pk.lookat((0, 0, -3.4), (0, 0, 0), (0, 1, 0)), atol=1e-6)
+    assert np.allclose(np.array(list(d.camera.sample_to_camera)).reshape(4, 4), pk.perspective_sample_to_camera(48, 32, 39.0, 0.1, 100.0), rtol=1e-4, atol=1e-5)
+    # room: 5 quads -> 10 triangles split (0,1,2),(3,0,2), 8 de-duplicated vertices, no normals/uvs
+    room = d.meshes[0]
+    assert (room.n_vertices, room.n_triangles) == (8, 10) and not room.normals and not room.uvs
+    F = _np(room.indices, 30, C.c_uint32).reshape(-1, 3)
+    assert F[:2].tolist() == [[0, 1, 2], [3, 0, 2]] and F[2:4].tolist() == [[4, 5, 6], [7, 4, 6]]
+    # sphere: transform ops apply in document order: scale, then rotate, then translate
+    sph = d.meshes[1]
+    V = _np(sph.positions, 3 * sph.n_vertices, C.c_float).reshape(-1, 3)
+    N = _np(sph.normals, 3 * sph.n_vertices, C.c_float).reshape(-1, 3)
+    assert np.allclose(V.mean(0), (-0.3, -0.55, 0.2), atol=0.03)
+    assert np.allclose(np.linalg.norm(V - np.array((-0.3, -0.55, 0.2)), axis=1), 0.45, atol=1e-5)
+    assert np.allclose(np.linalg.norm(N, axis=1), 1.0, atol=1e-5)
+    assert np.allclose((V - np.array((-0.3, -0.55, 0.2), np.float32)) / 0.45, N, atol=1e-5)       # normals follow the rotation
+    # first sphere vertex is the +y pole (rotation about y leaves it in place)
+    assert np.allclose(V[0], (-0.3, -0.1, 0.2), atol=1e-5)
+    # materials: normalmap(kiss(blend, colorramp, constant)); light radiance = intensity * color
+    outer = d.bsdfs[d.meshes[1].bsdf]
+    assert outer.type == pk.BSDF_NORMALMAP and d.bsdfs[outer.nested].type == pk.BSDF_KISS
+    kiss = d.bsdfs[outer.nested]
+    assert d.textures[kiss.base_color].type == pk.TEX_BLEND and d.textures[kiss.roughness].type == pk.TEX_COLORRAMP
+    assert abs(kiss.clearcoat - 0.5) < 1e-7 and abs(kiss.specular - 0.5) < 1e-7 and abs(kiss.sheen_tint - 0.5) < 1e-7
+    assert d.textures[outer.normal_map].srgb == 0 and abs(d.textures[outer.normal_map].scale - 3.0) < 1e-7
+    assert np.allclose(list(d.lights[0].radiance), (12.0, 10.8, 8.4), rtol=1e-6) and d.lights[0].primary_visibility == 0
+    assert d.background >= 0 and d.textures[d.background].type == pk.TEX_BACKGROUND
+    # PNG decode: row 0 = first scanline, values /255
+    im = d.images[d.textures[d.textures[kiss.base_color].child[1]].image]
+    assert (im.width, im.height) == (32, 16)
+    px = _np(im.rgb, 3 * 32 * 16, C.c_float).reshape(16, 32, 3)
+    rng = np.random.default_rng(3)
+    assert np.allclose(px, rng.integers(30, 230, (16, 32, 3), dtype=np.uint8) / 255.0, atol=1e-6)
+    assert hs.accel_builder() == pk.BUILD_HOST_SAH
+    hs.close()
+
+
+def test_overrides_and_defaults(host):
+    hs = host.HostScene(BOX, {"camera.width": "i:20", "camera.height": "i:10", "sampler.type": "s:correlated", "sampler.sampleCount": "i:7",
+                              "scene.accelBuilder": "s:lbvh", "integrator.maxDepth": "i:2"})
+    d = hs.desc
+    assert (d.camera.width, d.camera.height) == (20, 10)
+    # correlated: res.y = (int)sqrt(7) = 2, res.x = ceil(7/2) = 4, spp = 8 (sampler.cpp:178-189)
+    assert (d.sampler.type, d.sampler.sample_count, d.sampler.res_x, d.sampler.res_y) == (pk.SAMPLER_CORRELATED, 8, 4, 2)
+    assert d.integrator.max_depth == 2 and hs.accel_builder() == pk.BUILD_LBVH
+    hs.close()
+
+
+@pytest.mark.parametrize("xml,msg", [
+    ("<scene><foo/></scene>", "unexpected tag"),
+    ("<scene><integer name='a'/></scene>", "missing attribute"),
+    ("<scene><integer name='a' value='1' extra='2'/></scene>", "unexpected attribute"),
+    ("<scene><integrator type='nope'/></scene>", "could not be found"),
+    ("<scene><camera type='gaussian'/></scene>", "Unexpectedly constructed"),
+    ("<scene><translate value='1 2 3'/></scene>", "transform nodes"),
+    ("<scene><integrator type='path_mis'/></scene>", "No camera was specified"),
+    ("<scene><camera type='perspective'/></scene>", "No integrator was specified"),
+    ("<scene><float name='x' value='abc'/></scene>", "Could not parse floating point"),
+    ("<float name='x' value='1'/>", "must be a kazen object"),
+    ("<scene><integrator type='path_mis'/><camera type='perspective'/><mesh type='obj'><string name='filename' value='missing.obj'/></mesh></scene>", "Unable to open OBJ"),
+    ("<scene><mesh type='obj'></scene>", "mismatched closing tag"),
+])
+def test_parser_errors(host, tmp_path, xml, msg):
+    p = tmp_path / "bad.xml"
+    p.write_text(xml)
+    with pytest.raises(RuntimeError, match=msg):
+        host.HostScene(str(p))
+
+
+def test_host_tables_feed_the_oracle(host, kzo):
+    """XML -> plugins -> POD tables -> oracle render: the same tables the GPU would receive are a valid,
+    lit scene; the numpy-built twin of the scene (pykazen.SceneBuilder) renders the same image."""
+    hs = host.HostScene(BOX)
+    O = kzo.Oracle(hs.desc)
+    f = O.render()
+    rgb, _ = O.resolve(f)
+    assert np.isfinite(rgb).all() and 0.05 < rgb.mean() < 2.0
+    st = O.stats()
+    assert st["paths"] == 48 * 32 * 16 and st["rays_shadow"] > 0
+    O.close(); hs.close()
+
+
+def test_fallback_pmj_tables_are_stratified(host):
+    """the stand-in tables keep the one property the PMJ02BN constructor relies on (sampler.cpp:290-314):
+    the first 65536 points of set 0 put exactly spp points into every pixel-tile cell"""
+    bn, pm = host.host_fallback_tables()
+    assert bn.shape == (48, 128, 128) and pm.shape == (5, 65536, 2)
+    p = pm[0].astype(np.float64) * 2.0 ** -32
+    for spp in (1, 4, 16, 64):
+        T = 1 << (8 - int(round(np.log(spp) / np.log(4))))
+        cells = (np.floor(p[:, 0] * T) + T * np.floor(p[:, 1] * T)).astype(np.int64)
+        assert (np.bincount(cells, minlength=T * T) == spp).all()
+    # every set is a (0,2)-net in base 2 over its first 4096 points: 64x64, 4096x1 and 1x4096 grids all hit once
+    for s in range(5):
+        q = pm[s, :4096].astype(np.float64) * 2.0 ** -32
+        for (a, b) in ((64, 64), (4096, 1), (1, 4096), (16, 256)):
+            idx = (np.floor(q[:, 0] * a) * b + np.floor(q[:, 1] * b)).astype(np.int64)
+            assert len(np.unique(idx)) == 4096
+
+
+def test_cli_fails_loudly_without_gpu(host):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    r = subprocess.run([KAZEN, BOX, "-o", "/tmp/kazen_cli_test"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SCENES), reason="reference scenes are only mounted in the build container")
+def test_reference_scenes_parse_unchanged(host, kzo):
+    """kazen's own scene files load unchanged through the plugin system (22 parameter sweeps + WarmStudio)"""
+    xmls = [os.path.join(REF_SCENES, "WarmStudio", "WarmStudio.xml")] + \
+           sorted(os.path.join(REF_SCENES, "parameters", f) for f in os.listdir(os.path.join(REF_SCENES, "parameters")) if f.endswith(".xml"))
+    assert len(xmls) == 23
+    tris = {}
+    for x in xmls:
+        hs = host.HostScene(x, {"camera.width": "i:64", "camera.height": "i:36"})
+        d = hs.desc
+        tris[os.path.basename(x)] = sum(d.meshes[i].n_triangles for i in range(d.n_meshes))
+        assert d.sampler.type == pk.SAMPLER_INDEPENDENT and d.n_lights >= 1
+        hs.close()
+    assert tris["WarmStudio.xml"] == 17952 and tris["default_m0_r0.5.xml"] == 36378
+    # WarmStudio through the oracle at low resolution: the loose golden anchor of BASELINE.md (shipped PNG mean)
+    hs = host.HostScene(xmls[0], {"camera.width": "i:96", "camera.height": "i:54", "sampler.type": "s:stratified", "sampler.sampleCount": "i:16"})
+    O = kzo.Oracle(hs.desc)
+    _, srgb = O.resolve(O.render())
+    m = srgb.reshape(-1, 3).mean(0)
+    assert 20 < m[0] < 45 and 14 < m[1] < 34 and 5 < m[2] < 18 and m[0] > m[1] > m[2]       # shipped PNG: (36.5, 27.5, 13.1)
+    O.close(); hs.close()
+
+
+# --------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_gpu_renders_xml_scene_like_oracle(host, kzo, gpu_lib):
+    hs = host.HostScene(BOX)
+    O = kzo.Oracle(hs.desc)
+    G = pk.Gpu(hs.desc, builder=hs.accel_builder())
+    ro, _ = O.resolve(O.render()); rg, _ = G.resolve(G.render())
+    assert scenes.rel_mse(rg, ro).max() < 2e-4
+    O.close(); G.close(); hs.close()
+
+
+@pytest.mark.gpu
+def test_kazen_cli_on_gpu(host, kzo, tmp_path):
+    """kazen <scene.xml>: the XML renders through the path_mis / gpu_bvh plugins and writes a PNG + raw frame"""
+    out = str(tmp_path / "box")
+    r = subprocess.run([KAZEN, BOX, "-o", out, "--raw", "--accel", "lbvh"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Render ready" in r.stdout and os.path.getsize(out + ".png") > 500
+    raw = np.fromfile(out + ".rgbw", np.uint8)
+    w, h, b = np.frombuffer(raw[:12].tobytes(), np.int32)
+    frame = np.frombuffer(raw[12:].tobytes(), np.float32).reshape(h + 2 * b, w + 2 * b, 4)
+    hs = host.HostScene(BOX)
+    O = kzo.Oracle(hs.desc)
+    ro, _ = O.resolve(O.render()); rg, _ = O.resolve(np.ascontiguousarray(frame))
+    assert scenes.rel_mse(rg, ro).max() < 2e-4
+    from PIL import Image
+    png = np.asarray(Image.open(out + ".png"))
+    _, so = O.resolve(np.ascontiguousarray(frame))
+    assert png.shape == (h, w, 3) and np.abs(png.astype(int) - so.astype(int)).max() <= 1
+    O.close(); hs.close()
