@@ -228,8 +228,8 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
             {
                 Timed t(d, s, CAT_TRACE);
                 k_bounce_reset<<<1, 32, 0, s>>>(d.ctl, nxt);
-                if (b == 0) k_extend<true><<<d.grid_extend0, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur, b);
-                else k_extend<false><<<d.grid_extend, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur, b);
+                if (b == 0) k_extend<true><<<d.grid_extend0, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur);
+                else k_extend<false><<<d.grid_extend, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur);
                 d.launches += 2;
             }
             {
@@ -361,6 +361,7 @@ int kzgpu_accel_build(kzgpu_ctx *ctx, int builder) {
     if (builder == KZ_BUILD_HOST_SAH) {
         kzbvh::Built built;
         kzbvh::buildHostSah(ctx->hs->tris, 0, built);
+        if (2 * built.depth + 2 > KZ_SHORT_STACK + KZ_LOCAL_STACK) return fail(ctx, KZ_ERR_UNSUPPORTED, "accel deeper than the traversal stack allows");
         for (Device &d : ctx->devs) {
             KZ_CUDA(ctx, cudaSetDevice(d.id));
             if ((rc = upload_accel(ctx, d, built))) return rc;
@@ -375,6 +376,7 @@ int kzgpu_accel_build(kzgpu_ctx *ctx, int builder) {
             std::string err;
             rc = kzlbvh::build(ctx->hs->tris, d.stream, d.accel_allocs, r, err);
             if (rc) return fail(ctx, rc, err);
+            if (2 * r.depth + 2 > KZ_SHORT_STACK + KZ_LOCAL_STACK) return fail(ctx, KZ_ERR_UNSUPPORTED, "accel deeper than the traversal stack allows");
             d.sc.nodes = r.nodes; d.sc.tris = r.tris; d.sc.n_nodes = r.n_nodes; d.sc.n_tris = r.n_tris; d.sc.scene_max_abs = r.max_abs;
             d.has_accel = true;
             d.launches += r.launches;

@@ -86,6 +86,94 @@ __device__ __forceinline__ void kz_flush_counters(KzControl *ctl, const KzCounte
     }
 }
 
+/* ---- warp-cooperative persistent traversal ----------------------------------------------------
+ * One warp owns 32 ray slots.  Lanes whose ray is finished are refilled from the work queue (one
+ * ballot + one atomicAdd per refill) once enough loop iterations have been lost to idle lanes
+ * (Aila/Laine persistent threads; thresholds as in Ylitie et al. 2017), and a lane postpones its
+ * leaf tests (pushes the triangle group back on its stack) while fewer than 1/5 of the active lanes
+ * have triangles to test, so node steps and Pluecker tests run with fuller warps.
+ * Traversal order therefore differs per launch, results do not: ties resolve by (geomID, primID).
+ *
+ * Job: per-lane policy object.
+ *   void begin(uint32_t item, KzRayIn &r)                   load the ray of work item `item`
+ *   bool end(uint32_t item, const KzHit &h, KzRayIn &r)     consume the closest hit; return true and fill `r`
+ *                                                           to continue the same item with a follow-up ray */
+struct KzRayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
+#define KZ_FETCH_ND 4
+#define KZ_FETCH_NW 16
+
+template <class Job>
+__device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRef &stk, uint32_t *cursor, uint32_t n, Job &job) {
+    KzTrav t;
+    KzLocalStack ls;
+    t.sp = 0; t.ng_y = 0u; t.tg_y = 0u;
+    bool active = false, exhausted = false;
+    uint32_t item = 0u;
+    const uint32_t lane = kz_lane(), lt = (1u << lane) - 1u;
+    for (;;) {
+        if (!exhausted) {
+            const uint32_t idle = __ballot_sync(KZ_FULL, !active);
+            if (idle) {
+                const uint32_t leader = (uint32_t)__ffs((int)idle) - 1u;
+                uint32_t base = 0u;
+                if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+                base = __shfl_sync(KZ_FULL, base, (int)leader);
+                if (!active) {
+                    const uint32_t idx = base + (uint32_t)__popc(idle & lt);
+                    if (idx < n) {
+                        item = idx;
+                        KzRayIn r;
+                        job.begin(item, r);
+                        kz_trav_init(sc, t, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tmin, r.tmax);
+                        active = true;
+                    }
+                }
+                exhausted = base + (uint32_t)__popc(idle) >= n;
+            }
+        }
+        if (!__any_sync(KZ_FULL, active)) break;
+        int lost = 0;
+        while (active) {
+            if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
+            else { t.tg_x = t.ng_x; t.tg_y = t.ng_y; t.ng_x = 0u; t.ng_y = 0u; }
+            const int total = __popc(__activemask());
+            while (t.tg_y != 0u) {
+                if (__popc(__activemask()) * 5 < total && t.sp < KZ_SHORT_STACK + KZ_LOCAL_STACK - 1) {       /* too few lanes have triangles: postpone */
+                    kz_trav_push(t, stk, ls, t.tg_x, t.tg_y);
+                    t.tg_y = 0u;
+                    break;
+                }
+                kz_trav_tri(sc, t);
+            }
+            if (t.ng_y <= 0x00FFFFFFu) {
+                if (t.sp == 0) {
+                    KzRayIn r;
+                    if (job.end(item, t.best, r)) kz_trav_init(sc, t, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tmin, r.tmax);
+                    else active = false;
+                } else {
+                    kz_trav_pop(t, stk, ls);
+                }
+            }
+            if (!exhausted) {
+                lost += 32 - __popc(__activemask()) - KZ_FETCH_ND;
+                if (lost >= KZ_FETCH_NW) break;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+/* Append under divergence: the lanes that reach this call together are grouped by queue. */
+__device__ __forceinline__ void kz_push_divergent(uint32_t *const *queues, uint32_t *counters, int which, uint32_t value) {
+    const uint32_t peers = __match_any_sync(__activemask(), which);
+    const uint32_t lane = kz_lane();
+    const uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
+    uint32_t base = 0u;
+    if (lane == leader) base = atomicAdd(counters + which, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, (int)leader);
+    queues[which][base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = value;
+}
+
 __global__ void k_chunk_reset(KzControl *ctl) {
     if (threadIdx.x == 0) {
         ctl->n_ext[0] = ctl->n_ext[1] = 0u;
@@ -126,27 +214,53 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_raygen(KzScene sc, KzPathS
 
 /* ---- extend: Scene::rayIntersect for every queued path, then sort by material class ------- */
 template <bool FIRST>
-__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_extend(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int cur, int bounce) {
+struct KzExtendJob {
+    const KzScene &sc; const KzPathState &st; KzControl *ctl; const KzQueues &q; const uint32_t *queue;
+    KzCounters cnt;
+    uint32_t slot;
+    KzHit first_hit; bool retraced;
+    kz3 d;
+    __device__ KzExtendJob(const KzScene &s, const KzPathState &p, KzControl *c, const KzQueues &qq, const uint32_t *qu)
+        : sc(s), st(p), ctl(c), q(qq), queue(qu) { cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull; }
+    __device__ __forceinline__ void begin(uint32_t item, KzRayIn &r) {
+        slot = queue[item];
+        const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+        r.ox = ro.x; r.oy = ro.y; r.oz = ro.z; r.tmin = ro.w; r.dx = rd.x; r.dy = rd.y; r.dz = rd.z; r.tmax = rd.w;
+        d = mk3(rd.x, rd.y, rd.z);
+        retraced = false;
+    }
+    __device__ __forceinline__ bool end(uint32_t, const KzHit &hit, KzRayIn &r) {
+        cnt.rays_ext += 1;
+        KzHit h = hit;
+        if (FIRST) {
+            if (retraced) { if (h.geom == KZ_INVALID_ID) h = first_hit; }     /* a miss keeps the light hit */
+            else if (h.geom != KZ_INVALID_ID) {
+                const uint32_t fl = sc.meshes[h.geom].flags;
+                if ((fl & KZ_MESH_IS_LIGHT) && !(fl & KZ_MESH_LIGHT_VISIBLE)) {
+                    /* integrator.cpp:214-219: one re-trace from its.p + eps*d with a default Ray3f */
+                    KzIts its; its.acc_rough = 0.f;
+                    fill_intersection(sc, h, its, mk3(0.f));
+                    const kz3 o = its.p + sc.integrator.trace_bias * d;
+                    r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = KZ_EPSILON; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = KZ_INF;
+                    first_hit = h; retraced = true;
+                    return true;
+                }
+            }
+        }
+        st.hit[slot] = mkf4(h.t, h.u, h.v, kz_u2f(h.prim));
+        st.hit_geom[slot] = h.geom;
+        kz_push_divergent(q.cls, ctl->n_class, kz_classify(sc, h.geom), slot);
+        return false;
+    }
+};
+
+template <bool FIRST>
+__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_extend(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int cur) {
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
-    const uint32_t n = ctl->n_ext[cur];
-    const uint32_t *queue = q.ext[cur];
-    KzCounters cnt; cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull;
-    for (;;) {
-        const uint32_t base = kz_fetch32(&ctl->head_ext);
-        if (base >= n) break;
-        const uint32_t idx = base + kz_lane();
-        const bool active = idx < n;
-        uint32_t slot = 0u; int cls = -1;
-        if (active) {
-            slot = queue[idx];
-            cls = kz_extend_item(sc, stk, st, slot, FIRST ? 0 : bounce, cnt);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < KZ_NUM_CLASSES; ++c) kz_push(q.cls[c], &ctl->n_class[c], cls == c, slot);
-    }
-    kz_flush_counters(ctl, cnt);
+    KzExtendJob<FIRST> job(sc, st, ctl, q, q.ext[cur]);
+    kz_warp_trace(sc, stk, &ctl->head_ext, ctl->n_ext[cur], job);
+    kz_flush_counters(ctl, job.cnt);
 }
 
 /* ---- shade: one integrator loop iteration for every path of one material class ------------ */
@@ -173,19 +287,54 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_shade(KzScene sc, KzPathSt
 }
 
 /* ---- shadow: integrator.cpp:259-294 ------------------------------------------------------- */
+/* The closest-hit walk through invisible lights (kz_occluded_walk) as a job: every segment is one ray. */
+struct KzWalk {
+    kz3 o, d; float tmax; int seg;
+    __device__ __forceinline__ void start(KzRayIn &r, kz3 o_, kz3 d_, float tmin, float tmax_) {
+        o = o_; d = d_; tmax = tmax_; seg = 0;
+        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = tmin; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = tmax;
+    }
+    /* returns 0 = unoccluded, 1 = occluded, 2 = continue with the ray written to r */
+    __device__ __forceinline__ int step(const KzScene &sc, const KzHit &h, float eps, KzRayIn &r) {
+        ++seg;
+        if (h.geom == KZ_INVALID_ID) return 0;
+        const uint32_t fl = sc.meshes[h.geom].flags;
+        if (!(fl & KZ_MESH_IS_LIGHT) || (fl & KZ_MESH_LIGHT_VISIBLE)) return 1;
+        if (seg > 4096) return 0;
+        o = o + d * (h.t + eps);
+        tmax = tmax - h.t;
+        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = eps; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = tmax;
+        return 2;
+    }
+};
+struct KzShadowJob {
+    const KzScene &sc; const KzPathState &st; const uint32_t *queue;
+    KzCounters cnt; uint32_t slot; KzWalk walk;
+    __device__ KzShadowJob(const KzScene &s, const KzPathState &p, const uint32_t *qu) : sc(s), st(p), queue(qu) { cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull; }
+    __device__ __forceinline__ void begin(uint32_t item, KzRayIn &r) {
+        slot = queue[item];
+        const KzF4 so = st.sray_o[slot], sd = st.sray_d[slot];
+        walk.start(r, mk3(so.x, so.y, so.z), mk3(sd.x, sd.y, sd.z), so.w, sd.w);
+    }
+    __device__ __forceinline__ bool end(uint32_t, const KzHit &h, KzRayIn &r) {
+        cnt.rays_shadow += 1;
+        const int s = walk.step(sc, h, sc.integrator.trace_bias, r);
+        if (s == 2) return true;
+        if (s == 0) {
+            const KzF4 p = st.pending[slot];
+            KzF4 L = st.L[slot];
+            L.x += p.x; L.y += p.y; L.z += p.z;
+            st.L[slot] = L;
+        }
+        return false;
+    }
+};
 __global__ void __launch_bounds__(KZ_TRACE_THREADS) k_shadow(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q) {
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
-    const uint32_t n = ctl->n_shadow;
-    KzCounters cnt; cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull;
-    for (;;) {
-        const uint32_t base = kz_fetch32(&ctl->head_shadow);
-        if (base >= n) break;
-        const uint32_t idx = base + kz_lane();
-        if (idx < n) kz_shadow_item(sc, stk, st, q.shadow[idx], cnt);
-        __syncwarp();
-    }
-    kz_flush_counters(ctl, cnt);
+    KzShadowJob job(sc, st, q.shadow);
+    kz_warp_trace(sc, stk, &ctl->head_shadow, ctl->n_shadow, job);
+    kz_flush_counters(ctl, job.cnt);
 }
 
 /* ---- accumulate: ImageBlock::put over the whole chunk (block.cpp:56-85) ------------------- */
@@ -197,46 +346,53 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_accumulate(KzScene sc, KzP
 
 /* ---- batch entry points (parity tests + intersection microbench) -------------------------- */
 /* kzgpu_trace: rays/hits in the C-ABI's AoS layout (32 B in, 20 B out). */
+struct KzTraceJob {
+    const KzF4 *rays; float *hits;
+    __device__ __forceinline__ void begin(uint32_t item, KzRayIn &r) {
+        const KzU4 a = kz_load_u4(rays + 2 * (size_t)item), b = kz_load_u4(rays + 2 * (size_t)item + 1);
+        r.ox = kz_u2f(a.x); r.oy = kz_u2f(a.y); r.oz = kz_u2f(a.z); r.tmin = kz_u2f(a.w);
+        r.dx = kz_u2f(b.x); r.dy = kz_u2f(b.y); r.dz = kz_u2f(b.z); r.tmax = kz_u2f(b.w);
+    }
+    __device__ __forceinline__ bool end(uint32_t item, const KzHit &h, KzRayIn &) {
+        float *o = hits + 5 * (size_t)item;
+        o[0] = h.t; o[1] = h.u; o[2] = h.v; o[3] = kz_u2f(h.prim); o[4] = kz_u2f(h.geom);
+        return false;
+    }
+};
 __global__ void __launch_bounds__(KZ_TRACE_THREADS) k_trace(KzScene sc, const KzF4 *rays, uint32_t n, float *hits, uint32_t *cursor, KzControl *ctl) {
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
-    for (;;) {
-        const uint32_t base = kz_fetch32(cursor);
-        if (base >= n) break;
-        const uint32_t idx = base + kz_lane();
-        if (idx < n) {
-            const KzU4 a = kz_load_u4(rays + 2 * (size_t)idx), b = kz_load_u4(rays + 2 * (size_t)idx + 1);
-            const KzHit h = kz_trace(sc, stk, kz_u2f(a.x), kz_u2f(a.y), kz_u2f(a.z), kz_u2f(b.x), kz_u2f(b.y), kz_u2f(b.z),
-                                     kz_u2f(a.w), kz_u2f(b.w), false);
-            float *o = hits + 5 * (size_t)idx;
-            o[0] = h.t; o[1] = h.u; o[2] = h.v; o[3] = kz_u2f(h.prim); o[4] = kz_u2f(h.geom);
-        }
-        __syncwarp();
-    }
+    KzTraceJob job; job.rays = rays; job.hits = hits;
+    kz_warp_trace(sc, stk, cursor, n, job);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->rays_ext, (unsigned long long)n);
 }
 
+struct KzOccludedJob {
+    const KzScene &sc; const KzF4 *rays; float eps; uint8_t *occ, *segments;
+    KzCounters cnt; KzWalk walk;
+    __device__ KzOccludedJob(const KzScene &s, const KzF4 *r, float e, uint8_t *o, uint8_t *sg) : sc(s), rays(r), eps(e), occ(o), segments(sg) {
+        cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull;
+    }
+    __device__ __forceinline__ void begin(uint32_t item, KzRayIn &r) {
+        const KzU4 a = kz_load_u4(rays + 2 * (size_t)item), b = kz_load_u4(rays + 2 * (size_t)item + 1);
+        walk.start(r, mk3(kz_u2f(a.x), kz_u2f(a.y), kz_u2f(a.z)), mk3(kz_u2f(b.x), kz_u2f(b.y), kz_u2f(b.z)), kz_u2f(a.w), kz_u2f(b.w));
+    }
+    __device__ __forceinline__ bool end(uint32_t item, const KzHit &h, KzRayIn &r) {
+        cnt.rays_shadow += 1;
+        const int s = walk.step(sc, h, eps, r);
+        if (s == 2) return true;
+        occ[item] = (uint8_t)s;
+        if (segments) segments[item] = (uint8_t)(walk.seg > 255 ? 255 : walk.seg);
+        return false;
+    }
+};
 __global__ void __launch_bounds__(KZ_TRACE_THREADS) k_occluded(KzScene sc, const KzF4 *rays, uint32_t n, float eps, uint8_t *occ, uint8_t *segments,
                                                                 uint32_t *cursor, KzControl *ctl) {
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
-    KzCounters cnt; cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull;
-    for (;;) {
-        const uint32_t base = kz_fetch32(cursor);
-        if (base >= n) break;
-        const uint32_t idx = base + kz_lane();
-        if (idx < n) {
-            const KzU4 a = kz_load_u4(rays + 2 * (size_t)idx), b = kz_load_u4(rays + 2 * (size_t)idx + 1);
-            int seg;
-            const bool o = kz_occluded_walk(sc, stk, mk3(kz_u2f(a.x), kz_u2f(a.y), kz_u2f(a.z)), mk3(kz_u2f(b.x), kz_u2f(b.y), kz_u2f(b.z)),
-                                            kz_u2f(a.w), kz_u2f(b.w), eps, &seg);
-            occ[idx] = o ? 1 : 0;
-            if (segments) segments[idx] = (uint8_t)(seg > 255 ? 255 : seg);
-            cnt.rays_shadow += (unsigned long long)seg;
-        }
-        __syncwarp();
-    }
-    kz_flush_counters(ctl, cnt);
+    KzOccludedJob job(sc, rays, eps, occ, segments);
+    kz_warp_trace(sc, stk, cursor, n, job);
+    kz_flush_counters(ctl, job.cnt);
 }
 
 /* kzgpu_sample_dump: sampler.cpp generateSample + draw pattern, one thread per (pixel, sample) */

@@ -30,6 +30,7 @@ struct Result {
     uint32_t n_nodes = 0, n_tris = 0;
     float max_abs = 0.f;
     uint64_t launches = 0;
+    int depth = 0;               /* wide-tree levels */
 };
 
 struct Box6 { float lo[3], hi[3]; };
@@ -392,7 +393,7 @@ inline int build(const std::vector<kzbvh::Tri> &tris, cudaStream_t s, std::vecto
         cs.in = in; cs.out = out; cs.n_in = n_in;
         KZL_CUDA(cudaMemsetAsync(cs.out_count, 0, 4, s));
         k_collapse<<<(n_in + 63u) / 64u, 64, 0, s>>>(cs);
-        ++r.launches;
+        ++r.launches; ++r.depth;
         KZL_CUDA(cudaMemcpyAsync(&n_in, cs.out_count, 4, cudaMemcpyDeviceToHost, s));
         KZL_CUDA(cudaStreamSynchronize(s));
         std::swap(in, out);

@@ -99,128 +99,155 @@ struct KzStackRef {
 #endif
 };
 
-/* The traversal proper.  `stk` gives the shared-memory short stack on the device; on the host
+/* Per-ray traversal state.  The loop is split into steps (init / node / triangle / pop) so that the
+ * same arithmetic serves the plain per-ray loop below (kz_trace: host emulation, BSDF-side helpers)
+ * and the warp-cooperative persistent loop of kz_kernels.cuh (lane refill + postponed leaf tests). */
+struct KzTrav {
+    float ox, oy, oz, dx, dy, dz, tmin;
+    float rdx, rdy, rdz;
+    float onx, ony, onz, ofx, ofy, ofz;      /* origins for the near / far planes (slab widened by slack) */
+    uint32_t oct_inv;                        /* 7 - ray octant */
+    KzHit best;
+    uint32_t ng_x, ng_y;                     /* node group: (child base, hits<<24 | imask) */
+    uint32_t tg_x, tg_y;                     /* triangle group: (tri base, hit bits)        */
+    int sp;                                  /* stacked entries */
+};
+struct KzLocalStack { uint32_t x[KZ_LOCAL_STACK], y[KZ_LOCAL_STACK]; };
+
+KZ_HD void kz_trav_init(const KzScene &sc, KzTrav &t, float ox, float oy, float oz, float dx, float dy, float dz, float tmin, float tmax) {
+    t.ox = ox; t.oy = oy; t.oz = oz; t.dx = dx; t.dy = dy; t.dz = dz; t.tmin = tmin;
+    t.best.t = tmax; t.best.u = 0.f; t.best.v = 0.f; t.best.prim = KZ_INVALID_ID; t.best.geom = KZ_INVALID_ID;
+    const float slack = (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + sc.scene_max_abs) * 3.814697265625e-06f;
+    t.rdx = kz_rcp_safe(dx); t.rdy = kz_rcp_safe(dy); t.rdz = kz_rcp_safe(dz);
+    const bool nx = t.rdx < 0.f, ny = t.rdy < 0.f, nz = t.rdz < 0.f;
+    t.onx = nx ? ox - slack : ox + slack; t.ofx = nx ? ox + slack : ox - slack;
+    t.ony = ny ? oy - slack : oy + slack; t.ofy = ny ? oy + slack : oy - slack;
+    t.onz = nz ? oz - slack : oz + slack; t.ofz = nz ? oz + slack : oz - slack;
+    t.oct_inv = ((nx ? 0u : 1u) | (ny ? 0u : 2u) | (nz ? 0u : 4u));
+    t.ng_x = 0u; t.ng_y = sc.n_nodes ? 0x80000000u : 0u;      /* root; an empty scene starts with nothing to do */
+    t.tg_x = 0u; t.tg_y = 0u;
+    t.sp = 0;
+}
+
+KZ_HD void kz_trav_push(KzTrav &t, const KzStackRef &stk, KzLocalStack &ls, uint32_t x, uint32_t y) {
+#if KZ_DEVICE_CODE
+    if (t.sp < KZ_SHORT_STACK) stk.smem[t.sp * stk.stride] = make_uint2(x, y);
+    else { ls.x[t.sp - KZ_SHORT_STACK] = x; ls.y[t.sp - KZ_SHORT_STACK] = y; }
+#else
+    (void)stk; ls.x[t.sp] = x; ls.y[t.sp] = y;
+#endif
+    ++t.sp;
+}
+KZ_HD void kz_trav_pop(KzTrav &t, const KzStackRef &stk, const KzLocalStack &ls) {
+    --t.sp;
+#if KZ_DEVICE_CODE
+    if (t.sp < KZ_SHORT_STACK) { const uint2 e = stk.smem[t.sp * stk.stride]; t.ng_x = e.x; t.ng_y = e.y; }
+    else { t.ng_x = ls.x[t.sp - KZ_SHORT_STACK]; t.ng_y = ls.y[t.sp - KZ_SHORT_STACK]; }
+#else
+    (void)stk; t.ng_x = ls.x[t.sp]; t.ng_y = ls.y[t.sp];
+#endif
+}
+
+/* Takes the next child of the current node group (ng_y > 0x00FFFFFF), intersects its 8 child boxes and
+ * leaves the new node group in ng and the new triangle group in tg. */
+KZ_HD void kz_trav_node(const KzScene &sc, KzTrav &t, const KzStackRef &stk, KzLocalStack &ls) {
+    const uint32_t hits_imask = t.ng_y;
+    const uint32_t bit = kz_bfind(hits_imask);
+    const uint32_t child_base = t.ng_x;
+    t.ng_y &= ~(1u << bit);
+    if (t.ng_y > 0x00FFFFFFu) kz_trav_push(t, stk, ls, t.ng_x, t.ng_y);     /* siblings left: push the rest of the group */
+    const uint32_t slot = (bit - 24u) ^ t.oct_inv;
+    const uint32_t rel = kz_popc(hits_imask & ~(0xFFFFFFFFu << slot));
+    const KzNode8 *node = sc.nodes + (child_base + rel);
+    const KzU4 n0 = kz_load_u4(reinterpret_cast<const char *>(node));
+    const KzU4 n1 = kz_load_u4(reinterpret_cast<const char *>(node) + 16);
+    const KzU4 n2 = kz_load_u4(reinterpret_cast<const char *>(node) + 32);
+    const KzU4 n3 = kz_load_u4(reinterpret_cast<const char *>(node) + 48);
+    const KzU4 n4 = kz_load_u4(reinterpret_cast<const char *>(node) + 64);
+    const float px = kz_u2f(n0.x), py = kz_u2f(n0.y), pz = kz_u2f(n0.z);
+    const uint32_t ex = n0.w & 0xFFu, ey = (n0.w >> 8) & 0xFFu, ez = (n0.w >> 16) & 0xFFu, imask = n0.w >> 24;
+    /* t = q * (2^e * rd) + (p - o') * rd */
+    const float adx = kz_u2f(ex << 23) * t.rdx, ady = kz_u2f(ey << 23) * t.rdy, adz = kz_u2f(ez << 23) * t.rdz;
+    const float anx = (px - t.onx) * t.rdx, any_ = (py - t.ony) * t.rdy, anz = (pz - t.onz) * t.rdz;
+    const float afx = (px - t.ofx) * t.rdx, afy = (py - t.ofy) * t.rdy, afz = (pz - t.ofz) * t.rdz;
+    const bool nx = !(t.oct_inv & 1u), ny = !(t.oct_inv & 2u), nz = !(t.oct_inv & 4u);
+    const uint32_t oct_inv4 = t.oct_inv * 0x01010101u;
+    uint32_t hitmask = 0u;
+#if KZ_DEVICE_CODE
+#pragma unroll
+#endif
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = kz_byte_perm(is_inner4 << 3, 0u, 0xBA98u);   /* sign-extend each byte */
+        const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+        const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+        const uint32_t qnx = nx ? qhix : qlox, qfx = nx ? qlox : qhix;
+        const uint32_t qny = ny ? qhiy : qloy, qfy = ny ? qloy : qhiy;
+        const uint32_t qnz = nz ? qhiz : qloz, qfz = nz ? qloz : qhiz;
+#if KZ_DEVICE_CODE
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; ++j) {
+            const int sh = 8 * j;
+            const float tnx = fmaf((float)((qnx >> sh) & 0xFFu), adx, anx);
+            const float tny = fmaf((float)((qny >> sh) & 0xFFu), ady, any_);
+            const float tnz = fmaf((float)((qnz >> sh) & 0xFFu), adz, anz);
+            const float tfx = fmaf((float)((qfx >> sh) & 0xFFu), adx, afx);
+            const float tfy = fmaf((float)((qfy >> sh) & 0xFFu), ady, afy);
+            const float tfz = fmaf((float)((qfz >> sh) & 0xFFu), adz, afz);
+            const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t.tmin));
+            const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, t.best.t));
+            if (cmin <= cmax) {
+                const uint32_t cb = (child_bits4 >> sh) & 0xFFu;
+                const uint32_t bi = (bit_index4 >> sh) & 0xFFu;
+                hitmask |= cb << bi;
+            }
+        }
+    }
+    t.ng_x = n1.x;
+    t.ng_y = (hitmask & 0xFF000000u) | imask;
+    t.tg_x = n1.y;
+    t.tg_y = hitmask & 0x00FFFFFFu;
+}
+
+/* Tests the next triangle of the current triangle group (tg_y != 0). */
+KZ_HD void kz_trav_tri(const KzScene &sc, KzTrav &t) {
+    const uint32_t ti = kz_bfind(t.tg_y);
+    t.tg_y &= ~(1u << ti);
+    const KzF4 *tp = sc.tris + (size_t)(t.tg_x + ti) * 3;
+    const KzU4 a = kz_load_u4(tp), b = kz_load_u4(tp + 1), c = kz_load_u4(tp + 2);
+    float tt, u, v;
+    if (kz_pluecker(t.ox, t.oy, t.oz, t.dx, t.dy, t.dz, t.tmin, t.best.t, a, b, c, tt, u, v)) {
+        const uint32_t geom = a.w, prim = b.w;
+        const bool better = tt < t.best.t || geom < t.best.geom || (geom == t.best.geom && prim < t.best.prim);
+        if (better) { t.best.t = tt; t.best.u = u; t.best.v = v; t.best.geom = geom; t.best.prim = prim; }
+    }
+}
+
+/* The plain per-ray loop.  `stk` gives the shared-memory short stack on the device; on the host
  * everything lives in the local array.  any_hit: return at the first accepted hit. */
 KZ_HD KzHit kz_trace(const KzScene &sc, const KzStackRef &stk, float ox, float oy, float oz, float dx, float dy, float dz,
                      float tmin, float tmax, bool any_hit) {
-    KzHit best; best.t = tmax; best.u = 0.f; best.v = 0.f; best.prim = KZ_INVALID_ID; best.geom = KZ_INVALID_ID;
-    if (sc.n_nodes == 0) return best;
-
-    const float slack = (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + sc.scene_max_abs) * 3.814697265625e-06f;
-    const float rdx = kz_rcp_safe(dx), rdy = kz_rcp_safe(dy), rdz = kz_rcp_safe(dz);
-    const bool nx = rdx < 0.f, ny = rdy < 0.f, nz = rdz < 0.f;
-    /* origins used for the near / far planes (slab widened by slack in position space) */
-    const float onx = nx ? ox - slack : ox + slack, ofx = nx ? ox + slack : ox - slack;
-    const float ony = ny ? oy - slack : oy + slack, ofy = ny ? oy + slack : oy - slack;
-    const float onz = nz ? oz - slack : oz + slack, ofz = nz ? oz + slack : oz - slack;
-    const uint32_t oct_inv = ((nx ? 0u : 1u) | (ny ? 0u : 2u) | (nz ? 0u : 4u));   /* 7 - octant */
-    const uint32_t oct_inv4 = oct_inv * 0x01010101u;
-
-    uint32_t lstack_x[KZ_LOCAL_STACK], lstack_y[KZ_LOCAL_STACK];
-    int sp = 0;   /* number of stacked entries */
-
-    uint32_t ng_x = 0u, ng_y = 0x80000000u;   /* node group: (child base, hits<<24 | imask) */
-    uint32_t tg_x = 0u, tg_y = 0u;            /* triangle group: (tri base, hit bits)        */
-
+    KzTrav t;
+    KzLocalStack ls;
+    kz_trav_init(sc, t, ox, oy, oz, dx, dy, dz, tmin, tmax);
+    if (sc.n_nodes == 0) return t.best;
     for (;;) {
-        if (ng_y > 0x00FFFFFFu) {
-            const uint32_t hits_imask = ng_y;
-            const uint32_t bit = kz_bfind(hits_imask);
-            const uint32_t child_base = ng_x;
-            ng_y &= ~(1u << bit);
-            if (ng_y > 0x00FFFFFFu) {           /* siblings left: push the rest of the group */
-#if KZ_DEVICE_CODE
-                if (sp < KZ_SHORT_STACK) stk.smem[sp * stk.stride] = make_uint2(ng_x, ng_y);
-                else { lstack_x[sp - KZ_SHORT_STACK] = ng_x; lstack_y[sp - KZ_SHORT_STACK] = ng_y; }
-#else
-                lstack_x[sp] = ng_x; lstack_y[sp] = ng_y;
-#endif
-                ++sp;
-            }
-            const uint32_t slot = (bit - 24u) ^ oct_inv;
-            const uint32_t rel = kz_popc(hits_imask & ~(0xFFFFFFFFu << slot));
-            const KzNode8 *node = sc.nodes + (child_base + rel);
-            const KzU4 n0 = kz_load_u4(reinterpret_cast<const char *>(node));
-            const KzU4 n1 = kz_load_u4(reinterpret_cast<const char *>(node) + 16);
-            const KzU4 n2 = kz_load_u4(reinterpret_cast<const char *>(node) + 32);
-            const KzU4 n3 = kz_load_u4(reinterpret_cast<const char *>(node) + 48);
-            const KzU4 n4 = kz_load_u4(reinterpret_cast<const char *>(node) + 64);
-            const float px = kz_u2f(n0.x), py = kz_u2f(n0.y), pz = kz_u2f(n0.z);
-            const uint32_t ex = n0.w & 0xFFu, ey = (n0.w >> 8) & 0xFFu, ez = (n0.w >> 16) & 0xFFu, imask = n0.w >> 24;
-            /* t = q * (2^e * rd) + (p - o') * rd */
-            const float adx = kz_u2f(ex << 23) * rdx, ady = kz_u2f(ey << 23) * rdy, adz = kz_u2f(ez << 23) * rdz;
-            const float anx = (px - onx) * rdx, any_ = (py - ony) * rdy, anz = (pz - onz) * rdz;
-            const float afx = (px - ofx) * rdx, afy = (py - ofy) * rdy, afz = (pz - ofz) * rdz;
-            uint32_t hitmask = 0u;
-#if KZ_DEVICE_CODE
-#pragma unroll
-#endif
-            for (int half = 0; half < 2; ++half) {
-                const uint32_t meta4 = half ? n1.w : n1.z;
-                const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t inner_mask4 = kz_byte_perm(is_inner4 << 3, 0u, 0xBA98u);   /* sign-extend each byte */
-                const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1F1F1F1Fu;
-                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
-                const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
-                const uint32_t qnx = nx ? qhix : qlox, qfx = nx ? qlox : qhix;
-                const uint32_t qny = ny ? qhiy : qloy, qfy = ny ? qloy : qhiy;
-                const uint32_t qnz = nz ? qhiz : qloz, qfz = nz ? qloz : qhiz;
-#if KZ_DEVICE_CODE
-#pragma unroll
-#endif
-                for (int j = 0; j < 4; ++j) {
-                    const int sh = 8 * j;
-                    const float tnx = fmaf((float)((qnx >> sh) & 0xFFu), adx, anx);
-                    const float tny = fmaf((float)((qny >> sh) & 0xFFu), ady, any_);
-                    const float tnz = fmaf((float)((qnz >> sh) & 0xFFu), adz, anz);
-                    const float tfx = fmaf((float)((qfx >> sh) & 0xFFu), adx, afx);
-                    const float tfy = fmaf((float)((qfy >> sh) & 0xFFu), ady, afy);
-                    const float tfz = fmaf((float)((qfz >> sh) & 0xFFu), adz, afz);
-                    const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-                    const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, best.t));
-                    if (cmin <= cmax) {
-                        const uint32_t cb = (child_bits4 >> sh) & 0xFFu;
-                        const uint32_t bi = (bit_index4 >> sh) & 0xFFu;
-                        hitmask |= cb << bi;
-                    }
-                }
-            }
-            ng_x = n1.x;
-            ng_y = (hitmask & 0xFF000000u) | imask;
-            tg_x = n1.y;
-            tg_y = hitmask & 0x00FFFFFFu;
-        } else {
-            tg_x = ng_x; tg_y = ng_y;
-            ng_x = 0u; ng_y = 0u;
+        if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
+        else { t.tg_x = t.ng_x; t.tg_y = t.ng_y; t.ng_x = 0u; t.ng_y = 0u; }
+        while (t.tg_y != 0u) {
+            kz_trav_tri(sc, t);
+            if (any_hit && t.best.geom != KZ_INVALID_ID) return t.best;
         }
-
-        while (tg_y != 0u) {
-            const uint32_t ti = kz_bfind(tg_y);
-            tg_y &= ~(1u << ti);
-            const KzF4 *tp = sc.tris + (size_t)(tg_x + ti) * 3;
-            const KzU4 a = kz_load_u4(tp), b = kz_load_u4(tp + 1), c = kz_load_u4(tp + 2);
-            float t, u, v;
-            if (kz_pluecker(ox, oy, oz, dx, dy, dz, tmin, best.t, a, b, c, t, u, v)) {
-                const uint32_t geom = a.w, prim = b.w;
-                const bool better = t < best.t || geom < best.geom || (geom == best.geom && prim < best.prim);
-                if (better) { best.t = t; best.u = u; best.v = v; best.geom = geom; best.prim = prim; }
-                if (any_hit) return best;
-            }
-        }
-
-        if (ng_y <= 0x00FFFFFFu) {
-            if (sp == 0) break;
-            --sp;
-#if KZ_DEVICE_CODE
-            if (sp < KZ_SHORT_STACK) { const uint2 e = stk.smem[sp * stk.stride]; ng_x = e.x; ng_y = e.y; }
-            else { ng_x = lstack_x[sp - KZ_SHORT_STACK]; ng_y = lstack_y[sp - KZ_SHORT_STACK]; }
-#else
-            ng_x = lstack_x[sp]; ng_y = lstack_y[sp];
-#endif
+        if (t.ng_y <= 0x00FFFFFFu) {
+            if (t.sp == 0) break;
+            kz_trav_pop(t, stk, ls);
         }
     }
-    return best;
+    return t.best;
 }
 
 #endif
