@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -48,7 +49,9 @@ struct Built {
     int depth = 0;
 };
 
-static const int kMaxLeaf = 3;
+static const int kMaxLeafLimit = 3;
+inline int maxLeaf() { static int v = [] { const char *e = getenv("KZ_SAH_MAXLEAF"); int k = e ? atoi(e) : 3; return k < 1 ? 1 : (k > kMaxLeafLimit ? kMaxLeafLimit : k); }(); return v; }
+inline float travCost() { static float v = [] { const char *e = getenv("KZ_SAH_TRAVCOST"); return e ? (float)atof(e) : 0.3f; }(); return v; }
 static const int kBins = 16;
 
 /* ---------------- BVH2 by binned SAH (task-parallel over subtrees) ---------------- */
@@ -141,10 +144,10 @@ private:
                     if (cost < bestCost) { bestCost = cost; bestAxis = a; bestBin = k; }
                 }
             }
-            if (cnt <= (size_t)kMaxLeaf) {
+            if (cnt <= (size_t)maxLeaf()) {
                 /* leaf unless splitting is clearly cheaper (traversal cost 1, intersection cost 1) */
                 float leafCost = (float)cnt * bb.area();
-                if (bestAxis < 0 || bestCost + bb.area() >= leafCost) { nd.left = (int32_t)j.b; nd.count = (int32_t)cnt; continue; }
+                if (bestAxis < 0 || bestCost + travCost() * bb.area() >= leafCost) { nd.left = (int32_t)j.b; nd.count = (int32_t)cnt; continue; }
             }
             size_t mid;
             if (bestAxis >= 0) {

@@ -99,8 +99,19 @@ __device__ __forceinline__ void kz_flush_counters(KzControl *ctl, const KzCounte
  *   bool end(uint32_t item, const KzHit &h, KzRayIn &r)     consume the closest hit; return true and fill `r`
  *                                                           to continue the same item with a follow-up ray */
 struct KzRayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
+#ifndef KZ_FETCH_ND
 #define KZ_FETCH_ND 4
+#endif
+#ifndef KZ_FETCH_NW
 #define KZ_FETCH_NW 16
+#endif
+#ifndef KZ_TRAV_MODE
+#define KZ_TRAV_MODE 0          /* 0: one node step + postponed leaf tests per iteration; 1: while-while */
+#endif
+#ifndef KZ_POSTPONE_NUM
+#define KZ_POSTPONE_NUM 1       /* postpone leaf tests while active lanes < NUM/DEN of the lanes in the loop */
+#define KZ_POSTPONE_DEN 5
+#endif
 
 template <class Job>
 __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRef &stk, uint32_t *cursor, uint32_t n, Job &job) {
@@ -133,12 +144,40 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
         }
         if (!__any_sync(KZ_FULL, active)) break;
         int lost = 0;
+#if KZ_TRAV_MODE == 1
+        /* while-while: every lane descends until it holds triangles (or is finished), then the warp tests triangles together */
+        while (active) {
+            for (;;) {
+                if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
+                else if (t.ng_y != 0u) { t.tg_x = t.ng_x; t.tg_y = t.ng_y; t.ng_x = 0u; t.ng_y = 0u; }
+                if (t.tg_y != 0u) break;
+                if (t.ng_y <= 0x00FFFFFFu) {
+                    if (t.sp == 0) break;
+                    kz_trav_pop(t, stk, ls);
+                }
+            }
+            while (t.tg_y != 0u) kz_trav_tri(sc, t);
+            if (t.ng_y <= 0x00FFFFFFu) {
+                if (t.sp == 0) {
+                    KzRayIn r;
+                    if (job.end(item, t.best, r)) kz_trav_init(sc, t, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tmin, r.tmax);
+                    else active = false;
+                } else {
+                    kz_trav_pop(t, stk, ls);
+                }
+            }
+            if (!exhausted) {
+                lost += 32 - __popc(__activemask()) - KZ_FETCH_ND;
+                if (lost >= KZ_FETCH_NW) break;
+            }
+        }
+#else
         while (active) {
             if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
             else { t.tg_x = t.ng_x; t.tg_y = t.ng_y; t.ng_x = 0u; t.ng_y = 0u; }
             const int total = __popc(__activemask());
             while (t.tg_y != 0u) {
-                if (__popc(__activemask()) * 5 < total && t.sp < KZ_SHORT_STACK + KZ_LOCAL_STACK - 1) {       /* too few lanes have triangles: postpone */
+                if (__popc(__activemask()) * KZ_POSTPONE_DEN < total * KZ_POSTPONE_NUM && t.sp < KZ_SHORT_STACK + KZ_LOCAL_STACK - 1) {   /* too few lanes have triangles: postpone */
                     kz_trav_push(t, stk, ls, t.tg_x, t.tg_y);
                     t.tg_y = 0u;
                     break;
@@ -159,6 +198,7 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
                 if (lost >= KZ_FETCH_NW) break;
             }
         }
+#endif
         __syncwarp();
     }
 }
