@@ -27,7 +27,7 @@ struct EvPair { cudaEvent_t a, b; int cat; };
 struct Device {
     int id = -1;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
     std::vector<void *> scene_allocs, accel_allocs, pool_allocs;
     KzScene sc;                      /* device pointers */
     bool has_accel = false;
@@ -244,7 +244,7 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
             }
             if (b < max_depth && sc.n_light_meshes > 0) {
                 Timed t(d, s, CAT_TRACE);
-                k_shadow<<<d.grid_shadow, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q);
+                k_shadow<<<d.grid_shadow, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt);
                 ++d.launches;
             }
         }
@@ -324,6 +324,8 @@ void kzgpu_destroy(kzgpu_ctx *ctx) {
         for (int k = 0; k < 3; ++k) if (d.scratch[k]) cudaFree(d.scratch[k]);
         cudaFree(d.ctl); cudaFree(d.cursor);
         cudaStreamDestroy(d.stream);
+        if (d.copy_in) cudaStreamDestroy(d.copy_in);
+        if (d.copy_out) cudaStreamDestroy(d.copy_out);
     }
     delete ctx;
 }
@@ -418,13 +420,32 @@ int kzgpu_trace(kzgpu_ctx *ctx, int device, const kz_ray *rays, size_t n, int sh
     if ((rc = select(ctx, device, &d))) return rc;
     if (n == 0) return KZ_OK;
     if (!rays || !hits) return fail(ctx, KZ_ERR_INVALID, "null ray/hit buffer");
+    if (n > 0x7FFFFFFFull) return fail(ctx, KZ_ERR_INVALID, "batch larger than 2^31-1 rays");
     if ((rc = ensure_scratch(ctx, *d, 0, n * sizeof(kz_ray)))) return rc;
     if ((rc = ensure_scratch(ctx, *d, 1, n * sizeof(kz_hit)))) return rc;
-    Timed total_t(*d, d->stream, CAT_TOTAL);
-    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], rays, n * sizeof(kz_ray), cudaMemcpyHostToDevice, d->stream));
-    if ((rc = kzgpu_trace_device(ctx, device, d->scratch[0], n, shadow, d->scratch[1], d->stream))) return rc;
-    KZ_CUDA(ctx, cudaMemcpyAsync(hits, d->scratch[1], n * sizeof(kz_hit), cudaMemcpyDeviceToHost, d->stream));
-    KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    /* Three-stage pipeline over ray chunks: H2D of chunk c+1, traversal of chunk c and D2H of chunk c-1 run
+     * concurrently (PCIe is full duplex; with pinned host buffers the call costs max(copy, trace), not the sum). */
+    if (!d->copy_in) KZ_CUDA(ctx, cudaStreamCreateWithFlags(&d->copy_in, cudaStreamNonBlocking));
+    if (!d->copy_out) KZ_CUDA(ctx, cudaStreamCreateWithFlags(&d->copy_out, cudaStreamNonBlocking));
+    const size_t chunk = std::min<size_t>(n, std::max<size_t>(1u << 20, (n + 15) / 16));
+    std::vector<cudaEvent_t> evs;
+    char *d_rays = reinterpret_cast<char *>(d->scratch[0]), *d_hits = reinterpret_cast<char *>(d->scratch[1]);
+    for (size_t first = 0; first < n && rc == KZ_OK; first += chunk) {
+        const size_t cnt = std::min(chunk, n - first);
+        cudaEvent_t e_in = get_event(*d), e_k = get_event(*d);
+        evs.push_back(e_in); evs.push_back(e_k);
+        cudaMemcpyAsync(d_rays + first * sizeof(kz_ray), rays + first, cnt * sizeof(kz_ray), cudaMemcpyHostToDevice, d->copy_in);
+        cudaEventRecord(e_in, d->copy_in);
+        cudaStreamWaitEvent(d->stream, e_in, 0);
+        rc = kzgpu_trace_device(ctx, device, d_rays + first * sizeof(kz_ray), cnt, shadow, d_hits + first * sizeof(kz_hit), d->stream);
+        cudaEventRecord(e_k, d->stream);
+        cudaStreamWaitEvent(d->copy_out, e_k, 0);
+        cudaMemcpyAsync(hits + first, d_hits + first * sizeof(kz_hit), cnt * sizeof(kz_hit), cudaMemcpyDeviceToHost, d->copy_out);
+    }
+    const cudaError_t e1 = cudaStreamSynchronize(d->copy_out), e2 = cudaStreamSynchronize(d->stream), e3 = cudaStreamSynchronize(d->copy_in);
+    for (cudaEvent_t e : evs) d->free_events.push_back(e);
+    if (rc) return rc;
+    KZ_CUDA(ctx, e1); KZ_CUDA(ctx, e2); KZ_CUDA(ctx, e3);
     return KZ_OK;
 }
 

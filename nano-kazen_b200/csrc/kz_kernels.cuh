@@ -25,11 +25,12 @@
 #define KZ_SHADE_THREADS 128
 
 struct KzControl {
-    uint32_t n_ext[2];                    /* extension-ray queue counts (ping-pong)         */
+    /* [k]: low word = entries of the extension queue k (ping-pong), high word = entries of the shadow queue
+     * filled by the same shade pass -- packed so one 64-bit atomic reserves space in both queues */
+    unsigned long long ext_shadow[2];
     uint32_t n_class[KZ_NUM_CLASSES];     /* material-class queue counts                    */
-    uint32_t n_shadow;
     uint32_t head_ext, head_shadow, head_trace;   /* persistent-fetch cursors               */
-    uint32_t pad[2];
+    uint32_t pad[1];
     unsigned long long paths, rays_ext, rays_shadow, vertices;
 };
 
@@ -62,6 +63,22 @@ __device__ __forceinline__ void kz_push(uint32_t *queue, uint32_t *counter, bool
     if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
     base = __shfl_sync(KZ_FULL, base, (int)leader);
     if (pred) queue[base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__device__ __forceinline__ uint32_t *kz_ext_counter(KzControl *ctl, int k) { return reinterpret_cast<uint32_t *>(&ctl->ext_shadow[k]); }
+__device__ __forceinline__ uint32_t kz_ext_count(const KzControl *ctl, int k) { return (uint32_t)(ctl->ext_shadow[k] & 0xFFFFFFFFull); }
+__device__ __forceinline__ uint32_t kz_shadow_count(const KzControl *ctl, int k) { return (uint32_t)(ctl->ext_shadow[k] >> 32); }
+
+/* Appends `value` to queue A and/or queue B with ONE atomic per warp (counters packed lo|hi); all 32 lanes must call. */
+__device__ __forceinline__ void kz_push2(uint32_t *qa, uint32_t *qb, unsigned long long *counter, bool pa, bool pb, uint32_t value) {
+    const uint32_t ma = __ballot_sync(KZ_FULL, pa), mb = __ballot_sync(KZ_FULL, pb);
+    if ((ma | mb) == 0u) return;
+    const uint32_t lane = kz_lane(), lt = (1u << lane) - 1u;
+    unsigned long long base = 0ull;
+    if (lane == 0u) base = atomicAdd(counter, (unsigned long long)__popc(ma) | ((unsigned long long)__popc(mb) << 32));
+    base = __shfl_sync(KZ_FULL, base, 0);
+    if (pa) qa[(uint32_t)(base & 0xFFFFFFFFull) + (uint32_t)__popc(ma & lt)] = value;
+    if (pb) qb[(uint32_t)(base >> 32) + (uint32_t)__popc(mb & lt)] = value;
 }
 
 /* Next 32-item packet of a queue for this warp (persistent threads). */
@@ -216,16 +233,16 @@ __device__ __forceinline__ void kz_push_divergent(uint32_t *const *queues, uint3
 
 __global__ void k_chunk_reset(KzControl *ctl) {
     if (threadIdx.x == 0) {
-        ctl->n_ext[0] = ctl->n_ext[1] = 0u;
+        ctl->ext_shadow[0] = ctl->ext_shadow[1] = 0ull;
         for (int c = 0; c < KZ_NUM_CLASSES; ++c) ctl->n_class[c] = 0u;
-        ctl->n_shadow = 0u; ctl->head_ext = ctl->head_shadow = ctl->head_trace = 0u;
+        ctl->head_ext = ctl->head_shadow = ctl->head_trace = 0u;
     }
 }
 __global__ void k_bounce_reset(KzControl *ctl, int nxt) {
     if (threadIdx.x == 0) {
-        ctl->n_ext[nxt] = 0u;
+        ctl->ext_shadow[nxt] = 0ull;
         for (int c = 0; c < KZ_NUM_CLASSES; ++c) ctl->n_class[c] = 0u;
-        ctl->n_shadow = 0u; ctl->head_ext = ctl->head_shadow = 0u;
+        ctl->head_ext = ctl->head_shadow = 0u;
     }
 }
 
@@ -247,7 +264,7 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_raygen(KzScene sc, KzPathS
         if (valid) kz_raygen_item(sc, st, i, x, y, (uint32_t)(ch.spp_begin + (int)s_local));
         else st.pix[i] = 0xFFFFFFFFu;
     }
-    kz_push(q0, &ctl->n_ext[0], valid, i);
+    kz_push(q0, kz_ext_counter(ctl, 0), valid, i);
     const uint32_t nvalid = (uint32_t)__popc(__ballot_sync(KZ_FULL, valid));
     if (kz_lane() == 0u && nvalid) atomicAdd(&ctl->paths, (unsigned long long)nvalid);
 }
@@ -299,7 +316,7 @@ __global__ void __launch_bounds__(KZ_TRACE_THREADS) k_extend(KzScene sc, KzPathS
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
     KzExtendJob<FIRST> job(sc, st, ctl, q, q.ext[cur]);
-    kz_warp_trace(sc, stk, &ctl->head_ext, ctl->n_ext[cur], job);
+    kz_warp_trace(sc, stk, &ctl->head_ext, kz_ext_count(ctl, cur), job);
     kz_flush_counters(ctl, job.cnt);
 }
 
@@ -318,10 +335,8 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_shade(KzScene sc, KzPathSt
             flags = kz_shade_item<CLS>(sc, st, slot, bounce, cnt);
         }
         __syncwarp();
-        if (CLS != KZ_CLASS_TERMINAL) {
-            kz_push(q.ext[nxt], &ctl->n_ext[nxt], (flags & KZ_SHADE_CONTINUE) != 0u, slot);
-            kz_push(q.shadow, &ctl->n_shadow, (flags & KZ_SHADE_SHADOW) != 0u, slot);
-        }
+        if (CLS != KZ_CLASS_TERMINAL)
+            kz_push2(q.ext[nxt], q.shadow, &ctl->ext_shadow[nxt], (flags & KZ_SHADE_CONTINUE) != 0u, (flags & KZ_SHADE_SHADOW) != 0u, slot);
     }
     kz_flush_counters(ctl, cnt);
 }
@@ -369,11 +384,11 @@ struct KzShadowJob {
         return false;
     }
 };
-__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_shadow(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q) {
+__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_shadow(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int nxt) {
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
     KzShadowJob job(sc, st, q.shadow);
-    kz_warp_trace(sc, stk, &ctl->head_shadow, ctl->n_shadow, job);
+    kz_warp_trace(sc, stk, &ctl->head_shadow, kz_shadow_count(ctl, nxt), job);
     kz_flush_counters(ctl, job.cnt);
 }
 

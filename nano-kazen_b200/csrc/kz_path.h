@@ -143,7 +143,7 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     float eta = thr4.w, bsdfWeight = L4.w;
     const kz_integrator_desc I = sc.integrator;
 
-    if (h.geom == KZ_INVALID_ID) {
+    if (CLS <= KZ_CLASS_TERMINAL && h.geom == KZ_INVALID_ID) {     /* material-class queues never hold misses */
         /* bounce 0: camera rays never see the background (integrator.cpp:210-212);
          * later: Li += throughput * background(ray.d) (integrator.cpp:315-318) */
         if (bounce > 0) {

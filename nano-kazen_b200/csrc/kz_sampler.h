@@ -41,9 +41,14 @@ KZ_HD uint64_t kz_mix_bits(uint64_t v) {
     v ^= (v >> 33);
     return v;
 }
+/* n / d and n % d; d is a per-scene constant and almost always a power of two (16, 64, 256 spp) */
+KZ_HD void kz_divmod(uint32_t n, uint32_t d, uint32_t &q, uint32_t &r) {
+    if ((d & (d - 1u)) == 0u) { q = n >> kz_bfind(d); r = n & (d - 1u); }
+    else { q = n / d; r = n - q * d; }
+}
 KZ_HD uint32_t kz_permute(uint32_t i, uint32_t l, uint32_t p) {
-    uint32_t w = l - 1;
-    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    /* w = l-1 with every bit below its top bit set (common.cpp:318-323 builds it with five shift-ors) */
+    const uint32_t w = l > 1u ? 0xFFFFFFFFu >> (31u - kz_bfind(l - 1u)) : 0u;
     do {
         i ^= p;             i *= 0xe170893du;
         i ^= p >> 16;
@@ -58,7 +63,8 @@ KZ_HD uint32_t kz_permute(uint32_t i, uint32_t l, uint32_t p) {
         i &= w;
         i ^= i >> 5;
     } while (i >= l);
-    return (i + p) % l;
+    const uint32_t r = i + p;
+    return ((l & (l - 1u)) == 0u) ? (r & (l - 1u)) : r % l;
 }
 
 #define KZ_PCG_MULT 0x5851f42d4c957f2dULL
@@ -156,7 +162,8 @@ KZ_HD kz2 kz_next2d(const KzScene &sc, KzSampler &s) {
             uint64_t h = kz_hash_pixel_dim_seed(s.px, s.py, s.dim, sc.seed);
             int stratum = (int)kz_permute(s.sample_index, sc.sample_count, (uint32_t)h);
             s.dim += 2;
-            int x = stratum % sc.res_x, y = stratum / sc.res_x;
+            uint32_t x, y;
+            kz_divmod((uint32_t)stratum, (uint32_t)sc.res_x, y, x);
             float dx = kz_pcg_float(s);
             float dy = kz_pcg_float(s);
             return mk2(kz_div(kz_add((float)x, dx), (float)sc.res_x), kz_div(kz_add((float)y, dy), (float)sc.res_x));
@@ -164,8 +171,8 @@ KZ_HD kz2 kz_next2d(const KzScene &sc, KzSampler &s) {
         case KZ_SAMPLER_CORRELATED: {
             uint64_t h = kz_hash_pixel_dim_seed(s.px, s.py, s.dim, sc.seed);
             uint32_t sidx = kz_permute(s.sample_index, sc.sample_count, (uint32_t)(h * 0x51633e2dull));
-            uint32_t y = sidx / (uint32_t)sc.res_x;
-            uint32_t x = sidx % (uint32_t)sc.res_x;
+            uint32_t x, y;
+            kz_divmod(sidx, (uint32_t)sc.res_x, y, x);
             uint32_t sx = kz_permute(x, (uint32_t)sc.res_x, (uint32_t)(h * 0x68bc21ebull));
             uint32_t sy = kz_permute(y, (uint32_t)sc.res_y, (uint32_t)(h * 0x02e5be93ull));
             float jx = kz_pcg_float(s);

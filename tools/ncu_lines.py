@@ -19,9 +19,12 @@ for l in sass[start + 1:]:
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout.splitlines()
 rows = list(csv.reader(out))
 # the report may hold several launches: take the LAST one (incoherent batch) unless KZ_LAUNCH is set
-blocks = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+# kernel-name filters match the base name only; template instances are told apart by the substring KZ_NAME_HAS
+names = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+has = os.environ.get("KZ_NAME_HAS", "")
+blocks = [i + 1 for i in names if has in rows[i][1] and i + 1 < len(rows) and rows[i + 1] and rows[i + 1][0] == "Address"]
 which = int(os.environ.get("KZ_LAUNCH", len(blocks) - 1))
-b = blocks[which]; e = blocks[which + 1] - 1 if which + 1 < len(blocks) else len(rows)
+b = blocks[which]; nxt = [i for i in names if i > b]; e = nxt[0] if nxt else len(rows)
 hdr = rows[b]; body = [r for r in rows[b + 1:e] if len(r) == len(hdr)]
 ci, ti, si = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
 assert len(body) == len(lines), (len(body), len(lines))
@@ -30,7 +33,8 @@ for (ln, txt), r in zip(lines, body):
     a = agg.setdefault(ln, [0, 0, 0]); a[0] += int(r[ci]); a[1] += int(r[ti]); a[2] += int(r[si]); tot += int(r[ci]); tott += int(r[ti]); tots += int(r[si])
 print(f"launch {which}: {tot} warp instructions, {tott/tot:.1f} threads/inst, {tots} samples")
 src = {}
-for (f, n), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+skey = 2 if os.environ.get("KZ_SORT") == "smp" else 0
+for (f, n), a in sorted(agg.items(), key=lambda kv: -kv[1][skey])[:top]:
     if f not in src:
         try: src[f] = open(os.path.join(root, "nano-kazen_b200/csrc", f)).read().splitlines()
         except Exception: src[f] = []
