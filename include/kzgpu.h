@@ -255,6 +255,11 @@ int  kzgpu_camera_rays(kzgpu_ctx *ctx, const float *samples4, size_t n, kz_ray *
 int  kzgpu_bsdf_query(kzgpu_ctx *ctx, int bsdf, int mode, const float wi[3], const float wo[3], const float uv[2],
                       float accumulated_roughness, float sample1, const float sample2[2], float out[8]);
 
+/* Texture probe: periodic bicubic lookup of image `image` at mip `level` (0 = finest; the pyramid is built on the GPU at
+ * upload and stays resident in HBM) for n (s,t) pairs -> n rgb triples.  ImageTexture::eval's texture() call with zero
+ * derivatives (texture.cpp:46-64) is level 0 with s = u*scale, t = (1-v)*scale. */
+int  kzgpu_image_lookup(kzgpu_ctx *ctx, int image, int level, const float *st, size_t n, float *rgb);
+
 /* Whole-frame render into a host frame ((H+2b)*(W+2b)*4 floats). Multi-device contexts
  * shard [spp_begin,spp_end) by sample index across their devices and sum the frames. */
 int  kzgpu_render(kzgpu_ctx *ctx, const kz_render_req *req, float *frame_rgbw);

@@ -158,6 +158,18 @@ int upload_scene(kzgpu_ctx *ctx, Device &d) {
     UP(images, h.images); UP(texels, h.texels); UP(lights, h.lights); UP(blue_noise, h.blue_noise); UP(pmj02bn, h.pmj);
     UP(pmj_pixel_samples, h.pmj_pixel_samples);
 #undef UP
+    /* mip pyramids: level l from level l-1, on the device */
+    for (const KzImageRec &im : h.images) {
+        size_t src = im.texel_offset; int sw = im.width, sh = im.height;
+        for (int l = 1; l <= im.n_levels; ++l) {
+            const int dw = sw > 1 ? sw >> 1 : 1, dh = sh > 1 ? sh >> 1 : 1;
+            const size_t dst = src + (size_t)sw * sh;
+            dim3 blk(32, 8), grd((unsigned)(dw + 31) / 32, (unsigned)(dh + 7) / 8);
+            k_mip_level<<<grd, blk, 0, d.stream>>>(const_cast<KzF4 *>(d.sc.texels), src, sw, sh, dst, dw, dh);
+            ++d.launches;
+            src = dst; sw = dw; sh = dh;
+        }
+    }
     /* frame */
     const size_t texels = (size_t)(h.sc.camera.width + 2 * h.sc.border) * (size_t)(h.sc.camera.height + 2 * h.sc.border);
     if ((rc = dev_alloc(ctx, d.scene_allocs, texels, &d.frame))) return rc;
@@ -536,6 +548,26 @@ int kzgpu_bsdf_query(kzgpu_ctx *ctx, int bsdf, int mode, const float wi[3], cons
     k_bsdf_query<<<1, 32, 0, d->stream>>>(d->sc, reinterpret_cast<const KzBsdfQuery *>(d->scratch[0]), 1u, reinterpret_cast<float *>(d->scratch[1]));
     ++d->launches;
     KZ_CUDA(ctx, cudaMemcpyAsync(out, d->scratch[1], 32, cudaMemcpyDeviceToHost, d->stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    return KZ_OK;
+}
+
+int kzgpu_image_lookup(kzgpu_ctx *ctx, int image, int level, const float *st, size_t n, float *rgb) {
+    int rc = check_ready(ctx, false);
+    if (rc) return rc;
+    Device *d;
+    if ((rc = select(ctx, 0, &d))) return rc;
+    if (image < 0 || image >= (int)ctx->hs->images.size()) return fail(ctx, KZ_ERR_INVALID, "image index out of range");
+    if (level < 0) return fail(ctx, KZ_ERR_INVALID, "negative mip level");
+    if (n == 0) return KZ_OK;
+    if (!st || !rgb) return fail(ctx, KZ_ERR_INVALID, "null argument");
+    if ((rc = ensure_scratch(ctx, *d, 0, n * 8))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 1, n * 12))) return rc;
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], st, n * 8, cudaMemcpyHostToDevice, d->stream));
+    k_image_lookup<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(d->sc, image, level, reinterpret_cast<const float *>(d->scratch[0]), (uint32_t)n,
+                                                                       reinterpret_cast<float *>(d->scratch[1]));
+    ++d->launches;
+    KZ_CUDA(ctx, cudaMemcpyAsync(rgb, d->scratch[1], n * 12, cudaMemcpyDeviceToHost, d->stream));
     KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
     return KZ_OK;
 }

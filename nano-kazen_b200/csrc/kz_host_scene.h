@@ -49,14 +49,15 @@ struct KzHostScene {
             if (t.type == KZ_TEX_IMAGE && (t.image < 0 || t.image >= (int)d->n_images)) { error = "image index out of range"; return false; }
             for (int c = 0; c < 3; ++c) if (t.child[c] >= (int)d->n_textures) { error = "texture child out of range"; return false; }
         }
-        /* images: level 0 as float4 texels; a box-filtered mip pyramid follows (built on the GPU
-         * in the product; on the host here only level 0 is stored) */
+        /* images: level 0 as float4 texels followed by room for the mip pyramid (filled on the GPU by k_mip_level) */
         for (uint32_t i = 0; i < d->n_images; ++i) {
             const kz_image_desc &im = d->images[i];
             if (im.width <= 0 || im.height <= 0 || !im.rgb) { error = "bad image"; return false; }
             KzImageRec r; r.width = im.width; r.height = im.height; r.texel_offset = (uint32_t)texels.size(); r.n_levels = 0;
-            size_t n = (size_t)im.width * im.height;
-            texels.resize(texels.size() + n);
+            size_t n = (size_t)im.width * im.height, total = n;
+            for (int w = im.width, h = im.height; w > 1 || h > 1;) { w = w > 1 ? w >> 1 : 1; h = h > 1 ? h >> 1 : 1; total += (size_t)w * h; ++r.n_levels; }
+            if (texels.size() + total > 0xFFFFFFFFull) { error = "texture atlas larger than 2^32 texels"; return false; }
+            texels.resize(texels.size() + total, KzF4{0.f, 0.f, 0.f, 0.f});
             for (size_t k = 0; k < n; ++k) {
                 KzF4 &t = texels[r.texel_offset + k];
                 t.x = im.rgb[3 * k]; t.y = im.rgb[3 * k + 1]; t.z = im.rgb[3 * k + 2]; t.w = 1.f;

@@ -499,6 +499,23 @@ __global__ void k_bsdf_query(KzScene sc, const KzBsdfQuery *qs, uint32_t n, floa
     if (q.mode == 0) { o[0] = f.x; o[1] = f.y; o[2] = f.z; } else o[0] = pdf;
 }
 
+/* ---- textures: mip pyramid build + lookup probe ----------------------------------------- */
+__global__ void k_mip_level(KzF4 *texels, size_t src_off, int sw, int sh, size_t dst_off, int dw, int dh) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const int x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
+    const KzF4 a = texels[src_off + (size_t)y0 * sw + x0], b = texels[src_off + (size_t)y0 * sw + x1];
+    const KzF4 c = texels[src_off + (size_t)y1 * sw + x0], d = texels[src_off + (size_t)y1 * sw + x1];
+    KzF4 r; r.x = 0.25f * (a.x + b.x + c.x + d.x); r.y = 0.25f * (a.y + b.y + c.y + d.y); r.z = 0.25f * (a.z + b.z + c.z + d.z); r.w = 1.f;
+    texels[dst_off + (size_t)y * dw + x] = r;
+}
+__global__ void k_image_lookup(KzScene sc, int image, int level, const float *st, uint32_t n, float *rgb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const kz3 c = kz_image_bicubic(sc, image, st[2 * i], st[2 * i + 1], level);
+    rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z;
+}
+
 /* ---- resolve: block.cpp:39-45 + common.cpp:352-366 + bitmap.cpp:46-54 --------------------- */
 __global__ void k_resolve(const KzF4 *frame, int width, int height, int border, float *rgb, uint8_t *srgb8) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;

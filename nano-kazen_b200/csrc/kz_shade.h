@@ -51,23 +51,36 @@ KZ_HD void kz_bspline_weights(float f, float w[4]) {
     w[2] = 2.0f / 3.0f - 0.5f * one_f * one_f * (2.0f - one_f);
     w[3] = (f * f * f) / 6.0f;
 }
-/* finest mip level, periodic wrap, bicubic B-spline (OIIO default with zero derivatives) */
-KZ_HD_NOINLINE kz3 kz_image_bicubic(const KzScene &sc, int image, float s, float t) {
+/* Mip pyramid resident in HBM: level l (max(1,w>>l) x max(1,h>>l) float4 texels) follows level l-1; built on the GPU
+ * at upload by 2x2 box filtering (k_mip_level).  kazen calls OIIO with zero derivatives (texture.cpp:52-57), which selects
+ * the finest level, so the render path always passes level 0; coarser levels serve filtered lookups (kzgpu_image_lookup). */
+KZ_HD void kz_mip_level(const KzImageRec &im, int level, int &w, int &h, size_t &offset) {
+    w = im.width; h = im.height; offset = im.texel_offset;
+    if (level > im.n_levels) level = im.n_levels;
+    for (int l = 0; l < level; ++l) {
+        offset += (size_t)w * (size_t)h;
+        w = w > 1 ? w >> 1 : 1; h = h > 1 ? h >> 1 : 1;
+    }
+}
+/* periodic wrap, bicubic B-spline (OIIO's default interpolation when magnifying) */
+KZ_HD_NOINLINE kz3 kz_image_bicubic(const KzScene &sc, int image, float s, float t, int level = 0) {
     const KzImageRec im = sc.images[image];
-    float x = s * im.width - 0.5f, y = t * im.height - 0.5f;
+    int w = im.width, h = im.height; size_t off = im.texel_offset;
+    if (level > 0) kz_mip_level(im, level, w, h, off);
+    float x = s * w - 0.5f, y = t * h - 0.5f;
     float fx = floorf(x), fy = floorf(y);
     int ix = (int)fx, iy = (int)fy;
     float wx[4], wy[4];
     kz_bspline_weights(x - fx, wx);
     kz_bspline_weights(y - fy, wy);
     kz3 acc = mk3(0.f);
-    const KzF4 *base = sc.texels + im.texel_offset;
+    const KzF4 *base = sc.texels + off;
     for (int j = 0; j < 4; ++j) {
-        int yy = kz_wrapi(iy - 1 + j, im.height);
+        int yy = kz_wrapi(iy - 1 + j, h);
         kz3 row = mk3(0.f);
         for (int i = 0; i < 4; ++i) {
-            int xx = kz_wrapi(ix - 1 + i, im.width);
-            const KzF4 p = base[(size_t)yy * im.width + xx];
+            int xx = kz_wrapi(ix - 1 + i, w);
+            const KzF4 p = base[(size_t)yy * w + xx];
             row += mk3(p.x, p.y, p.z) * wx[i];
         }
         acc += row * wy[j];

@@ -465,6 +465,12 @@ class Gpu(_Backend):
         self._call("bsdf_query", self.h, C.c_int(bsdf), C.c_int(mode), f3(wi), f3(wo), f2(uv), C.c_float(acc_rough), C.c_float(s1), f2(s2), out)
         return np.array(list(out), np.float32)
 
+    def image_lookup(self, image, st, level=0):
+        st = np.ascontiguousarray(st, np.float32).reshape(-1, 2)
+        out = np.zeros((st.shape[0], 3), np.float32)
+        self._call("image_lookup", self.h, C.c_int(image), C.c_int(level), st.ctypes.data_as(c_float_p), C.c_size_t(st.shape[0]), out.ctypes.data_as(c_float_p))
+        return out
+
     def stats(self, reset=False):
         s = Stats()
         self._call("stats", self.h, C.byref(s))

@@ -242,3 +242,27 @@ def test_errors(gpu_lib):
     assert lib.kzgpu_render(h, C.byref(bad), frame.ctypes.data_as(pk.c_float_p)) == -1
     assert b"rectangle" in lib.kzgpu_last_error(h)
     lib.kzgpu_destroy(h)
+
+
+def test_mip_pyramid_resident(gpu_lib):
+    """the GPU-built mip pyramid: level l is the 2x2 box filter of level l-1; the periodic B-spline lookup is a partition
+    of unity, so the mean over all texel centres of a level equals that level's texel mean (== level-0 mean for 2^k sizes)"""
+    sb = scenes.cornell_scene(8, 8, 1, with_texture=True)
+    G = pk.Gpu(sb.desc())
+    img = np.ctypeslib.as_array(sb.images[0].rgb, shape=(32, 64, 3)).copy()
+    cur = img.astype(np.float64)
+    for level in range(0, 6):
+        h, w = cur.shape[:2]
+        ys, xs = np.mgrid[0:h, 0:w]
+        st = np.stack([(xs + 0.5) / w, (ys + 0.5) / h], -1).reshape(-1, 2)
+        got = G.image_lookup(0, st, level).reshape(h, w, 3)
+        assert np.allclose(got.mean(axis=(0, 1)), cur.mean(axis=(0, 1)), rtol=1e-4, atol=1e-5), level
+        # B-spline at texel centres = (1/6, 2/3, 1/6) x (1/6, 2/3, 1/6) periodic stencil of the level's texels
+        k = np.array([1 / 6, 2 / 3, 1 / 6])
+        exp = sum(k[a] * k[b] * np.roll(np.roll(cur, 1 - a, axis=0), 1 - b, axis=1) for a in range(3) for b in range(3))
+        assert np.allclose(got, exp, rtol=1e-4, atol=1e-5), level
+        if h == 1 and w == 1:
+            break
+        nh, nw = max(1, h // 2), max(1, w // 2)
+        cur = 0.25 * (cur[0:2 * nh:2, 0:2 * nw:2] + cur[0:2 * nh:2, 1:2 * nw:2] + cur[1:2 * nh:2, 0:2 * nw:2] + cur[1:2 * nh:2, 1:2 * nw:2]) if h > 1 and w > 1 else cur
+    G.close()
