@@ -110,20 +110,31 @@ typedef struct kz_image_desc {
 } kz_image_desc;
 
 enum kz_bsdf_type {
-    KZ_BSDF_DIFFUSE   = 0,  /* "diffuse"        bsdf.cpp:20-92     */
-    KZ_BSDF_KISS      = 1,  /* "kazenstandard"  bsdf.cpp:1157-1418 */
-    KZ_BSDF_NORMALMAP = 2   /* "normalmap"      bsdf.cpp:281-417   */
+    KZ_BSDF_DIFFUSE         = 0,  /* "diffuse"          bsdf.cpp:20-92     */
+    KZ_BSDF_KISS            = 1,  /* "kazenstandard"    bsdf.cpp:1157-1418 */
+    KZ_BSDF_NORMALMAP       = 2,  /* "normalmap"        bsdf.cpp:281-417   */
+    /* the remaining BSDF plugins */
+    KZ_BSDF_DIELECTRIC      = 3,  /* "dielectric"       bsdf.cpp:98-156    */
+    KZ_BSDF_MIRROR          = 4,  /* "mirror"           bsdf.cpp:162-196   */
+    KZ_BSDF_LAMBERTIAN      = 5,  /* "lambertian"       bsdf.cpp:202-276   */
+    KZ_BSDF_GGX             = 6,  /* "ggx"              bsdf.cpp:629-690   */
+    KZ_BSDF_ROUGHCONDUCTOR  = 7,  /* "roughconductor"   bsdf.cpp:693-812   */
+    KZ_BSDF_ROUGHPLASTIC    = 8,  /* "roughplastic"     bsdf.cpp:815-944   */
+    KZ_BSDF_ROUGHDIELECTRIC = 9   /* "roughdielectric"  bsdf.cpp:947-1145  */
 };
 
 typedef struct kz_bsdf_desc {
     int32_t type;
-    float   albedo[3];                           /* DIFFUSE                       */
-    int32_t base_color, roughness, metallic;     /* KISS: texture node indices    */
-    float   anisotropy, specular, specular_tint; /* KISS scalars bsdf.cpp:1159-1167 */
+    float   albedo[3];                           /* DIFFUSE albedo; ROUGHPLASTIC kd */
+    int32_t base_color, roughness, metallic;     /* KISS: texture node indices; LAMBERTIAN/GGX: base_color = albedo texture */
+    float   anisotropy, specular, specular_tint; /* KISS scalars bsdf.cpp:1159-1167; GGX: anisotropy */
     float   clearcoat, clearcoat_roughness;
     float   sheen, sheen_tint;
     int32_t normal_map;                          /* NORMALMAP: texture node       */
     int32_t nested;                              /* NORMALMAP: bsdf index         */
+    float   int_ior, ext_ior;                    /* DIELECTRIC, ROUGHPLASTIC, ROUGHDIELECTRIC */
+    float   alpha;                               /* ROUGHCONDUCTOR/ROUGHPLASTIC/ROUGHDIELECTRIC: max(1e-3, roughness^2); GGX: roughness as given */
+    float   eta[3], k[3];                        /* ROUGHCONDUCTOR complex IOR (bsdf.cpp:703-714) */
 } kz_bsdf_desc;
 
 /* AreaLight (light.cpp:7-66); radiance = intensity * color. */

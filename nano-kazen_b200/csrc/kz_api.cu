@@ -43,7 +43,7 @@ struct Device {
     void *scratch[3] = {nullptr, nullptr, nullptr};
     size_t scratch_bytes[3] = {0, 0, 0};
     /* launch geometry */
-    int grid_extend0 = 0, grid_extend = 0, grid_shadow = 0, grid_trace = 0, grid_occ = 0, grid_shade[KZ_NUM_CLASSES] = {0, 0, 0, 0};
+    int grid_extend0 = 0, grid_extend = 0, grid_shadow = 0, grid_trace = 0, grid_occ = 0, grid_shade[KZ_NUM_CLASSES] = {0, 0, 0, 0, 0};
     /* timing */
     std::vector<EvPair> pending;
     std::vector<cudaEvent_t> free_events;
@@ -56,7 +56,7 @@ struct Device {
 struct kzgpu_ctx {
     std::vector<Device> devs;
     std::unique_ptr<KzHostScene> hs;
-    bool class_present[KZ_NUM_CLASSES] = {true, false, false, false};
+    bool class_present[KZ_NUM_CLASSES] = {true, false, false, false, false};
     bool uploaded = false, built = false;
     uint32_t pool_cap = 1u << 22;
     kz_stats totals{};
@@ -252,6 +252,7 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
                     if (ctx->class_present[KZ_CLASS_DIFFUSE]) { k_shade<KZ_CLASS_DIFFUSE><<<d.grid_shade[1], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
                     if (ctx->class_present[KZ_CLASS_KISS]) { k_shade<KZ_CLASS_KISS><<<d.grid_shade[2], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
                     if (ctx->class_present[KZ_CLASS_NORMALMAP]) { k_shade<KZ_CLASS_NORMALMAP><<<d.grid_shade[3], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
+                    if (ctx->class_present[KZ_CLASS_GENERIC]) { k_shade<KZ_CLASS_GENERIC><<<d.grid_shade[4], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
                 }
             }
             if (b < max_depth && sc.n_light_meshes > 0) {
@@ -319,6 +320,7 @@ int kzgpu_create(const int *device_ids, int n_devices, kzgpu_ctx **out) {
         d.grid_shade[1] = persistent_grid(d, k_shade<KZ_CLASS_DIFFUSE>, KZ_SHADE_THREADS);
         d.grid_shade[2] = persistent_grid(d, k_shade<KZ_CLASS_KISS>, KZ_SHADE_THREADS);
         d.grid_shade[3] = persistent_grid(d, k_shade<KZ_CLASS_NORMALMAP>, KZ_SHADE_THREADS);
+        d.grid_shade[4] = persistent_grid(d, k_shade<KZ_CLASS_GENERIC>, KZ_SHADE_THREADS);
         ctx->devs.push_back(d);
     }
     *out = ctx.release();
@@ -355,7 +357,7 @@ int kzgpu_scene_upload(kzgpu_ctx *ctx, const kz_scene_desc *scene) {
     for (const KzMeshRec &m : ctx->hs->meshes) {
         if (m.flags & KZ_MESH_IS_LIGHT) continue;
         const int t = ctx->hs->bsdfs[(size_t)m.bsdf].type;
-        ctx->class_present[t == KZ_BSDF_DIFFUSE ? KZ_CLASS_DIFFUSE : (t == KZ_BSDF_KISS ? KZ_CLASS_KISS : KZ_CLASS_NORMALMAP)] = true;
+        ctx->class_present[t == KZ_BSDF_DIFFUSE ? KZ_CLASS_DIFFUSE : (t == KZ_BSDF_KISS ? KZ_CLASS_KISS : (t == KZ_BSDF_NORMALMAP ? KZ_CLASS_NORMALMAP : KZ_CLASS_GENERIC))] = true;
     }
     for (Device &d : ctx->devs) {
         KZ_CUDA(ctx, cudaSetDevice(d.id));

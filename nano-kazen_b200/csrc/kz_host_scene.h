@@ -42,7 +42,9 @@ struct KzHostScene {
             } else if (b.type == KZ_BSDF_NORMALMAP) {
                 if (!texok(b.normal_map) || b.nested < 0 || b.nested >= (int)d->n_bsdfs) { error = "normalmap needs a texture and a nested bsdf"; return false; }
                 if (d->bsdfs[b.nested].type == KZ_BSDF_NORMALMAP) { error = "nested normalmap is unsupported"; return false; }
-            } else if (b.type != KZ_BSDF_DIFFUSE) { error = "bsdf type outside the hot-path scope"; return false; }
+            } else if (b.type == KZ_BSDF_LAMBERTIAN || b.type == KZ_BSDF_GGX) {
+                if (!texok(b.base_color)) { error = "lambertian / ggx need an albedo texture"; return false; }
+            } else if (b.type < KZ_BSDF_DIFFUSE || b.type > KZ_BSDF_ROUGHDIELECTRIC) { error = "bsdf type outside the hot-path scope"; return false; }
         }
         for (uint32_t i = 0; i < d->n_textures; ++i) {
             const kz_texture_desc &t = d->textures[i];

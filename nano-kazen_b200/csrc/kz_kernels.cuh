@@ -487,8 +487,8 @@ __global__ void k_bsdf_query(KzScene sc, const KzBsdfQuery *qs, uint32_t n, floa
     for (int k = 0; k < 8; ++k) o[k] = 0.f;
     const kz3 wi = mk3(q.wi[0], q.wi[1], q.wi[2]);
     if (q.mode == 2) {
-        kz3 w_o; float pdf; int measure;
-        const kz3 w = bsdf_sample(bc, its, wi, q.s1, mk2(q.s2[0], q.s2[1]), &w_o, &pdf, &measure);
+        kz3 w_o; float pdf, eta_s; int measure;
+        const kz3 w = bsdf_sample(bc, its, wi, q.s1, mk2(q.s2[0], q.s2[1]), &w_o, &pdf, &measure, &eta_s);
         o[0] = w.x; o[1] = w.y; o[2] = w.z;
         if (!iszero(w)) { o[3] = w_o.x; o[4] = w_o.y; o[5] = w_o.z; o[7] = pdf; }
         o[6] = (float)measure;

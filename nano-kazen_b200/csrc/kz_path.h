@@ -102,7 +102,7 @@ KZ_HD int kz_classify(const KzScene &sc, uint32_t geom) {
     const KzMeshRec m = sc.meshes[geom];
     if (m.flags & KZ_MESH_IS_LIGHT) return KZ_CLASS_TERMINAL;
     const int t = sc.bsdfs[m.bsdf].type;
-    return t == KZ_BSDF_DIFFUSE ? KZ_CLASS_DIFFUSE : (t == KZ_BSDF_KISS ? KZ_CLASS_KISS : KZ_CLASS_NORMALMAP);
+    return t == KZ_BSDF_DIFFUSE ? KZ_CLASS_DIFFUSE : (t == KZ_BSDF_KISS ? KZ_CLASS_KISS : (t == KZ_BSDF_NORMALMAP ? KZ_CLASS_NORMALMAP : KZ_CLASS_GENERIC));
 }
 
 /* ---- extend -------------------------------------------------------------------------------- */
@@ -159,7 +159,7 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     if (bounce > 0 && isLight) {   /* integrator.cpp:322-327 */
         const kz3 wi = normalized(its.p - rayO);
         const float lightPdf_ = light_pdf(mesh.inv_area, rayO, its.p, its.sh.n, wi);
-        bsdfWeight = power_heuristic(misc.x, lightPdf_);
+        bsdfWeight = misc.x < 0.f ? 1.f : power_heuristic(misc.x, lightPdf_);
     }
     if (bounce >= I.max_depth) return 0u;          /* depth++ ; while (depth < maxDepth) */
     if (isLight) {       /* integrator.cpp:226-231 */
@@ -240,9 +240,11 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     /* ---- BSDF sampling, integrator.cpp:304-314 ---- */
     const float s1 = kz_next1d(sc, sm);
     const kz2 s2 = kz_next2d(sc, sm);
-    kz3 wo; float bsdfPdf; int measure;
-    const kz3 weight = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &bsdfPdf, &measure);
+    kz3 wo; float bsdfPdf, sampledEta; int measure;
+    const kz3 weight = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &bsdfPdf, &measure, &sampledEta);
     throughput *= weight;
+    eta *= sampledEta;
+    if (measure == KZ_MEASURE_DISCRETE) bsdfPdf = -1.f;      /* flag for the next vertex: bsdfWeight = 1 (integrator.cpp:329-331) */
     st.rng_state[slot] = sm.state; st.dim[slot] = sm.dim;
     st.thr[slot] = mkf4(throughput.x, throughput.y, throughput.z, eta);
     st.L[slot] = mkf4(L.x, L.y, L.z, bsdfWeight);

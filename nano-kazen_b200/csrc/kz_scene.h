@@ -47,7 +47,8 @@ struct KzMeshRec {
 #define KZ_CLASS_DIFFUSE 1
 #define KZ_CLASS_KISS 2
 #define KZ_CLASS_NORMALMAP 3
-#define KZ_NUM_CLASSES 4
+#define KZ_CLASS_GENERIC 4    /* the other BSDF plugins, dispatched at run time */
+#define KZ_NUM_CLASSES 5
 
 struct KzImageRec {
     int32_t  width, height;

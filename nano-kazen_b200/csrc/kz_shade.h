@@ -290,9 +290,256 @@ KZ_HD_NOINLINE kz3 kiss_sample(const kz_bsdf_desc &m, const KzKissParams &kp, Kz
     return kiss_eval(m, kp, b) / pdf;
 }
 
+/* ---- dielectric, mirror, lambertian, ggx, roughconductor, roughplastic, roughdielectric ------------ */
+KZ_HD float fresnel_ext_int(float cosThetaI, float extIOR, float intIOR) {                  /* common.cpp:447-476 */
+    float etaI = extIOR, etaT = intIOR;
+    if (extIOR == intIOR) return 0.0f;
+    if (cosThetaI < 0.0f) { const float t = etaI; etaI = etaT; etaT = t; cosThetaI = -cosThetaI; }
+    const float eta = etaI / etaT, sinThetaTSqr = eta * eta * (1 - cosThetaI * cosThetaI);
+    if (sinThetaTSqr > 1.0f) return 1.0f;
+    const float cosThetaT = sqrtf(1.0f - sinThetaTSqr);
+    const float Rs = (etaI * cosThetaI - etaT * cosThetaT) / (etaI * cosThetaI + etaT * cosThetaT);
+    const float Rp = (etaT * cosThetaI - etaI * cosThetaT) / (etaT * cosThetaI + etaI * cosThetaT);
+    return (Rs * Rs + Rp * Rp) / 2.0f;
+}
+KZ_HD float fresnel_dielectric(float cosThetaI_, float eta, float &cosThetaT_) {            /* common.cpp:493-518 */
+    const float scale = (cosThetaI_ > 0.f) ? 1 / eta : eta, cosThetaTSqr = 1 - (1 - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
+    const float cosThetaI = fabsf(cosThetaI_), cosThetaT = sqrtf(cosThetaTSqr);
+    const float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    const float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
+    return 0.5f * (Rs * Rs + Rp * Rp);
+}
+KZ_HD kz3 refract_dir(kz3 wi, kz3 n, float eta) {                                           /* common.cpp:525-534 */
+    const float cosThetaI = dot(wi, n);
+    if (cosThetaI < 0) eta = 1.0f / eta;
+    const float cosThetaT2 = 1 - (1 - cosThetaI * cosThetaI) * (eta * eta);
+    if (cosThetaT2 <= 0.0f) return mk3(0.0f);
+    const float sign = cosThetaI >= 0.0f ? 1.0f : -1.0f;
+    return n * (-cosThetaI * eta + sign * sqrtf(cosThetaT2)) + wi * eta;
+}
+KZ_HD float tan_theta(kz3 v) { const float t = 1 - v.z * v.z; return t <= 0.0f ? 0.0f : sqrtf(t) / v.z; }   /* frame.h:63-68 */
+KZ_HD kz3 square_to_beckmann(kz2 s, float alpha) {                                          /* warp.cpp:121-125 */
+    const float phi = 2 * KZ_PI * s.x;
+    const float theta = atanf(alpha * sqrtf(logf(1 / (1 - s.y))));
+    return mk3(sinf(theta) * cosf(phi), sinf(theta) * sinf(phi), cosf(theta));
+}
+KZ_HD float square_to_beckmann_pdf(kz3 m, float alpha) {                                    /* warp.cpp:127-130 */
+    const float theta = acosf(m.z / norm(m));
+    const bool ok = fabsf(norm(m) - 1) < KZ_EPSILON && m.z >= 0;
+    return ok ? expf(-powf(tanf(theta), 2.f) / (alpha * alpha)) / (KZ_PI * alpha * alpha * powf(cosf(theta), 3.f)) : 0.f;
+}
+KZ_HD float beckmann_d(kz3 m, float alpha) {                                                /* bsdf.cpp:730-736 */
+    const float temp = tan_theta(m) / alpha, ct = m.z, ct2 = ct * ct;
+    return expf(-temp * temp) / (KZ_PI * alpha * alpha * ct2 * ct2);
+}
+KZ_HD float beckmann_g1(kz3 v, kz3 m, float alpha) {                                        /* bsdf.cpp:739-762 */
+    if (dot(v, m) * v.z <= 0.0f) return 0.0f;
+    const float tanTheta = fabsf(tan_theta(v));
+    if (tanTheta == 0.0f) return 1.0f;
+    const float a = 1.0f / (alpha * tanTheta);
+    if (a >= 1.6f) return 1.0f;
+    const float aSqr = a * a;
+    return (3.535f * a + 2.181f * aSqr) / (1.0f + 2.276f * a + 2.577f * aSqr);
+}
+KZ_HD kz3 fresnel_cond(float c, kz3 eta, kz3 k) {                                           /* bsdf.cpp:718-727 */
+    const kz3 tmp_f = eta * eta + k * k;
+    const kz3 tmp = tmp_f * (c * c);
+    const kz3 e2 = 2.f * eta * c;
+    const kz3 Rparl2 = (tmp - e2 + mk3(1.f)) / (tmp + e2 + mk3(1.f));
+    const kz3 Rperp2 = (tmp_f - e2 + mk3(c * c)) / (tmp_f + e2 + mk3(c * c));
+    return (Rparl2 + Rperp2) * 0.5f;
+}
+KZ_HD float kd_max(const kz_bsdf_desc &m) { return fmaxf(m.albedo[0], fmaxf(m.albedo[1], m.albedo[2])); }
+
+KZ_HD_NOINLINE kz3 extra_eval(const KzScene &sc, const kz_bsdf_desc &m, const KzBRec &b) {
+    const kz3 wi = b.wi, wo = b.wo;
+    switch (m.type) {
+        case KZ_BSDF_LAMBERTIAN:                                                             /* bsdf.cpp:211-221 */
+            if (b.measure != KZ_MEASURE_SOLID_ANGLE || wi.z <= 0 || wo.z <= 0) return mk3(0.f);
+            return kz_tex_uv(sc, m.base_color, b.uv) * KZ_INV_PI * wo.z;
+        case KZ_BSDF_GGX:                                                                    /* bsdf.cpp:640-647 */
+            if (wi.z <= 0 || wo.z <= 0) return mk3(0.f);
+            return ggx_smith_brdf(wi, wo, kz_tex_uv(sc, m.base_color, b.uv), m.alpha, m.anisotropy) * wo.z;
+        case KZ_BSDF_ROUGHCONDUCTOR: {                                                       /* bsdf.cpp:765-775 */
+            if (wi.z <= 0 || wo.z <= 0) return mk3(0.f);
+            const kz3 wh = normalized(wi + wo);
+            const kz3 F = fresnel_cond(dot(wh, wo), mk3(m.eta[0], m.eta[1], m.eta[2]), mk3(m.k[0], m.k[1], m.k[2]));
+            const float D = beckmann_d(wh, m.alpha);
+            const float G = beckmann_g1(wi, wh, m.alpha) * beckmann_g1(wo, wh, m.alpha);
+            return D * F * G / (4.f * wi.z);
+        }
+        case KZ_BSDF_ROUGHPLASTIC: {                                                         /* bsdf.cpp:881-893 */
+            if (wi.z <= 0 || wo.z <= 0) return mk3(0.f);
+            const kz3 kd = mk3(m.albedo[0], m.albedo[1], m.albedo[2]);
+            const float ks = 1 - kd_max(m);
+            const kz3 wh = normalized(wi + wo);
+            const float D = beckmann_d(wh, m.alpha);
+            const float F = fresnel_ext_int(dot(wh, wo), m.ext_ior, m.int_ior);
+            const float G = beckmann_g1(wo, wh, m.alpha) * beckmann_g1(wi, wh, m.alpha);
+            return kd * KZ_INV_PI * wo.z + mk3(ks * (D * F * G) / (4.f * wi.z));
+        }
+        case KZ_BSDF_ROUGHDIELECTRIC: {                                                      /* bsdf.cpp:969-1014 */
+            if (wi.z == 0) return mk3(0.f);
+            const float m_eta = m.int_ior / m.ext_ior, m_invEta = m.ext_ior / m.int_ior;
+            const float cosThetaI = wi.z, cosThetaO = wo.z;
+            const bool reflectS = cosThetaI * cosThetaO > 0.f;
+            const float eta = cosThetaI > 0.f ? m_eta : m_invEta;
+            kz3 wm = reflectS ? normalized(wi + wo) : normalized(wi + wo * eta);
+            wm = wm * (wm.z > 0.f ? 1.f : -1.f);                                             /* math::sign */
+            float ct;
+            const float F = fresnel_dielectric(dot(wi, wm), m_eta, ct);
+            const float D = beckmann_d(wm, m.alpha);
+            const float G = beckmann_g1(wo, wm, m.alpha) * beckmann_g1(wi, wm, m.alpha);
+            if (reflectS) return mk3((F * G * D) / (4.f * fabsf(cosThetaI)));
+            const float denom = dot(wi, wm) + eta * dot(wo, wm);
+            const float value = ((1 - F) * D * G * eta * eta * dot(wi, wm) * dot(wo, wm)) / (cosThetaI * sqr(denom));
+            return mk3(fabsf(value));
+        }
+        default: return mk3(0.f);                                                            /* dielectric, mirror: discrete */
+    }
+}
+KZ_HD_NOINLINE float extra_pdf(const kz_bsdf_desc &m, const KzBRec &b) {
+    const kz3 wi = b.wi, wo = b.wo;
+    switch (m.type) {
+        case KZ_BSDF_LAMBERTIAN:                                                             /* bsdf.cpp:223-239 */
+            if (b.measure != KZ_MEASURE_SOLID_ANGLE || wi.z <= 0 || wo.z <= 0) return 0.f;
+            return KZ_INV_PI * wo.z;
+        case KZ_BSDF_GGX: {                                                                  /* bsdf.cpp:649-657 */
+            if (wi.z <= 0 || wo.z <= 0) return 0.f;
+            const kz3 H = normalized(wi + wo);
+            return ggx_vndf(wi, H, roughness_to_alpha(m.alpha, m.anisotropy)) / (4.0f * dot(wi, H));
+        }
+        case KZ_BSDF_ROUGHCONDUCTOR: {                                                       /* bsdf.cpp:778-785 */
+            if (wi.z <= 0 || wo.z <= 0) return 0.f;
+            const kz3 wh = normalized(wi + wo);
+            return beckmann_d(wh, m.alpha) * wh.z * (1.f / (4.f * dot(wh, wo)));
+        }
+        case KZ_BSDF_ROUGHPLASTIC: {                                                         /* bsdf.cpp:895-903 */
+            if (wi.z <= 0 || wo.z <= 0) return 0.f;
+            const float ks = 1 - kd_max(m);
+            const kz3 wh = normalized(wi + wo);
+            const float Jh = 1.f / (4.f * fabsf(dot(wh, wo)));
+            return ks * beckmann_d(wh, m.alpha) * wh.z * Jh + (1 - ks) * wo.z * KZ_INV_PI;
+        }
+        case KZ_BSDF_ROUGHDIELECTRIC: {                                                      /* bsdf.cpp:1016-1048 */
+            const float m_eta = m.int_ior / m.ext_ior, m_invEta = m.ext_ior / m.int_ior;
+            const float cosThetaI = wi.z, cosThetaO = wo.z;
+            const bool reflectS = cosThetaI * cosThetaO > 0.f;
+            const float eta = cosThetaI > 0.f ? m_eta : m_invEta;
+            kz3 wm; float dwm_dwo;
+            if (reflectS) { wm = normalized(wi + wo); dwm_dwo = 1.0f / (4.0f * dot(wo, wm)); }
+            else {
+                wm = normalized(wi + wo * eta);
+                const float sqrtDenom = dot(wi, wm) + eta * dot(wo, wm);
+                dwm_dwo = (eta * eta * dot(wo, wm)) / (sqrtDenom * sqrtDenom);
+            }
+            wm = wm * (wm.z > 0.f ? 1.f : -1.f);
+            float ct;
+            const float F = fresnel_dielectric(dot(wi, wm), m_eta, ct);
+            float prob = beckmann_d(wm, m.alpha) * wm.z;
+            prob *= reflectS ? F : (1 - F);
+            return fabsf(prob * dwm_dwo);
+        }
+        default: return 0.f;
+    }
+}
+/* returns the weight; *pdf_out = pdf(bRec) as the integrator queries it afterwards (integrator.cpp:314) */
+KZ_HD_NOINLINE kz3 extra_sample(const KzScene &sc, const kz_bsdf_desc &m, KzBRec &b, float sample1, kz2 sample2, float *pdf_out) {
+    *pdf_out = 0.f;
+    kz3 w = mk3(0.f);
+    switch (m.type) {
+        case KZ_BSDF_DIELECTRIC: {                                                           /* bsdf.cpp:118-144 */
+            b.measure = KZ_MEASURE_DISCRETE;
+            const float fr = fresnel_ext_int(b.wi.z, m.ext_ior, m.int_ior);
+            if (sample1 < fr) { b.wo = mk3(-b.wi.x, -b.wi.y, b.wi.z); b.eta = 1.f; return mk3(1.0f); }
+            kz3 n = mk3(0.f, 0.f, 1.f);
+            float factor = m.int_ior / m.ext_ior;
+            if (b.wi.z < 0.f) { factor = m.ext_ior / m.int_ior; n.z = -1.0f; }
+            b.wo = refract_dir(-b.wi, n, factor);
+            b.eta = m.int_ior / m.ext_ior;
+            return mk3(1.0f);
+        }
+        case KZ_BSDF_MIRROR:                                                                 /* bsdf.cpp:176-191 */
+            if (b.wi.z <= 0) return mk3(0.f);
+            b.wo = mk3(-b.wi.x, -b.wi.y, b.wi.z);
+            b.measure = KZ_MEASURE_DISCRETE; b.eta = 1.0f;
+            return mk3(1.0f);
+        case KZ_BSDF_LAMBERTIAN:                                                             /* bsdf.cpp:241-257 */
+            if (b.wi.z <= 0) return mk3(0.f);
+            b.measure = KZ_MEASURE_SOLID_ANGLE;
+            b.wo = square_to_cosine_hemisphere(sample2);
+            b.eta = 1.0f;
+            w = kz_tex_uv(sc, m.base_color, b.uv);
+            break;
+        case KZ_BSDF_GGX: {                                                                  /* bsdf.cpp:659-670 + ggx_brdf.h:175-203 (measure / eta keep their defaults) */
+            if (b.wi.z <= 0) return mk3(0.f);
+            const kz3 albedo = kz_tex_uv(sc, m.base_color, b.uv);
+            const kz2 alpha = roughness_to_alpha(m.alpha, m.anisotropy);
+            const kz3 H = sample_ggx_vndf(b.wi, alpha, sample2);
+            b.wo = reflect3(b.wi, H);
+            const float pdf = ggx_vndf(b.wi, H, alpha) / (4.0f * dot(b.wi, H));
+            const kz3 color = ggx_smith_brdf(b.wi, b.wo, albedo, m.alpha, m.anisotropy);
+            if (b.wo.z <= 0) return mk3(0.f);
+            w = color * b.wo.z / pdf;
+            break;
+        }
+        case KZ_BSDF_ROUGHCONDUCTOR: {                                                       /* bsdf.cpp:788-799 */
+            if (b.wi.z <= 0) return mk3(0.f);
+            const kz3 wh = square_to_beckmann(sample2, m.alpha);
+            b.wo = normalized(reflect3(b.wi, wh));
+            if (b.wo.z <= 0) return mk3(0.f);
+            const float p = extra_pdf(m, b);
+            *pdf_out = p;
+            return extra_eval(sc, m, b) / p;
+        }
+        case KZ_BSDF_ROUGHPLASTIC: {                                                         /* bsdf.cpp:905-918 */
+            if (b.wi.z <= 0) return mk3(0.f);
+            const float ks = 1 - kd_max(m);
+            if (sample1 < ks) {
+                const kz3 wh = square_to_beckmann(sample2, m.alpha);
+                b.wo = normalized((2.f * dot(wh, b.wi) * wh) - b.wi);
+            } else b.wo = square_to_cosine_hemisphere(sample2);
+            if (b.wo.z <= 0) return mk3(0.f);
+            const float p = extra_pdf(m, b);
+            *pdf_out = p;
+            return extra_eval(sc, m, b) / p;
+        }
+        case KZ_BSDF_ROUGHDIELECTRIC: {                                                      /* bsdf.cpp:1050-1096 */
+            const float m_eta = m.int_ior / m.ext_ior, m_invEta = m.ext_ior / m.int_ior;
+            const float alpha = m.alpha * (1.2f - 0.2f * sqrtf(fabsf(b.wi.z)));
+            const kz3 wm = square_to_beckmann(sample2, alpha);
+            const float pdf = square_to_beckmann_pdf(wm, alpha);
+            if (pdf == 0.f) return mk3(0.f);
+            float cosThetaT;
+            const float F = fresnel_dielectric(dot(b.wi, wm), m_eta, cosThetaT);
+            if (!(sample1 > F)) {
+                b.wo = reflect3(b.wi, wm);
+                b.eta = 1.0f;
+                if (b.wi.z * b.wo.z <= 0) return mk3(0.f);
+            } else {
+                if (cosThetaT == 0) return mk3(0.f);
+                const float e = cosThetaT < 0 ? 1.f / m_eta : m_eta;                          /* RoughDielectric::refract, bsdf.cpp:1135-1139 */
+                b.wo = wm * (dot(b.wi, wm) * e + cosThetaT) - b.wi * e;
+                b.eta = cosThetaT < 0.f ? m_eta : m_invEta;
+                if (b.wi.z * b.wo.z >= 0) return mk3(0.f);
+            }
+            const float D = beckmann_d(wm, alpha);
+            const float G = beckmann_g1(b.wo, wm, alpha) * beckmann_g1(b.wi, wm, alpha);
+            w = mk3(fabsf(D * G * dot(b.wi, wm) / (pdf * b.wi.z)));
+            break;
+        }
+        default: return mk3(0.f);
+    }
+    *pdf_out = extra_pdf(m, b);
+    return w;
+}
+
 /* One shading vertex: the hit mesh's BSDF with its (single) optional normal-map wrapper resolved.
  * Supported nesting (everything kazen's scenes use): diffuse | kiss | normalmap(diffuse|kiss). */
 struct KzBsdfCtx {
+    const KzScene *sc;
     const kz_bsdf_desc *outer;     /* mesh BSDF */
     const kz_bsdf_desc *leaf;      /* nested (== outer when not a normal map) */
     KzKissParams kp;               /* leaf kiss parameters at uv */
@@ -306,6 +553,7 @@ struct KzBsdfCtx {
 template <int CLS = -1>
 KZ_HD KzBsdfCtx bsdf_ctx(const KzScene &sc, const KzIts &its) {
     KzBsdfCtx c;
+    c.sc = &sc;
     c.outer = sc.bsdfs + sc.meshes[its.mesh].bsdf;
     c.is_nmap = CLS == KZ_CLASS_NORMALMAP ? true : (CLS >= 0 ? false : c.outer->type == KZ_BSDF_NORMALMAP);
     c.leaf = c.is_nmap ? sc.bsdfs + c.outer->nested : c.outer;
@@ -327,16 +575,19 @@ KZ_HD KzBsdfCtx bsdf_ctx(const KzScene &sc, const KzIts &its) {
 }
 KZ_HD kz3 leaf_eval(const KzBsdfCtx &c, const KzBRec &b) {
     if (c.leaf_type == KZ_BSDF_KISS) return kiss_eval(*c.leaf, c.kp, b);
+    if (c.leaf_type > KZ_BSDF_NORMALMAP) return extra_eval(*c.sc, *c.leaf, b);
     if (b.measure != KZ_MEASURE_SOLID_ANGLE || b.wi.z <= 0 || b.wo.z <= 0) return mk3(0.0f);   /* bsdf.cpp:27-36 */
     return mk3(c.leaf->albedo[0], c.leaf->albedo[1], c.leaf->albedo[2]) * KZ_INV_PI * b.wo.z;
 }
 KZ_HD float leaf_pdf(const KzBsdfCtx &c, const KzBRec &b) {
     if (c.leaf_type == KZ_BSDF_KISS) return kiss_pdf(*c.leaf, c.kp, b);
+    if (c.leaf_type > KZ_BSDF_NORMALMAP) return extra_pdf(*c.leaf, b);
     if (b.measure != KZ_MEASURE_SOLID_ANGLE || b.wi.z <= 0 || b.wo.z <= 0) return 0.0f;        /* bsdf.cpp:39-55 */
     return KZ_INV_PI * b.wo.z;
 }
 KZ_HD kz3 leaf_sample(const KzBsdfCtx &c, KzBRec &b, float s1, kz2 s2, float *pdf_out) {
     if (c.leaf_type == KZ_BSDF_KISS) return kiss_sample(*c.leaf, c.kp, b, s1, s2, pdf_out);
+    if (c.leaf_type > KZ_BSDF_NORMALMAP) return extra_sample(*c.sc, *c.leaf, b, s1, s2, pdf_out);
     *pdf_out = 0.f;                                                                            /* bsdf.cpp:58-75 */
     if (b.wi.z <= 0) return mk3(0.0f);
     b.measure = KZ_MEASURE_SOLID_ANGLE;
@@ -362,12 +613,12 @@ KZ_HD void bsdf_eval_pdf(const KzBsdfCtx &c, const KzIts &its, kz3 wi, kz3 wo, k
 
 /* sample() of the mesh BSDF + the integrator's follow-up pdf(bRec) query (integrator.cpp:307-314).
  * wo is returned in the ORIGINAL shading frame. */
-KZ_HD kz3 bsdf_sample(const KzBsdfCtx &c, const KzIts &its, kz3 wi, float s1, kz2 s2, kz3 *wo, float *pdf, int *measure) {
+KZ_HD kz3 bsdf_sample(const KzBsdfCtx &c, const KzIts &its, kz3 wi, float s1, kz2 s2, kz3 *wo, float *pdf, int *measure, float *eta) {
     KzBRec b; b.wi = wi; b.wo = mk3(0.f); b.uv = its.uv; b.acc_rough = its.acc_rough; b.eta = 1.f; b.measure = KZ_MEASURE_UNKNOWN;
     if (!c.is_nmap || (wi.z > 0 && dot(c.nm_n, wi) <= 0)) {
         float p;
         kz3 w = leaf_sample(c, b, s1, s2, &p);
-        *wo = b.wo; *measure = b.measure;
+        *wo = b.wo; *measure = b.measure; *eta = b.eta;
         /* integrator's pdf(bRec): for a normal map this re-enters NormalMap::pdf with the sampled wo */
         if (c.is_nmap && !iszero(w)) { kz3 f; bsdf_eval_pdf(c, its, wi, b.wo, &f, &p); }
         *pdf = p;
@@ -380,10 +631,10 @@ KZ_HD kz3 bsdf_sample(const KzBsdfCtx &c, const KzIts &its, kz3 wi, float s1, kz
     float p;
     kz3 result = leaf_sample(c, pq, s1, s2, &p);
     *measure = KZ_MEASURE_UNKNOWN;          /* bRec.measure is never written back on this path */
-    *pdf = 0.f;
+    *pdf = 0.f; *eta = 1.f;
     if (!iszero(result)) {
         kz3 w = to_local(its.sh, to_world(c.pert, pq.wo));
-        *wo = w;
+        *wo = w; *eta = pq.eta;
         if (w.z * pq.wo.z <= 0) return mk3(0.f);
         /* integrator's pdf(bRec) with measure == unknown: kiss ignores the measure, diffuse returns 0 */
         KzBRec q = b; q.wo = w;

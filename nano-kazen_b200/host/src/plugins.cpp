@@ -188,6 +188,7 @@ KAZEN_REGISTER_CLASS(BlendTexture, "blend");
 static kz_bsdf_desc blankBsdf(int type) {
     kz_bsdf_desc b; memset(&b, 0, sizeof(b));
     b.type = type; b.base_color = b.roughness = b.metallic = b.normal_map = b.nested = -1;
+    b.int_ior = 1.5046f; b.ext_ior = 1.000277f;
     return b;
 }
 class Diffuse : public BSDF {       /* bsdf.cpp:20-92 */
@@ -258,9 +259,97 @@ public:
 private:
     Texture *m_normalMap = nullptr; BSDF *m_nested = nullptr;
 };
+/* ---- the remaining BSDF plugins (bsdf.cpp:98-276, 629-1145) ---- */
+static float alphaFromRoughness(float roughness) { return std::max(0.001f, roughness * roughness); }     /* bsdf.cpp:696-701 */
+class SimpleBsdf : public BSDF {        /* parameter-only BSDFs share the flatten boilerplate */
+public:
+    int flatten(FlattenCtx &ctx) const override {
+        int k = memoized(ctx, this); if (k >= 0) return k;
+        kz_bsdf_desc b = m_desc;
+        if (m_albedoTex) b.base_color = m_albedoTex->flatten(ctx);
+        ctx.bsdfs.push_back(b);
+        return ctx.memo[this] = (int)ctx.bsdfs.size() - 1;
+    }
+    ~SimpleBsdf() override { delete m_albedoTex; }
+protected:
+    kz_bsdf_desc m_desc = blankBsdf(KZ_BSDF_DIFFUSE);
+    Texture *m_albedoTex = nullptr;
+};
+class Dielectric : public SimpleBsdf {
+public:
+    Dielectric(const PropertyList &p) { m_desc = blankBsdf(KZ_BSDF_DIELECTRIC); m_desc.int_ior = p.getFloat("intIOR", 1.5046f); m_desc.ext_ior = p.getFloat("extIOR", 1.000277f); }
+    std::string toString() const override { return fmt("Dielectric[intIOR=%f, extIOR=%f]", m_desc.int_ior, m_desc.ext_ior); }
+};
+class Mirror : public SimpleBsdf {
+public:
+    Mirror(const PropertyList &) { m_desc = blankBsdf(KZ_BSDF_MIRROR); }
+    std::string toString() const override { return "Mirror[]"; }
+};
+class Lambertian : public SimpleBsdf {
+public:
+    Lambertian(const PropertyList &) { m_desc = blankBsdf(KZ_BSDF_LAMBERTIAN); }
+    void addChild(Object *o) override {
+        if (o->getClassType() != ETexture) throw Exception("addChild is not supported other than albedi maps");
+        delete m_albedoTex; m_albedoTex = static_cast<Texture *>(o);
+    }
+    void activate() override { if (!m_albedoTex) throw Exception("lambertian needs an albedo texture"); }
+    std::string toString() const override { return "Lambertian[]"; }
+};
+class GGX : public SimpleBsdf {
+public:
+    GGX(const PropertyList &p) { m_desc = blankBsdf(KZ_BSDF_GGX); m_desc.alpha = p.getFloat("roughness", 0.5f); m_desc.anisotropy = p.getFloat("anisotropy", 0.f); }
+    void addChild(Object *o) override {
+        if (o->getClassType() != ETexture) throw Exception("addChild is not supported other than albedi maps");
+        delete m_albedoTex; m_albedoTex = static_cast<Texture *>(o);
+    }
+    void activate() override { if (!m_albedoTex) throw Exception("ggx needs an albedo texture"); }
+    std::string toString() const override { return "GGX[]"; }
+};
+class RoughConductor : public SimpleBsdf {
+public:
+    RoughConductor(const PropertyList &p) {
+        m_desc = blankBsdf(KZ_BSDF_ROUGHCONDUCTOR);
+        m_desc.alpha = alphaFromRoughness(p.getFloat("alpha", 0.1f));
+        const std::string mat = p.getString("material", "Au");
+        static const float tab[3][6] = {{0.1431189557f, 0.3749570432f, 1.4424785571f, 3.9831604247f, 2.3857207478f, 1.6032152899f},
+                                        {0.2004376970f, 0.9240334304f, 1.1022119527f, 3.9129485033f, 2.4528477015f, 2.1421879552f},
+                                        {4.3696828663f, 2.9167024892f, 1.6547005413f, 5.2064337956f, 4.2313645277f, 3.7549467933f}};
+        const int k = mat == "Au" ? 0 : (mat == "Cu" ? 1 : (mat == "Cr" ? 2 : -1));
+        if (k < 0) throw Exception("roughconductor: unknown material \"" + mat + "\" (Au | Cu | Cr); the reference leaves eta/k uninitialised here");
+        for (int c = 0; c < 3; ++c) { m_desc.eta[c] = tab[k][c]; m_desc.k[c] = tab[k][3 + c]; }
+    }
+    std::string toString() const override { return fmt("RoughConductor[alpha=%f]", m_desc.alpha); }
+};
+class RoughPlastic : public SimpleBsdf {
+public:
+    RoughPlastic(const PropertyList &p) {
+        m_desc = blankBsdf(KZ_BSDF_ROUGHPLASTIC);
+        m_desc.alpha = alphaFromRoughness(p.getFloat("alpha", 0.1f));
+        m_desc.int_ior = p.getFloat("intIOR", 1.5046f); m_desc.ext_ior = p.getFloat("extIOR", 1.000277f);
+        const Color3 kd = p.getColor("kd", Color3{0.5f, 0.5f, 0.5f});
+        m_desc.albedo[0] = kd.r; m_desc.albedo[1] = kd.g; m_desc.albedo[2] = kd.b;
+    }
+    std::string toString() const override { return fmt("RoughPlastic[alpha=%f]", m_desc.alpha); }
+};
+class RoughDielectric : public SimpleBsdf {
+public:
+    RoughDielectric(const PropertyList &p) {
+        m_desc = blankBsdf(KZ_BSDF_ROUGHDIELECTRIC);
+        m_desc.int_ior = p.getFloat("intIOR", 1.5046f); m_desc.ext_ior = p.getFloat("extIOR", 1.000277f);
+        m_desc.alpha = alphaFromRoughness(p.getFloat("roughness", 0.1f));
+    }
+    std::string toString() const override { return "RoughDielectric"; }
+};
 KAZEN_REGISTER_CLASS(Diffuse, "diffuse");
 KAZEN_REGISTER_CLASS(KazenStandardSurface, "kazenstandard");
 KAZEN_REGISTER_CLASS(NormalMap, "normalmap");
+KAZEN_REGISTER_CLASS(Dielectric, "dielectric");
+KAZEN_REGISTER_CLASS(Mirror, "mirror");
+KAZEN_REGISTER_CLASS(Lambertian, "lambertian");
+KAZEN_REGISTER_CLASS(GGX, "ggx");
+KAZEN_REGISTER_CLASS(RoughConductor, "roughconductor");
+KAZEN_REGISTER_CLASS(RoughPlastic, "roughplastic");
+KAZEN_REGISTER_CLASS(RoughDielectric, "roughdielectric");
 
 /* =============================================================== lights (light.cpp:7-66) */
 class AreaLight : public Light {

@@ -17,7 +17,10 @@ KZ_OK = 0
 KZ_ERR_NO_DEVICE = -2
 
 TEX_CONSTANT, TEX_IMAGE, TEX_BACKGROUND, TEX_COLORRAMP, TEX_BLEND = range(5)
-BSDF_DIFFUSE, BSDF_KISS, BSDF_NORMALMAP = range(3)
+BSDF_DIFFUSE, BSDF_KISS, BSDF_NORMALMAP, BSDF_DIELECTRIC, BSDF_MIRROR, BSDF_LAMBERTIAN, BSDF_GGX, BSDF_ROUGHCONDUCTOR, BSDF_ROUGHPLASTIC, BSDF_ROUGHDIELECTRIC = range(10)
+CONDUCTORS = {"Au": ((0.1431189557, 0.3749570432, 1.4424785571), (3.9831604247, 2.3857207478, 1.6032152899)),
+              "Cu": ((0.2004376970, 0.9240334304, 1.1022119527), (3.9129485033, 2.4528477015, 2.1421879552)),
+              "Cr": ((4.3696828663, 2.9167024892, 1.6547005413), (5.2064337956, 4.2313645277, 3.7549467933))}
 CAM_PERSPECTIVE, CAM_THINLENS = range(2)
 SAMPLER_INDEPENDENT, SAMPLER_STRATIFIED, SAMPLER_CORRELATED, SAMPLER_PMJ02BN = range(4)
 BUILD_HOST_SAH, BUILD_LBVH = 0, 1
@@ -48,7 +51,8 @@ class BsdfDesc(C.Structure):
     _fields_ = [("type", C.c_int32), ("albedo", C.c_float * 3), ("base_color", C.c_int32), ("roughness", C.c_int32),
                 ("metallic", C.c_int32), ("anisotropy", C.c_float), ("specular", C.c_float), ("specular_tint", C.c_float),
                 ("clearcoat", C.c_float), ("clearcoat_roughness", C.c_float), ("sheen", C.c_float), ("sheen_tint", C.c_float),
-                ("normal_map", C.c_int32), ("nested", C.c_int32)]
+                ("normal_map", C.c_int32), ("nested", C.c_int32), ("int_ior", C.c_float), ("ext_ior", C.c_float), ("alpha", C.c_float),
+                ("eta", C.c_float * 3), ("k", C.c_float * 3)]
 
 
 class LightDesc(C.Structure):
@@ -221,6 +225,45 @@ class SceneBuilder:
     def bsdf_normalmap(self, normal_tex, nested):
         b = BsdfDesc(); b.type = BSDF_NORMALMAP; b.normal_map = normal_tex; b.nested = nested
         b.base_color = b.roughness = b.metallic = -1
+        self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    def _blank(self, t):
+        b = BsdfDesc(); b.type = t
+        b.base_color = b.roughness = b.metallic = b.normal_map = b.nested = -1
+        b.int_ior, b.ext_ior = 1.5046, 1.000277
+        return b
+
+    def bsdf_dielectric(self, int_ior=1.5046, ext_ior=1.000277):
+        b = self._blank(BSDF_DIELECTRIC); b.int_ior, b.ext_ior = int_ior, ext_ior
+        self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    def bsdf_mirror(self):
+        self.bsdfs.append(self._blank(BSDF_MIRROR)); return len(self.bsdfs) - 1
+
+    def bsdf_lambertian(self, albedo_tex):
+        b = self._blank(BSDF_LAMBERTIAN); b.base_color = albedo_tex
+        self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    def bsdf_ggx(self, albedo_tex, roughness=0.5, anisotropy=0.0):
+        b = self._blank(BSDF_GGX); b.base_color = albedo_tex; b.alpha = roughness; b.anisotropy = anisotropy
+        self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    @staticmethod
+    def _alpha(roughness):
+        return float(max(np.float32(0.001), np.float32(roughness) * np.float32(roughness)))
+
+    def bsdf_roughconductor(self, alpha=0.1, material="Au"):
+        b = self._blank(BSDF_ROUGHCONDUCTOR); b.alpha = self._alpha(alpha)
+        b.eta[:] = CONDUCTORS[material][0]; b.k[:] = CONDUCTORS[material][1]
+        self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    def bsdf_roughplastic(self, alpha=0.1, int_ior=1.5046, ext_ior=1.000277, kd=(0.5, 0.5, 0.5)):
+        b = self._blank(BSDF_ROUGHPLASTIC); b.alpha = self._alpha(alpha); b.int_ior, b.ext_ior = int_ior, ext_ior
+        b.albedo[:] = [float(c) for c in kd]
+        self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    def bsdf_roughdielectric(self, roughness=0.1, int_ior=1.5046, ext_ior=1.000277):
+        b = self._blank(BSDF_ROUGHDIELECTRIC); b.alpha = self._alpha(roughness); b.int_ior, b.ext_ior = int_ior, ext_ior
         self.bsdfs.append(b); return len(self.bsdfs) - 1
 
     def light(self, radiance, primary_visibility=False):

@@ -91,6 +91,7 @@ struct Bvh2Node {
     float lo[3], hi[3];
     int32_t left;    /* internal: index of left child (right = left+1); leaf: first triangle */
     int32_t count;   /* 0 = internal, >0 = leaf triangle count */
+    int32_t axis;    /* internal: split axis (left child holds the lower centroids) */
 };
 
 struct Accel {
@@ -168,7 +169,7 @@ inline void Accel::build() {
                          [axis](const Ref &x, const Ref &y) { return x.c[axis] < y.c[axis]; });
         int l = (int)nodes.size();
         nodes.push_back(Bvh2Node()); nodes.push_back(Bvh2Node());
-        nodes[j.node].left = l; nodes[j.node].count = 0;
+        nodes[j.node].left = l; nodes[j.node].count = 0; nodes[j.node].axis = axis;
         stack.push_back(Job{l, j.b, mid});
         stack.push_back(Job{l + 1, mid, j.e});
     }
@@ -186,6 +187,8 @@ inline HitRec Accel::traceBvh(const kz_ray &r) const {
     double mag = std::max((double)slack, (double)std::max(std::fabs(org.x), std::max(std::fabs(org.y), std::fabs(org.z))));
     double pad = 1e-5 * mag + 1e-30;
     double o[3] = {org.x, org.y, org.z}, d[3] = {dir.x, dir.y, dir.z};
+    double inv[3];
+    for (int a = 0; a < 3; ++a) inv[a] = d[a] != 0.0 ? 1.0 / d[a] : 0.0;
     int stack[128]; int sp = 0; stack[sp++] = 0;
     while (sp) {
         const Bvh2Node &nd = nodes[stack[--sp]];
@@ -198,7 +201,8 @@ inline HitRec Accel::traceBvh(const kz_ray &r) const {
             if (d[a] == 0.0) {
                 if (o[a] < lo || o[a] > hi) hitbox = false;
             } else {
-                double ta = (lo - o[a]) / d[a], tb = (hi - o[a]) / d[a];
+                /* reciprocal instead of two divisions: the extra rounding (1 ulp of a double) is far inside the 1e-9 margin below */
+                double ta = (lo - o[a]) * inv[a], tb = (hi - o[a]) * inv[a];
                 if (ta > tb) std::swap(ta, tb);
                 ta -= 1e-9 * std::fabs(ta); tb += 1e-9 * std::fabs(tb);
                 if (ta > t0) t0 = ta;
@@ -213,6 +217,8 @@ inline HitRec Accel::traceBvh(const kz_ray &r) const {
                 float t, u, v;
                 if (plueckerIntersect(org, dir, r.tmin, best.t, tri, t, u, v)) considerHit(best, t, u, v, tri.geom, tri.prim);
             }
+        } else if (d[nd.axis] >= 0.0) {      /* near child last on the stack = visited first (order does not change the result) */
+            stack[sp++] = nd.left + 1; stack[sp++] = nd.left;
         } else {
             stack[sp++] = nd.left; stack[sp++] = nd.left + 1;
         }

@@ -295,6 +295,250 @@ inline V3 kissSample(const SceneData &sc, const kz_bsdf_desc &m, BSDFQueryRecord
     return kissEval(sc, m, bRec) / kissPdf(sc, m, bRec);
 }
 
+/* ---- the remaining BSDF plugins ------------------------------------------------- */
+/* common.cpp:447-476 */
+inline float fresnelExtInt(float cosThetaI, float extIOR, float intIOR) {
+    float etaI = extIOR, etaT = intIOR;
+    if (extIOR == intIOR) return 0.0f;
+    if (cosThetaI < 0.0f) { std::swap(etaI, etaT); cosThetaI = -cosThetaI; }
+    float eta = etaI / etaT, sinThetaTSqr = eta * eta * (1 - cosThetaI * cosThetaI);
+    if (sinThetaTSqr > 1.0f) return 1.0f;
+    float cosThetaT = std::sqrt(1.0f - sinThetaTSqr);
+    float Rs = (etaI * cosThetaI - etaT * cosThetaT) / (etaI * cosThetaI + etaT * cosThetaT);
+    float Rp = (etaT * cosThetaI - etaI * cosThetaT) / (etaT * cosThetaI + etaI * cosThetaT);
+    return (Rs * Rs + Rp * Rp) / 2.0f;
+}
+/* common.cpp:493-523 */
+inline float fresnelDielectric(float cosThetaI_, float eta, float &cosThetaT_) {
+    float scale = (cosThetaI_ > 0.f) ? 1 / eta : eta, cosThetaTSqr = 1 - (1 - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
+    float cosThetaI = std::fabs(cosThetaI_), cosThetaT = std::sqrt(cosThetaTSqr);
+    float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
+    return 0.5f * (Rs * Rs + Rp * Rp);
+}
+/* common.cpp:525-534 */
+inline V3 refractDir(const V3 &wi, const V3 &n, float eta) {
+    float cosThetaI = dot(wi, n);
+    if (cosThetaI < 0) eta = 1.0f / eta;
+    float cosThetaT2 = 1 - (1 - cosThetaI * cosThetaI) * (eta * eta);
+    if (cosThetaT2 <= 0.0f) return V3(0.0f);
+    float sign = cosThetaI >= 0.0f ? 1.0f : -1.0f;
+    return n * (-cosThetaI * eta + sign * std::sqrt(cosThetaT2)) + wi * eta;
+}
+/* frame.h:63-68 */
+inline float tanThetaLocal(const V3 &v) { float temp = 1 - v.z * v.z; return temp <= 0.0f ? 0.0f : std::sqrt(temp) / v.z; }
+/* warp.cpp:121-130 */
+inline V3 squareToBeckmann(V2 sample, float alpha) {
+    float phi = 2 * kPi * sample.x;
+    float theta = std::atan(alpha * std::sqrt(std::log(1 / (1 - sample.y))));
+    return V3(std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta));
+}
+inline float squareToBeckmannPdf(const V3 &m, float alpha) {
+    float theta = std::acos(m.z / norm(m));
+    bool ok = std::fabs(norm(m) - 1) < kEpsilon && m.z >= 0;
+    return ok ? std::exp(-std::pow(std::tan(theta), 2.f) / (alpha * alpha)) / (kPi * alpha * alpha * std::pow(std::cos(theta), 3.f)) : 0.f;
+}
+/* bsdf.cpp:730-762 (identical copies at :848-878 and :1103-1133) */
+inline float evalBeckmann(const V3 &m, float alpha) {
+    float temp = tanThetaLocal(m) / alpha, ct = m.z, ct2 = ct * ct;
+    return std::exp(-temp * temp) / (kPi * alpha * alpha * ct2 * ct2);
+}
+inline float smithBeckmannG1(const V3 &v, const V3 &m, float alpha) {
+    if (dot(v, m) * v.z <= 0.0f) return 0.0f;
+    float tanTheta = std::fabs(tanThetaLocal(v));
+    if (tanTheta == 0.0f) return 1.0f;
+    float a = 1.0f / (alpha * tanTheta);
+    if (a >= 1.6f) return 1.0f;
+    float aSqr = a * a;
+    return (3.535f * a + 2.181f * aSqr) / (1.0f + 2.276f * a + 2.577f * aSqr);
+}
+/* bsdf.cpp:718-727 */
+inline V3 fresnelCond(float c, V3 eta, V3 k) {
+    V3 tmp_f = eta * eta + k * k;
+    V3 tmp = tmp_f * (c * c);
+    V3 Rparl2 = (tmp - (2.f * eta * c) + V3(1.f)) / (tmp + (2.f * eta * c) + V3(1.f));
+    V3 Rperp2 = (tmp_f - (2.f * eta * c) + V3(c * c)) / (tmp_f + (2.f * eta * c) + V3(c * c));
+    return (Rparl2 + Rperp2) / 2.0f;
+}
+/* ggx_brdf.h:151-170 with the Fresnel term (evaluateGGXSmithBRDF) is ggxSmithBRDF above */
+
+inline V3 extraEval(const SceneData &sc, const kz_bsdf_desc &m, const BSDFQueryRecord &bRec) {
+    const V3 wi = bRec.wi, wo = bRec.wo;
+    switch (m.type) {
+        case KZ_BSDF_DIELECTRIC: case KZ_BSDF_MIRROR: return V3(0.f);                      /* discrete: bsdf.cpp:108-116,166-174 */
+        case KZ_BSDF_LAMBERTIAN:                                                             /* bsdf.cpp:211-221 */
+            if (bRec.measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return V3(0.f);
+            return evalTextureUV(sc, m.base_color, bRec.uv) * kInvPi * wo.z;
+        case KZ_BSDF_GGX: {                                                                  /* bsdf.cpp:640-647 */
+            if (wi.z <= 0 || wo.z <= 0) return V3(0.f);
+            return ggxSmithBRDF(wi, wo, evalTextureUV(sc, m.base_color, bRec.uv), m.alpha, m.anisotropy) * wo.z;
+        }
+        case KZ_BSDF_ROUGHCONDUCTOR: {                                                       /* bsdf.cpp:765-775 */
+            if (wi.z <= 0 || wo.z <= 0) return V3(0.f);
+            V3 wh = normalized(wi + wo);
+            V3 F = fresnelCond(dot(wh, wo), V3(m.eta[0], m.eta[1], m.eta[2]), V3(m.k[0], m.k[1], m.k[2]));
+            float D = evalBeckmann(wh, m.alpha);
+            float G = smithBeckmannG1(wi, wh, m.alpha) * smithBeckmannG1(wo, wh, m.alpha);
+            return D * F * G / (4.f * wi.z);
+        }
+        case KZ_BSDF_ROUGHPLASTIC: {                                                         /* bsdf.cpp:881-893 */
+            if (wi.z <= 0 || wo.z <= 0) return V3(0.f);
+            V3 kd(m.albedo[0], m.albedo[1], m.albedo[2]);
+            float ks = 1 - maxcoeff(kd);
+            V3 wh = normalized(wi + wo);
+            float D = evalBeckmann(wh, m.alpha);
+            float F = fresnelExtInt(dot(wh, wo), m.ext_ior, m.int_ior);
+            float G = smithBeckmannG1(wo, wh, m.alpha) * smithBeckmannG1(wi, wh, m.alpha);
+            return kd * kInvPi * wo.z + V3(ks * (D * F * G) / (4.f * wi.z));
+        }
+        case KZ_BSDF_ROUGHDIELECTRIC: {                                                      /* bsdf.cpp:969-1014 */
+            if (wi.z == 0) return V3(0.f);
+            const float m_eta = m.int_ior / m.ext_ior, m_invEta = m.ext_ior / m.int_ior;
+            float cosThetaI = wi.z, cosThetaO = wo.z;
+            bool reflectS = cosThetaI * cosThetaO > 0.f;
+            float eta = cosThetaI > 0.f ? m_eta : m_invEta;
+            V3 wm = reflectS ? normalized(wi + wo) : normalized(wi + wo * eta);
+            wm = wm * (wm.z > 0.f ? 1.f : -1.f);                                             /* math::sign, common.h:266-268 */
+            float ct;
+            float F = fresnelDielectric(dot(wi, wm), m_eta, ct);
+            float D = evalBeckmann(wm, m.alpha);
+            float G = smithBeckmannG1(wo, wm, m.alpha) * smithBeckmannG1(wi, wm, m.alpha);
+            if (reflectS) return V3((F * G * D) / (4.f * std::fabs(cosThetaI)));
+            float denom = dot(wi, wm) + eta * dot(wo, wm);
+            float value = ((1 - F) * D * G * eta * eta * dot(wi, wm) * dot(wo, wm)) / (cosThetaI * sqr(denom));
+            return V3(std::fabs(value));
+        }
+    }
+    return V3(0.f);
+}
+inline float extraPdf(const SceneData &sc, const kz_bsdf_desc &m, const BSDFQueryRecord &bRec) {
+    (void)sc;
+    const V3 wi = bRec.wi, wo = bRec.wo;
+    switch (m.type) {
+        case KZ_BSDF_DIELECTRIC: case KZ_BSDF_MIRROR: return 0.f;
+        case KZ_BSDF_LAMBERTIAN:                                                             /* bsdf.cpp:223-239 */
+            if (bRec.measure != ESolidAngle || wi.z <= 0 || wo.z <= 0) return 0.f;
+            return kInvPi * wo.z;
+        case KZ_BSDF_GGX: {                                                                  /* bsdf.cpp:649-657 */
+            if (wi.z <= 0 || wo.z <= 0) return 0.f;
+            V3 H = normalized(wi + wo);
+            return ggxVNDF(wi, H, roughnessToAlpha(m.alpha, m.anisotropy)) / (4.0f * dot(wi, H));
+        }
+        case KZ_BSDF_ROUGHCONDUCTOR: {                                                       /* bsdf.cpp:778-785 */
+            if (wi.z <= 0 || wo.z <= 0) return 0.f;
+            V3 wh = normalized(wi + wo);
+            return evalBeckmann(wh, m.alpha) * wh.z * (1.f / (4.f * dot(wh, wo)));
+        }
+        case KZ_BSDF_ROUGHPLASTIC: {                                                         /* bsdf.cpp:895-903 */
+            if (wi.z <= 0 || wo.z <= 0) return 0.f;
+            float ks = 1 - std::max(m.albedo[0], std::max(m.albedo[1], m.albedo[2]));
+            V3 wh = normalized(wi + wo);
+            float Jh = 1.f / (4.f * std::fabs(dot(wh, wo)));
+            return ks * evalBeckmann(wh, m.alpha) * wh.z * Jh + (1 - ks) * wo.z * kInvPi;
+        }
+        case KZ_BSDF_ROUGHDIELECTRIC: {                                                      /* bsdf.cpp:1016-1048 */
+            const float m_eta = m.int_ior / m.ext_ior, m_invEta = m.ext_ior / m.int_ior;
+            float cosThetaI = wi.z, cosThetaO = wo.z;
+            bool reflectS = cosThetaI * cosThetaO > 0.f;
+            float eta = cosThetaI > 0.f ? m_eta : m_invEta;
+            V3 wm; float dwm_dwo;
+            if (reflectS) { wm = normalized(wi + wo); dwm_dwo = 1.0f / (4.0f * dot(wo, wm)); }
+            else {
+                wm = normalized(wi + wo * eta);
+                float sqrtDenom = dot(wi, wm) + eta * dot(wo, wm);
+                dwm_dwo = (eta * eta * dot(wo, wm)) / (sqrtDenom * sqrtDenom);
+            }
+            wm = wm * (wm.z > 0.f ? 1.f : -1.f);
+            float ct;
+            float F = fresnelDielectric(dot(wi, wm), m_eta, ct);
+            float prob = evalBeckmann(wm, m.alpha) * wm.z;
+            prob *= reflectS ? F : (1 - F);
+            return std::fabs(prob * dwm_dwo);
+        }
+    }
+    return 0.f;
+}
+inline V3 extraSample(const SceneData &sc, const kz_bsdf_desc &m, BSDFQueryRecord &bRec, float sample1, V2 sample2) {
+    switch (m.type) {
+        case KZ_BSDF_DIELECTRIC: {                                                           /* bsdf.cpp:118-144 */
+            bRec.measure = EDiscrete;
+            float fr = fresnelExtInt(bRec.wi.z, m.ext_ior, m.int_ior);
+            if (sample1 < fr) { bRec.wo = V3(-bRec.wi.x, -bRec.wi.y, bRec.wi.z); bRec.eta = 1.f; return V3(1.0f); }
+            V3 n(0.f, 0.f, 1.f);
+            float factor = m.int_ior / m.ext_ior;
+            if (bRec.wi.z < 0.f) { factor = m.ext_ior / m.int_ior; n.z = -1.0f; }
+            bRec.wo = refractDir(-bRec.wi, n, factor);
+            bRec.eta = m.int_ior / m.ext_ior;
+            return V3(1.0f);
+        }
+        case KZ_BSDF_MIRROR:                                                                 /* bsdf.cpp:176-191 */
+            if (bRec.wi.z <= 0) return V3(0.f);
+            bRec.wo = V3(-bRec.wi.x, -bRec.wi.y, bRec.wi.z);
+            bRec.measure = EDiscrete; bRec.eta = 1.0f;
+            return V3(1.0f);
+        case KZ_BSDF_LAMBERTIAN:                                                             /* bsdf.cpp:241-257 */
+            if (bRec.wi.z <= 0) return V3(0.f);
+            bRec.measure = ESolidAngle;
+            bRec.wo = squareToCosineHemisphere(sample2);
+            bRec.eta = 1.0f;
+            return evalTextureUV(sc, m.base_color, bRec.uv);
+        case KZ_BSDF_GGX: {                                                                  /* bsdf.cpp:659-670 + ggx_brdf.h:175-203; measure/eta stay at their defaults */
+            if (bRec.wi.z <= 0) return V3(0.f);
+            V3 albedo = evalTextureUV(sc, m.base_color, bRec.uv);
+            V2 alpha = roughnessToAlpha(m.alpha, m.anisotropy);
+            V3 H = sampleGGXVNDF(bRec.wi, alpha, sample2);                                   /* flip is dead: wi.z > 0 */
+            bRec.wo = reflect(bRec.wi, H);
+            float pdf = ggxVNDF(bRec.wi, H, alpha) / (4.0f * dot(bRec.wi, H));
+            V3 color = ggxSmithBRDF(bRec.wi, bRec.wo, albedo, m.alpha, m.anisotropy);
+            if (bRec.wo.z <= 0) return V3(0.f);
+            return color * bRec.wo.z / pdf;
+        }
+        case KZ_BSDF_ROUGHCONDUCTOR: {                                                       /* bsdf.cpp:788-799 */
+            if (bRec.wi.z <= 0) return V3(0.f);
+            V3 wh = squareToBeckmann(sample2, m.alpha);
+            bRec.wo = normalized(reflect(bRec.wi, wh));
+            if (bRec.wo.z <= 0) return V3(0.f);
+            return extraEval(sc, m, bRec) / extraPdf(sc, m, bRec);
+        }
+        case KZ_BSDF_ROUGHPLASTIC: {                                                         /* bsdf.cpp:905-918 */
+            if (bRec.wi.z <= 0) return V3(0.f);
+            float ks = 1 - std::max(m.albedo[0], std::max(m.albedo[1], m.albedo[2]));
+            if (sample1 < ks) {
+                V3 wh = squareToBeckmann(sample2, m.alpha);
+                bRec.wo = normalized((2.f * dot(wh, bRec.wi) * wh) - bRec.wi);
+            } else bRec.wo = squareToCosineHemisphere(sample2);
+            if (bRec.wo.z <= 0) return V3(0.f);
+            return extraEval(sc, m, bRec) / extraPdf(sc, m, bRec);
+        }
+        case KZ_BSDF_ROUGHDIELECTRIC: {                                                      /* bsdf.cpp:1050-1096 */
+            const float m_eta = m.int_ior / m.ext_ior, m_invEta = m.ext_ior / m.int_ior;
+            float alpha = m.alpha * (1.2f - 0.2f * std::sqrt(std::fabs(bRec.wi.z)));
+            V3 wm = squareToBeckmann(sample2, alpha);
+            float pdf = squareToBeckmannPdf(wm, alpha);
+            if (pdf == 0.f) return V3(0.f);
+            float cosThetaT;
+            float F = fresnelDielectric(dot(bRec.wi, wm), m_eta, cosThetaT);
+            if (!(sample1 > F)) {
+                bRec.wo = reflect(bRec.wi, wm);
+                bRec.eta = 1.0f;
+                if (bRec.wi.z * bRec.wo.z <= 0) return V3(0.f);
+            } else {
+                if (cosThetaT == 0) return V3(0.f);
+                float e = cosThetaT < 0 ? 1.f / m_eta : m_eta;                               /* RoughDielectric::refract, bsdf.cpp:1135-1139 */
+                bRec.wo = wm * (dot(bRec.wi, wm) * e + cosThetaT) - bRec.wi * e;
+                bRec.eta = cosThetaT < 0.f ? m_eta : m_invEta;
+                if (bRec.wi.z * bRec.wo.z >= 0) return V3(0.f);
+            }
+            float D = evalBeckmann(wm, alpha);
+            float G = smithBeckmannG1(bRec.wo, wm, alpha) * smithBeckmannG1(bRec.wi, wm, alpha);
+            return V3(std::fabs(D * G * dot(bRec.wi, wm) / (pdf * bRec.wi.z)));
+        }
+    }
+    return V3(0.f);
+}
+
 /* bsdf.cpp:366-374 */
 inline Frame normalMapFrame(const Intersection &its, V3 n) {
     Frame r;
@@ -323,6 +567,7 @@ inline V3 bsdfEval(const SceneData &sc, int b, const BSDFQueryRecord &bRec) {
             pq.uv = bRec.uv; pq.measure = bRec.measure; pq.eta = bRec.eta;
             return bsdfEval(sc, m.nested, pq);
         }
+        default: return extraEval(sc, m, bRec);
     }
     return V3(0.f);
 }
@@ -345,6 +590,7 @@ inline float bsdfPdf(const SceneData &sc, int b, const BSDFQueryRecord &bRec) {
             pq.uv = bRec.uv; pq.measure = bRec.measure; pq.eta = bRec.eta;
             return bsdfPdf(sc, m.nested, pq);
         }
+        default: return extraPdf(sc, m, bRec);
     }
     return 0.f;
 }
@@ -378,6 +624,7 @@ inline V3 bsdfSample(const SceneData &sc, int b, BSDFQueryRecord &bRec, float s1
             }
             return result;
         }
+        default: return extraSample(sc, m, bRec, s1, s2);
     }
     return V3(0.f);
 }

@@ -116,8 +116,8 @@ int kzemu_bsdf_query(kzemu *e, int mesh_bsdf, int mode, const float wi[3], const
     KzBsdfCtx bc = bsdf_ctx(sc, its);
     for (int i = 0; i < 8; ++i) out[i] = 0.f;
     if (mode == 2) {
-        kz3 w_o; float pdf; int measure;
-        kz3 w = bsdf_sample(bc, its, mk3(wi[0], wi[1], wi[2]), sample1, mk2(sample2[0], sample2[1]), &w_o, &pdf, &measure);
+        kz3 w_o; float pdf, eta_s; int measure;
+        kz3 w = bsdf_sample(bc, its, mk3(wi[0], wi[1], wi[2]), sample1, mk2(sample2[0], sample2[1]), &w_o, &pdf, &measure, &eta_s);
         out[0] = w.x; out[1] = w.y; out[2] = w.z;
         if (!iszero(w)) { out[3] = w_o.x; out[4] = w_o.y; out[5] = w_o.z; out[7] = pdf; }
         out[6] = (float)measure;

@@ -149,6 +149,52 @@ def cornell_scene(width=64, height=64, spp=16, sampler="stratified", with_textur
     return sb
 
 
+def gallery_scene(width=64, height=48, spp=16, sampler="stratified", max_depth=6):
+    """Every remaining BSDF plugin in one closed room: dielectric sphere, mirror wall, lambertian (textured) floor,
+    ggx block, roughconductor / roughplastic / roughdielectric spheres, plus a normal-mapped roughplastic."""
+    sb = pk.SceneBuilder()
+    rng = np.random.default_rng(21)
+    img = rng.uniform(0.2, 0.9, (16, 16, 3)).astype(np.float32)
+    white = sb.bsdf_diffuse((0.7, 0.7, 0.7))
+    lamb = sb.bsdf_lambertian(sb.tex_image(img, scale=4.0, srgb=False))
+    mirror = sb.bsdf_mirror()
+    glass = sb.bsdf_dielectric()
+    ggx = sb.bsdf_ggx(sb.tex_constant((0.9, 0.6, 0.3)), roughness=0.4, anisotropy=0.2)
+    gold = sb.bsdf_roughconductor(0.3, "Au")
+    plastic = sb.bsdf_roughplastic(0.25, kd=(0.2, 0.3, 0.6))
+    frosted = sb.bsdf_roughdielectric(0.35)
+    nm = np.zeros((8, 8, 3), np.float32); nm[..., 0] = 0.5 + 0.15 * rng.uniform(-1, 1, (8, 8)); nm[..., 1] = 0.5 + 0.15 * rng.uniform(-1, 1, (8, 8)); nm[..., 2] = 0.95
+    bumpy = sb.bsdf_normalmap(sb.tex_image(nm, scale=2.0, srgb=False), sb.bsdf_roughplastic(0.2, kd=(0.6, 0.2, 0.2)))
+    for (a, b, c, d, m) in [
+        ((-2, -1, -1), (2, -1, -1), (2, -1, 1.5), (-2, -1, 1.5), lamb),         # floor
+        ((-2, 1.2, -1), (-2, 1.2, 1.5), (2, 1.2, 1.5), (2, 1.2, -1), white),    # ceiling
+        ((-2, -1, 1.5), (2, -1, 1.5), (2, 1.2, 1.5), (-2, 1.2, 1.5), mirror),   # back wall: mirror
+        ((-2, -1, -1), (-2, -1, 1.5), (-2, 1.2, 1.5), (-2, 1.2, -1), white),
+        ((2, -1, -1), (2, 1.2, -1), (2, 1.2, 1.5), (2, -1, 1.5), white),
+    ]:
+        P, F = orient(*quad(a, b, c, d), (0, 0, 0.2), away=False)
+        if m == lamb:
+            sb.mesh(P, F, m, uvs=np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32), normals=np.tile(np.array([[0, 1, 0]], np.float32), (4, 1)))
+        else:
+            sb.mesh(P, F, m)
+    for k, m in enumerate((glass, gold, plastic, frosted, bumpy)):
+        P, N, UV, F = uv_sphere((-1.4 + 0.7 * k, -0.65, 0.3 + 0.15 * (k % 2)), 0.33, nu=20, nv=10)
+        sb.mesh(P, F, m, normals=N, uvs=UV)
+    bx = np.array([[-0.3, -1, -0.6], [0.3, -1, -0.6], [0.3, -1, -0.2], [-0.3, -1, -0.2], [-0.3, -0.8, -0.6], [0.3, -0.8, -0.6], [0.3, -0.8, -0.2], [-0.3, -0.8, -0.2]], np.float32)
+    bf = np.array([[4, 5, 6], [7, 4, 6], [0, 1, 5], [4, 0, 5], [1, 2, 6], [5, 1, 6], [2, 3, 7], [6, 2, 7], [3, 0, 4], [7, 3, 4]], np.uint32)
+    bx, bf = orient(bx, bf, (0, -0.9, -0.4), away=True)
+    sb.mesh(bx, bf, ggx, uvs=np.zeros((8, 2), np.float32), normals=None)
+    lt = sb.light((14.0, 13.0, 11.0))
+    P, F = orient(*quad((-0.5, 1.18, 0.0), (0.5, 1.18, 0.0), (0.5, 1.18, 0.8), (-0.5, 1.18, 0.8)), (0, 0, 0.2), away=False)
+    sb.mesh(P, F, white, light=lt)
+    sb.background = sb.tex_background(1.0, sb.tex_constant((0.05, 0.06, 0.08)))
+    sb.set_camera(width, height, 50.0, pk.lookat((0, 0.1, -3.2), (0, -0.3, 0.3), (0, 1, 0)), near=0.1, far=100.0)
+    sb.set_sampler(sampler, spp)
+    sb.set_filter("gaussian")
+    sb.set_integrator(max_depth=max_depth)
+    return sb
+
+
 def rel_mse(a, b, eps=1e-2):
     """per-channel relative MSE of image a against reference b"""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)

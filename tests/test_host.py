@@ -32,7 +32,8 @@ def test_registered_plugin_names(host):
     names = set(host.host_registered_plugins())
     # every plugin on the hot path keeps kazen's registered name; gpu_bvh is the new accel plugin
     for n in ("scene obj diffuse kazenstandard normalmap area perspective thinlens independent stratified correlated pmj02bn "
-              "constanttexture imagetexture background colorramp blend gaussian mitchell tent box path_mis gpu_bvh").split():
+              "constanttexture imagetexture background colorramp blend gaussian mitchell tent box path_mis gpu_bvh "
+              "dielectric mirror lambertian ggx roughconductor roughplastic roughdielectric").split():
         assert n in names
 
 
@@ -146,6 +147,34 @@ def test_fallback_pmj_tables_are_stratified(host):
         for (a, b) in ((64, 64), (4096, 1), (1, 4096), (16, 256)):
             idx = (np.floor(q[:, 0] * a) * b + np.floor(q[:, 1] * b)).astype(np.int64)
             assert len(np.unique(idx)) == 4096
+
+
+def test_extra_bsdf_plugins_from_xml(host, tmp_path):
+    """SURVEY 8(f)-1 plugins keep kazen's property names and defaults (bsdf.cpp:100-106,632-633,696-714,818-842,951-961)"""
+    (tmp_path / "q.obj").write_text("v -1 -1 0\nv 1 -1 0\nv 1 1 0\nv -1 1 0\nf 1 2 3 4\n")
+    bs = ['<bsdf type="dielectric"/>', '<bsdf type="dielectric"><float name="intIOR" value="1.33"/></bsdf>', '<bsdf type="mirror"/>',
+          '<bsdf type="lambertian"><texture type="constanttexture"><color name="color" value="0.1 0.2 0.3"/></texture></bsdf>',
+          '<bsdf type="ggx"><float name="roughness" value="0.3"/><texture type="constanttexture"/></bsdf>',
+          '<bsdf type="roughconductor"><string name="material" value="Cu"/><float name="alpha" value="0.2"/></bsdf>',
+          '<bsdf type="roughplastic"><color name="kd" value="0.2 0.3 0.4"/></bsdf>', '<bsdf type="roughdielectric"/>']
+    xml = "<scene><integrator type='path_mis'/><camera type='perspective'/>" + "".join(
+        f"<mesh type='obj'><string name='filename' value='q.obj'/>{b}</mesh>" for b in bs) + "</scene>"
+    (tmp_path / "s.xml").write_text(xml)
+    hs = host.HostScene(str(tmp_path / "s.xml"))
+    d = hs.desc
+    B = [d.bsdfs[d.meshes[i].bsdf] for i in range(d.n_meshes)]
+    assert [b.type for b in B] == [pk.BSDF_DIELECTRIC, pk.BSDF_DIELECTRIC, pk.BSDF_MIRROR, pk.BSDF_LAMBERTIAN, pk.BSDF_GGX, pk.BSDF_ROUGHCONDUCTOR,
+                                   pk.BSDF_ROUGHPLASTIC, pk.BSDF_ROUGHDIELECTRIC]
+    assert abs(B[0].int_ior - 1.5046) < 1e-6 and abs(B[0].ext_ior - 1.000277) < 1e-6 and abs(B[1].int_ior - 1.33) < 1e-6
+    assert d.textures[B[3].base_color].type == pk.TEX_CONSTANT and abs(d.textures[B[3].base_color].color[1] - 0.2) < 1e-7
+    assert abs(B[4].alpha - 0.3) < 1e-7 and B[4].anisotropy == 0.0
+    assert abs(B[5].alpha - 0.04) < 1e-7 and np.allclose(list(B[5].eta), pk.CONDUCTORS["Cu"][0]) and np.allclose(list(B[5].k), pk.CONDUCTORS["Cu"][1])
+    assert abs(B[6].alpha - 0.01) < 1e-7 and np.allclose(list(B[6].albedo), (0.2, 0.3, 0.4))
+    assert abs(B[7].alpha - 0.01) < 1e-7
+    hs.close()
+    (tmp_path / "bad.xml").write_text(xml.replace('value="Cu"', 'value="Zz"'))
+    with pytest.raises(RuntimeError, match="unknown material"):
+        host.HostScene(str(tmp_path / "bad.xml"))
 
 
 def test_cli_fails_loudly_without_gpu(host):

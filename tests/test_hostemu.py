@@ -133,3 +133,40 @@ def test_render_is_shardable(kzo, emu):
     tiles = E.render(rect=(0, 0, 10, 24)) + E.render(rect=(10, 0, 24, 11)) + E.render(rect=(10, 11, 24, 24))
     assert np.allclose(whole, tiles, rtol=1e-5, atol=1e-6)
     O.close(); E.close()
+
+
+def test_extra_bsdf_queries(kzo, emu):
+    """dielectric / mirror / lambertian / ggx / roughconductor / roughplastic / roughdielectric + normal-mapped
+    roughplastic, eval / pdf / sample, device routines vs oracle"""
+    sb = scenes.gallery_scene(8, 8, 1)
+    O, E = _pair(kzo, emu, sb)
+    rng = np.random.default_rng(13)
+    checked = 0
+    for bsdf in range(len(sb.bsdfs)):
+        if not any(m.bsdf == bsdf for m in sb.meshes):
+            continue
+        for _ in range(60):
+            wi = rng.normal(size=3); wi[2] = (abs(wi[2]) + 0.05) * rng.choice([1, 1, 1, -1]); wi /= np.linalg.norm(wi)
+            wo = rng.normal(size=3); wo[2] = (abs(wo[2]) + 0.02) * rng.choice([1, 1, -1]); wo /= np.linalg.norm(wo)
+            uv = rng.uniform(0, 1, 2); s1 = float(rng.uniform()); s2 = rng.uniform(0.001, 0.999, 2)
+            for mode in (0, 1, 2):
+                a = O.bsdf_query(bsdf, mode, wi, wo, uv, 0.0, s1, s2)
+                b = E.bsdf_query(bsdf, mode, wi, wo, uv, 0.0, s1, s2)
+                n = 3 if mode == 0 else (1 if mode == 1 else 7)
+                assert np.allclose(a[:n], b[:n], rtol=5e-4, atol=2e-6), (sb.bsdfs[bsdf].type, mode, a, b)
+                checked += 1
+    assert checked > 1000
+    O.close(); E.close()
+
+
+def test_extra_bsdf_render_matches_oracle(kzo, emu):
+    sb = scenes.gallery_scene(40, 30, 16)
+    O, E = _pair(kzo, emu, sb)
+    fo, fe = O.render(), E.render()
+    ro, _ = O.resolve(fo); re, _ = O.resolve(fe)
+    assert np.allclose(fo[..., 3], fe[..., 3], rtol=1e-5, atol=1e-6)
+    assert scenes.rel_mse(re, ro).max() < 1e-5
+    assert ro.mean() > 0.02
+    so, se = O.stats(), E.stats()
+    assert so["paths"] == se["paths"] and abs(so["vertices"] - se["vertices"]) <= 2e-4 * so["vertices"]
+    O.close(); E.close()
