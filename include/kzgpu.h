@@ -175,12 +175,21 @@ typedef struct kz_sampler_desc {
     const uint32_t *pmj02bn;        /* [5][65536][2]            */
 } kz_sampler_desc;
 
-/* PathMisIntegrator properties (integrator.cpp:187-193). */
+enum kz_integrator_type {
+    KZ_INTEGRATOR_PATH_MIS  = 0,   /* "path_mis"   integrator.cpp:185-355 (the hot path)         */
+    KZ_INTEGRATOR_NORMALS   = 1,   /* "normals"    integrator.cpp:11-34             */
+    KZ_INTEGRATOR_AO        = 2,   /* "ao"         integrator.cpp:37-70                          */
+    KZ_INTEGRATOR_WHITTED   = 3,   /* "whitted"    integrator.cpp:74-134                         */
+    KZ_INTEGRATOR_PATH_MATS = 4    /* "path_mats"  integrator.cpp:137-181                        */
+};
+
+/* PathMisIntegrator properties (integrator.cpp:187-193); the other integrators have none. */
 typedef struct kz_integrator_desc {
     int32_t max_depth;
     float   trace_bias;
     int32_t regularization;
     float   accumulated_roughness;
+    int32_t type;                  /* kz_integrator_type */
 } kz_integrator_desc;
 
 /* Reconstruction filter tabulated as ImageBlock does (block.cpp:13-21). */

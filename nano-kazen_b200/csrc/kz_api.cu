@@ -225,6 +225,7 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
     const int max_depth = sc.integrator.max_depth;
     /* the pass after the last vertex only resolves "miss -> background" (integrator.cpp:315-318) */
     const int last_pass = sc.background >= 0 ? max_depth : max_depth - 1;
+    const bool alt = sc.integrator.type != KZ_INTEGRATOR_PATH_MIS;
     Timed total_t(d, s, CAT_TOTAL);
     for (unsigned long long first = 0; first < total; first += d.pool_cap) {
         ch.first = first;
@@ -235,6 +236,37 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
             k_raygen<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q.ext[0], ch);
             d.launches += 2;
         }
+        if (alt) {
+            /* normals / ao: one pass; whitted / path_mats: unbounded loops ended by Russian roulette -- the only place the host
+             * looks at a queue count (every 8 passes), because these loops have no a-priori length */
+            const int passes = (sc.integrator.type == KZ_INTEGRATOR_NORMALS || sc.integrator.type == KZ_INTEGRATOR_AO) ? 1 : 4096;
+            for (int b = 0; b < passes; ++b) {
+                const int cur = b & 1, nxt = cur ^ 1;
+                {
+                    Timed t(d, s, CAT_TRACE);
+                    k_bounce_reset<<<1, 32, 0, s>>>(d.ctl, nxt);
+                    if (b == 0) k_extend<true><<<d.grid_extend0, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur);
+                    else k_extend<false><<<d.grid_extend, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur);
+                    d.launches += 2;
+                }
+                {
+                    Timed t(d, s, CAT_SHADE);
+                    k_shade<KZ_CLASS_GENERIC><<<d.grid_shade[4], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b);
+                    ++d.launches;
+                }
+                if (sc.integrator.type == KZ_INTEGRATOR_AO || sc.integrator.type == KZ_INTEGRATOR_WHITTED) {
+                    Timed t(d, s, CAT_TRACE);
+                    k_shadow<<<d.grid_shadow, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt);
+                    ++d.launches;
+                }
+                if (passes > 1 && (b & 7) == 7) {
+                    unsigned long long left = 0;
+                    KZ_CUDA(ctx, cudaMemcpyAsync(&left, &d.ctl->ext_shadow[nxt], sizeof(left), cudaMemcpyDeviceToHost, s));
+                    KZ_CUDA(ctx, cudaStreamSynchronize(s));
+                    if ((left & 0xFFFFFFFFull) == 0ull) break;
+                }
+            }
+        } else
         for (int b = 0; b <= last_pass; ++b) {
             const int cur = b & 1, nxt = cur ^ 1;
             {

@@ -134,6 +134,7 @@ struct KzHostScene {
         if (sc.background >= (int)d->n_textures) { error = "background texture out of range"; return false; }
         sc.camera = d->camera;
         sc.integrator = d->integrator;
+        if (sc.integrator.type < KZ_INTEGRATOR_PATH_MIS || sc.integrator.type > KZ_INTEGRATOR_PATH_MATS) { error = "unknown integrator type"; return false; }
         sc.filter = d->filter;
         sc.border = (int32_t)ceilf(d->filter.radius - 0.5f);
         sc.sampler_type = d->sampler.type;

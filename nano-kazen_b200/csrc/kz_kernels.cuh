@@ -291,7 +291,7 @@ struct KzExtendJob {
         KzHit h = hit;
         if (FIRST) {
             if (retraced) { if (h.geom == KZ_INVALID_ID) h = first_hit; }     /* a miss keeps the light hit */
-            else if (h.geom != KZ_INVALID_ID) {
+            else if (h.geom != KZ_INVALID_ID && sc.integrator.type == KZ_INTEGRATOR_PATH_MIS) {
                 const uint32_t fl = sc.meshes[h.geom].flags;
                 if ((fl & KZ_MESH_IS_LIGHT) && !(fl & KZ_MESH_LIGHT_VISIBLE)) {
                     /* integrator.cpp:214-219: one re-trace from its.p + eps*d with a default Ray3f */
@@ -354,7 +354,7 @@ struct KzWalk {
         ++seg;
         if (h.geom == KZ_INVALID_ID) return 0;
         const uint32_t fl = sc.meshes[h.geom].flags;
-        if (!(fl & KZ_MESH_IS_LIGHT) || (fl & KZ_MESH_LIGHT_VISIBLE)) return 1;
+        if (!(fl & KZ_MESH_IS_LIGHT) || (fl & KZ_MESH_LIGHT_VISIBLE) || sc.integrator.type != KZ_INTEGRATOR_PATH_MIS) return 1;     /* ao / whitted: any hit occludes */
         if (seg > 4096) return 0;
         o = o + d * (h.t + eps);
         tmax = tmax - h.t;

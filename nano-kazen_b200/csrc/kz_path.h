@@ -98,6 +98,7 @@ KZ_HD void kz_raygen_item(const KzScene &sc, const KzPathState &st, uint32_t slo
 }
 
 KZ_HD int kz_classify(const KzScene &sc, uint32_t geom) {
+    if (sc.integrator.type != KZ_INTEGRATOR_PATH_MIS) return KZ_CLASS_GENERIC;     /* the other integrators are not material sorted */
     if (geom == KZ_INVALID_ID) return KZ_CLASS_TERMINAL;
     const KzMeshRec m = sc.meshes[geom];
     if (m.flags & KZ_MESH_IS_LIGHT) return KZ_CLASS_TERMINAL;
@@ -111,7 +112,7 @@ KZ_HD int kz_extend_item(const KzScene &sc, const KzStackRef &stk, const KzPathS
     const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
     KzHit h = kz_trace(sc, stk, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, false);
     cnt.rays_ext += 1;
-    if (bounce == 0 && h.geom != KZ_INVALID_ID) {
+    if (bounce == 0 && h.geom != KZ_INVALID_ID && sc.integrator.type == KZ_INTEGRATOR_PATH_MIS) {
         const KzMeshRec m = sc.meshes[h.geom];
         if ((m.flags & KZ_MESH_IS_LIGHT) && !(m.flags & KZ_MESH_LIGHT_VISIBLE)) {
             /* integrator.cpp:214-219: one re-trace from its.p + eps*d; a miss keeps the light hit */
@@ -131,9 +132,12 @@ KZ_HD int kz_extend_item(const KzScene &sc, const KzStackRef &stk, const KzPathS
 }
 
 /* ---- shade --------------------------------------------------------------------------------- */
+KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &st, uint32_t slot, int bounce, KzCounters &cnt);
+
 /* CLS = material class of the queue this item was sorted into (-1: unknown, resolve at run time) */
 template <int CLS = -1>
 KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t slot, int bounce, KzCounters &cnt) {
+    if ((CLS < 0 || CLS == KZ_CLASS_GENERIC) && sc.integrator.type != KZ_INTEGRATOR_PATH_MIS) return kz_shade_alt_item(sc, st, slot, bounce, cnt);
     const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
     const kz3 rayO = mk3(ro.x, ro.y, ro.z), rayD = mk3(rd.x, rd.y, rd.z);
     const KzF4 hv = st.hit[slot];
@@ -256,6 +260,127 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     return flags | KZ_SHADE_CONTINUE;
 }
 
+/* ---- the other integrators: normals / ao / whitted / path_mats, integrator.cpp:11-181 -------------------- */
+KZ_HD kz3 square_to_uniform_hemisphere(kz2 s) {            /* warp.cpp:68-79 */
+    const float z = s.x, tmp = sqrtf(1.0f - z * z), phi = 2.0f * KZ_PI * s.y;
+    return mk3(cosf(phi) * tmp, sinf(phi) * tmp, z);
+}
+/* One loop iteration of the selected integrator; thr = running weight, L = accumulated colour.  Every hit (and miss) goes
+ * through this routine: these integrators are not material sorted. */
+KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &st, uint32_t slot, int bounce, KzCounters &cnt) {
+    const int type = sc.integrator.type;
+    const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+    const kz3 rayO = mk3(ro.x, ro.y, ro.z), rayD = mk3(rd.x, rd.y, rd.z);
+    const KzF4 hv = st.hit[slot];
+    KzHit h; h.t = hv.x; h.u = hv.y; h.v = hv.z; h.prim = kz_f2u(hv.w); h.geom = st.hit_geom[slot];
+    if (h.geom == KZ_INVALID_ID) return 0u;                /* every one of them returns what it has on a miss */
+    KzF4 thr4 = st.thr[slot], L4 = st.L[slot];
+    kz3 weight = mk3(thr4.x, thr4.y, thr4.z), L = mk3(L4.x, L4.y, L4.z);
+    KzIts its; its.acc_rough = 0.f;
+    fill_intersection(sc, h, its, mk3(0.f));
+    const KzMeshRec mesh = sc.meshes[its.mesh];
+    if (type == KZ_INTEGRATOR_NORMALS) {                   /* integrator.cpp:19-29 */
+        st.L[slot] = mkf4(fabsf(its.geo_n.x), fabsf(its.geo_n.y), fabsf(its.geo_n.z), 1.f);
+        return 0u;
+    }
+    KzSampler sm;
+    sm.state = st.rng_state[slot]; sm.inc = st.rng_inc[slot]; sm.dim = st.dim[slot];
+    const uint32_t pix = st.pix[slot];
+    sm.px = (int32_t)(pix & 0xFFFFu); sm.py = (int32_t)(pix >> 16); sm.sample_index = st.sidx[slot];
+    if (type == KZ_INTEGRATOR_AO) {                        /* integrator.cpp:43-62 */
+        const kz3 sample = square_to_uniform_hemisphere(kz_next2d(sc, sm));
+        kz3 point = to_world(its.sh, sample);
+        st.sray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, KZ_EPSILON);
+        st.sray_d[slot] = mkf4(point.x, point.y, point.z, KZ_INF);
+        const float cosTheta = dot(normalized(point), normalized(its.sh.n));
+        const float v = (cosTheta / KZ_PI) / (0.5f * KZ_INV_PI);
+        st.pending[slot] = mkf4(v, v, v, 0.f);
+        return KZ_SHADE_SHADOW;
+    }
+    const kz3 wiLocal = to_local(its.sh, -rayD);
+    kz3 Le = mk3(0.f);
+    if (mesh.flags & KZ_MESH_IS_LIGHT) {
+        const kz3 lwi = normalized(its.p - rayO);
+        if (dot(its.sh.n, -lwi) > 0.f) { const kz_light_desc l = sc.lights[mesh.light]; Le = mk3(l.radiance[0], l.radiance[1], l.radiance[2]); }
+    }
+    uint32_t flags = 0u;
+    if (type == KZ_INTEGRATOR_WHITTED) {                   /* integrator.cpp:80-128 with the recursion unrolled */
+        const KzBsdfCtx bc = bsdf_ctx(sc, its);
+        if (!bc.is_nmap && bc.leaf_type == KZ_BSDF_DIFFUSE) {            /* BSDF::isDiffuse(), bsdf.cpp:77 */
+            L += weight * Le;
+            const float rnd = kz_next1d(sc, sm);
+            if (sc.n_light_meshes > 0) {
+                const uint32_t nl = (uint32_t)sc.n_light_meshes;
+                uint32_t index = (uint32_t)floorf((float)nl * rnd);
+                if (index > nl - 1) index = nl - 1;
+                const KzMeshRec lm = sc.meshes[sc.light_meshes[index]];
+                const uint32_t tri = cdf_sample(sc.light_cdf + lm.cdf_offset, lm.n_triangles, kz_next1d(sc, sm));
+                const float su0 = sqrtf(kz_next1d(sc, sm));
+                const float u = 1 - su0, v = kz_next1d(sc, sm) * su0;
+                const uint32_t *F = sc.indices + 3 * (size_t)(lm.index_offset + tri);
+                const kz3 p0 = kz_vpos(sc, lm, F[0]), p1 = kz_vpos(sc, lm, F[1]), p2 = kz_vpos(sc, lm, F[2]);
+                const kz3 lp = p0 + u * (p1 - p0) + v * (p2 - p0);
+                kz3 ln;
+                if (lm.flags & KZ_MESH_HAS_NORMALS) { const kz3 n0 = kz_vnrm(sc, lm, F[0]), n1 = kz_vnrm(sc, lm, F[1]), n2 = kz_vnrm(sc, lm, F[2]); ln = n0 + u * (n1 - n0) + v * (n2 - n0); }
+                else ln = normalized(cross(p1 - p0, p2 - p0));
+                const kz3 lwi = normalized(lp - its.p);
+                const float dist = norm(lp - its.p);
+                const float lpdf = light_pdf(lm.inv_area, its.p, lp, ln, lwi);
+                if (lpdf > 0.f && !isnan(lpdf) && !isinf(lpdf)) {
+                    const kz_light_desc l = sc.lights[lm.light];
+                    const kz3 Ls = mk3(l.radiance[0], l.radiance[1], l.radiance[2]) / lpdf;
+                    float cosTheta = to_local(its.sh, lwi).z;
+                    if (cosTheta < 0.f) cosTheta = 0.f;
+                    kz3 f; float pdf_unused;
+                    bsdf_eval_pdf(bc, its, wiLocal, to_local(its.sh, lwi), &f, &pdf_unused);
+                    const kz3 Lr = weight * (f * Ls * cosTheta) / (1.0f / (float)nl);
+                    if (!iszero(Lr)) {
+                        st.sray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, 0.f);          /* Ray3f(ref, wi, 0, dist): light.cpp:24 */
+                        st.sray_d[slot] = mkf4(lwi.x, lwi.y, lwi.z, dist);
+                        st.pending[slot] = mkf4(Lr.x, Lr.y, Lr.z, 0.f);
+                        flags |= KZ_SHADE_SHADOW;
+                    }
+                }
+            }
+            st.L[slot] = mkf4(L.x, L.y, L.z, 1.f);
+            return flags;
+        }
+        const float s1 = kz_next1d(sc, sm);
+        const kz2 s2 = kz_next2d(sc, sm);
+        kz3 wo; float p; int measure; float e;
+        const kz3 refl = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &p, &measure, &e);
+        if (!(kz_next1d(sc, sm) < 0.95f)) { st.L[slot] = mkf4(0.f, 0.f, 0.f, 1.f); return 0u; }      /* the whole recursion returns 0 */
+        weight = weight * refl / 0.95f;
+        st.rng_state[slot] = sm.state; st.dim[slot] = sm.dim;
+        st.thr[slot] = mkf4(weight.x, weight.y, weight.z, 1.f);
+        if (iszero(weight) || bounce >= 4095) { st.L[slot] = mkf4(0.f, 0.f, 0.f, 1.f); return 0u; }
+        const kz3 wow = to_world(its.sh, wo);
+        st.ray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, KZ_EPSILON);
+        st.ray_d[slot] = mkf4(wow.x, wow.y, wow.z, KZ_INF);
+        return KZ_SHADE_CONTINUE;
+    }
+    /* path_mats, integrator.cpp:142-173 */
+    L += weight * Le;
+    st.L[slot] = mkf4(L.x, L.y, L.z, 1.f);
+    const float probability = fminf(weight.x, 0.95f);
+    if (kz_next1d(sc, sm) >= probability) return 0u;
+    weight = weight / probability;
+    cnt.vertices += 1;
+    const KzBsdfCtx bc = bsdf_ctx(sc, its);
+    const float s1 = kz_next1d(sc, sm);
+    const kz2 s2 = kz_next2d(sc, sm);
+    kz3 wo; float p; int measure; float e;
+    const kz3 f = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &p, &measure, &e);
+    weight *= f;
+    st.rng_state[slot] = sm.state; st.dim[slot] = sm.dim;
+    st.thr[slot] = mkf4(weight.x, weight.y, weight.z, 1.f);
+    if (iszero(weight) || bounce >= 4095) return 0u;
+    const kz3 wow = to_world(its.sh, wo);
+    st.ray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, KZ_EPSILON);
+    st.ray_d[slot] = mkf4(wow.x, wow.y, wow.z, KZ_INF);
+    return KZ_SHADE_CONTINUE;
+}
+
 /* ---- shadow -------------------------------------------------------------------------------- */
 /* integrator.cpp:259-278; returns true when occluded; *segments = closest-hit queries issued */
 KZ_HD bool kz_occluded_walk(const KzScene &sc, const KzStackRef &stk, kz3 o, kz3 d, float tmin, float tmax, float eps, int *segments) {
@@ -266,7 +391,7 @@ KZ_HD bool kz_occluded_walk(const KzScene &sc, const KzStackRef &stk, kz3 o, kz3
         const KzHit h = kz_trace(sc, stk, o.x, o.y, o.z, d.x, d.y, d.z, tmin, tmax, false);
         if (h.geom == KZ_INVALID_ID) break;
         const uint32_t fl = sc.meshes[h.geom].flags;
-        if (!(fl & KZ_MESH_IS_LIGHT) || (fl & KZ_MESH_LIGHT_VISIBLE)) { occluded = true; break; }
+        if (!(fl & KZ_MESH_IS_LIGHT) || (fl & KZ_MESH_LIGHT_VISIBLE) || sc.integrator.type != KZ_INTEGRATOR_PATH_MIS) { occluded = true; break; }
         o = o + d * (h.t + eps);
         tmin = eps;
         tmax = tmax - h.t;

@@ -670,7 +670,9 @@ public:
         m_desc.trace_bias = p.getFloat("traceBias", 0.001f);
         m_desc.regularization = p.getBoolean("regularization", false) ? 1 : 0;
         m_desc.accumulated_roughness = p.getFloat("accumulatedRoughness", 0.5f);
+        m_desc.type = KZ_INTEGRATOR_PATH_MIS;
     }
+    GpuPathMisIntegrator(const PropertyList &, int type) { m_desc = kz_integrator_desc{5, 0.001f, 0, 0.5f, type}; }
     ~GpuPathMisIntegrator() override { if (m_ctx) kzgpu_destroy(m_ctx); }
     kz_integrator_desc describe() const override { return m_desc; }
 
@@ -695,11 +697,22 @@ public:
         return true;
     }
     kzgpu_ctx *context() const { return m_ctx; }
-    std::string toString() const override { return fmt("GpuPathMisIntegrator[maxDepth=%d, traceBias=%g, regularization=%d]", m_desc.max_depth, m_desc.trace_bias, m_desc.regularization); }
+    std::string toString() const override {
+        static const char *names[] = {"GpuPathMisIntegrator", "GpuNormalIntegrator", "GpuAmbientOcclusionIntegrator", "GpuWhittedIntegrator", "GpuPathMatsIntegrator"};
+        return fmt("%s[maxDepth=%d, traceBias=%g, regularization=%d]", names[m_desc.type], m_desc.max_depth, m_desc.trace_bias, m_desc.regularization);
+    }
 private:
     kz_integrator_desc m_desc; kzgpu_ctx *m_ctx = nullptr;
 };
 KAZEN_REGISTER_CLASS(GpuPathMisIntegrator, "path_mis");
+/* the other integrators run through the same wavefront (integrator.cpp:11-181) */
+#define KZ_ALT_INTEGRATOR(cls, name, type)                                                                         \
+    class cls : public GpuPathMisIntegrator { public: cls(const PropertyList &p) : GpuPathMisIntegrator(p, type) {} };   \
+    KAZEN_REGISTER_CLASS(cls, name)
+KZ_ALT_INTEGRATOR(GpuNormalIntegrator, "normals", KZ_INTEGRATOR_NORMALS)
+KZ_ALT_INTEGRATOR(GpuAmbientOcclusionIntegrator, "ao", KZ_INTEGRATOR_AO)
+KZ_ALT_INTEGRATOR(GpuWhittedIntegrator, "whitted", KZ_INTEGRATOR_WHITTED)
+KZ_ALT_INTEGRATOR(GpuPathMatsIntegrator, "path_mats", KZ_INTEGRATOR_PATH_MATS)
 
 namespace renderer {
 void render(Scene *scene, const std::string &outputName, bool writeRaw) {

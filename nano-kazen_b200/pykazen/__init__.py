@@ -72,7 +72,7 @@ class SamplerDesc(C.Structure):
 
 class IntegratorDesc(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("trace_bias", C.c_float), ("regularization", C.c_int32),
-                ("accumulated_roughness", C.c_float)]
+                ("accumulated_roughness", C.c_float), ("type", C.c_int32)]
 
 
 class FilterDesc(C.Structure):
@@ -169,7 +169,7 @@ class SceneBuilder:
         self.background = -1
         self.camera = CameraDesc()
         self.sampler = SamplerDesc()
-        self.integrator = IntegratorDesc(5, 1e-3, 0, 0.5)
+        self.integrator = IntegratorDesc(5, 1e-3, 0, 0.5, 0)
         self.filter = FilterDesc()
         self.set_filter("gaussian")
         self.set_sampler("independent", 1)
@@ -318,8 +318,9 @@ class SceneBuilder:
         self.filter.radius = r
         self.filter.table[:] = tab.tolist()
 
-    def set_integrator(self, max_depth=5, trace_bias=1e-3, regularization=False, accumulated_roughness=0.5):
-        self.integrator = IntegratorDesc(min(512, max_depth), trace_bias, int(regularization), accumulated_roughness)
+    def set_integrator(self, max_depth=5, trace_bias=1e-3, regularization=False, accumulated_roughness=0.5, kind="path_mis"):
+        t = {"path_mis": 0, "normals": 1, "ao": 2, "whitted": 3, "path_mats": 4}[kind]
+        self.integrator = IntegratorDesc(min(512, max_depth), trace_bias, int(regularization), accumulated_roughness, t)
 
     def desc(self):
         d = SceneDesc()

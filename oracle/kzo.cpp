@@ -364,6 +364,99 @@ static V3 Li(kzo_scene *s, Sampler &sampler, const kz_ray &ray_, PathCounters &p
     return L;
 }
 
+/* ---- normals / ao / whitted / path_mats (integrator.cpp:11-181) --------------------------------- */
+static V3 squareToUniformHemisphere(V2 sample) {          /* warp.cpp:68-79 */
+    float z = sample.x;
+    float tmp = std::sqrt(1.0f - z * z);
+    float phi = 2.0f * kPi * sample.y;
+    return V3(std::cos(phi) * tmp, std::sin(phi) * tmp, z);
+}
+static bool anyHit(const SceneData &sc, const kz_ray &ray, PathCounters &pc) {       /* Scene::rayIntersect(ray): closest-hit query, boolean */
+    ++pc.shadow;
+    return sc.accel.traceBvh(ray).geom != KZ_INVALID_ID;
+}
+static V3 LiAlt(kzo_scene *s, Sampler &sampler, const kz_ray &ray_, PathCounters &pc) {
+    const SceneData &sc = s->sc;
+    const int type = sc.integrator.type;
+    kz_ray ray = ray_;
+    Intersection its;
+    if (type == KZ_INTEGRATOR_NORMALS) {                                               /* integrator.cpp:19-29 */
+        if (!rayIntersect(sc, ray, its, pc)) return V3(0.f);
+        return V3(std::fabs(its.geoFrame.n.x), std::fabs(its.geoFrame.n.y), std::fabs(its.geoFrame.n.z));
+    }
+    if (type == KZ_INTEGRATOR_AO) {                                                    /* integrator.cpp:43-62 */
+        if (!rayIntersect(sc, ray, its, pc)) return V3(0.f);
+        V3 sample = squareToUniformHemisphere(sampler.next2D());
+        V3 point = its.toWorld(sample);
+        kz_ray shadowRay{{its.p.x, its.p.y, its.p.z}, kEpsilon, {point.x, point.y, point.z}, INFINITY};
+        if (!anyHit(sc, shadowRay, pc)) {
+            V3 n = normalized(its.shFrame.n);
+            point = normalized(point);
+            float cosTheta = dot(point, n);          /* shFrame.cosTheta(toLocal(point)) with the re-normalised n */
+            return V3(cosTheta / kPi) / (0.5f * kInvPi);
+        }
+        return V3(0.f);
+    }
+    if (type == KZ_INTEGRATOR_WHITTED) {                                               /* integrator.cpp:80-128, recursion unrolled */
+        V3 weight(1.f);
+        for (int depth = 0; depth < 4096; ++depth) {
+            if (!rayIntersect(sc, ray, its, pc)) return V3(0.f);
+            const MeshData &mesh = sc.meshes[its.mesh];
+            V3 rayO(ray.o[0], ray.o[1], ray.o[2]), rayD(ray.d[0], ray.d[1], ray.d[2]);
+            V3 Le(0.f);
+            if (mesh.light >= 0) { LightQueryRecord leRec(rayO, its.p, its.shFrame.n); Le = lightEval(sc.lights[mesh.light], leRec); }
+            if (sc.bsdfs[mesh.bsdf].type == KZ_BSDF_DIFFUSE) {                         /* the only BSDF with isDiffuse() == true, bsdf.cpp:77 */
+                float rnd = sampler.next1D();
+                size_t nl = sc.lightMeshes.size();
+                if (nl == 0) return weight * Le;
+                size_t index = std::min((size_t)std::floor(nl * rnd), nl - 1);
+                const MeshData &lm = sc.meshes[sc.lightMeshes[index]];
+                LightQueryRecord rec(its.p);
+                V3 Ls = lightSample(sc.lights[lm.light], lm, rec, sampler);
+                if (anyHit(sc, rec.shadowRay, pc)) Ls = V3(0.f);
+                float cosTheta = its.shFrame.toLocal(rec.wi).z;
+                if (cosTheta < 0.f) cosTheta = 0.f;
+                BSDFQueryRecord bRec(its.toLocal(-rayD), its.toLocal(rec.wi), ESolidAngle);
+                V3 f = bsdfEval(sc, mesh.bsdf, bRec);
+                V3 Lr = f * Ls * cosTheta;
+                return weight * (Le + Lr / (1.0f / nl));
+            }
+            BSDFQueryRecord bRec(its.toLocal(-rayD));
+            bRec.its = its; bRec.uv = its.uv;          /* the reference leaves bRec.its/uv default here; every BSDF that reads them would see zeros */
+            float s1 = sampler.next1D(); V2 s2 = sampler.next2D();
+            V3 refl = bsdfSample(sc, mesh.bsdf, bRec, s1, s2);
+            if (!(sampler.next1D() < 0.95f)) return V3(0.f);
+            weight = weight * refl / 0.95f;
+            if (iszero(weight)) return V3(0.f);
+            V3 wo = its.toWorld(bRec.wo);
+            ray = kz_ray{{its.p.x, its.p.y, its.p.z}, kEpsilon, {wo.x, wo.y, wo.z}, INFINITY};
+        }
+        return V3(0.f);
+    }
+    /* path_mats, integrator.cpp:142-173 */
+    V3 color(0.f), t(1.f);
+    for (int depth = 0; depth < 4096; ++depth) {
+        if (!rayIntersect(sc, ray, its, pc)) return color;
+        const MeshData &mesh = sc.meshes[its.mesh];
+        V3 rayO(ray.o[0], ray.o[1], ray.o[2]), rayD(ray.d[0], ray.d[1], ray.d[2]);
+        if (mesh.light >= 0) { LightQueryRecord lRecE(rayO, its.p, its.shFrame.n); color += t * lightEval(sc.lights[mesh.light], lRecE); }
+        float probability = std::min(t.x, 0.95f);
+        if (sampler.next1D() >= probability) return color;
+        t /= probability;
+        ++pc.vertices;
+        BSDFQueryRecord bRec(its.shFrame.toLocal(-rayD));
+        bRec.uv = its.uv; bRec.its = its;
+        bRec.its.accumulatedRoughness = 0.f;
+        float s1 = sampler.next1D(); V2 s2 = sampler.next2D();
+        V3 f = bsdfSample(sc, mesh.bsdf, bRec, s1, s2);
+        t *= f;
+        if (iszero(t)) return color;               /* dead path, as in Li above */
+        V3 wo = its.toWorld(bRec.wo);
+        ray = kz_ray{{its.p.x, its.p.y, its.p.z}, kEpsilon, {wo.x, wo.y, wo.z}, INFINITY};
+    }
+    return color;
+}
+
 /* ------------------------------------------------------------------- film */
 /* block.cpp:56-85 on the full bordered frame (offset 0): the per-tile blocks of the reference
  * never clip a splat (border = ceil(r-0.5)), so tile-local and whole-frame puts are identical
@@ -429,7 +522,7 @@ extern "C" int kzo_render(kzo_scene *s, const kz_render_req *req, int threads, f
                         V2 pixelSample{float(x) + pix.x, float(y) + pix.y};
                         V2 apertureSample = sampler.next2D();
                         kz_ray ray = cameraRay(sc.camera, pixelSample, apertureSample);
-                        V3 value = V3(1.0f) * Li(s, sampler, ray, counters[t]);
+                        V3 value = V3(1.0f) * (sc.integrator.type == KZ_INTEGRATOR_PATH_MIS ? Li(s, sampler, ray, counters[t]) : LiAlt(s, sampler, ray, counters[t]));
                         filmPut(sc, b, f.data(), pixelSample, value);
                         ++npaths[t];
                     }

@@ -154,7 +154,8 @@ int kzemu_render(kzemu *e, const kz_render_req *req, float *frame_rgbw) {
             }
     std::mutex mu;
     KzCounters tot{B, 0, 0, 0};
-    for (int bounce = 0; bounce <= sc.integrator.max_depth && !q.empty(); ++bounce) {
+    const int max_pass = sc.integrator.type == KZ_INTEGRATOR_PATH_MIS ? sc.integrator.max_depth : (sc.integrator.type <= KZ_INTEGRATOR_AO ? 0 : 4095);
+    for (int bounce = 0; bounce <= max_pass && !q.empty(); ++bounce) {
         qn.clear(); qs.clear();
         pfor(q.size(), [&](size_t bb, size_t ee) {
             KzStackRef stk; KzCounters c{0, 0, 0, 0};

@@ -297,3 +297,15 @@ def test_extra_bsdf_render_gpu(kzo, gpu_lib):
     st_o, st_g = O.stats(), G.stats()
     assert abs(st_g["vertices"] - st_o["vertices"]) <= 5e-3 * st_o["vertices"]
     O.close(); G.close()
+
+
+@pytest.mark.parametrize("kind", ["normals", "ao", "whitted", "path_mats"])
+def test_other_integrators_gpu(kzo, gpu_lib, kind):
+    sb = scenes.cornell_scene(64, 48, 16, "stratified", visible_light=True)
+    sb.set_integrator(kind=kind)
+    O, G = _pair(kzo, sb)
+    ro, _ = O.resolve(O.render()); rg, _ = G.resolve(G.render())
+    # whitted is ill-conditioned by construction (see tests/test_hostemu.py): statistical tolerance
+    assert scenes.rel_mse(rg, ro).max() < (1e-6 if kind == "normals" else (2e-2 if kind == "whitted" else 5e-4))
+    assert G.stats()["paths"] == 64 * 48 * 16
+    O.close(); G.close()

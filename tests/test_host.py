@@ -33,7 +33,7 @@ def test_registered_plugin_names(host):
     # every plugin on the hot path keeps kazen's registered name; gpu_bvh is the new accel plugin
     for n in ("scene obj diffuse kazenstandard normalmap area perspective thinlens independent stratified correlated pmj02bn "
               "constanttexture imagetexture background colorramp blend gaussian mitchell tent box path_mis gpu_bvh "
-              "dielectric mirror lambertian ggx roughconductor roughplastic roughdielectric").split():
+              "dielectric mirror lambertian ggx roughconductor roughplastic roughdielectric normals ao whitted path_mats").split():
         assert n in names
 
 
