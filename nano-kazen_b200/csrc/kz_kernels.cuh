@@ -321,8 +321,11 @@ __global__ void __launch_bounds__(KZ_TRACE_THREADS) k_extend(KzScene sc, KzPathS
 }
 
 /* ---- shade: one integrator loop iteration for every path of one material class ------------ */
+#ifndef KZ_SHADE_MIN_BLOCKS
+#define KZ_SHADE_MIN_BLOCKS 1
+#endif
 template <int CLS>
-__global__ void __launch_bounds__(KZ_SHADE_THREADS) k_shade(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int nxt, int bounce) {
+__global__ void __launch_bounds__(KZ_SHADE_THREADS, KZ_SHADE_MIN_BLOCKS) k_shade(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int nxt, int bounce) {
     const uint32_t n = ctl->n_class[CLS];
     const uint32_t *queue = q.cls[CLS];
     const uint32_t stride = gridDim.x * blockDim.x;

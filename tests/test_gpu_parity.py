@@ -309,3 +309,109 @@ def test_other_integrators_gpu(kzo, gpu_lib, kind):
     assert scenes.rel_mse(rg, ro).max() < (1e-6 if kind == "normals" else (2e-2 if kind == "whitted" else 5e-4))
     assert G.stats()["paths"] == 64 * 48 * 16
     O.close(); G.close()
+
+
+def _tie_scene():
+    """two meshes holding the SAME triangle (exact t tie) + a coplanar shifted copy: the documented tie rule is
+    smallest (geomID, primID) -- independent of BVH and traversal order"""
+    sb = pk.SceneBuilder()
+    m = sb.bsdf_diffuse((0.5, 0.5, 0.5))
+    T = np.array([[-1, -1, 0.5], [1, -1, 0.5], [0, 1, 0.5]], np.float32)
+    F = np.array([[0, 1, 2]], np.uint32)
+    sb.mesh(np.concatenate([T + np.float32([0.25, 0, 0]), T]), np.array([[0, 1, 2], [3, 4, 5]], np.uint32), m)      # geom 0: prim 1 == the shared triangle
+    sb.mesh(T, F, m)                                                                                               # geom 1: prim 0 == the shared triangle
+    sb.mesh(np.concatenate([T, T]), np.array([[3, 4, 5], [0, 1, 2]], np.uint32), m)                                # geom 2: twice
+    sb.set_camera(16, 16, 40.0, pk.lookat((0, 0, -3), (0, 0, 0), (0, 1, 0)))
+    return sb
+
+
+@pytest.mark.parametrize("builder", [pk.BUILD_HOST_SAH, pk.BUILD_LBVH])
+def test_exact_ties_resolve_by_ids(kzo, gpu_lib, builder):
+    sb = _tie_scene()
+    O, G = _pair(kzo, sb, builder)
+    rays = scenes.primary_rays(96, 40.0, (0, 0, -3.0))
+    a, b = O.trace(rays, brute=True), G.trace(rays)
+    assert a.tobytes() == b.tobytes() == O.trace(rays, brute=False).tobytes()
+    hit = a["geom_id"] != 0xFFFFFFFF
+    assert hit.any() and (a["geom_id"][hit] == 0).all()              # geom 0 always wins a tie
+    # where only the shared triangle is hit (outside the shifted copy) prim 1 of geom 0 is reported; in the overlap prim 0 < prim 1 wins
+    assert set(np.unique(a["prim_id"][hit]).tolist()) == {0, 1}
+    O.close(); G.close()
+
+
+def test_empty_and_tiny_scenes(kzo, gpu_lib):
+    """no meshes at all (empty accel), a single triangle, a 1x1 film, one sample"""
+    sb = pk.SceneBuilder()
+    sb.set_camera(1, 1, 40.0, pk.lookat((0, 0, -3), (0, 0, 0), (0, 1, 0)))
+    sb.set_sampler("stratified", 1)
+    sb.background = sb.tex_background(2.0, sb.tex_constant((0.1, 0.2, 0.3)))
+    for builder in (pk.BUILD_HOST_SAH, pk.BUILD_LBVH):
+        G = pk.Gpu(sb.desc(), builder=builder)
+        rays = scenes.incoherent_rays(100)
+        h = G.trace(rays)
+        assert (h["geom_id"] == 0xFFFFFFFF).all() and np.array_equal(h["t"], rays["tmax"])
+        f = G.render()
+        rgb, _ = G.resolve(f)
+        assert rgb.shape == (1, 1, 3) and np.all(rgb == 0)             # camera rays never see the background (integrator.cpp:210-212)
+        occ, seg = G.occluded(rays, 1e-3)
+        assert not occ.any() and (seg == 1).all()
+        G.close()
+    sb.mesh(np.array([[-5, -5, 1], [5, -5, 1], [0, 5, 1]], np.float32), np.array([[0, 2, 1]], np.uint32), sb.bsdf_diffuse((0.5, 0.5, 0.5)))
+    O, G = _pair(kzo, sb)
+    fo, fg = O.render(), G.render()
+    assert np.allclose(fo, fg, rtol=1e-5, atol=1e-6) and fo[..., :3].max() > 0          # one bounce to the background
+    O.close(); G.close()
+
+
+def test_far_from_origin_and_huge_triangles(kzo, gpu_lib):
+    """coordinates around 1e4 with millimetre triangles next to kilometre ones: culling stays conservative"""
+    rng = np.random.default_rng(4)
+    n = 3000
+    c = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32) * np.float32(50) + np.float32(1e4)
+    P = (c + rng.uniform(-0.5, 0.5, (n, 3, 3)).astype(np.float32)).reshape(-1, 3)
+    big = np.array([[9000, 9000, 10060], [11000, 9000, 10060], [10000, 11000, 10060]], np.float32)
+    P = np.concatenate([P, big])
+    F = np.arange(P.shape[0], dtype=np.uint32).reshape(-1, 3)
+    sb = pk.SceneBuilder()
+    sb.mesh(P, F, sb.bsdf_diffuse((0.5, 0.5, 0.5)))
+    sb.set_camera(8, 8, 40.0, pk.lookat((1e4, 1e4, 1e4 - 200), (1e4, 1e4, 1e4), (0, 1, 0)))
+    rays = scenes.incoherent_rays(20000, extent=60.0)
+    rays["o"] += np.float32(1e4); rays["tmax"] = 500.0
+    for builder in (pk.BUILD_HOST_SAH, pk.BUILD_LBVH):
+        O, G = _pair(kzo, sb, builder)
+        a, b = O.trace(rays, brute=True), G.trace(rays)
+        assert a.tobytes() == b.tobytes() and (a["geom_id"] != 0xFFFFFFFF).mean() > 0.3
+        O.close(); G.close()
+
+
+def test_render_rect_and_spp_edges(kzo, gpu_lib):
+    """non-square sample counts, a one-pixel-wide rectangle, maxDepth 1, tent and box filters (border 1 and 0)"""
+    for filt in ("tent", "box", "mitchell"):
+        sb = scenes.cornell_scene(33, 17, 7, "correlated", max_depth=1)
+        sb.set_filter(filt)
+        O, G = _pair(kzo, sb)
+        fo, fg = O.render(), G.render()
+        ro, _ = O.resolve(fo); rg, _ = G.resolve(fg)
+        assert fo.shape == fg.shape and scenes.rel_mse(rg, ro).max() < IMAGE_RELMSE_TOL
+        part_o = O.render(2, 5, rect=(16, 3, 17, 11)); part_g = G.render(2, 5, rect=(16, 3, 17, 11))
+        assert np.allclose(part_o, part_g, rtol=1e-3, atol=1e-5)
+        O.close(); G.close()
+
+
+def test_multi_device_context(kzo, gpu_lib):
+    """one kzgpu_ctx over all visible devices: sample-index shards rendered concurrently, frames summed"""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    sb = scenes.cornell_scene(64, 64, 16, "stratified")
+    d = sb.desc()
+    G1 = pk.Gpu(d, devices=(0,))
+    GN = pk.Gpu(d, devices=tuple(range(n)))
+    f1, fn = G1.render(), GN.render()
+    assert np.allclose(f1, fn, rtol=1e-4, atol=1e-5)
+    st = GN.stats()
+    assert st["paths"] == 64 * 64 * 16
+    rays = scenes.incoherent_rays(10000, extent=0.9)
+    assert G1.trace(rays).tobytes() == GN.trace(rays, device=n - 1).tobytes()
+    G1.close(); GN.close()

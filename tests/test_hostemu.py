@@ -186,3 +186,15 @@ def test_other_integrators_match_oracle(kzo, emu, kind):
     assert scenes.rel_mse(re, ro).max() < (5e-3 if kind == "whitted" else 1e-6)
     assert ro.mean() > (0.005 if kind == "whitted" else 0.05)
     O.close(); E.close()
+
+
+def test_exact_ties_resolve_by_ids_cpu(kzo, emu):
+    from test_gpu_parity import _tie_scene
+    sb = _tie_scene()
+    O, E = _pair(kzo, emu, sb)
+    rays = scenes.primary_rays(64, 40.0, (0, 0, -3.0))
+    a = O.trace(rays, brute=True)
+    assert a.tobytes() == O.trace(rays, brute=False).tobytes() == E.trace(rays).tobytes()
+    hit = a["geom_id"] != 0xFFFFFFFF
+    assert hit.any() and (a["geom_id"][hit] == 0).all()
+    O.close(); E.close()
