@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -651,30 +652,39 @@ int kzgpu_render(kzgpu_ctx *ctx, const kz_render_req *req, float *frame_rgbw) {
     const int nd = (int)ctx->devs.size();
     const int nS = req->spp_end - req->spp_begin;
     const size_t texels = ctx->devs[0].frame_texels;
-    /* shard by sample index: device g takes a contiguous slice of [spp_begin, spp_end) */
-    for (int g = 0; g < nd; ++g) {
+    /* shard by sample index: device g takes a contiguous slice of [spp_begin, spp_end).  One host thread per
+     * device: a long render is thousands of launches, and a single thread would block on the first device's launch queue
+     * before it ever reaches the second one. */
+    std::vector<std::vector<float>> parts((size_t)nd);
+    std::vector<int> rcs((size_t)nd, KZ_OK);
+    std::vector<std::string> errs((size_t)nd);
+    auto work = [&](int g) {
         Device &d = ctx->devs[(size_t)g];
-        KZ_CUDA(ctx, cudaSetDevice(d.id));
+        auto bail = [&](cudaError_t e, const char *what) { rcs[(size_t)g] = KZ_ERR_CUDA; errs[(size_t)g] = std::string(what) + ": " + cudaGetErrorString(e); };
+        cudaError_t e = cudaSetDevice(d.id);
+        if (e != cudaSuccess) return bail(e, "cudaSetDevice");
         kz_render_req r = *req;
         r.spp_begin = req->spp_begin + (int)((long long)nS * g / nd);
         r.spp_end = req->spp_begin + (int)((long long)nS * (g + 1) / nd);
-        KZ_CUDA(ctx, cudaMemsetAsync(d.frame, 0, texels * sizeof(KzF4), d.stream));
-        if ((rc = enqueue_render(ctx, d, r, d.stream))) return rc;
-    }
-    std::vector<float> tmp;
+        if ((e = cudaMemsetAsync(d.frame, 0, texels * sizeof(KzF4), d.stream)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
+        const int rc = enqueue_render(ctx, d, r, d.stream);
+        if (rc != KZ_OK) { rcs[(size_t)g] = rc; errs[(size_t)g] = g_error; return; }
+        float *dst = (g == 0 && req->clear_frame) ? frame_rgbw : (parts[(size_t)g].resize(texels * 4), parts[(size_t)g].data());
+        if ((e = cudaMemcpyAsync(dst, d.frame, texels * sizeof(KzF4), cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess) return bail(e, "cudaMemcpyAsync");
+        if ((e = cudaStreamSynchronize(d.stream)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");
+    };
+    std::vector<std::thread> pool;
+    for (int g = 1; g < nd; ++g) pool.emplace_back(work, g);
+    work(0);
+    for (std::thread &t : pool) t.join();
+    for (int g = 0; g < nd; ++g)
+        if (rcs[(size_t)g] != KZ_OK) return fail(ctx, rcs[(size_t)g], "device " + std::to_string(g) + ": " + errs[(size_t)g]);
     for (int g = 0; g < nd; ++g) {
-        Device &d = ctx->devs[(size_t)g];
-        KZ_CUDA(ctx, cudaSetDevice(d.id));
-        if (g == 0 && req->clear_frame) {
-            KZ_CUDA(ctx, cudaMemcpyAsync(frame_rgbw, d.frame, texels * sizeof(KzF4), cudaMemcpyDeviceToHost, d.stream));
-            KZ_CUDA(ctx, cudaStreamSynchronize(d.stream));
-        } else {
-            tmp.resize(texels * 4);
-            KZ_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d.frame, texels * sizeof(KzF4), cudaMemcpyDeviceToHost, d.stream));
-            KZ_CUDA(ctx, cudaStreamSynchronize(d.stream));
-            for (size_t i = 0; i < texels * 4; ++i) frame_rgbw[i] += tmp[i];
-        }
+        if (parts[(size_t)g].empty()) continue;
+        const float *src = parts[(size_t)g].data();
+        for (size_t i = 0; i < texels * 4; ++i) frame_rgbw[i] += src[i];
     }
+    KZ_CUDA(ctx, cudaSetDevice(ctx->devs[0].id));
     return KZ_OK;
 }
 
