@@ -123,7 +123,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Everything that libraries print on stdout (NCCL's version banner, ...) is sent to stderr; the ONE JSON line is
+    written to the original stdout by emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -297,7 +316,7 @@ def main():
                            "builder": args.builder, "accel_build_ms": build_ms, "primary_hit_fraction": hit_frac,
                            "l2": "inputs larger than L2 (512 MiB of rays + 320 MiB of hits per batch)", "parallelism": f"replicas x{world}"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_matches_device": same, "gpu_launches": launches, "clocks": clk, "paths": paths}
-        print(json.dumps(line), flush=True)
+        emit(line)
     G.close()
     if world > 1:
         dist.destroy_process_group()
