@@ -120,7 +120,7 @@ def run_reference(args):
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU port of the reference path (oracle: median-split BVH2 + Embree-robust Pluecker test, std::thread over all cores); "
                     "the reference itself (Embree 3.13 + TBB + OIIO) cannot be built in this image"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 _JSON_FD = None
