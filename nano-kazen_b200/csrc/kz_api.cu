@@ -231,6 +231,7 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
     for (unsigned long long first = 0; first < total; first += d.pool_cap) {
         ch.first = first;
         ch.count = (uint32_t)std::min<unsigned long long>(d.pool_cap, total - first);
+        if (d.pending.size() > 8192) fold_events(d);       /* very long renders: bound the number of live timing events */
         {
             Timed t(d, s, CAT_SHADE);
             k_chunk_reset<<<1, 32, 0, s>>>(d.ctl);
