@@ -124,7 +124,11 @@ KZ_HD void kz_trav_init(const KzScene &sc, KzTrav &t, float ox, float oy, float 
     t.ony = ny ? oy - slack : oy + slack; t.ofy = ny ? oy + slack : oy - slack;
     t.onz = nz ? oz - slack : oz + slack; t.ofz = nz ? oz + slack : oz - slack;
     t.oct_inv = ((nx ? 0u : 1u) | (ny ? 0u : 2u) | (nz ? 0u : 4u));
-    t.ng_x = 0u; t.ng_y = sc.n_nodes ? 0x80000000u : 0u;      /* root; an empty scene starts with nothing to do */
+    /* A ray with a NaN component can never be accepted by the triangle test (every comparison fails), but fminf/fmaxf drop
+     * NaNs, so the slab test would let it walk the whole tree.  Such rays do occur -- the reference's cosine-hemisphere warp
+     * yields sqrt(-eps) for a sample that is exactly 0 (warp.cpp:85-115) -- so they are turned into an immediate miss. */
+    const bool has_nan = isnan(ox) || isnan(oy) || isnan(oz) || isnan(dx) || isnan(dy) || isnan(dz) || isnan(tmin) || isnan(tmax);
+    t.ng_x = 0u; t.ng_y = (sc.n_nodes && !has_nan) ? 0x80000000u : 0u;      /* root; an empty scene starts with nothing to do */
     t.tg_x = 0u; t.tg_y = 0u;
     t.sp = 0;
 }

@@ -181,6 +181,11 @@ inline HitRec Accel::traceBvh(const kz_ray &r) const {
     HitRec best = missRec(r.tmax);
     if (nodes.empty()) return best;
     V3 org(r.o[0], r.o[1], r.o[2]), dir(r.d[0], r.d[1], r.d[2]);
+    /* NaN rays fail every comparison of the triangle test: a miss by construction (and not worth walking the whole tree) */
+    if (std::isnan(org.x + org.y + org.z) || std::isnan(dir.x) || std::isnan(dir.y) || std::isnan(dir.z) || std::isnan(r.tmin) || std::isnan(r.tmax)) {
+        bool inf_only = !std::isnan(org.x) && !std::isnan(org.y) && !std::isnan(org.z);
+        if (!inf_only || std::isnan(dir.x) || std::isnan(dir.y) || std::isnan(dir.z) || std::isnan(r.tmin) || std::isnan(r.tmax)) return best;
+    }
     /* Conservative culling in double precision: inflate boxes by 1e-5 of the magnitude of
      * everything involved (far more than the triangle test's few-ulp tolerance), and the
      * t-interval by a relative 1e-5.  The BVH only prunes; identity comes from the test. */

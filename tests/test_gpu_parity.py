@@ -415,3 +415,18 @@ def test_multi_device_context(kzo, gpu_lib):
     rays = scenes.incoherent_rays(10000, extent=0.9)
     assert G1.trace(rays).tobytes() == GN.trace(rays, device=n - 1).tobytes()
     G1.close(); GN.close()
+
+
+def test_nan_rays_are_misses(kzo, gpu_lib):
+    """NaN rays (the cosine-hemisphere warp yields one for a sample that is exactly 0) are immediate misses, not full-tree walks"""
+    import time
+    sb = scenes.soup_scene(200000)
+    O, G = _pair(kzo, sb, pk.BUILD_LBVH)
+    rays = scenes.incoherent_rays(4096)
+    rays["d"][::7, 0] = np.nan; rays["o"][3::11, 2] = np.nan; rays["tmax"][5::13] = np.nan
+    t0 = time.time(); b = G.trace(rays); dt = time.time() - t0
+    a = O.trace(rays)
+    assert a.tobytes() == b.tobytes()
+    bad = np.isnan(rays["d"]).any(1) | np.isnan(rays["o"]).any(1) | np.isnan(rays["tmax"])
+    assert (b["geom_id"][bad] == 0xFFFFFFFF).all() and dt < 2.0
+    O.close(); G.close()
