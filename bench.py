@@ -260,12 +260,11 @@ def main():
            "d2h_bytes_per_step": rays_per_step * 20, "steps": e2e_steps, "api": "kzgpu_trace (pinned host buffers)"}
     same = bool(torch.equal(batches[1]["host_hits"].view(torch.int32), batches[1]["hits"].cpu().view(torch.int32)))   # bit compare (miss ids are NaN patterns)
 
-    # ------------------------------------------------------------------ path-tracing leg (Mpaths/s)
-    paths = None
-    if not args.no_paths:
+    # ------------------------------------------------------------------ path-tracing legs (Mpaths/s)
+    def path_leg(make_scene, label):
         import scenes
         W = H = 512; spp = 64
-        sbp = scenes.cornell_scene(W, H, spp, "stratified")
+        sbp = make_scene(scenes, W, H, spp)
         GP = pk.Gpu(sbp.desc(), devices=(local,), builder=pk.BUILD_HOST_SAH)
         fh, fw, _ = GP.frame_shape()
         frame = torch.zeros((fh, fw, 4), dtype=torch.float32, device="cuda")
@@ -289,15 +288,22 @@ def main():
         ps = GP.stats()
         npaths = W * H * spp                                  # strong scaling: total work fixed
         rays_total = sum_over_ranks(ps["rays_extension"] + ps["rays_shadow"]) / psteps
-        paths = {"value": npaths / (pms * 1e-3) / 1e6, "unit": "Mpaths/s", "mrays_per_s": rays_total / (pms * 1e-3) / 1e6, "ms_per_frame": pms,
-                 "scene": f"cornell-class (kiss + diffuse + 2 invisible mesh lights), {W}x{H}, {spp} spp, stratified, path_mis maxDepth 5",
-                 "rays_per_path": rays_total / npaths, "scaling": "strong (sample-index shards + one NCCL reduce)",
-                 "ms_trace": ps["ms_trace"] / psteps, "ms_shade": ps["ms_shade"] / psteps, "mean_rgb": None}
+        out = {"value": npaths / (pms * 1e-3) / 1e6, "unit": "Mpaths/s", "mrays_per_s": rays_total / (pms * 1e-3) / 1e6, "ms_per_frame": pms,
+               "scene": label + f", {W}x{H}, {spp} spp, stratified, path_mis maxDepth 5",
+               "rays_per_path": rays_total / npaths, "scaling": "strong (sample-index shards + one NCCL reduce)",
+               "ms_trace": ps["ms_trace"] / psteps, "ms_shade": ps["ms_shade"] / psteps, "mean_rgb": None}
         if rank == 0:
-            fr = frame.cpu().numpy()
-            rgb, _ = GP.resolve(fr)
-            paths["mean_rgb"] = float(rgb.mean())
+            rgb, _ = GP.resolve(frame.cpu().numpy())
+            out["mean_rgb"] = float(rgb.mean())
         GP.close()
+        return out
+
+    paths = paths_cornell = None
+    if not args.no_paths:
+        paths = path_leg(lambda sc, W, H, spp: sc.studio_scene(W, H, spp, "stratified"),
+                         "WarmStudio stand-in (15872-tri kiss ball, 2048-tri diffuse backdrop, 32-tri invisible mesh light; BASELINE configs[0] class)")
+        paths_cornell = path_leg(lambda sc, W, H, spp: sc.cornell_scene(W, H, spp, "stratified"),
+                                 "cornell-class (kiss + diffuse + 2 invisible mesh lights)")
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1)
     cpu = None
@@ -324,7 +330,7 @@ def main():
                            "tris": args.tris, "rays_per_step_per_gpu": rays_per_step, "primary": batches[0]["n"], "incoherent_shadow": batches[1]["n"],
                            "builder": args.builder, "accel_build_ms": build_ms, "primary_hit_fraction": hit_frac,
                            "l2": "inputs larger than L2 (512 MiB of rays + 320 MiB of hits per batch)", "parallelism": f"replicas x{world}"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_matches_device": same, "gpu_launches": launches, "clocks": clk, "paths": paths}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_matches_device": same, "gpu_launches": launches, "clocks": clk, "paths": paths, "paths_cornell": paths_cornell}
         emit(line)
     G.close()
     if world > 1:

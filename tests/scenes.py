@@ -195,6 +195,54 @@ def gallery_scene(width=64, height=48, spp=16, sampler="stratified", max_depth=6
     return sb
 
 
+def studio_scene(width=512, height=512, spp=64, sampler="stratified"):
+    """Procedural stand-in for kazen's smallest shipped scene (scene/2022_q1/WarmStudio: 15 872-triangle kiss ball on a
+    2 048-triangle diffuse backdrop, lit by a 32-triangle invisible mesh light array, mitchell filter; BASELINE configs[0]).
+    Same triangle counts, materials, light radiance and camera; the geometry is generated here, not copied."""
+    sb = pk.SceneBuilder()
+    ball = sb.bsdf_kiss(sb.tex_constant((0.871, 0.376, 0.0)), sb.tex_constant((0.0, 0.0, 1.0)), sb.tex_constant((0.0, 0.0, 0.0)),
+                        anisotropy=0.0, specular=0.5, specular_tint=0.0, clearcoat=0.0, clearcoat_roughness=0.0, sheen=0.0, sheen_tint=0.0)
+    P, N, UV, F = uv_sphere((0.0, 1.0071, 0.0), 0.988, nu=128, nv=63)
+    assert F.shape[0] == 15872
+    sb.mesh(P, F, ball, normals=N, uvs=UV)
+    # backdrop: floor -> quarter cylinder -> wall, swept along z (32 x 32 quads = 2048 triangles), normals towards the camera side
+    prof = []
+    for k in range(33):
+        t = k / 32.0
+        if t < 0.4: prof.append((-7.8 + 8.2 * (t / 0.4) * 1.0 + 0.0, 0.0))                    # floor x from -7.8 .. 0.4 (camera is at x = -4.86 looking +x)
+        elif t < 0.7:
+            a = (t - 0.4) / 0.3 * (np.pi / 2); prof.append((0.4 + 3.0 * np.sin(a), 3.0 - 3.0 * np.cos(a)))
+        else: prof.append((3.4, 3.0 + (t - 0.7) / 0.3 * 6.9))
+    prof = np.array(prof)
+    zs = np.linspace(-8.1, 8.1, 33)
+    BP = np.array([[x, y, z] for z in zs for (x, y) in prof], np.float32)
+    BF = []
+    for j in range(32):
+        for i in range(32):
+            a = j * 33 + i; b = a + 1; c = a + 33; d = c + 1
+            BF += [[a, b, d], [a, d, c]]
+    BP, BF = orient(BP, np.array(BF, np.uint32), (-3.0, 3.0, 0.0), away=False)
+    assert BF.shape[0] == 2048
+    sb.mesh(BP, BF, sb.bsdf_diffuse((0.05, 0.05, 0.05)))
+    # 4 x 4 array of 1 x 1 light panels, tilted towards the ball
+    LP, LF = [], []
+    for r in range(4):
+        for c in range(4):
+            x0 = -2.246 + 1.165 * c; y0 = 1.857 + 1.13 * r; z0 = -3.97 + 0.755 * r
+            q = [(x0 + 1, y0, z0), (x0, y0, z0), (x0 + 1, y0 + 0.828, z0 + 0.56), (x0, y0 + 0.828, z0 + 0.56)]
+            k = len(LP); LP += q; LF += [[k, k + 1, k + 3], [k, k + 3, k + 2]]
+    LP, LF = orient(np.array(LP, np.float32), np.array(LF, np.uint32), (0.0, 1.0, 0.0), away=False)
+    lt = sb.light((4.0 * 0.63827, 4.0 * 0.572175, 4.0 * 0.420238), primary_visibility=False)
+    sb.mesh(LP, LF, sb.bsdf_diffuse((0.5, 0.5, 0.5)), light=lt)
+    c2w = np.array([[4.371138828673793e-08, -4.371138828673793e-08, 1.0, -4.857681751251221], [0.0, 1.0, 4.371138828673793e-08, 0.9879673719406128],
+                    [-1.0, -1.910685676922942e-15, 4.371138828673793e-08, 0.0], [0, 0, 0, 1]], np.float32)
+    sb.set_camera(width, height, 49.13434207760448, c2w, near=0.10000000149011612, far=100.0)
+    sb.set_sampler(sampler, spp)
+    sb.set_filter("mitchell")
+    sb.set_integrator(max_depth=5)
+    return sb
+
+
 def rel_mse(a, b, eps=1e-2):
     """per-channel relative MSE of image a against reference b"""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)

@@ -430,3 +430,30 @@ def test_nan_rays_are_misses(kzo, gpu_lib):
     bad = np.isnan(rays["d"]).any(1) | np.isnan(rays["o"]).any(1) | np.isnan(rays["tmax"])
     assert (b["geom_id"][bad] == 0xFFFFFFFF).all() and dt < 2.0
     O.close(); G.close()
+
+
+def test_studio_scene_matches_oracle(kzo, gpu_lib):
+    """the WarmStudio stand-in (BASELINE configs[0] class): smooth 15 872-triangle kiss ball, invisible light array, mitchell filter"""
+    sb = scenes.studio_scene(160, 90, 16)
+    O, G = _pair(kzo, sb)
+    ro, _ = O.resolve(O.render()); rg, _ = G.resolve(G.render())
+    assert scenes.rel_mse(rg, ro).max() < IMAGE_RELMSE_TOL
+    assert 0.005 < ro.mean() < 0.2
+    O.close(); G.close()
+
+
+def test_c4_standin_pmj02bn_terminator_regularization(kzo, gpu_lib):
+    """BASELINE configs[3] stand-in: pmj02bn sampler (stand-in tables from the C++ host: the pbrt tables are not in the reference's
+    public tree), low-poly smooth-shaded sphere (Hanika shadow-terminator offset, accel.cpp:141-153), per-bounce roughness bias"""
+    bn, pm = pk.host_fallback_tables()
+    sb = scenes.cornell_scene(96, 54, 16, "stratified", regularization=True, with_texture=True)
+    P, N, UV, F = scenes.uv_sphere((0.45, 0.1, -0.2), 0.3, nu=8, nv=5)          # coarse: terminator artefacts without the offset
+    sb.mesh(P, F, sb.bsdf_kiss(sb.tex_constant((0.8, 0.8, 0.8)), sb.tex_constant((0.3, 0, 0)), sb.tex_constant((0.0, 0, 0))), normals=N, uvs=UV)
+    sb.set_sampler("pmj02bn", 16, tables=(bn, pm))
+    sb.set_integrator(max_depth=6, regularization=True, accumulated_roughness=0.5)
+    O, G = _pair(kzo, sb)
+    tr = np.array([[x, y, j] for x in (0, 17, 95) for y in (2, 53) for j in (0, 7, 15)], np.int32)
+    assert O.sample_dump(tr, "P2121212121212").tobytes() == G.sample_dump(tr, "P2121212121212").tobytes()
+    ro, _ = O.resolve(O.render()); rg, _ = G.resolve(G.render())
+    assert scenes.rel_mse(rg, ro).max() < IMAGE_RELMSE_TOL
+    O.close(); G.close()
