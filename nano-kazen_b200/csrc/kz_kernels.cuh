@@ -21,7 +21,9 @@
 #define KZ_KERNELS_CUH
 #include "kz_path.h"
 
+#ifndef KZ_TRACE_THREADS
 #define KZ_TRACE_THREADS 128
+#endif
 #define KZ_SHADE_THREADS 128
 
 struct KzControl {

@@ -90,7 +90,7 @@ KZ_HD float kz_rcp_safe(float d) {
 #ifndef KZ_SHORT_STACK
 #define KZ_SHORT_STACK 8          /* entries per thread kept in shared memory */
 #endif
-#define KZ_LOCAL_STACK 56         /* overflow entries in local memory          */
+#define KZ_LOCAL_STACK (64 - KZ_SHORT_STACK)   /* overflow entries in local memory */
 
 struct KzStackRef {
 #if defined(__CUDACC__)
