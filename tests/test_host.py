@@ -241,3 +241,33 @@ def test_kazen_cli_on_gpu(host, kzo, tmp_path):
     _, so = O.resolve(np.ascontiguousarray(frame))
     assert png.shape == (h, w, 3) and np.abs(png.astype(int) - so.astype(int)).max() <= 1
     O.close(); hs.close()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SCENES), reason="reference scenes are only mounted in the build container")
+def test_kiss_parameter_sweeps_follow_the_golden_images(host, kzo):
+    """The reference ships one golden PNG per parameter-sweep scene (kiss metallic / roughness / specular / specularTint / clearcoat /
+    clearcoatRoughness / sheen / sheenTint).  The goldens predate the Q2 changes and are 8-bit, so absolute means sit ~0.02-0.03
+    lower here, but the EFFECT of every parameter (difference of frame means between two scenes of a sweep) must match the
+    reference's own images: that pins the kiss parameter semantics of the oracle (and so of the GPU path) to reference output."""
+    import json
+    gold = json.load(open(os.path.join(HERE, "golden", "param_means.json")))
+    ours = {}
+    for name in gold:
+        if name == "WarmStudio":
+            continue
+        hs = host.HostScene(os.path.join(REF_SCENES, "parameters", name + ".xml"),
+                            {"camera.width": "i:192", "camera.height": "i:108", "sampler.sampleCount": "i:36", "sampler.type": "s:stratified"})
+        O = kzo.Oracle(hs.desc)
+        rgb, _ = O.resolve(O.render())
+        ours[name] = np.minimum(rgb, 1.0).mean(axis=(0, 1))
+        O.close(); hs.close()
+        d = ours[name] - np.array(gold[name])
+        assert (-0.045 < d).all() and (d < 0.005).all(), (name, d)
+    sweeps = [("m0_r0_spec0", "m0_r0_spec0.5"), ("m0_r0_spec0.5", "m0_r0_spec1"), ("m0_r0_spec1", "m0_r0_spec1_st0.5"), ("m0_r0_spec1_st0.5", "m0_r0_spec1_st1"),
+              ("r0.5_c0", "r0.5_c0.5"), ("r0.5_c0.5", "r0.5_c1"), ("r0.5_c1", "r0.5_c1_cr0.5"), ("r0.5_c1_cr0.5", "r0.5_c1_cr1"),
+              ("r0_s0", "r0_s0.5"), ("r0_s0.5", "r0_s1"), ("r0_s1", "r0_s1_st0.5"), ("r0_s1_st0.5", "r0_s1_st1"),
+              ("m0.0_r0", "m0.0_r0.5"), ("m0.0_r0.5", "m0.0_r1"), ("m1_r0.5", "m1_r1")]
+    for a, b in sweeps:
+        eff_ours = ours[b] - ours[a]
+        eff_gold = np.array(gold[b]) - np.array(gold[a])
+        assert np.abs(eff_ours - eff_gold).max() < 2.5e-3, (a, b, eff_ours, eff_gold)
