@@ -56,6 +56,13 @@ int kazen_host_registered(char *buf, size_t n) {
     snprintf(buf, n, "%s", s.c_str());
     return (int)s.size();
 }
+/* decode an image file the way imagetexture does; rgb must hold 3*w*h floats when non-NULL (call twice) */
+int kazen_host_read_image(const char *path, int *w, int *h, float *rgb) {
+    std::vector<float> px; std::string err;
+    if (!readImage(path, *w, *h, px, err)) { g_err = err; return -1; }
+    if (rgb) memcpy(rgb, px.data(), px.size() * sizeof(float));
+    return 0;
+}
 void kazen_host_fallback_tables(uint16_t *blue_noise, uint32_t *pmj) {
     std::vector<uint16_t> bn; std::vector<uint32_t> pm;
     fallbackPmjTables(bn, pm);

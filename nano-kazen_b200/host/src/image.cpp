@@ -1,10 +1,12 @@
 /* image.cpp -- minimal image I/O for the host: PNG writer (bitmap.cpp:38-64 wrote PNG through
- * OpenImageIO), PNG (8/16-bit, non-interlaced) and PFM readers for imagetexture, and the stand-in
+ * OpenImageIO), PNG (8/16-bit, non-interlaced), PFM, Radiance HDR and scanline OpenEXR readers for imagetexture, and the stand-in
  * pmj02bn / blue-noise tables.  Only zlib is used. */
 #include <kazen/scene.h>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 #include <zlib.h>
 
 namespace kazen {
@@ -105,13 +107,150 @@ static bool readPNG(const std::string &path, int &w, int &h, std::vector<float> 
     return true;
 }
 
+/* Radiance RGBE (.hdr): flat and new-style RLE scanlines, -Y H +X W orientation */
+static bool readHDR(const std::string &path, int &w, int &h, std::vector<float> &rgb, std::string &err) {
+    std::ifstream f(path, std::ios::binary);
+    std::string line;
+    bool fmt_ok = false;
+    while (std::getline(f, line) && !line.empty() && line != "\r") if (line.find("32-bit_rle_rgbe") != std::string::npos) fmt_ok = true;
+    if (!std::getline(f, line)) { err = "truncated HDR header"; return false; }
+    if (!fmt_ok || sscanf(line.c_str(), "-Y %d +X %d", &h, &w) != 2 || w <= 0 || h <= 0) { err = "unsupported HDR variant (need 32-bit_rle_rgbe, -Y H +X W)"; return false; }
+    std::vector<uint8_t> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    size_t p = 0;
+    std::vector<uint8_t> scan((size_t)w * 4);
+    rgb.resize((size_t)w * h * 3);
+    for (int y = 0; y < h; ++y) {
+        if (p + 4 <= d.size() && d[p] == 2 && d[p + 1] == 2 && !(d[p + 2] & 0x80) && ((d[p + 2] << 8) | d[p + 3]) == w && w >= 8 && w < 32768) {
+            p += 4;
+            for (int c = 0; c < 4; ++c)
+                for (int x = 0; x < w;) {
+                    if (p >= d.size()) { err = "truncated HDR"; return false; }
+                    int n = d[p++];
+                    if (n > 128) { n -= 128; if (p >= d.size() || x + n > w) { err = "bad HDR run"; return false; } const uint8_t v = d[p++]; while (n--) scan[(size_t)4 * x++ + c] = v; }
+                    else { if (n == 0 || p + n > d.size() || x + n > w) { err = "bad HDR run"; return false; } while (n--) scan[(size_t)4 * x++ + c] = d[p++]; }
+                }
+        } else {
+            if (p + (size_t)w * 4 > d.size()) { err = "truncated HDR"; return false; }
+            memcpy(scan.data(), &d[p], (size_t)w * 4); p += (size_t)w * 4;
+        }
+        for (int x = 0; x < w; ++x) {
+            const uint8_t *q = &scan[(size_t)4 * x];
+            const float sc = q[3] ? std::ldexp(1.0f, (int)q[3] - 136) : 0.f;
+            for (int c = 0; c < 3; ++c) rgb[3 * ((size_t)y * w + x) + c] = q[c] * sc;
+        }
+    }
+    return true;
+}
+
+/* OpenEXR, single-part scanline files: compression NONE / RLE / ZIPS / ZIP, HALF or FLOAT channels R,G,B (or Y) */
+static float halfToFloat(uint16_t hbits) {
+    const uint32_t s = (hbits >> 15) & 1u, e = (hbits >> 10) & 31u, m = hbits & 1023u;
+    uint32_t u;
+    if (e == 0) {
+        if (m == 0) u = s << 31;
+        else { int k = 0; uint32_t mm = m; while (!(mm & 1024u)) { mm <<= 1; ++k; } u = (s << 31) | ((uint32_t)(113 - k) << 23) | ((mm & 1023u) << 13); }
+    } else if (e == 31) u = (s << 31) | 0x7f800000u | (m << 13);
+    else u = (s << 31) | ((e + 112u) << 23) | (m << 13);
+    float fl; memcpy(&fl, &u, 4); return fl;
+}
+static bool readEXR(const std::string &path, int &w, int &h, std::vector<float> &rgb, std::string &err) {
+    std::ifstream f(path, std::ios::binary);
+    std::vector<uint8_t> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (d.size() < 16 || d[0] != 0x76 || d[1] != 0x2f || d[2] != 0x31 || d[3] != 0x01) { err = "not an OpenEXR file"; return false; }
+    if (d[5] & 0x1E) { err = "tiled / deep / multi-part EXR is not supported"; return false; }
+    size_t p = 8;
+    auto cstr = [&](std::string &out) { out.clear(); while (p < d.size() && d[p]) out += (char)d[p++]; ++p; return p <= d.size(); };
+    auto i32 = [&](size_t o) { int32_t v; memcpy(&v, &d[o], 4); return v; };
+    struct Chan { std::string name; int type; };
+    std::vector<Chan> chans;
+    int comp = -1, xmin = 0, ymin = 0, xmax = -1, ymax = -1;
+    for (;;) {
+        std::string name, type;
+        if (!cstr(name)) { err = "truncated EXR header"; return false; }
+        if (name.empty()) break;
+        if (!cstr(type) || p + 4 > d.size()) { err = "truncated EXR header"; return false; }
+        const int size = i32(p); p += 4;
+        if (size < 0 || p + (size_t)size > d.size()) { err = "truncated EXR header"; return false; }
+        if (name == "channels") {
+            size_t q = p;
+            while (q < p + size && d[q]) {
+                Chan c; while (d[q]) c.name += (char)d[q++]; ++q;
+                c.type = i32(q); q += 16;
+                chans.push_back(c);
+            }
+        } else if (name == "compression") comp = d[p];
+        else if (name == "dataWindow") { xmin = i32(p); ymin = i32(p + 4); xmax = i32(p + 8); ymax = i32(p + 12); }
+        p += (size_t)size;
+    }
+    w = xmax - xmin + 1; h = ymax - ymin + 1;
+    if (w <= 0 || h <= 0 || chans.empty()) { err = "bad EXR header"; return false; }
+    if (comp < 0 || comp > 3) { err = "EXR compression other than NONE / RLE / ZIPS / ZIP is not supported"; return false; }
+    size_t bytesPerLine = 0;
+    std::vector<size_t> chanOff;
+    for (const Chan &c : chans) {
+        if (c.type != 1 && c.type != 2) { err = "EXR channel type must be HALF or FLOAT"; return false; }
+        chanOff.push_back(bytesPerLine); bytesPerLine += (size_t)w * (c.type == 1 ? 2 : 4);
+    }
+    int idx[3] = {-1, -1, -1};
+    for (size_t k = 0; k < chans.size(); ++k) { if (chans[k].name == "R") idx[0] = (int)k; if (chans[k].name == "G") idx[1] = (int)k; if (chans[k].name == "B") idx[2] = (int)k; }
+    if (idx[0] < 0) for (size_t k = 0; k < chans.size(); ++k) if (chans[k].name == "Y") idx[0] = idx[1] = idx[2] = (int)k;
+    if (idx[0] < 0 || idx[1] < 0 || idx[2] < 0) { err = "EXR needs R,G,B or Y channels"; return false; }
+    const int linesPerBlock = comp == 3 ? 16 : 1;
+    const int nblocks = (h + linesPerBlock - 1) / linesPerBlock;
+    if (p + (size_t)nblocks * 8 > d.size()) { err = "truncated EXR offset table"; return false; }
+    rgb.assign((size_t)w * h * 3, 0.f);
+    std::vector<uint8_t> tmp, raw;
+    for (int b = 0; b < nblocks; ++b) {
+        uint64_t off; memcpy(&off, &d[p + (size_t)b * 8], 8);
+        if (off + 8 > d.size()) { err = "bad EXR block offset"; return false; }
+        const int y0 = i32((size_t)off) - ymin, size = i32((size_t)off + 4);
+        if (size < 0 || off + 8 + (size_t)size > d.size() || y0 < 0 || y0 >= h) { err = "bad EXR block"; return false; }
+        const int lines = std::min(linesPerBlock, h - y0);
+        const size_t expect = bytesPerLine * lines;
+        const uint8_t *src = &d[(size_t)off + 8];
+        raw.resize(expect);
+        if (comp == 0 || (size_t)size == expect) memcpy(raw.data(), src, expect);
+        else {
+            tmp.resize(expect);
+            if (comp == 1) {      /* RLE */
+                size_t o = 0; int q = 0;
+                while (q < size && o < expect) {
+                    const int n = (int8_t)src[q++];
+                    if (n < 0) { const int c = -n; if (q + c > size || o + c > expect) { err = "bad EXR RLE"; return false; } memcpy(&tmp[o], src + q, (size_t)c); q += c; o += (size_t)c; }
+                    else { const int c = n + 1; if (q >= size || o + c > expect) { err = "bad EXR RLE"; return false; } memset(&tmp[o], src[q++], (size_t)c); o += (size_t)c; }
+                }
+                if (o != expect) { err = "bad EXR RLE"; return false; }
+            } else {
+                uLongf rl = (uLongf)expect;
+                if (uncompress(tmp.data(), &rl, src, (uLong)size) != Z_OK || rl != expect) { err = "EXR inflate failed"; return false; }
+            }
+            for (size_t i = 1; i < expect; ++i) tmp[i] = (uint8_t)(tmp[i - 1] + tmp[i] - 128);      /* predictor */
+            const size_t half = (expect + 1) / 2;                                                     /* de-interleave */
+            for (size_t i = 0; i < expect; ++i) raw[i] = (i & 1) ? tmp[half + i / 2] : tmp[i / 2];
+        }
+        for (int l = 0; l < lines; ++l)
+            for (int c = 0; c < 3; ++c) {
+                const Chan &ch = chans[(size_t)idx[c]];
+                const uint8_t *q = raw.data() + bytesPerLine * l + chanOff[(size_t)idx[c]];
+                for (int x = 0; x < w; ++x) {
+                    float v;
+                    if (ch.type == 1) { uint16_t hb; memcpy(&hb, q + 2 * (size_t)x, 2); v = halfToFloat(hb); } else memcpy(&v, q + 4 * (size_t)x, 4);
+                    rgb[3 * ((size_t)(y0 + l) * w + x) + c] = v;
+                }
+            }
+    }
+    return true;
+}
+
 bool readImage(const std::string &path, int &w, int &h, std::vector<float> &rgb, std::string &err) {
     std::ifstream probe(path, std::ios::binary);
     if (!probe) { err = "cannot open file"; return false; }
-    char m[2] = {0, 0}; probe.read(m, 2);
+    char m[4] = {0, 0, 0, 0}; probe.read(m, 4);
     if (m[0] == 'P' && (m[1] == 'F' || m[1] == 'f')) return readPFM(path, w, h, rgb, err);
     if ((uint8_t)m[0] == 0x89 && m[1] == 'P') return readPNG(path, w, h, rgb, err);
-    err = "unsupported image format (this build decodes PNG and PFM; the reference used OpenImageIO)";
+    if (m[0] == '#' && m[1] == '?') return readHDR(path, w, h, rgb, err);
+    if ((uint8_t)m[0] == 0x76 && (uint8_t)m[1] == 0x2f && (uint8_t)m[2] == 0x31 && (uint8_t)m[3] == 0x01) return readEXR(path, w, h, rgb, err);
+    err = "unsupported image format (this build decodes PNG, PFM, Radiance HDR and scanline OpenEXR; the reference used OpenImageIO)";
     return false;
 }
 

@@ -407,6 +407,18 @@ def host_registered_plugins(lib_path=LIB_HOST):
     return buf.value.decode().split()
 
 
+def host_read_image(path, lib_path=LIB_HOST):
+    """Decode an image file with the C++ host's imagetexture readers (PNG / PFM / HDR / EXR) -> (H, W, 3) float32."""
+    lib = C.CDLL(lib_path)
+    lib.kazen_host_last_error.restype = C.c_char_p
+    w, h = C.c_int(), C.c_int()
+    if lib.kazen_host_read_image(os.fsencode(path), C.byref(w), C.byref(h), None) != 0:
+        raise RuntimeError(lib.kazen_host_last_error().decode())
+    out = np.zeros((h.value, w.value, 3), np.float32)
+    lib.kazen_host_read_image(os.fsencode(path), C.byref(w), C.byref(h), out.ctypes.data_as(c_float_p))
+    return out
+
+
 def host_fallback_tables(lib_path=LIB_HOST):
     lib = C.CDLL(lib_path)
     bn = np.zeros((48, 128, 128), np.uint16); pm = np.zeros((5, 65536, 2), np.uint32)

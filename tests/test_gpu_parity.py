@@ -457,3 +457,17 @@ def test_c4_standin_pmj02bn_terminator_regularization(kzo, gpu_lib):
     ro, _ = O.resolve(O.render()); rg, _ = G.resolve(G.render())
     assert scenes.rel_mse(rg, ro).max() < IMAGE_RELMSE_TOL
     O.close(); G.close()
+
+
+def test_latlong_environment_map(kzo, gpu_lib):
+    """image-backed background (BackgroundTexture -> ImageTexture::eval(dir), texture.cpp:66-81,121-126): lat-long lookup on the GPU"""
+    rng = np.random.default_rng(17)
+    env = rng.uniform(0.0, 2.0, (16, 32, 3)).astype(np.float32)
+    sb = scenes.cornell_scene(64, 48, 16, "stratified", max_depth=4)
+    sb.background = sb.tex_background(1.5, sb.tex_image(env, srgb=False))
+    # open the box: drop the ceiling and the light meshes so that most paths escape to the environment
+    sb.meshes = [m for i, m in enumerate(sb.meshes) if i != 1 and m.light < 0]
+    O, G = _pair(kzo, sb)
+    ro, _ = O.resolve(O.render()); rg, _ = G.resolve(G.render())
+    assert ro.mean() > 0.05 and scenes.rel_mse(rg, ro).max() < IMAGE_RELMSE_TOL
+    O.close(); G.close()

@@ -271,3 +271,30 @@ def test_kiss_parameter_sweeps_follow_the_golden_images(host, kzo):
         eff_ours = ours[b] - ours[a]
         eff_gold = np.array(gold[b]) - np.array(gold[a])
         assert np.abs(eff_ours - eff_gold).max() < 2.5e-3, (a, b, eff_ours, eff_gold)
+
+
+def test_image_readers(host, tmp_path):
+    """imagetexture decoders of the host: PNG, PFM, Radiance HDR, scanline OpenEXR (NONE / RLE / ZIPS / ZIP, HALF / FLOAT)"""
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(8)
+    img = rng.uniform(0.0, 4.0, (19, 37, 3)).astype(np.float32)          # odd sizes: ZIP blocks of 16 lines with a ragged tail
+    bgr = np.ascontiguousarray(img[..., ::-1])
+    for comp in (cv2.IMWRITE_EXR_COMPRESSION_NO, cv2.IMWRITE_EXR_COMPRESSION_RLE, cv2.IMWRITE_EXR_COMPRESSION_ZIPS, cv2.IMWRITE_EXR_COMPRESSION_ZIP):
+        for typ, tol in ((cv2.IMWRITE_EXR_TYPE_FLOAT, 0.0), (cv2.IMWRITE_EXR_TYPE_HALF, 2e-3)):
+            p = str(tmp_path / f"t_{comp}_{typ}.exr")
+            assert cv2.imwrite(p, bgr, [cv2.IMWRITE_EXR_COMPRESSION, comp, cv2.IMWRITE_EXR_TYPE, typ])
+            got = host.host_read_image(p)
+            assert got.shape == img.shape and np.allclose(got, img, rtol=tol, atol=tol * 4), (comp, typ)
+    smooth = np.tile(np.linspace(0.1, 3.0, 64, dtype=np.float32)[None, :, None], (9, 1, 3))       # runs: exercises the HDR RLE path
+    p = str(tmp_path / "t.hdr")
+    assert cv2.imwrite(p, np.ascontiguousarray(smooth[..., ::-1]))
+    got = host.host_read_image(p)
+    assert got.shape == smooth.shape and np.allclose(got, smooth, rtol=1e-2)
+    # PFM written by hand (bottom-to-top scanlines, little endian)
+    p = str(tmp_path / "t.pfm")
+    with open(p, "wb") as f:
+        f.write(b"PF\n37 19\n-1.0\n"); f.write(img[::-1].tobytes())
+    assert np.array_equal(host.host_read_image(p), img)
+    with pytest.raises(RuntimeError, match="unsupported image format"):
+        (tmp_path / "x.jpg").write_bytes(b"\xff\xd8\xff\xe0junk"); host.host_read_image(str(tmp_path / "x.jpg"))

@@ -198,3 +198,15 @@ def test_exact_ties_resolve_by_ids_cpu(kzo, emu):
     hit = a["geom_id"] != 0xFFFFFFFF
     assert hit.any() and (a["geom_id"][hit] == 0).all()
     O.close(); E.close()
+
+
+def test_latlong_environment_map_cpu(kzo, emu):
+    rng = np.random.default_rng(17)
+    env = rng.uniform(0.0, 2.0, (16, 32, 3)).astype(np.float32)
+    sb = scenes.cornell_scene(32, 24, 16, "stratified", max_depth=4)
+    sb.background = sb.tex_background(1.5, sb.tex_image(env, srgb=False))
+    sb.meshes = [m for i, m in enumerate(sb.meshes) if i != 1 and m.light < 0]
+    O, E = _pair(kzo, emu, sb)
+    ro, _ = O.resolve(O.render()); re, _ = O.resolve(E.render())
+    assert ro.mean() > 0.05 and scenes.rel_mse(re, ro).max() < 1e-6
+    O.close(); E.close()
