@@ -349,6 +349,7 @@ int kzgpu_create(const int *device_ids, int n_devices, kzgpu_ctx **out) {
         d.grid_extend = persistent_grid(d, k_extend<false>, KZ_TRACE_THREADS);
         d.grid_shadow = persistent_grid(d, k_shadow, KZ_TRACE_THREADS);
         d.grid_trace = persistent_grid(d, k_trace, KZ_TRACE_THREADS);
+        if (const char *p = getenv("KZGPU_TRACE_CTAS_PER_SM")) { const int k = atoi(p); if (k >= 1 && k <= 16) d.grid_trace = d.sm_count * k; }     /* tuning experiments */
         d.grid_occ = persistent_grid(d, k_occluded, KZ_TRACE_THREADS);
         d.grid_shade[0] = persistent_grid(d, k_shade<KZ_CLASS_TERMINAL>, KZ_SHADE_THREADS);
         d.grid_shade[1] = persistent_grid(d, k_shade<KZ_CLASS_DIFFUSE>, KZ_SHADE_THREADS);

@@ -24,6 +24,9 @@
 #ifndef KZ_TRACE_THREADS
 #define KZ_TRACE_THREADS 128
 #endif
+#ifndef KZ_TRACE_MIN_BLOCKS
+#define KZ_TRACE_MIN_BLOCKS 1
+#endif
 #define KZ_SHADE_THREADS 128
 
 struct KzControl {
@@ -419,7 +422,7 @@ struct KzTraceJob {
         return false;
     }
 };
-__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_trace(KzScene sc, const KzF4 *rays, uint32_t n, float *hits, uint32_t *cursor, KzControl *ctl) {
+__global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_trace(KzScene sc, const KzF4 *rays, uint32_t n, float *hits, uint32_t *cursor, KzControl *ctl) {
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
     KzTraceJob job; job.rays = rays; job.hits = hits;
