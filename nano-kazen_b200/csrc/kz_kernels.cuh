@@ -25,7 +25,10 @@
 #define KZ_TRACE_THREADS 128
 #endif
 #ifndef KZ_TRACE_MIN_BLOCKS
-#define KZ_TRACE_MIN_BLOCKS 1
+#define KZ_TRACE_MIN_BLOCKS 0       /* k_extend / k_shadow: 0 = let ptxas choose (72-80 registers, no spills) */
+#endif
+#ifndef KZ_BATCH_MIN_BLOCKS
+#define KZ_BATCH_MIN_BLOCKS 8       /* k_trace / k_occluded: 8 CTAs of 128 threads = 64 registers, no spills (measured best) */
 #endif
 #define KZ_SHADE_THREADS 128
 
@@ -317,7 +320,7 @@ struct KzExtendJob {
 };
 
 template <bool FIRST>
-__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_extend(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int cur) {
+__global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_extend(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int cur) {
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
     KzExtendJob<FIRST> job(sc, st, ctl, q, q.ext[cur]);
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(KZ_TRACE_THREADS) k_extend(KzScene sc, KzPathS
 
 /* ---- shade: one integrator loop iteration for every path of one material class ------------ */
 #ifndef KZ_SHADE_MIN_BLOCKS
-#define KZ_SHADE_MIN_BLOCKS 1
+#define KZ_SHADE_MIN_BLOCKS 4
 #endif
 template <int CLS>
 __global__ void __launch_bounds__(KZ_SHADE_THREADS, KZ_SHADE_MIN_BLOCKS) k_shade(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int nxt, int bounce) {
@@ -392,7 +395,7 @@ struct KzShadowJob {
         return false;
     }
 };
-__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_shadow(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int nxt) {
+__global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_shadow(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int nxt) {
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
     KzShadowJob job(sc, st, q.shadow);
@@ -422,7 +425,7 @@ struct KzTraceJob {
         return false;
     }
 };
-__global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_trace(KzScene sc, const KzF4 *rays, uint32_t n, float *hits, uint32_t *cursor, KzControl *ctl) {
+__global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_BATCH_MIN_BLOCKS) k_trace(KzScene sc, const KzF4 *rays, uint32_t n, float *hits, uint32_t *cursor, KzControl *ctl) {
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
     KzTraceJob job; job.rays = rays; job.hits = hits;
@@ -449,7 +452,7 @@ struct KzOccludedJob {
         return false;
     }
 };
-__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_occluded(KzScene sc, const KzF4 *rays, uint32_t n, float eps, uint8_t *occ, uint8_t *segments,
+__global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_BATCH_MIN_BLOCKS) k_occluded(KzScene sc, const KzF4 *rays, uint32_t n, float eps, uint8_t *occ, uint8_t *segments,
                                                                 uint32_t *cursor, KzControl *ctl) {
     __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
     KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;

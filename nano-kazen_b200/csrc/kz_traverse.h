@@ -82,11 +82,18 @@ KZ_HD bool kz_pluecker(float ox, float oy, float oz, float dx, float dy, float d
     return true;
 }
 
+KZ_HD float kz_magic_adjust(float v, float k) { return fmaf(fabsf(v), k, v); }
 KZ_HD float kz_rcp_safe(float d) {
     if (fabsf(d) < 1e-18f) d = (kz_f2u(d) >> 31) ? -1e-18f : 1e-18f;
     return 1.0f / d;
 }
 
+#ifndef KZ_PRMT_AXES
+#define KZ_PRMT_AXES 4      /* bit mask: near x,y,z = 1,2,4; far x,y,z = 8,16,32; measured best: 8 of the 48 conversions */
+#endif
+#ifndef KZ_SLACK
+#define KZ_SLACK 3.814697265625e-06f
+#endif
 #ifndef KZ_SHORT_STACK
 #define KZ_SHORT_STACK 8          /* entries per thread kept in shared memory */
 #endif
@@ -117,7 +124,7 @@ struct KzLocalStack { uint32_t x[KZ_LOCAL_STACK], y[KZ_LOCAL_STACK]; };
 KZ_HD void kz_trav_init(const KzScene &sc, KzTrav &t, float ox, float oy, float oz, float dx, float dy, float dz, float tmin, float tmax) {
     t.ox = ox; t.oy = oy; t.oz = oz; t.dx = dx; t.dy = dy; t.dz = dz; t.tmin = tmin;
     t.best.t = tmax; t.best.u = 0.f; t.best.v = 0.f; t.best.prim = KZ_INVALID_ID; t.best.geom = KZ_INVALID_ID;
-    const float slack = (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + sc.scene_max_abs) * 3.814697265625e-06f;
+    const float slack = (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + sc.scene_max_abs) * KZ_SLACK;
     t.rdx = kz_rcp_safe(dx); t.rdy = kz_rcp_safe(dy); t.rdz = kz_rcp_safe(dz);
     const bool nx = t.rdx < 0.f, ny = t.rdy < 0.f, nz = t.rdz < 0.f;
     t.onx = nx ? ox - slack : ox + slack; t.ofx = nx ? ox + slack : ox - slack;
@@ -174,6 +181,14 @@ KZ_HD void kz_trav_node(const KzScene &sc, KzTrav &t, const KzStackRef &stk, KzL
     const float adx = kz_u2f(ex << 23) * t.rdx, ady = kz_u2f(ey << 23) * t.rdy, adz = kz_u2f(ez << 23) * t.rdz;
     const float anx = (px - t.onx) * t.rdx, any_ = (py - t.ony) * t.rdy, anz = (pz - t.onz) * t.rdz;
     const float afx = (px - t.ofx) * t.rdx, afy = (py - t.ofy) * t.rdy, afz = (pz - t.ofz) * t.rdz;
+    /* plane constants for the permute-built operands (32768 + q): a - 32768*ad, moved outwards by 2^-22 |.| which covers the
+     * rounding of this extra operation (<= 2^-24 |.|), so culling stays conservative */
+#define KZ_MAGIC_NEAR(a, ad) kz_magic_adjust(fmaf(-32768.f, ad, a), -2.384185791015625e-07f)
+#define KZ_MAGIC_FAR(a, ad) kz_magic_adjust(fmaf(-32768.f, ad, a), 2.384185791015625e-07f)
+    const float anx_m = KZ_MAGIC_NEAR(anx, adx), any_m = KZ_MAGIC_NEAR(any_, ady), anz_m = KZ_MAGIC_NEAR(anz, adz);
+    const float afx_m = KZ_MAGIC_FAR(afx, adx), afy_m = KZ_MAGIC_FAR(afy, ady), afz_m = KZ_MAGIC_FAR(afz, adz);
+#undef KZ_MAGIC_NEAR
+#undef KZ_MAGIC_FAR
     const bool nx = !(t.oct_inv & 1u), ny = !(t.oct_inv & 2u), nz = !(t.oct_inv & 4u);
     const uint32_t oct_inv4 = t.oct_inv * 0x01010101u;
     uint32_t hitmask = 0u;
@@ -196,12 +211,19 @@ KZ_HD void kz_trav_node(const KzScene &sc, KzTrav &t, const KzStackRef &stk, KzL
 #endif
         for (int j = 0; j < 4; ++j) {
             const int sh = 8 * j;
-            const float tnx = fmaf((float)((qnx >> sh) & 0xFFu), adx, anx);
-            const float tny = fmaf((float)((qny >> sh) & 0xFFu), ady, any_);
-            const float tnz = fmaf((float)((qnz >> sh) & 0xFFu), adz, anz);
-            const float tfx = fmaf((float)((qfx >> sh) & 0xFFu), adx, afx);
-            const float tfy = fmaf((float)((qfy >> sh) & 0xFFu), ady, afy);
-            const float tfz = fmaf((float)((qfz >> sh) & 0xFFu), adz, afz);
+            /* byte -> float: either a conversion (I2F.U8, XU pipe) or the bit pattern 0x4700bb00 = 32768 + b built by one
+             * byte permute (ALU pipe) with the 32768 folded into the plane constant; KZ_PRMT_AXES spreads the 48 conversions
+             * of a node step over the two pipes. */
+#define KZ_Q2F(w) ((float)(((w) >> sh) & 0xFFu))
+#define KZ_Q2M(w) kz_u2f(kz_byte_perm((w), 0x47000000u, 0x7404u | ((uint32_t)j << 4)))
+            const float tnx = (KZ_PRMT_AXES & 1) ? fmaf(KZ_Q2M(qnx), adx, anx_m) : fmaf(KZ_Q2F(qnx), adx, anx);
+            const float tny = (KZ_PRMT_AXES & 2) ? fmaf(KZ_Q2M(qny), ady, any_m) : fmaf(KZ_Q2F(qny), ady, any_);
+            const float tnz = (KZ_PRMT_AXES & 4) ? fmaf(KZ_Q2M(qnz), adz, anz_m) : fmaf(KZ_Q2F(qnz), adz, anz);
+            const float tfx = (KZ_PRMT_AXES & 8) ? fmaf(KZ_Q2M(qfx), adx, afx_m) : fmaf(KZ_Q2F(qfx), adx, afx);
+            const float tfy = (KZ_PRMT_AXES & 16) ? fmaf(KZ_Q2M(qfy), ady, afy_m) : fmaf(KZ_Q2F(qfy), ady, afy);
+            const float tfz = (KZ_PRMT_AXES & 32) ? fmaf(KZ_Q2M(qfz), adz, afz_m) : fmaf(KZ_Q2F(qfz), adz, afz);
+#undef KZ_Q2F
+#undef KZ_Q2M
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t.tmin));
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, t.best.t));
             if (cmin <= cmax) {

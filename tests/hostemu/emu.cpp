@@ -63,6 +63,34 @@ int kzemu_trace(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits) {
     return KZ_OK;
 }
 
+/* Traversal statistics of the plain per-ray loop (tuning aid): out = {node steps, triangle tests, triangle groups, accepted hits, max stack}. */
+int kzemu_trace_stats(kzemu *e, const kz_ray *rays, size_t n, uint64_t *out) {
+    const KzScene &sc = e->hs.sc;
+    std::atomic<uint64_t> a_nodes{0}, a_tris{0}, a_groups{0}, a_hits{0}, a_sp{0};
+    pfor(n, [&](size_t b, size_t en) {
+        KzStackRef stk;
+        uint64_t nodes = 0, tris = 0, groups = 0, hits = 0, maxsp = 0;
+        for (size_t i = b; i < en; ++i) {
+            const kz_ray &r = rays[i];
+            KzTrav t; KzLocalStack ls;
+            kz_trav_init(sc, t, r.o[0], r.o[1], r.o[2], r.d[0], r.d[1], r.d[2], r.tmin, r.tmax);
+            if (sc.n_nodes == 0) continue;
+            for (;;) {
+                if (t.ng_y > 0x00FFFFFFu) { kz_trav_node(sc, t, stk, ls); ++nodes; }
+                else { t.tg_x = t.ng_x; t.tg_y = t.ng_y; t.ng_x = 0u; t.ng_y = 0u; }
+                if (t.tg_y) ++groups;
+                while (t.tg_y != 0u) { const float before = t.best.t; const uint32_t bp = t.best.prim; kz_trav_tri(sc, t); ++tris; if (t.best.t != before || t.best.prim != bp) ++hits; }
+                if ((uint64_t)t.sp > maxsp) maxsp = t.sp;
+                if (t.ng_y <= 0x00FFFFFFu) { if (t.sp == 0) break; kz_trav_pop(t, stk, ls); }
+            }
+        }
+        a_nodes += nodes; a_tris += tris; a_groups += groups; a_hits += hits;
+        uint64_t cur = a_sp.load(); while (maxsp > cur && !a_sp.compare_exchange_weak(cur, maxsp)) {}
+    });
+    out[0] = a_nodes; out[1] = a_tris; out[2] = a_groups; out[3] = a_hits; out[4] = a_sp;
+    return KZ_OK;
+}
+
 int kzemu_occluded(kzemu *e, const kz_ray *rays, size_t n, float trace_bias, uint8_t *occ, uint8_t *segments) {
     const KzScene &sc = e->hs.sc;
     pfor(n, [&](size_t b, size_t en) {
