@@ -186,8 +186,7 @@ int ensure_pool(kzgpu_ctx *ctx, Device &d, uint32_t cap) {
     d.pool_cap = 0;
     int rc;
 #define AL(ptr) if ((rc = dev_alloc(ctx, d.pool_allocs, (size_t)cap, &(ptr)))) return rc
-    AL(d.st.ray_o); AL(d.st.ray_d); AL(d.st.hit); AL(d.st.hit_geom); AL(d.st.sray_o); AL(d.st.sray_d); AL(d.st.pending);
-    AL(d.st.thr); AL(d.st.L); AL(d.st.misc); AL(d.st.rng_state); AL(d.st.rng_inc); AL(d.st.dim); AL(d.st.pix); AL(d.st.sidx);
+    AL(d.st.a); AL(d.st.b); AL(d.st.c);
     AL(d.q.ext[0]); AL(d.q.ext[1]); AL(d.q.shadow);
     for (int c = 0; c < KZ_NUM_CLASSES; ++c) AL(d.q.cls[c]);
 #undef AL

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_raygen(KzScene sc, KzPathS
         const int y = ch.y0 + (int)((tile / ch.tiles_x) * 4u + (in_tile >> 3));
         valid = x < ch.x1 && y < ch.y1;
         if (valid) kz_raygen_item(sc, st, i, x, y, (uint32_t)(ch.spp_begin + (int)s_local));
-        else st.pix[i] = 0xFFFFFFFFu;
+        else st.b[i].smp.pix = 0xFFFFFFFFu;
     }
     kz_push(q0, kz_ext_counter(ctl, 0), valid, i);
     const uint32_t nvalid = (uint32_t)__popc(__ballot_sync(KZ_FULL, valid));
@@ -289,7 +289,8 @@ struct KzExtendJob {
         : sc(s), st(p), ctl(c), q(qq), queue(qu) { cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull; }
     __device__ __forceinline__ void begin(uint32_t item, KzRayIn &r) {
         slot = queue[item];
-        const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+        const KzRayRec ray = st.a[slot].ray;
+        const KzF4 ro = ray.o, rd = ray.d;
         r.ox = ro.x; r.oy = ro.y; r.oz = ro.z; r.tmin = ro.w; r.dx = rd.x; r.dy = rd.y; r.dz = rd.z; r.tmax = rd.w;
         d = mk3(rd.x, rd.y, rd.z);
         retraced = false;
@@ -312,8 +313,7 @@ struct KzExtendJob {
                 }
             }
         }
-        st.hit[slot] = mkf4(h.t, h.u, h.v, kz_u2f(h.prim));
-        st.hit_geom[slot] = h.geom;
+        st.a[slot].hit = mk_hit_rec(h);
         kz_push_divergent(q.cls, ctl->n_class, kz_classify(sc, h.geom), slot);
         return false;
     }
@@ -379,18 +379,19 @@ struct KzShadowJob {
     __device__ KzShadowJob(const KzScene &s, const KzPathState &p, const uint32_t *qu) : sc(s), st(p), queue(qu) { cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull; }
     __device__ __forceinline__ void begin(uint32_t item, KzRayIn &r) {
         slot = queue[item];
-        const KzF4 so = st.sray_o[slot], sd = st.sray_d[slot];
-        walk.start(r, mk3(so.x, so.y, so.z), mk3(sd.x, sd.y, sd.z), so.w, sd.w);
+        const KzF4 so = st.a[slot].ray.o;
+        const KzShdRec shd = st.c[slot].shd;
+        walk.start(r, mk3(so.x, so.y, so.z), mk3(shd.d.x, shd.d.y, shd.d.z), shd.pending.w, shd.d.w);
     }
     __device__ __forceinline__ bool end(uint32_t, const KzHit &h, KzRayIn &r) {
         cnt.rays_shadow += 1;
         const int s = walk.step(sc, h, sc.integrator.trace_bias, r);
         if (s == 2) return true;
         if (s == 0) {
-            const KzF4 p = st.pending[slot];
-            KzF4 L = st.L[slot];
+            const KzF4 p = st.c[slot].shd.pending;
+            KzF4 L = st.b[slot].rad.L;
             L.x += p.x; L.y += p.y; L.z += p.z;
-            st.L[slot] = L;
+            st.b[slot].rad.L = L;
         }
         return false;
     }
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_shado
 /* ---- accumulate: ImageBlock::put over the whole chunk (block.cpp:56-85) ------------------- */
 __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_accumulate(KzScene sc, KzPathState st, uint32_t count, KzF4 *frame) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count || st.pix[i] == 0xFFFFFFFFu) return;
+    if (i >= count || st.b[i].smp.pix == 0xFFFFFFFFu) return;
     kz_accumulate_item(sc, st, i, frame);
 }
 

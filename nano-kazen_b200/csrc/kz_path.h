@@ -18,23 +18,29 @@
 #define KZ_PATH_H
 #include "kz_shade.h"
 
+/* Path state: three 64-byte blocks per slot, grouped by which stage touches what, so that every access of a stage is a
+ * whole 32-byte DRAM sector (slots are visited in queue order, i.e. scattered: the former one-array-per-field layout moved a
+ * 32-byte sector for every 16- or 4-byte field, 12 sectors per shaded vertex instead of 5).  All members are 16-byte aligned,
+ * so a record moves as 128-bit loads / stores.
+ *   A = ray (read by extend, written by shade)      | hit (written by extend, read by shade)
+ *   B = throughput|eta, Li|bsdfWeight (shade, shadow, accumulate) | sampler state
+ *   C = shadow ray d|tmax, pending rgb|tmin (origin = A.ray.o)   | misc: bsdfPdf, accumulatedRoughness, pixelSample.xy */
+struct alignas(16) KzRayRec { KzF4 o, d; };                          /* o.xyz tmin | d.xyz tmax */
+struct alignas(16) KzHitRec { float t, u, v; uint32_t prim, geom, pad0, pad1, pad2; };
+struct alignas(64) KzBlockA { KzRayRec ray; KzHitRec hit; };
+struct alignas(16) KzRadRec { KzF4 thr, L; };                        /* throughput rgb, eta | Li rgb, bsdfWeight */
+struct alignas(16) KzSmpRec { uint64_t rng_state, rng_inc; uint32_t dim, pix /* px | py << 16 */, sidx, pad; };
+struct alignas(64) KzBlockB { KzRadRec rad; KzSmpRec smp; };
+struct alignas(16) KzShdRec { KzF4 d, pending; };                    /* d.xyz tmax | NEE rgb awaiting visibility, tmin */
+struct alignas(64) KzBlockC { KzShdRec shd; KzF4 misc; KzF4 pad; };
+static_assert(sizeof(KzBlockA) == 64 && sizeof(KzBlockB) == 64 && sizeof(KzBlockC) == 64, "path state blocks are 64 bytes");
+
 struct KzPathState {
-    KzF4 *ray_o;      /* o.xyz, tmin */
-    KzF4 *ray_d;      /* d.xyz, tmax */
-    KzF4 *hit;        /* t, u, v, prim(bits) */
-    uint32_t *hit_geom;
-    KzF4 *sray_o;     /* shadow ray */
-    KzF4 *sray_d;
-    KzF4 *pending;    /* rgb of the NEE contribution awaiting visibility */
-    KzF4 *thr;        /* throughput rgb, eta */
-    KzF4 *L;          /* Li rgb, bsdfWeight */
-    KzF4 *misc;       /* bsdfPdf, accumulatedRoughness, pixelSample.x, pixelSample.y */
-    uint64_t *rng_state;
-    uint64_t *rng_inc;
-    uint32_t *dim;
-    uint32_t *pix;    /* px | py << 16 */
-    uint32_t *sidx;   /* sample index */
+    KzBlockA *a;
+    KzBlockB *b;
+    KzBlockC *c;
 };
+KZ_HD KzHitRec mk_hit_rec(const KzHit &h) { KzHitRec r; r.t = h.t; r.u = h.u; r.v = h.v; r.prim = h.prim; r.geom = h.geom; r.pad0 = r.pad1 = r.pad2 = 0u; return r; }
 
 struct KzCounters {
     unsigned long long paths, rays_ext, rays_shadow, vertices;
@@ -79,6 +85,16 @@ KZ_HD void kz_camera_ray(const kz_camera_desc &c, kz2 samplePosition, kz2 apertu
 
 KZ_HD KzF4 mkf4(float x, float y, float z, float w) { KzF4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
+KZ_HD KzSmpRec kz_sampler_save(const KzSampler &sm) {
+    KzSmpRec r; r.rng_state = sm.state; r.rng_inc = sm.inc; r.dim = sm.dim;
+    r.pix = (uint32_t)sm.px | ((uint32_t)sm.py << 16); r.sidx = sm.sample_index; r.pad = 0u;
+    return r;
+}
+KZ_HD void kz_sampler_load(KzSampler &sm, const KzSmpRec &r) {
+    sm.state = r.rng_state; sm.inc = r.rng_inc; sm.dim = r.dim;
+    sm.px = (int32_t)(r.pix & 0xFFFFu); sm.py = (int32_t)(r.pix >> 16); sm.sample_index = r.sidx;
+}
+
 /* ---- raygen -------------------------------------------------------------------------------- */
 KZ_HD void kz_raygen_item(const KzScene &sc, const KzPathState &st, uint32_t slot, int px, int py, uint32_t sample_index) {
     KzSampler sm;
@@ -88,13 +104,12 @@ KZ_HD void kz_raygen_item(const KzScene &sc, const KzPathState &st, uint32_t slo
     kz2 aperture = kz_next2d(sc, sm);
     KzF4 ro, rd;
     kz_camera_ray(sc.camera, pixelSample, aperture, ro, rd);
-    st.ray_o[slot] = ro; st.ray_d[slot] = rd;
-    st.thr[slot] = mkf4(1.f, 1.f, 1.f, 1.f);
-    st.L[slot] = mkf4(0.f, 0.f, 0.f, 1.f);
-    st.misc[slot] = mkf4(0.f, 0.f, pixelSample.x, pixelSample.y);
-    st.rng_state[slot] = sm.state; st.rng_inc[slot] = sm.inc; st.dim[slot] = sm.dim;
-    st.pix[slot] = (uint32_t)px | ((uint32_t)py << 16);
-    st.sidx[slot] = sample_index;
+    KzRayRec ray; ray.o = ro; ray.d = rd;
+    st.a[slot].ray = ray;
+    KzRadRec rad; rad.thr = mkf4(1.f, 1.f, 1.f, 1.f); rad.L = mkf4(0.f, 0.f, 0.f, 1.f);
+    st.b[slot].rad = rad;
+    st.b[slot].smp = kz_sampler_save(sm);
+    st.c[slot].misc = mkf4(0.f, 0.f, pixelSample.x, pixelSample.y);
 }
 
 KZ_HD int kz_classify(const KzScene &sc, uint32_t geom) {
@@ -109,7 +124,8 @@ KZ_HD int kz_classify(const KzScene &sc, uint32_t geom) {
 /* ---- extend -------------------------------------------------------------------------------- */
 /* Traces the path's current ray, stores the hit, returns the material class of the hit. */
 KZ_HD int kz_extend_item(const KzScene &sc, const KzStackRef &stk, const KzPathState &st, uint32_t slot, int bounce, KzCounters &cnt) {
-    const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+    const KzRayRec ray = st.a[slot].ray;
+    const KzF4 ro = ray.o, rd = ray.d;
     KzHit h = kz_trace(sc, stk, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, false);
     cnt.rays_ext += 1;
     if (bounce == 0 && h.geom != KZ_INVALID_ID && sc.integrator.type == KZ_INTEGRATOR_PATH_MIS) {
@@ -126,8 +142,7 @@ KZ_HD int kz_extend_item(const KzScene &sc, const KzStackRef &stk, const KzPathS
             if (h2.geom != KZ_INVALID_ID) h = h2;
         }
     }
-    st.hit[slot] = mkf4(h.t, h.u, h.v, kz_u2f(h.prim));
-    st.hit_geom[slot] = h.geom;
+    st.a[slot].hit = mk_hit_rec(h);
     return kz_classify(sc, h.geom);
 }
 
@@ -138,11 +153,12 @@ KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &
 template <int CLS = -1>
 KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t slot, int bounce, KzCounters &cnt) {
     if ((CLS < 0 || CLS == KZ_CLASS_GENERIC) && sc.integrator.type != KZ_INTEGRATOR_PATH_MIS) return kz_shade_alt_item(sc, st, slot, bounce, cnt);
-    const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+    const KzBlockA A = st.a[slot];
+    const KzF4 ro = A.ray.o, rd = A.ray.d;
     const kz3 rayO = mk3(ro.x, ro.y, ro.z), rayD = mk3(rd.x, rd.y, rd.z);
-    const KzF4 hv = st.hit[slot];
-    KzHit h; h.t = hv.x; h.u = hv.y; h.v = hv.z; h.prim = kz_f2u(hv.w); h.geom = st.hit_geom[slot];
-    KzF4 thr4 = st.thr[slot], L4 = st.L[slot], misc = st.misc[slot];
+    KzHit h; h.t = A.hit.t; h.u = A.hit.u; h.v = A.hit.v; h.prim = A.hit.prim; h.geom = A.hit.geom;
+    const KzRadRec rad = st.b[slot].rad;
+    const KzF4 thr4 = rad.thr, L4 = rad.L, misc = st.c[slot].misc;
     kz3 throughput = mk3(thr4.x, thr4.y, thr4.z), L = mk3(L4.x, L4.y, L4.z);
     float eta = thr4.w, bsdfWeight = L4.w;
     const kz_integrator_desc I = sc.integrator;
@@ -152,7 +168,7 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
          * later: Li += throughput * background(ray.d) (integrator.cpp:315-318) */
         if (bounce > 0) {
             L += throughput * kz_background(sc, rayD);
-            st.L[slot] = mkf4(L.x, L.y, L.z, bsdfWeight);
+            st.b[slot].rad.L = mkf4(L.x, L.y, L.z, bsdfWeight);
         }
         return 0u;
     }
@@ -172,16 +188,14 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
         if (cosTheta > 0.f) {
             const kz_light_desc l = sc.lights[mesh.light];
             L += bsdfWeight * throughput * mk3(l.radiance[0], l.radiance[1], l.radiance[2]);
-            st.L[slot] = mkf4(L.x, L.y, L.z, bsdfWeight);
+            st.b[slot].rad.L = mkf4(L.x, L.y, L.z, bsdfWeight);
         }
         return 0u;
     }
     if (CLS == KZ_CLASS_TERMINAL) return 0u;      /* that queue only holds misses and light hits */
 
     KzSampler sm;
-    sm.state = st.rng_state[slot]; sm.inc = st.rng_inc[slot]; sm.dim = st.dim[slot];
-    const uint32_t pix = st.pix[slot];
-    sm.px = (int32_t)(pix & 0xFFFFu); sm.py = (int32_t)(pix >> 16); sm.sample_index = st.sidx[slot];
+    kz_sampler_load(sm, st.b[slot].smp);
 
     if (bounce >= 3) {   /* integrator.cpp:237-244 */
         const float probability = fminf(maxcoeff(throughput) * eta * eta, 0.95f);
@@ -230,9 +244,8 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
             const float lightWeight = power_heuristic(lpdf, bsdfPdf);
             const kz3 contrib = throughput * Ls * f * lightWeight;
             if (!iszero(contrib)) {
-                st.sray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, eps);
-                st.sray_d[slot] = mkf4(lwi.x, lwi.y, lwi.z, dist - eps);
-                st.pending[slot] = mkf4(contrib.x, contrib.y, contrib.z, 0.f);
+                KzShdRec shd; shd.d = mkf4(lwi.x, lwi.y, lwi.z, dist - eps); shd.pending = mkf4(contrib.x, contrib.y, contrib.z, eps);
+                st.c[slot].shd = shd;            /* origin: A.ray.o, written below */
                 flags |= KZ_SHADE_SHADOW;
             }
         }
@@ -249,14 +262,16 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     throughput *= weight;
     eta *= sampledEta;
     if (measure == KZ_MEASURE_DISCRETE) bsdfPdf = -1.f;      /* flag for the next vertex: bsdfWeight = 1 (integrator.cpp:329-331) */
-    st.rng_state[slot] = sm.state; st.dim[slot] = sm.dim;
-    st.thr[slot] = mkf4(throughput.x, throughput.y, throughput.z, eta);
-    st.L[slot] = mkf4(L.x, L.y, L.z, bsdfWeight);
-    if (iszero(throughput)) return flags;    /* dead path: every later term is multiplied by 0 */
+    KzBlockB B; B.rad.thr = mkf4(throughput.x, throughput.y, throughput.z, eta); B.rad.L = mkf4(L.x, L.y, L.z, bsdfWeight); B.smp = kz_sampler_save(sm);
+    st.b[slot] = B;
+    if (iszero(throughput)) {                /* dead path: every later term is multiplied by 0 */
+        if (flags) st.a[slot].ray.o = mkf4(its.p.x, its.p.y, its.p.z, eps);
+        return flags;
+    }
     const kz3 wow = to_world(its.sh, wo);
-    st.ray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, eps);
-    st.ray_d[slot] = mkf4(wow.x, wow.y, wow.z, KZ_INF);
-    st.misc[slot] = mkf4(bsdfPdf, its.acc_rough, misc.z, misc.w);
+    KzRayRec ray; ray.o = mkf4(its.p.x, its.p.y, its.p.z, eps); ray.d = mkf4(wow.x, wow.y, wow.z, KZ_INF);
+    st.a[slot].ray = ray;
+    st.c[slot].misc = mkf4(bsdfPdf, its.acc_rough, misc.z, misc.w);
     return flags | KZ_SHADE_CONTINUE;
 }
 
@@ -269,32 +284,31 @@ KZ_HD kz3 square_to_uniform_hemisphere(kz2 s) {            /* warp.cpp:68-79 */
  * through this routine: these integrators are not material sorted. */
 KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &st, uint32_t slot, int bounce, KzCounters &cnt) {
     const int type = sc.integrator.type;
-    const KzF4 ro = st.ray_o[slot], rd = st.ray_d[slot];
+    const KzBlockA A = st.a[slot];
+    const KzF4 ro = A.ray.o, rd = A.ray.d;
     const kz3 rayO = mk3(ro.x, ro.y, ro.z), rayD = mk3(rd.x, rd.y, rd.z);
-    const KzF4 hv = st.hit[slot];
-    KzHit h; h.t = hv.x; h.u = hv.y; h.v = hv.z; h.prim = kz_f2u(hv.w); h.geom = st.hit_geom[slot];
+    KzHit h; h.t = A.hit.t; h.u = A.hit.u; h.v = A.hit.v; h.prim = A.hit.prim; h.geom = A.hit.geom;
     if (h.geom == KZ_INVALID_ID) return 0u;                /* every one of them returns what it has on a miss */
-    KzF4 thr4 = st.thr[slot], L4 = st.L[slot];
+    const KzRadRec rad = st.b[slot].rad;
+    KzF4 thr4 = rad.thr, L4 = rad.L;
     kz3 weight = mk3(thr4.x, thr4.y, thr4.z), L = mk3(L4.x, L4.y, L4.z);
     KzIts its; its.acc_rough = 0.f;
     fill_intersection(sc, h, its, mk3(0.f));
     const KzMeshRec mesh = sc.meshes[its.mesh];
     if (type == KZ_INTEGRATOR_NORMALS) {                   /* integrator.cpp:19-29 */
-        st.L[slot] = mkf4(fabsf(its.geo_n.x), fabsf(its.geo_n.y), fabsf(its.geo_n.z), 1.f);
+        st.b[slot].rad.L = mkf4(fabsf(its.geo_n.x), fabsf(its.geo_n.y), fabsf(its.geo_n.z), 1.f);
         return 0u;
     }
     KzSampler sm;
-    sm.state = st.rng_state[slot]; sm.inc = st.rng_inc[slot]; sm.dim = st.dim[slot];
-    const uint32_t pix = st.pix[slot];
-    sm.px = (int32_t)(pix & 0xFFFFu); sm.py = (int32_t)(pix >> 16); sm.sample_index = st.sidx[slot];
+    kz_sampler_load(sm, st.b[slot].smp);
     if (type == KZ_INTEGRATOR_AO) {                        /* integrator.cpp:43-62 */
         const kz3 sample = square_to_uniform_hemisphere(kz_next2d(sc, sm));
         kz3 point = to_world(its.sh, sample);
-        st.sray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, KZ_EPSILON);
-        st.sray_d[slot] = mkf4(point.x, point.y, point.z, KZ_INF);
         const float cosTheta = dot(normalized(point), normalized(its.sh.n));
         const float v = (cosTheta / KZ_PI) / (0.5f * KZ_INV_PI);
-        st.pending[slot] = mkf4(v, v, v, 0.f);
+        st.a[slot].ray.o = mkf4(its.p.x, its.p.y, its.p.z, KZ_EPSILON);
+        KzShdRec shd; shd.d = mkf4(point.x, point.y, point.z, KZ_INF); shd.pending = mkf4(v, v, v, KZ_EPSILON);
+        st.c[slot].shd = shd;
         return KZ_SHADE_SHADOW;
     }
     const kz3 wiLocal = to_local(its.sh, -rayD);
@@ -335,33 +349,33 @@ KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &
                     bsdf_eval_pdf(bc, its, wiLocal, to_local(its.sh, lwi), &f, &pdf_unused);
                     const kz3 Lr = weight * (f * Ls * cosTheta) / (1.0f / (float)nl);
                     if (!iszero(Lr)) {
-                        st.sray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, 0.f);          /* Ray3f(ref, wi, 0, dist): light.cpp:24 */
-                        st.sray_d[slot] = mkf4(lwi.x, lwi.y, lwi.z, dist);
-                        st.pending[slot] = mkf4(Lr.x, Lr.y, Lr.z, 0.f);
+                        st.a[slot].ray.o = mkf4(its.p.x, its.p.y, its.p.z, 0.f);         /* Ray3f(ref, wi, 0, dist): light.cpp:24 */
+                        KzShdRec shd; shd.d = mkf4(lwi.x, lwi.y, lwi.z, dist); shd.pending = mkf4(Lr.x, Lr.y, Lr.z, 0.f);
+                        st.c[slot].shd = shd;
                         flags |= KZ_SHADE_SHADOW;
                     }
                 }
             }
-            st.L[slot] = mkf4(L.x, L.y, L.z, 1.f);
+            st.b[slot].rad.L = mkf4(L.x, L.y, L.z, 1.f);
             return flags;
         }
         const float s1 = kz_next1d(sc, sm);
         const kz2 s2 = kz_next2d(sc, sm);
         kz3 wo; float p; int measure; float e;
         const kz3 refl = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &p, &measure, &e);
-        if (!(kz_next1d(sc, sm) < 0.95f)) { st.L[slot] = mkf4(0.f, 0.f, 0.f, 1.f); return 0u; }      /* the whole recursion returns 0 */
+        if (!(kz_next1d(sc, sm) < 0.95f)) { st.b[slot].rad.L = mkf4(0.f, 0.f, 0.f, 1.f); return 0u; }      /* the whole recursion returns 0 */
         weight = weight * refl / 0.95f;
-        st.rng_state[slot] = sm.state; st.dim[slot] = sm.dim;
-        st.thr[slot] = mkf4(weight.x, weight.y, weight.z, 1.f);
-        if (iszero(weight) || bounce >= 4095) { st.L[slot] = mkf4(0.f, 0.f, 0.f, 1.f); return 0u; }
+        st.b[slot].smp = kz_sampler_save(sm);
+        st.b[slot].rad.thr = mkf4(weight.x, weight.y, weight.z, 1.f);
+        if (iszero(weight) || bounce >= 4095) { st.b[slot].rad.L = mkf4(0.f, 0.f, 0.f, 1.f); return 0u; }
         const kz3 wow = to_world(its.sh, wo);
-        st.ray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, KZ_EPSILON);
-        st.ray_d[slot] = mkf4(wow.x, wow.y, wow.z, KZ_INF);
+        KzRayRec ray; ray.o = mkf4(its.p.x, its.p.y, its.p.z, KZ_EPSILON); ray.d = mkf4(wow.x, wow.y, wow.z, KZ_INF);
+        st.a[slot].ray = ray;
         return KZ_SHADE_CONTINUE;
     }
     /* path_mats, integrator.cpp:142-173 */
     L += weight * Le;
-    st.L[slot] = mkf4(L.x, L.y, L.z, 1.f);
+    st.b[slot].rad.L = mkf4(L.x, L.y, L.z, 1.f);
     const float probability = fminf(weight.x, 0.95f);
     if (kz_next1d(sc, sm) >= probability) return 0u;
     weight = weight / probability;
@@ -372,12 +386,12 @@ KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &
     kz3 wo; float p; int measure; float e;
     const kz3 f = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &p, &measure, &e);
     weight *= f;
-    st.rng_state[slot] = sm.state; st.dim[slot] = sm.dim;
-    st.thr[slot] = mkf4(weight.x, weight.y, weight.z, 1.f);
+    st.b[slot].smp = kz_sampler_save(sm);
+    st.b[slot].rad.thr = mkf4(weight.x, weight.y, weight.z, 1.f);
     if (iszero(weight) || bounce >= 4095) return 0u;
     const kz3 wow = to_world(its.sh, wo);
-    st.ray_o[slot] = mkf4(its.p.x, its.p.y, its.p.z, KZ_EPSILON);
-    st.ray_d[slot] = mkf4(wow.x, wow.y, wow.z, KZ_INF);
+    KzRayRec ray; ray.o = mkf4(its.p.x, its.p.y, its.p.z, KZ_EPSILON); ray.d = mkf4(wow.x, wow.y, wow.z, KZ_INF);
+    st.a[slot].ray = ray;
     return KZ_SHADE_CONTINUE;
 }
 
@@ -401,15 +415,15 @@ KZ_HD bool kz_occluded_walk(const KzScene &sc, const KzStackRef &stk, kz3 o, kz3
     return occluded;
 }
 KZ_HD void kz_shadow_item(const KzScene &sc, const KzStackRef &stk, const KzPathState &st, uint32_t slot, KzCounters &cnt) {
-    const KzF4 so = st.sray_o[slot], sd = st.sray_d[slot];
+    const KzF4 so = st.a[slot].ray.o;
+    const KzShdRec shd = st.c[slot].shd;
     int seg;
-    const bool occ = kz_occluded_walk(sc, stk, mk3(so.x, so.y, so.z), mk3(sd.x, sd.y, sd.z), so.w, sd.w, sc.integrator.trace_bias, &seg);
+    const bool occ = kz_occluded_walk(sc, stk, mk3(so.x, so.y, so.z), mk3(shd.d.x, shd.d.y, shd.d.z), shd.pending.w, shd.d.w, sc.integrator.trace_bias, &seg);
     cnt.rays_shadow += (unsigned long long)seg;
     if (!occ) {
-        const KzF4 p = st.pending[slot];
-        KzF4 L = st.L[slot];
-        L.x += p.x; L.y += p.y; L.z += p.z;
-        st.L[slot] = L;
+        KzF4 L = st.b[slot].rad.L;
+        L.x += shd.pending.x; L.y += shd.pending.y; L.z += shd.pending.z;
+        st.b[slot].rad.L = L;
     }
 }
 
@@ -421,7 +435,7 @@ KZ_HD void kz_shadow_item(const KzScene &sc, const KzStackRef &stk, const KzPath
 #endif
 /* ImageBlock::put on the whole bordered frame, block.cpp:56-85 */
 KZ_HD void kz_accumulate_item(const KzScene &sc, const KzPathState &st, uint32_t slot, KzF4 *frame) {
-    const KzF4 L = st.L[slot], misc = st.misc[slot];
+    const KzF4 L = st.b[slot].rad.L, misc = st.c[slot].misc;
     const kz3 value = mk3(L.x, L.y, L.z);
     if (!color_valid(value)) return;
     const int b = sc.border, cols = sc.camera.width + 2 * b, rows = sc.camera.height + 2 * b;

@@ -13,8 +13,8 @@
 #include "kz_common.h"
 #include "../../include/kzgpu.h"
 
-struct KzU4 { uint32_t x, y, z, w; };
-struct KzF4 { float x, y, z, w; };
+struct alignas(16) KzU4 { uint32_t x, y, z, w; };     /* 16-byte aligned: moves as one 128-bit load / store */
+struct alignas(16) KzF4 { float x, y, z, w; };
 
 struct alignas(16) KzNode8 {
     float    px, py, pz;          /* quantisation origin                                   */

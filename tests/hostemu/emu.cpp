@@ -166,11 +166,8 @@ int kzemu_render(kzemu *e, const kz_render_req *req, float *frame_rgbw) {
     if (req->clear_frame) memset(frame, 0, fsz * sizeof(KzF4));
     const int w = req->x1 - req->x0, hgt = req->y1 - req->y0, nS = req->spp_end - req->spp_begin;
     const size_t B = (size_t)w * hgt * nS;
-    std::vector<KzF4> ray_o(B), ray_d(B), hit(B), sray_o(B), sray_d(B), pending(B), thr(B), L(B), misc(B);
-    std::vector<uint32_t> hit_geom(B), dim(B), pix(B), sidx(B);
-    std::vector<uint64_t> rs(B), ri(B);
-    KzPathState st{ray_o.data(), ray_d.data(), hit.data(), hit_geom.data(), sray_o.data(), sray_d.data(), pending.data(),
-                   thr.data(), L.data(), misc.data(), rs.data(), ri.data(), dim.data(), pix.data(), sidx.data()};
+    std::vector<KzBlockA> sa(B); std::vector<KzBlockB> sb(B); std::vector<KzBlockC> scv(B);
+    KzPathState st{sa.data(), sb.data(), scv.data()};
     std::vector<uint32_t> q(B), qn, qs;
     size_t slot = 0;
     for (int y = req->y0; y < req->y1; ++y)
