@@ -154,7 +154,7 @@ int upload_scene(kzgpu_ctx *ctx, Device &d) {
     d.sc.nodes = nullptr; d.sc.tris = nullptr; d.sc.n_nodes = 0; d.sc.n_tris = 0;
     int rc;
 #define UP(field, vec) if ((rc = dev_upload(ctx, d, d.scene_allocs, (vec).data(), (vec).size(), &d.sc.field))) return rc
-    UP(meshes, h.meshes); UP(positions, h.positions); UP(normals, h.normals); UP(uvs, h.uvs); UP(indices, h.indices);
+    UP(meshes, h.meshes); UP(vertices, h.vertices); UP(indices, h.indices);
     UP(light_cdf, h.light_cdf); UP(light_meshes, h.light_meshes); UP(bsdfs, h.bsdfs); UP(textures, h.textures);
     UP(images, h.images); UP(texels, h.texels); UP(lights, h.lights); UP(blue_noise, h.blue_noise); UP(pmj02bn, h.pmj);
     UP(pmj_pixel_samples, h.pmj_pixel_samples);

@@ -12,8 +12,9 @@
 
 struct KzHostScene {
     std::vector<KzMeshRec> meshes;
-    std::vector<float> positions, normals, uvs, light_cdf;
-    std::vector<uint32_t> indices;
+    std::vector<KzVertex> vertices;
+    std::vector<float> light_cdf;
+    std::vector<KzU4> indices;
     std::vector<int32_t> light_meshes;
     std::vector<kz_bsdf_desc> bsdfs;
     std::vector<kz_texture_desc> textures;
@@ -67,8 +68,6 @@ struct KzHostScene {
             images.push_back(r);
         }
         uint32_t voff = 0, foff = 0;
-        bool anyN = false, anyUV = false;
-        for (uint32_t g = 0; g < d->n_meshes; ++g) { anyN |= d->meshes[g].normals != nullptr; anyUV |= d->meshes[g].uvs != nullptr; }
         for (uint32_t g = 0; g < d->n_meshes; ++g) {
             const kz_mesh_desc &m = d->meshes[g];
             if (!m.positions || !m.indices) { error = "mesh buffers missing"; return false; }
@@ -78,19 +77,20 @@ struct KzHostScene {
             r.vertex_offset = voff; r.index_offset = foff; r.n_triangles = m.n_triangles;
             r.bsdf = m.bsdf; r.light = m.light;
             r.flags = (m.normals ? KZ_MESH_HAS_NORMALS : 0u) | (m.uvs ? KZ_MESH_HAS_UVS : 0u);
-            positions.insert(positions.end(), m.positions, m.positions + (size_t)3 * m.n_vertices);
-            if (anyN) {
-                if (m.normals) normals.insert(normals.end(), m.normals, m.normals + (size_t)3 * m.n_vertices);
-                else normals.resize(normals.size() + (size_t)3 * m.n_vertices, 0.f);
+            vertices.reserve(vertices.size() + m.n_vertices);
+            for (uint32_t i = 0; i < m.n_vertices; ++i) {
+                KzVertex v; memset(&v, 0, sizeof(v));
+                v.px = m.positions[3 * (size_t)i]; v.py = m.positions[3 * (size_t)i + 1]; v.pz = m.positions[3 * (size_t)i + 2];
+                if (m.normals) { v.nx = m.normals[3 * (size_t)i]; v.ny = m.normals[3 * (size_t)i + 1]; v.nz = m.normals[3 * (size_t)i + 2]; }
+                if (m.uvs) { v.u = m.uvs[2 * (size_t)i]; v.v = m.uvs[2 * (size_t)i + 1]; }
+                vertices.push_back(v);
             }
-            if (anyUV) {
-                if (m.uvs) uvs.insert(uvs.end(), m.uvs, m.uvs + (size_t)2 * m.n_vertices);
-                else uvs.resize(uvs.size() + (size_t)2 * m.n_vertices, 0.f);
+            indices.reserve(indices.size() + m.n_triangles);
+            for (uint32_t f = 0; f < m.n_triangles; ++f) {
+                KzU4 t; t.x = m.indices[3 * (size_t)f]; t.y = m.indices[3 * (size_t)f + 1]; t.z = m.indices[3 * (size_t)f + 2]; t.w = 0u;
+                if (t.x >= m.n_vertices || t.y >= m.n_vertices || t.z >= m.n_vertices) { error = "vertex index out of range"; return false; }
+                indices.push_back(t);
             }
-            for (uint32_t f = 0; f < m.n_triangles; ++f)
-                for (int k = 0; k < 3; ++k)
-                    if (m.indices[3 * f + k] >= m.n_vertices) { error = "vertex index out of range"; return false; }
-            indices.insert(indices.end(), m.indices, m.indices + (size_t)3 * m.n_triangles);
             if (m.light >= 0) {
                 r.flags |= KZ_MESH_IS_LIGHT;
                 if (d->lights[m.light].primary_visibility) r.flags |= KZ_MESH_LIGHT_VISIBLE;
@@ -177,7 +177,7 @@ struct KzHostScene {
 
     void finalize() {
         sc.meshes = meshes.data();
-        sc.positions = positions.data(); sc.normals = normals.data(); sc.uvs = uvs.data();
+        sc.vertices = vertices.data();
         sc.indices = indices.data(); sc.light_cdf = light_cdf.data(); sc.light_meshes = light_meshes.data();
         sc.bsdfs = bsdfs.data(); sc.textures = textures.data(); sc.images = images.data(); sc.texels = texels.data();
         sc.lights = lights.data();

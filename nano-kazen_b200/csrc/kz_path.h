@@ -220,12 +220,13 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
         const float su0 = sqrtf(kz_next1d(sc, sm));
         const float u = 1 - su0;
         const float v = kz_next1d(sc, sm) * su0;
-        const uint32_t *F = sc.indices + 3 * (size_t)(lm.index_offset + tri);
-        const kz3 p0 = kz_vpos(sc, lm, F[0]), p1 = kz_vpos(sc, lm, F[1]), p2 = kz_vpos(sc, lm, F[2]);
+        const KzU4 F = sc.indices[(size_t)lm.index_offset + tri];
+        const KzVertex lv0 = kz_vertex(sc, lm, F.x), lv1 = kz_vertex(sc, lm, F.y), lv2 = kz_vertex(sc, lm, F.z);
+        const kz3 p0 = kz_vpos(lv0), p1 = kz_vpos(lv1), p2 = kz_vpos(lv2);
         const kz3 lp = p0 + u * (p1 - p0) + v * (p2 - p0);
         kz3 ln;
         if (lm.flags & KZ_MESH_HAS_NORMALS) {
-            const kz3 n0 = kz_vnrm(sc, lm, F[0]), n1 = kz_vnrm(sc, lm, F[1]), n2 = kz_vnrm(sc, lm, F[2]);
+            const kz3 n0 = kz_vnrm(lv0), n1 = kz_vnrm(lv1), n2 = kz_vnrm(lv2);
             ln = n0 + u * (n1 - n0) + v * (n2 - n0);          /* not normalised, mesh.cpp:128-129 */
         } else {
             ln = normalized(cross(p1 - p0, p2 - p0));
@@ -331,11 +332,12 @@ KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &
                 const uint32_t tri = cdf_sample(sc.light_cdf + lm.cdf_offset, lm.n_triangles, kz_next1d(sc, sm));
                 const float su0 = sqrtf(kz_next1d(sc, sm));
                 const float u = 1 - su0, v = kz_next1d(sc, sm) * su0;
-                const uint32_t *F = sc.indices + 3 * (size_t)(lm.index_offset + tri);
-                const kz3 p0 = kz_vpos(sc, lm, F[0]), p1 = kz_vpos(sc, lm, F[1]), p2 = kz_vpos(sc, lm, F[2]);
+                const KzU4 F = sc.indices[(size_t)lm.index_offset + tri];
+                const KzVertex lv0 = kz_vertex(sc, lm, F.x), lv1 = kz_vertex(sc, lm, F.y), lv2 = kz_vertex(sc, lm, F.z);
+                const kz3 p0 = kz_vpos(lv0), p1 = kz_vpos(lv1), p2 = kz_vpos(lv2);
                 const kz3 lp = p0 + u * (p1 - p0) + v * (p2 - p0);
                 kz3 ln;
-                if (lm.flags & KZ_MESH_HAS_NORMALS) { const kz3 n0 = kz_vnrm(sc, lm, F[0]), n1 = kz_vnrm(sc, lm, F[1]), n2 = kz_vnrm(sc, lm, F[2]); ln = n0 + u * (n1 - n0) + v * (n2 - n0); }
+                if (lm.flags & KZ_MESH_HAS_NORMALS) { const kz3 n0 = kz_vnrm(lv0), n1 = kz_vnrm(lv1), n2 = kz_vnrm(lv2); ln = n0 + u * (n1 - n0) + v * (n2 - n0); }
                 else ln = normalized(cross(p1 - p0, p2 - p0));
                 const kz3 lwi = normalized(lp - its.p);
                 const float dist = norm(lp - its.p);

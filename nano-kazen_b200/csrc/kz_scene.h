@@ -6,7 +6,7 @@
  *   tris  : 48 bytes per triangle in leaf order = 3 x float4
  *           (p0.xyz | geomID), (p1.xyz | primID), (p2.xyz | 0): raw vertices because the
  *           parity-contracted Pluecker test works on origin-relative vertices.
- * Shading: per-mesh vertex/normal/uv/index arrays concatenated, addressed through KzMeshRec.
+ * Shading: per-mesh interleaved vertex records (KzVertex) and 16-byte index records concatenated, addressed through KzMeshRec.
  */
 #ifndef KZ_SCENE_H
 #define KZ_SCENE_H
@@ -28,7 +28,7 @@ struct alignas(16) KzNode8 {
 static_assert(sizeof(KzNode8) == 80, "node must be 80 bytes");
 
 struct KzMeshRec {
-    uint32_t vertex_offset;   /* into positions/normals/uvs (in vertices) */
+    uint32_t vertex_offset;   /* into vertices */
     uint32_t index_offset;    /* into indices (in triangles)               */
     uint32_t n_triangles;
     uint32_t flags;           /* KZ_MESH_* */
@@ -50,6 +50,10 @@ struct KzMeshRec {
 #define KZ_CLASS_GENERIC 4    /* the other BSDF plugins, dispatched at run time */
 #define KZ_NUM_CLASSES 5
 
+/* All attributes of a vertex in one 32-byte record (a whole DRAM sector, two 128-bit or one 256-bit load) instead of three
+ * arrays: a shaded vertex touches 3 sectors of vertex data + 1 of indices instead of up to 12. */
+struct alignas(16) KzVertex { float px, py, pz, u, nx, ny, nz, v; };
+
 struct KzImageRec {
     int32_t  width, height;
     uint32_t texel_offset;    /* float4 index of mip level 0 */
@@ -65,10 +69,8 @@ struct KzScene {
     /* shading geometry */
     const KzMeshRec *meshes;
     uint32_t         n_meshes;
-    const float    *positions;
-    const float    *normals;
-    const float    *uvs;
-    const uint32_t *indices;
+    const KzVertex *vertices;         /* position|u, normal|v: one 32-byte sector per vertex              */
+    const KzU4     *indices;          /* i0, i1, i2, 0 per triangle: one 128-bit load                      */
     const float    *light_cdf;
     const int32_t  *light_meshes;     /* scene.cpp:42-46 order */
     int32_t         n_light_meshes;

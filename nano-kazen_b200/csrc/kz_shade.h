@@ -652,9 +652,10 @@ KZ_HD float bsdf_regularize(const KzBsdfCtx &c) {   /* bsdf.h:125, bsdf.cpp:412,
 }
 
 /* ---- lights -------------------------------------------------------------------------------- */
-KZ_HD kz3 kz_vpos(const KzScene &sc, const KzMeshRec &m, uint32_t i) { const float *p = sc.positions + 3 * (size_t)(m.vertex_offset + i); return mk3(p[0], p[1], p[2]); }
-KZ_HD kz3 kz_vnrm(const KzScene &sc, const KzMeshRec &m, uint32_t i) { const float *p = sc.normals + 3 * (size_t)(m.vertex_offset + i); return mk3(p[0], p[1], p[2]); }
-KZ_HD kz2 kz_vuv(const KzScene &sc, const KzMeshRec &m, uint32_t i) { const float *p = sc.uvs + 2 * (size_t)(m.vertex_offset + i); return mk2(p[0], p[1]); }
+KZ_HD KzVertex kz_vertex(const KzScene &sc, const KzMeshRec &m, uint32_t i) { return sc.vertices[(size_t)m.vertex_offset + i]; }
+KZ_HD kz3 kz_vpos(const KzVertex &v) { return mk3(v.px, v.py, v.pz); }
+KZ_HD kz3 kz_vnrm(const KzVertex &v) { return mk3(v.nx, v.ny, v.nz); }
+KZ_HD kz2 kz_vuv(const KzVertex &v) { return mk2(v.u, v.v); }
 
 /* dpdf.h:99-104: std::lower_bound over cdf[0..n], then index = clamp(pos-1, 0, n-1) */
 KZ_HD uint32_t cdf_sample(const float *cdf, uint32_t n, float v) {
@@ -678,13 +679,13 @@ KZ_HD float light_pdf(float inv_area, kz3 ref, kz3 p, kz3 n, kz3 wi) {
 KZ_HD void fill_intersection(const KzScene &sc, const KzHit &h, KzIts &its, kz3 prev_dpdu) {
     its.mesh = (int32_t)h.geom;
     const KzMeshRec m = sc.meshes[h.geom];
-    const uint32_t *F = sc.indices + 3 * (size_t)(m.index_offset + h.prim);
-    const uint32_t i0 = F[0], i1 = F[1], i2 = F[2];
+    const KzU4 F = sc.indices[(size_t)m.index_offset + h.prim];
+    const KzVertex v0 = kz_vertex(sc, m, F.x), v1 = kz_vertex(sc, m, F.y), v2 = kz_vertex(sc, m, F.z);
     const float b0 = 1 - (h.u + h.v), b1 = h.u, b2 = h.v;
     const bool hasN = (m.flags & KZ_MESH_HAS_NORMALS) != 0, hasUV = (m.flags & KZ_MESH_HAS_UVS) != 0;
-    const kz3 p0 = kz_vpos(sc, m, i0), p1 = kz_vpos(sc, m, i1), p2 = kz_vpos(sc, m, i2);
+    const kz3 p0 = kz_vpos(v0), p1 = kz_vpos(v1), p2 = kz_vpos(v2);
     kz3 n0 = mk3(0.f), n1 = mk3(0.f), n2 = mk3(0.f);
-    if (hasN) { n0 = kz_vnrm(sc, m, i0); n1 = kz_vnrm(sc, m, i1); n2 = kz_vnrm(sc, m, i2); }
+    if (hasN) { n0 = kz_vnrm(v0); n1 = kz_vnrm(v1); n2 = kz_vnrm(v2); }
     const kz3 orignP = b0 * p0 + b1 * p1 + b2 * p2;
     kz3 tmpu = orignP - p0, tmpv = orignP - p1, tmpw = orignP - p2;
     const float dotu = fminf(0.f, dot(tmpu, n0)), dotv = fminf(0.f, dot(tmpv, n1)), dotw = fminf(0.f, dot(tmpw, n2));
@@ -697,7 +698,7 @@ KZ_HD void fill_intersection(const KzScene &sc, const KzHit &h, KzIts &its, kz3 
     its.dpdu = prev_dpdu;
     kz2 uv0 = mk2(0, 0), uv1 = mk2(0, 0), uv2 = mk2(0, 0);
     if (hasUV) {
-        uv0 = kz_vuv(sc, m, i0); uv1 = kz_vuv(sc, m, i1); uv2 = kz_vuv(sc, m, i2);
+        uv0 = kz_vuv(v0); uv1 = kz_vuv(v1); uv2 = kz_vuv(v2);
         its.uv = mk2(b0 * uv0.x + b1 * uv1.x + b2 * uv2.x, b0 * uv0.y + b1 * uv1.y + b2 * uv2.y);
     }
     if (hasN && hasUV) {
