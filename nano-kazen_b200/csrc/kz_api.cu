@@ -59,7 +59,7 @@ struct kzgpu_ctx {
     std::unique_ptr<KzHostScene> hs;
     bool class_present[KZ_NUM_CLASSES] = {true, false, false, false, false};
     bool uploaded = false, built = false;
-    uint32_t pool_cap = 1u << 22;
+    uint32_t pool_cap = 1u << 23;     /* path slots per chunk (192 B each = 1.5 GiB): every launch costs ~18 us of ramp + tail, so few big chunks win */
     kz_stats totals{};
     double ms_build = 0;
     uint64_t bvh_nodes = 0, bvh_bytes = 0;

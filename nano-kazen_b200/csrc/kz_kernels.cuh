@@ -114,7 +114,7 @@ __device__ __forceinline__ void kz_flush_counters(KzControl *ctl, const KzCounte
 /* ---- warp-cooperative persistent traversal ----------------------------------------------------
  * One warp owns 32 ray slots.  Lanes whose ray is finished are refilled from the work queue (one
  * ballot + one atomicAdd per refill) once enough loop iterations have been lost to idle lanes
- * (Aila/Laine persistent threads; thresholds as in Ylitie et al. 2017), and a lane postpones its
+ * (Aila/Laine persistent threads; thresholds re-measured on B200: refill as soon as 8 lane-iterations are lost), and a lane postpones its
  * leaf tests (pushes the triangle group back on its stack) while fewer than 1/5 of the active lanes
  * have triangles to test, so node steps and Pluecker tests run with fuller warps.
  * Traversal order therefore differs per launch, results do not: ties resolve by (geomID, primID).
@@ -125,10 +125,10 @@ __device__ __forceinline__ void kz_flush_counters(KzControl *ctl, const KzCounte
  *                                                           to continue the same item with a follow-up ray */
 struct KzRayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
 #ifndef KZ_FETCH_ND
-#define KZ_FETCH_ND 4
+#define KZ_FETCH_ND 0
 #endif
 #ifndef KZ_FETCH_NW
-#define KZ_FETCH_NW 16
+#define KZ_FETCH_NW 8
 #endif
 #ifndef KZ_TRAV_MODE
 #define KZ_TRAV_MODE 0          /* 0: one node step + postponed leaf tests per iteration; 1: while-while */

@@ -183,6 +183,9 @@ __global__ void k_fit(BuildState b) {
     }
 }
 
+#ifndef KZ_LBVH_MAXLEAF
+#define KZ_LBVH_MAXLEAF 1u       /* triangles per leaf slot of the collapsed LBVH (1..3); measured on the 2^20-triangle soup: 1 -> 2146/1750, 2 -> 1999/1559, 3 -> 1905/1444 Mrays/s (every triangle gets its own child box) */
+#endif
 struct WorkItem { int32_t bnode; uint32_t wnode; };
 
 struct CollapseState {
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
     const WorkItem it = cs.in[wi];
     int ch[8]; Box6 bx[8]; int nch = 0;
     const int root = it.bnode;
-    if (root < 0 || sub_count(b, root) <= 3u) { ch[0] = root; bx[0] = child_box(b, root); nch = 1; }
+    if (root < 0 || sub_count(b, root) <= KZ_LBVH_MAXLEAF) { ch[0] = root; bx[0] = child_box(b, root); nch = 1; }
     else {
         ch[0] = b.left[root]; ch[1] = b.right[root];
         bx[0] = child_box(b, ch[0]); bx[1] = child_box(b, ch[1]); nch = 2;
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
     while (nch < 8) {
         int best = -1; float bestA = -1.f;
         for (int i = 0; i < nch; ++i) {
-            if (ch[i] < 0 || sub_count(b, ch[i]) <= 3u) continue;
+            if (ch[i] < 0 || sub_count(b, ch[i]) <= KZ_LBVH_MAXLEAF) continue;
             const float a = box_area(bx[i]);
             if (a > bestA) { bestA = a; best = i; }
         }
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
         if (childAt[s] < 0) continue;
         const int c = ch[childAt[s]];
         const uint32_t cnt = sub_count(b, c);
-        if (c >= 0 && cnt > 3u) ++n_internal; else n_tris += cnt;
+        if (c >= 0 && cnt > KZ_LBVH_MAXLEAF) ++n_internal; else n_tris += cnt;
     }
     const uint32_t child_base = n_internal ? atomicAdd(cs.node_counter, n_internal) : 0u;
     const uint32_t tri_base = n_tris ? atomicAdd(cs.tri_counter, n_tris) : 0u;
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
             qhi[a][s] = (uint8_t)fmin(255.0, fmax(0.0, hi));
         }
         const uint32_t cnt = sub_count(b, c);
-        if (c >= 0 && cnt > 3u) {
+        if (c >= 0 && cnt > KZ_LBVH_MAXLEAF) {
             imask |= (uint8_t)(1u << s);
             nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
             WorkItem w; w.bnode = c; w.wnode = child_base + rel;

@@ -13,10 +13,10 @@ sb.set_camera(W, H, 40.0, pk.lookat((0, 0, -3), (0, 0, 0), (0, 1, 0)))
 sb.set_sampler("stratified", spp)
 d = sb.desc()
 t1 = time.time()
-G = pk.Gpu(d, builder=pk.BUILD_LBVH)
+G = pk.Gpu(d, builder=pk.BUILD_LBVH, lib_path=os.environ.get("KZGPU_LIB", pk.LIB_GPU))
 t2 = time.time()
 st0 = G.stats()
-G.render_device(0, 1); torch.cuda.synchronize(); G.stats(reset=True)
+G.render_device(0, sb.sampler.sample_count); torch.cuda.synchronize(); G.stats(reset=True)      # warm-up at full size: the path pool is grown on demand
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); G.render_device(0, sb.sampler.sample_count); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1); st = G.stats()

@@ -15,11 +15,12 @@ for lib in libs:
           G.render_device(0, spp)
       torch.cuda.synchronize(); G.stats(reset=True)
       e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      e0.record()
+      e0.record(); h0 = time.perf_counter()
       for _ in range(3):
           G.render_device(0, spp)
+      h1 = time.perf_counter()
       e1.record(); torch.cuda.synchronize()
       ms = e0.elapsed_time(e1) / 3
       st = G.stats()
-      print(f"{os.path.basename(lib)} pool 2^{log2}: {ms:8.2f} ms/frame  {W*H*spp/ms/1e3:8.1f} Mpaths/s  trace {st['ms_trace']/3:7.2f} shade {st['ms_shade']/3:7.2f} launches {st['kernel_launches']//3}", flush=True)
+      print(f"{os.path.basename(lib)} pool 2^{log2}: {ms:8.2f} ms/frame  {W*H*spp/ms/1e3:8.1f} Mpaths/s  trace {st['ms_trace']/3:7.2f} shade {st['ms_shade']/3:7.2f} launches {st['kernel_launches']//3}  host enqueue {(h1-h0)*1e3/3:6.2f} ms/frame", flush=True)
       G.close()
