@@ -23,17 +23,19 @@
  * 32-byte sector for every 16- or 4-byte field, 12 sectors per shaded vertex instead of 5).  All members are 16-byte aligned,
  * so a record moves as 128-bit loads / stores.
  *   A = ray (read by extend, written by shade)      | hit (written by extend, read by shade)
- *   B = throughput|eta, Li|bsdfWeight (shade, shadow, accumulate) | sampler state
- *   C = shadow ray d|tmax, pending rgb|tmin (origin = A.ray.o)   | misc: bsdfPdf, accumulatedRoughness, pixelSample.xy */
+ *   B = throughput|eta, Li|bsdfPdf of the last sampled direction (shade, shadow, accumulate) | sampler state, accumulatedRoughness
+ *   C = shadow ray d|tmax, pending rgb|tmin (origin = A.ray.o); 32 bytes
+ * Not stored: bsdfWeight (only lives between the tail of one loop iteration and the head of the next, both inside one shade
+ * pass) and the pixel sample position (recomputed from the addressable sampler when the path is splatted). */
 struct alignas(16) KzRayRec { KzF4 o, d; };                          /* o.xyz tmin | d.xyz tmax */
 struct alignas(16) KzHitRec { float t, u, v; uint32_t prim, geom, pad0, pad1, pad2; };
 struct alignas(64) KzBlockA { KzRayRec ray; KzHitRec hit; };
-struct alignas(16) KzRadRec { KzF4 thr, L; };                        /* throughput rgb, eta | Li rgb, bsdfWeight */
-struct alignas(16) KzSmpRec { uint64_t rng_state, rng_inc; uint32_t dim, pix /* px | py << 16 */, sidx, pad; };
+struct alignas(16) KzRadRec { KzF4 thr, L; };                        /* throughput rgb, eta | Li rgb, bsdfPdf (< 0: discrete) */
+struct alignas(16) KzSmpRec { uint64_t rng_state, rng_inc; uint32_t dim, pix /* px | py << 16 */, sidx; float acc_rough; };
 struct alignas(64) KzBlockB { KzRadRec rad; KzSmpRec smp; };
 struct alignas(16) KzShdRec { KzF4 d, pending; };                    /* d.xyz tmax | NEE rgb awaiting visibility, tmin */
-struct alignas(64) KzBlockC { KzShdRec shd; KzF4 misc; KzF4 pad; };
-static_assert(sizeof(KzBlockA) == 64 && sizeof(KzBlockB) == 64 && sizeof(KzBlockC) == 64, "path state blocks are 64 bytes");
+struct alignas(32) KzBlockC { KzShdRec shd; };
+static_assert(sizeof(KzBlockA) == 64 && sizeof(KzBlockB) == 64 && sizeof(KzBlockC) == 32, "path state blocks are whole sectors");
 
 struct KzPathState {
     KzBlockA *a;
@@ -85,9 +87,9 @@ KZ_HD void kz_camera_ray(const kz_camera_desc &c, kz2 samplePosition, kz2 apertu
 
 KZ_HD KzF4 mkf4(float x, float y, float z, float w) { KzF4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
-KZ_HD KzSmpRec kz_sampler_save(const KzSampler &sm) {
+KZ_HD KzSmpRec kz_sampler_save(const KzSampler &sm, float acc_rough) {
     KzSmpRec r; r.rng_state = sm.state; r.rng_inc = sm.inc; r.dim = sm.dim;
-    r.pix = (uint32_t)sm.px | ((uint32_t)sm.py << 16); r.sidx = sm.sample_index; r.pad = 0u;
+    r.pix = (uint32_t)sm.px | ((uint32_t)sm.py << 16); r.sidx = sm.sample_index; r.acc_rough = acc_rough;
     return r;
 }
 KZ_HD void kz_sampler_load(KzSampler &sm, const KzSmpRec &r) {
@@ -106,10 +108,8 @@ KZ_HD void kz_raygen_item(const KzScene &sc, const KzPathState &st, uint32_t slo
     kz_camera_ray(sc.camera, pixelSample, aperture, ro, rd);
     KzRayRec ray; ray.o = ro; ray.d = rd;
     st.a[slot].ray = ray;
-    KzRadRec rad; rad.thr = mkf4(1.f, 1.f, 1.f, 1.f); rad.L = mkf4(0.f, 0.f, 0.f, 1.f);
-    st.b[slot].rad = rad;
-    st.b[slot].smp = kz_sampler_save(sm);
-    st.c[slot].misc = mkf4(0.f, 0.f, pixelSample.x, pixelSample.y);
+    KzBlockB B; B.rad.thr = mkf4(1.f, 1.f, 1.f, 1.f); B.rad.L = mkf4(0.f, 0.f, 0.f, 0.f); B.smp = kz_sampler_save(sm, 0.f);
+    st.b[slot] = B;
 }
 
 KZ_HD int kz_classify(const KzScene &sc, uint32_t geom) {
@@ -158,9 +158,10 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     const kz3 rayO = mk3(ro.x, ro.y, ro.z), rayD = mk3(rd.x, rd.y, rd.z);
     KzHit h; h.t = A.hit.t; h.u = A.hit.u; h.v = A.hit.v; h.prim = A.hit.prim; h.geom = A.hit.geom;
     const KzRadRec rad = st.b[slot].rad;
-    const KzF4 thr4 = rad.thr, L4 = rad.L, misc = st.c[slot].misc;
+    const KzF4 thr4 = rad.thr, L4 = rad.L;
     kz3 throughput = mk3(thr4.x, thr4.y, thr4.z), L = mk3(L4.x, L4.y, L4.z);
-    float eta = thr4.w, bsdfWeight = L4.w;
+    float eta = thr4.w, bsdfWeight = 1.f;       /* integrator.cpp:207: only changes when a sampled ray lands on a light (below) */
+    const float prevBsdfPdf = L4.w;
     const kz_integrator_desc I = sc.integrator;
 
     if (CLS <= KZ_CLASS_TERMINAL && h.geom == KZ_INVALID_ID) {     /* material-class queues never hold misses */
@@ -172,14 +173,14 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
         }
         return 0u;
     }
-    KzIts its; its.acc_rough = misc.y;
+    KzIts its; its.acc_rough = 0.f;
     fill_intersection(sc, h, its, mk3(0.f));
     const KzMeshRec mesh = sc.meshes[its.mesh];
     const bool isLight = (mesh.flags & KZ_MESH_IS_LIGHT) != 0;
     if (bounce > 0 && isLight) {   /* integrator.cpp:322-327 */
         const kz3 wi = normalized(its.p - rayO);
         const float lightPdf_ = light_pdf(mesh.inv_area, rayO, its.p, its.sh.n, wi);
-        bsdfWeight = misc.x < 0.f ? 1.f : power_heuristic(misc.x, lightPdf_);
+        bsdfWeight = prevBsdfPdf < 0.f ? 1.f : power_heuristic(prevBsdfPdf, lightPdf_);
     }
     if (bounce >= I.max_depth) return 0u;          /* depth++ ; while (depth < maxDepth) */
     if (isLight) {       /* integrator.cpp:226-231 */
@@ -195,7 +196,11 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     if (CLS == KZ_CLASS_TERMINAL) return 0u;      /* that queue only holds misses and light hits */
 
     KzSampler sm;
-    kz_sampler_load(sm, st.b[slot].smp);
+    {
+        const KzSmpRec smp = st.b[slot].smp;
+        kz_sampler_load(sm, smp);
+        its.acc_rough = smp.acc_rough;
+    }
 
     if (bounce >= 3) {   /* integrator.cpp:237-244 */
         const float probability = fminf(maxcoeff(throughput) * eta * eta, 0.95f);
@@ -263,7 +268,7 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     throughput *= weight;
     eta *= sampledEta;
     if (measure == KZ_MEASURE_DISCRETE) bsdfPdf = -1.f;      /* flag for the next vertex: bsdfWeight = 1 (integrator.cpp:329-331) */
-    KzBlockB B; B.rad.thr = mkf4(throughput.x, throughput.y, throughput.z, eta); B.rad.L = mkf4(L.x, L.y, L.z, bsdfWeight); B.smp = kz_sampler_save(sm);
+    KzBlockB B; B.rad.thr = mkf4(throughput.x, throughput.y, throughput.z, eta); B.rad.L = mkf4(L.x, L.y, L.z, bsdfPdf); B.smp = kz_sampler_save(sm, its.acc_rough);
     st.b[slot] = B;
     if (iszero(throughput)) {                /* dead path: every later term is multiplied by 0 */
         if (flags) st.a[slot].ray.o = mkf4(its.p.x, its.p.y, its.p.z, eps);
@@ -272,7 +277,6 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     const kz3 wow = to_world(its.sh, wo);
     KzRayRec ray; ray.o = mkf4(its.p.x, its.p.y, its.p.z, eps); ray.d = mkf4(wow.x, wow.y, wow.z, KZ_INF);
     st.a[slot].ray = ray;
-    st.c[slot].misc = mkf4(bsdfPdf, its.acc_rough, misc.z, misc.w);
     return flags | KZ_SHADE_CONTINUE;
 }
 
@@ -367,7 +371,7 @@ KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &
         const kz3 refl = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &p, &measure, &e);
         if (!(kz_next1d(sc, sm) < 0.95f)) { st.b[slot].rad.L = mkf4(0.f, 0.f, 0.f, 1.f); return 0u; }      /* the whole recursion returns 0 */
         weight = weight * refl / 0.95f;
-        st.b[slot].smp = kz_sampler_save(sm);
+        st.b[slot].smp = kz_sampler_save(sm, 0.f);
         st.b[slot].rad.thr = mkf4(weight.x, weight.y, weight.z, 1.f);
         if (iszero(weight) || bounce >= 4095) { st.b[slot].rad.L = mkf4(0.f, 0.f, 0.f, 1.f); return 0u; }
         const kz3 wow = to_world(its.sh, wo);
@@ -388,7 +392,7 @@ KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &
     kz3 wo; float p; int measure; float e;
     const kz3 f = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &p, &measure, &e);
     weight *= f;
-    st.b[slot].smp = kz_sampler_save(sm);
+    st.b[slot].smp = kz_sampler_save(sm, 0.f);
     st.b[slot].rad.thr = mkf4(weight.x, weight.y, weight.z, 1.f);
     if (iszero(weight) || bounce >= 4095) return 0u;
     const kz3 wow = to_world(its.sh, wo);
@@ -437,9 +441,17 @@ KZ_HD void kz_shadow_item(const KzScene &sc, const KzStackRef &stk, const KzPath
 #endif
 /* ImageBlock::put on the whole bordered frame, block.cpp:56-85 */
 KZ_HD void kz_accumulate_item(const KzScene &sc, const KzPathState &st, uint32_t slot, KzF4 *frame) {
-    const KzF4 L = st.b[slot].rad.L, misc = st.c[slot].misc;
+    const KzF4 L = st.b[slot].rad.L;
     const kz3 value = mk3(L.x, L.y, L.z);
     if (!color_valid(value)) return;
+    /* the pixel sample position is not carried with the path: the samplers are addressable by (pixel, sample index), so it is
+     * drawn again exactly as in raygen (renderer.cpp:25-26) */
+    const KzSmpRec smp = st.b[slot].smp;
+    KzSampler sm;
+    const int32_t ipx = (int32_t)(smp.pix & 0xFFFFu), ipy = (int32_t)(smp.pix >> 16);
+    kz_sampler_start(sc, sm, ipx, ipy, smp.sidx);
+    const kz2 jitter = kz_next_pixel2d(sc, sm);
+    KzF4 misc; misc.z = (float)ipx + jitter.x; misc.w = (float)ipy + jitter.y;
     const int b = sc.border, cols = sc.camera.width + 2 * b, rows = sc.camera.height + 2 * b;
     const float radius = sc.filter.radius;
     const float px = misc.z - 0.5f - (float)(0 - b), py = misc.w - 0.5f - (float)(0 - b);
