@@ -296,6 +296,8 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
         }
         {
             Timed t(d, s, CAT_SHADE);
+            /* (a tiled variant that pre-sums the taps of 256 neighbouring paths in shared memory was 10 % slower end to end:
+             * shared-memory float atomics are compare-and-swap loops, the 128-bit global reductions are not) */
             k_accumulate<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, d.st, ch.count, d.frame);
             ++d.launches;
         }

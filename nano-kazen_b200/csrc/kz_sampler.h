@@ -69,6 +69,15 @@ KZ_HD uint32_t kz_permute(uint32_t i, uint32_t l, uint32_t p) {
 
 #define KZ_PCG_MULT 0x5851f42d4c957f2dULL
 
+#if defined(__CUDACC__)
+#define KZ_CONSTEXPR_HD __host__ __device__ constexpr
+#else
+#define KZ_CONSTEXPR_HD constexpr
+#endif
+/* cur_mult and cur_plus / inc of pcg32::advance after 16 rounds with no bit set in delta */
+KZ_CONSTEXPR_HD uint64_t kz_pcg_mult_2_16() { uint64_t m = KZ_PCG_MULT; for (int i = 0; i < 16; ++i) m *= m; return m; }
+KZ_CONSTEXPR_HD uint64_t kz_pcg_plus_2_16() { uint64_t m = KZ_PCG_MULT, g = 1u; for (int i = 0; i < 16; ++i) { g = (m + 1u) * g; m *= m; } return g; }
+
 struct KzSampler {
     uint64_t state, inc;
     int32_t  px, py;
@@ -92,8 +101,13 @@ KZ_HD void kz_pcg_seed_advance(KzSampler &s, uint64_t initseq, uint64_t delta) {
     kz_pcg_next(s);
     s.state += kz_mix_bits(initseq);
     kz_pcg_next(s);
-    /* advance(delta) */
+    /* advance(delta), pcg32.h:145-166.  generateSample always jumps by sampleIndex * 65536, so the first 16 rounds of the
+     * loop only square the multiplier: they are folded into two compile-time constants (same arithmetic mod 2^64). */
     uint64_t cur_mult = KZ_PCG_MULT, cur_plus = s.inc, acc_mult = 1u, acc_plus = 0u;
+    if ((delta & 0xFFFFull) == 0ull) {
+        constexpr uint64_t m16 = kz_pcg_mult_2_16(), g16 = kz_pcg_plus_2_16();      /* evaluated by the compiler */
+        cur_mult = m16; cur_plus = g16 * s.inc; delta >>= 16;
+    }
     while (delta > 0) {
         if (delta & 1) {
             acc_mult *= cur_mult;
