@@ -234,7 +234,7 @@ def main():
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if it is of this workload
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tj = json.load(f)
         if tj["tris"] == args.tris and tj["rays_per_launch"] == batches[0]["n"] == batches[1]["n"]:
             traffic = tj["dram_bytes_per_launch_mean"]
