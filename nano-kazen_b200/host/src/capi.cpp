@@ -63,6 +63,9 @@ int kazen_host_read_image(const char *path, int *w, int *h, float *rgb) {
     if (rgb) memcpy(rgb, px.data(), px.size() * sizeof(float));
     return 0;
 }
+int kazen_host_write_exr(const char *path, int w, int h, const float *rgb) {
+    try { writeEXR(path, w, h, rgb); return 0; } catch (const std::exception &e) { g_err = e.what(); return -1; }
+}
 void kazen_host_fallback_tables(uint16_t *blue_noise, uint32_t *pmj) {
     std::vector<uint16_t> bn; std::vector<uint32_t> pm;
     fallbackPmjTables(bn, pm);

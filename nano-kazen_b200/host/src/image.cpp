@@ -19,6 +19,43 @@ static void chunk(std::vector<uint8_t> &out, const char *type, const std::vector
     out.insert(out.end(), td.begin(), td.end());
     put32(out, (uint32_t)crc32(0L, td.data(), (uInt)td.size()));
 }
+/* Linear scene-referred output (bitmap.cpp:23-36 saved EXR through OpenImageIO): single-part scanline OpenEXR, three 32-bit float
+ * channels, no compression, increasing Y -- the plainest file every EXR reader (ours included) accepts. */
+void writeEXR(const std::string &path, int w, int h, const float *rgb) {
+    std::vector<uint8_t> o;
+    auto put = [&](const void *p, size_t n) { const uint8_t *b = (const uint8_t *)p; o.insert(o.end(), b, b + n); };
+    auto str = [&](const char *t) { put(t, strlen(t) + 1); };
+    auto i32 = [&](int32_t v) { put(&v, 4); };
+    auto f32 = [&](float v) { put(&v, 4); };
+    auto attr = [&](const char *name, const char *type, int32_t size) { str(name); str(type); i32(size); };
+    const uint8_t magic[8] = {0x76, 0x2f, 0x31, 0x01, 2, 0, 0, 0};
+    put(magic, 8);
+    attr("channels", "chlist", 3 * 18 + 1);
+    for (const char *c : {"B", "G", "R"}) { str(c); i32(2); const uint8_t lin[4] = {0, 0, 0, 0}; put(lin, 4); i32(1); i32(1); }
+    o.push_back(0);
+    attr("compression", "compression", 1); o.push_back(0);
+    attr("dataWindow", "box2i", 16); i32(0); i32(0); i32(w - 1); i32(h - 1);
+    attr("displayWindow", "box2i", 16); i32(0); i32(0); i32(w - 1); i32(h - 1);
+    attr("lineOrder", "lineOrder", 1); o.push_back(0);
+    attr("pixelAspectRatio", "float", 4); f32(1.f);
+    attr("screenWindowCenter", "v2f", 8); f32(0.f); f32(0.f);
+    attr("screenWindowWidth", "float", 4); f32(1.f);
+    o.push_back(0);
+    const uint64_t table = o.size(), block = 8 + (uint64_t)w * 12;
+    for (int y = 0; y < h; ++y) { const uint64_t off = table + 8ull * h + block * y; put(&off, 8); }
+    std::vector<float> row((size_t)w);
+    for (int y = 0; y < h; ++y) {
+        i32(y); i32((int32_t)(w * 12));
+        for (int c = 2; c >= 0; --c) {          /* B, G, R */
+            for (int x = 0; x < w; ++x) row[x] = rgb[3 * ((size_t)y * w + x) + c];
+            put(row.data(), (size_t)w * 4);
+        }
+    }
+    std::ofstream f(path, std::ios::binary);
+    f.write((const char *)o.data(), (std::streamsize)o.size());
+    if (!f) throw std::runtime_error("cannot write " + path);
+}
+
 void writePNG(const std::string &path, int w, int h, const uint8_t *rgb8) {
     std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
     std::vector<uint8_t> ihdr;

@@ -730,8 +730,9 @@ void render(Scene *scene, const std::string &outputName, bool writeRaw) {
     std::cout << "Render ready. (took " << ms << " ms, " << paths / ms / 1e3 << " Mpaths/s)" << std::endl;
     GpuPathMisIntegrator *g = dynamic_cast<GpuPathMisIntegrator *>(integrator);
     std::vector<uint8_t> srgb((size_t)result.width * result.height * 3);
+    std::vector<float> linear((size_t)result.width * result.height * 3, 0.f);
     if (g && g->context()) {
-        if (kzgpu_resolve(g->context(), result.data.data(), nullptr, srgb.data()) != KZ_OK) throw Exception(std::string("resolve failed: ") + kzgpu_last_error(g->context()));
+        if (kzgpu_resolve(g->context(), result.data.data(), linear.data(), srgb.data()) != KZ_OK) throw Exception(std::string("resolve failed: ") + kzgpu_last_error(g->context()));
         kz_stats st;
         if (kzgpu_stats(g->context(), &st) == KZ_OK)
             std::cout << "paths " << st.paths << ", extension rays " << st.rays_extension << ", shadow rays " << st.rays_shadow << ", vertices " << st.vertices
@@ -739,13 +740,14 @@ void render(Scene *scene, const std::string &outputName, bool writeRaw) {
                       << " nodes / " << st.bvh_bytes / 1048576.0 << " MiB" << std::endl;
     }
     writePNG(outputName + ".png", result.width, result.height, srgb.data());
+    writeEXR(outputName + ".exr", result.width, result.height, linear.data());
     if (writeRaw) {
         std::ofstream f(outputName + ".rgbw", std::ios::binary);
         const int32_t hdr[3] = {result.width, result.height, result.border};
         f.write((const char *)hdr, sizeof(hdr));
         f.write((const char *)result.data.data(), (std::streamsize)(result.data.size() * sizeof(float)));
     }
-    std::cout << "Wrote " << outputName << ".png" << std::endl;
+    std::cout << "Wrote " << outputName << ".png and " << outputName << ".exr" << std::endl;
 }
 }  // namespace renderer
 

@@ -419,6 +419,15 @@ def host_read_image(path, lib_path=LIB_HOST):
     return out
 
 
+def host_write_exr(path, rgb, lib_path=LIB_HOST):
+    """Write (H, W, 3) float32 linear RGB with the C++ host's EXR writer (the file `kazen` saves next to the PNG)."""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    lib = C.CDLL(lib_path)
+    lib.kazen_host_last_error.restype = C.c_char_p
+    if lib.kazen_host_write_exr(os.fsencode(path), C.c_int(rgb.shape[1]), C.c_int(rgb.shape[0]), rgb.ctypes.data_as(c_float_p)) != 0:
+        raise RuntimeError(lib.kazen_host_last_error().decode())
+
+
 def host_fallback_tables(lib_path=LIB_HOST):
     lib = C.CDLL(lib_path)
     bn = np.zeros((48, 128, 128), np.uint16); pm = np.zeros((5, 65536, 2), np.uint32)

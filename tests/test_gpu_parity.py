@@ -471,3 +471,44 @@ def test_latlong_environment_map(kzo, gpu_lib):
     ro, _ = O.resolve(O.render()); rg, _ = G.resolve(G.render())
     assert ro.mean() > 0.05 and scenes.rel_mse(rg, ro).max() < IMAGE_RELMSE_TOL
     O.close(); G.close()
+
+
+@pytest.mark.parametrize("n_tris", [1 << 20, 10_000_000])
+def test_full_size_properties(gpu_lib, n_tris):
+    """BASELINE configs[1] sizes (1 M and 10 M triangle soup, 2^22-ray batches): size-independent properties instead of the
+    oracle, which would need minutes here.
+      - the hit does not depend on the accel: GPU-built LBVH and host SAH return identical bytes (1 M only: the host SAH of 10 M
+        triangles takes too long for a test);
+      - clipping: re-tracing a hit ray with tmax = t returns the same hit (the interval is closed), with tmax just below t a miss
+        (t was the closest hit) -- the erase/decode round trip of this domain;
+      - batching: a permuted batch returns the permuted hits, two half batches return the whole;
+      - occlusion: with no invisible lights the occlusion walk is `hit exists` with one segment per ray."""
+    sb = scenes.soup_scene(n_tris)
+    d = sb.desc()
+    G = pk.Gpu(d, builder=pk.BUILD_LBVH)
+    rays = np.concatenate([scenes.primary_rays(1024), scenes.incoherent_rays((1 << 22) - (1 << 20))])
+    h = G.trace(rays)
+    hit = h["geom_id"] != 0xFFFFFFFF
+    assert 0.5 < hit.mean() < 1.0
+    assert np.all(h["t"][hit] >= rays["tmin"][hit]) and np.all(h["t"][hit] <= rays["tmax"][hit])
+    assert np.all(h["prim_id"][hit] < n_tris) and np.all(h["geom_id"][hit] == 0)
+    if n_tris <= (1 << 20):
+        G2 = pk.Gpu(d, builder=pk.BUILD_HOST_SAH)
+        assert G2.trace(rays).tobytes() == h.tobytes()
+        G2.close()
+    # clipping round trip
+    clip = rays[hit].copy(); clip["tmax"] = h["t"][hit]
+    hc = G.trace(clip)
+    assert hc.tobytes() == h[hit].tobytes()
+    clip["tmax"] = np.nextafter(h["t"][hit], np.float32(0))
+    below = G.trace(clip)
+    assert np.all(below["geom_id"] == 0xFFFFFFFF)
+    # batching
+    perm = np.random.default_rng(3).permutation(len(rays))
+    assert G.trace(rays[perm]).tobytes() == h[perm].tobytes()
+    half = len(rays) // 2
+    assert np.concatenate([G.trace(rays[:half]), G.trace(rays[half:])]).tobytes() == h.tobytes()
+    # occlusion walk without invisible lights
+    occ, seg = G.occluded(rays[: 1 << 20], 1e-4)
+    assert np.array_equal(occ.astype(bool), hit[: 1 << 20]) and np.all(seg == 1)
+    G.close()

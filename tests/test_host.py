@@ -298,3 +298,9 @@ def test_image_readers(host, tmp_path):
     assert np.array_equal(host.host_read_image(p), img)
     with pytest.raises(RuntimeError, match="unsupported image format"):
         (tmp_path / "x.jpg").write_bytes(b"\xff\xd8\xff\xe0junk"); host.host_read_image(str(tmp_path / "x.jpg"))
+    # the host's own EXR writer (bitmap.cpp:23-36): read back by our reader and by an independent one (OpenCV)
+    p = str(tmp_path / "w.exr")
+    host.host_write_exr(p, img)
+    assert np.array_equal(host.host_read_image(p), img)
+    back = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+    assert back is not None and np.array_equal(back[..., ::-1], img)
