@@ -143,10 +143,19 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
     KzTrav t;
     KzLocalStack ls;
     t.sp = 0; t.ng_y = 0u; t.tg_y = 0u;
-    bool active = false, exhausted = false;
+    bool active = false, finished = false, exhausted = false;
     uint32_t item = 0u;
     const uint32_t lane = kz_lane(), lt = (1u << lane) - 1u;
     for (;;) {
+        /* The warp is converged here.  Lanes whose ray ended since the last visit consume their hit TOGETHER (job.end is the
+         * expensive, divergent part of the extension and shadow jobs: post-intersection, state stores, queue pushes); doing it
+         * at the moment a lane finishes ran it with one or two lanes active. */
+        if (finished) {
+            KzRayIn r;
+            if (job.end(item, t.best, r)) kz_trav_init(sc, t, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tmin, r.tmax);
+            else active = false;
+            finished = false;
+        }
         if (!exhausted) {
             const uint32_t idle = __ballot_sync(KZ_FULL, !active);
             if (idle) {
@@ -171,7 +180,7 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
         int lost = 0;
 #if KZ_TRAV_MODE == 1
         /* while-while: every lane descends until it holds triangles (or is finished), then the warp tests triangles together */
-        while (active) {
+        while (active && !finished) {
             for (;;) {
                 if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
                 else if (t.ng_y != 0u) { t.tg_x = t.ng_x; t.tg_y = t.ng_y; t.ng_x = 0u; t.ng_y = 0u; }
@@ -183,13 +192,8 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
             }
             while (t.tg_y != 0u) kz_trav_tri(sc, t);
             if (t.ng_y <= 0x00FFFFFFu) {
-                if (t.sp == 0) {
-                    KzRayIn r;
-                    if (job.end(item, t.best, r)) kz_trav_init(sc, t, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tmin, r.tmax);
-                    else active = false;
-                } else {
-                    kz_trav_pop(t, stk, ls);
-                }
+                if (t.sp == 0) finished = true;
+                else kz_trav_pop(t, stk, ls);
             }
             if (!exhausted) {
                 lost += 32 - __popc(__activemask()) - KZ_FETCH_ND;
@@ -197,7 +201,7 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
             }
         }
 #else
-        while (active) {
+        while (active && !finished) {
             if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
             else { t.tg_x = t.ng_x; t.tg_y = t.ng_y; t.ng_x = 0u; t.ng_y = 0u; }
             const int total = __popc(__activemask());
@@ -210,13 +214,8 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
                 kz_trav_tri(sc, t);
             }
             if (t.ng_y <= 0x00FFFFFFu) {
-                if (t.sp == 0) {
-                    KzRayIn r;
-                    if (job.end(item, t.best, r)) kz_trav_init(sc, t, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.tmin, r.tmax);
-                    else active = false;
-                } else {
-                    kz_trav_pop(t, stk, ls);
-                }
+                if (t.sp == 0) finished = true;
+                else kz_trav_pop(t, stk, ls);
             }
             if (!exhausted) {
                 lost += 32 - __popc(__activemask()) - KZ_FETCH_ND;
