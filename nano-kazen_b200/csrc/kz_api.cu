@@ -233,8 +233,8 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
         if (d.pending.size() > 8192) fold_events(d);       /* very long renders: bound the number of live timing events */
         {
             Timed t(d, s, CAT_SHADE);
-            k_chunk_reset<<<1, 32, 0, s>>>(d.ctl);
-            k_raygen<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q.ext[0], ch);
+            k_chunk_reset<<<1, 32, 0, s>>>(d.ctl, ch.count, first == 0 ? (unsigned long long)w * (unsigned long long)h * (unsigned long long)nS : 0ull);
+            k_raygen<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.q.ext[0], ch);
             d.launches += 2;
         }
         if (alt) {

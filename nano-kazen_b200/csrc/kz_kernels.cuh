@@ -238,9 +238,11 @@ __device__ __forceinline__ void kz_push_divergent(uint32_t *const *queues, uint3
     queues[which][base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = value;
 }
 
-__global__ void k_chunk_reset(KzControl *ctl) {
+/* Start of a chunk: raygen fills every slot, so the first extension queue is the identity over `count` slots (no atomics). */
+__global__ void k_chunk_reset(KzControl *ctl, uint32_t count, unsigned long long new_paths) {
     if (threadIdx.x == 0) {
-        ctl->ext_shadow[0] = ctl->ext_shadow[1] = 0ull;
+        ctl->ext_shadow[0] = (unsigned long long)count; ctl->ext_shadow[1] = 0ull;
+        ctl->paths += new_paths;
         for (int c = 0; c < KZ_NUM_CLASSES; ++c) ctl->n_class[c] = 0u;
         ctl->head_ext = ctl->head_shadow = ctl->head_trace = 0u;
     }
@@ -257,23 +259,25 @@ __global__ void k_bounce_reset(KzControl *ctl, int nxt) {
 /* Slot i of the chunk = global path index first+i = (sample-major, 8x4-pixel-tile-minor), so a
  * warp is one 8x4 pixel tile of one sample index: coherent primary rays, and the splats of a
  * warp land on neighbouring frame texels instead of piling onto one pixel. */
-__global__ void __launch_bounds__(KZ_SHADE_THREADS) k_raygen(KzScene sc, KzPathState st, KzControl *ctl, uint32_t *q0, KzChunk ch) {
+__global__ void __launch_bounds__(KZ_SHADE_THREADS) k_raygen(KzScene sc, KzPathState st, uint32_t *q0, KzChunk ch) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < ch.count;
-    if (valid) {
-        const unsigned long long g = ch.first + i;
-        const uint32_t s_local = (uint32_t)(g / ch.npx_padded);
-        const uint32_t pix = (uint32_t)(g % ch.npx_padded);
-        const uint32_t tile = pix >> 5, in_tile = pix & 31u;
-        const int x = ch.x0 + (int)((tile % ch.tiles_x) * 8u + (in_tile & 7u));
-        const int y = ch.y0 + (int)((tile / ch.tiles_x) * 4u + (in_tile >> 3));
-        valid = x < ch.x1 && y < ch.y1;
-        if (valid) kz_raygen_item(sc, st, i, x, y, (uint32_t)(ch.spp_begin + (int)s_local));
-        else st.b[i].smp.pix = 0xFFFFFFFFu;
+    if (i >= ch.count) return;
+    const unsigned long long g = ch.first + i;
+    const uint32_t s_local = (uint32_t)(g / ch.npx_padded);
+    const uint32_t pix = (uint32_t)(g % ch.npx_padded);
+    const uint32_t tile = pix >> 5, in_tile = pix & 31u;
+    const int x = ch.x0 + (int)((tile % ch.tiles_x) * 8u + (in_tile & 7u));
+    const int y = ch.y0 + (int)((tile / ch.tiles_x) * 4u + (in_tile >> 3));
+    if (x < ch.x1 && y < ch.y1) kz_raygen_item(sc, st, i, x, y, (uint32_t)(ch.spp_begin + (int)s_local));
+    else {
+        /* padding lane of a tile that sticks out of the rectangle: a NaN ray (k_extend<true> drops it without counting it)
+         * and the marker k_accumulate skips */
+        const float nan = kz_u2f(0x7FC00000u);
+        KzRayRec ray; ray.o = mkf4(0.f, 0.f, 0.f, 0.f); ray.d = mkf4(nan, nan, nan, 0.f);
+        st.a[i].ray = ray;
+        st.b[i].smp.pix = 0xFFFFFFFFu;
     }
-    kz_push(q0, kz_ext_counter(ctl, 0), valid, i);
-    const uint32_t nvalid = (uint32_t)__popc(__ballot_sync(KZ_FULL, valid));
-    if (kz_lane() == 0u && nvalid) atomicAdd(&ctl->paths, (unsigned long long)nvalid);
+    q0[i] = i;      /* one warp-sized run of the queue = one tile of one sample index */
 }
 
 /* ---- extend: Scene::rayIntersect for every queued path, then sort by material class ------- */
@@ -295,6 +299,7 @@ struct KzExtendJob {
         retraced = false;
     }
     __device__ __forceinline__ bool end(uint32_t, const KzHit &hit, KzRayIn &r) {
+        if (FIRST && isnan(d.x)) return false;          /* padding slot of k_raygen: not a path */
         cnt.rays_ext += 1;
         KzHit h = hit;
         if (FIRST) {
@@ -328,6 +333,9 @@ __global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_exten
 }
 
 /* ---- shade: one integrator loop iteration for every path of one material class ------------ */
+#ifndef KZ_SHADE_BLOCK_PUSH
+#define KZ_SHADE_BLOCK_PUSH 1
+#endif
 #ifndef KZ_SHADE_MIN_BLOCKS
 #define KZ_SHADE_MIN_BLOCKS 4
 #endif
@@ -337,6 +345,41 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS, KZ_SHADE_MIN_BLOCKS) k_shade
     const uint32_t *queue = q.cls[CLS];
     const uint32_t stride = gridDim.x * blockDim.x;
     KzCounters cnt; cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull;
+#if KZ_SHADE_BLOCK_PUSH
+    /* queue space for the whole CTA with ONE packed atomic per iteration (the counter is a single address: 1.8 M warp-level
+     * atomics per frame serialise in the L2) */
+    constexpr int NW = KZ_SHADE_THREADS / 32;
+    __shared__ uint32_t s_cnt[2][2][NW];
+    __shared__ unsigned long long s_base[2];
+    int par = 0;
+    for (uint32_t bbase = blockIdx.x * blockDim.x; bbase < n; bbase += stride, par ^= 1) {
+        const uint32_t idx = bbase + threadIdx.x;
+        uint32_t slot = 0u, flags = 0u;
+        if (idx < n) {
+            slot = queue[idx];
+            flags = kz_shade_item<CLS>(sc, st, slot, bounce, cnt);
+        }
+        if (CLS != KZ_CLASS_TERMINAL) {
+            const bool pa = (flags & KZ_SHADE_CONTINUE) != 0u, pb = (flags & KZ_SHADE_SHADOW) != 0u;
+            const uint32_t ma = __ballot_sync(KZ_FULL, pa), mb = __ballot_sync(KZ_FULL, pb);
+            const uint32_t w = threadIdx.x >> 5, lane = kz_lane(), lt = (1u << lane) - 1u;
+            if (lane == 0u) { s_cnt[par][0][w] = (uint32_t)__popc(ma); s_cnt[par][1][w] = (uint32_t)__popc(mb); }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t ta = 0u, tb = 0u;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) { ta += s_cnt[par][0][k]; tb += s_cnt[par][1][k]; }
+                s_base[par] = (ta | tb) ? atomicAdd(&ctl->ext_shadow[nxt], (unsigned long long)ta | ((unsigned long long)tb << 32)) : 0ull;
+            }
+            __syncthreads();
+            uint32_t oa = (uint32_t)(s_base[par] & 0xFFFFFFFFull), ob = (uint32_t)(s_base[par] >> 32);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) if ((uint32_t)k < w) { oa += s_cnt[par][0][k]; ob += s_cnt[par][1][k]; }
+            if (pa) q.ext[nxt][oa + (uint32_t)__popc(ma & lt)] = slot;
+            if (pb) q.shadow[ob + (uint32_t)__popc(mb & lt)] = slot;
+        }
+    }
+#else
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
         const uint32_t idx = base + kz_lane();
         uint32_t slot = 0u, flags = 0u;
@@ -348,6 +391,7 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS, KZ_SHADE_MIN_BLOCKS) k_shade
         if (CLS != KZ_CLASS_TERMINAL)
             kz_push2(q.ext[nxt], q.shadow, &ctl->ext_shadow[nxt], (flags & KZ_SHADE_CONTINUE) != 0u, (flags & KZ_SHADE_SHADOW) != 0u, slot);
     }
+#endif
     kz_flush_counters(ctl, cnt);
 }
 
