@@ -449,9 +449,12 @@ __global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_shado
 
 /* ---- accumulate: ImageBlock::put over the whole chunk (block.cpp:56-85) ------------------- */
 __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_accumulate(KzScene sc, KzPathState st, uint32_t count, KzF4 *frame) {
+    __shared__ float s_table[33];
+    if (threadIdx.x < 33) s_table[threadIdx.x] = sc.filter.table[threadIdx.x];
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count || st.b[i].smp.pix == 0xFFFFFFFFu) return;
-    kz_accumulate_item(sc, st, i, frame);
+    kz_accumulate_item(sc, st, i, frame, s_table);
 }
 
 /* ---- batch entry points (parity tests + intersection microbench) -------------------------- */

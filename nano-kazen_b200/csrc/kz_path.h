@@ -440,7 +440,9 @@ KZ_HD void kz_shadow_item(const KzScene &sc, const KzStackRef &stk, const KzPath
 #define KZ_FRAME_ADD(ptr, vr, vg, vb, vw) do { (ptr)->x += (vr); (ptr)->y += (vg); (ptr)->z += (vb); (ptr)->w += (vw); } while (0)
 #endif
 /* ImageBlock::put on the whole bordered frame, block.cpp:56-85 */
-KZ_HD void kz_accumulate_item(const KzScene &sc, const KzPathState &st, uint32_t slot, KzF4 *frame) {
+/* `table`: the 33-entry filter table (the kernel reads it from a shared-memory copy: a dynamically indexed kernel parameter
+ * serialises divergent lanes in the constant cache). */
+KZ_HD void kz_accumulate_item(const KzScene &sc, const KzPathState &st, uint32_t slot, KzF4 *frame, const float *table) {
     const KzF4 L = st.b[slot].rad.L;
     const kz3 value = mk3(L.x, L.y, L.z);
     if (!color_valid(value)) return;
@@ -461,9 +463,9 @@ KZ_HD void kz_accumulate_item(const KzScene &sc, const KzPathState &st, uint32_t
     x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
     x1 = x1 > cols - 1 ? cols - 1 : x1; y1 = y1 > rows - 1 ? rows - 1 : y1;
     for (int y = y0; y <= y1; ++y) {
-        const float wy = sc.filter.table[(int)(fabsf((float)y - py) * lookup)];
+        const float wy = table[(int)(fabsf((float)y - py) * lookup)];
         for (int x = x0; x <= x1; ++x) {
-            const float wx = sc.filter.table[(int)(fabsf((float)x - px) * lookup)];
+            const float wx = table[(int)(fabsf((float)x - px) * lookup)];
             KzF4 *p = frame + ((size_t)y * cols + x);
             KZ_FRAME_ADD(p, value.x * wx * wy, value.y * wx * wy, value.z * wx * wy, 1.0f * wx * wy);
         }

@@ -198,7 +198,7 @@ int kzemu_render(kzemu *e, const kz_render_req *req, float *frame_rgbw) {
         });
         q.swap(qn);
     }
-    for (size_t i = 0; i < B; ++i) kz_accumulate_item(sc, st, (uint32_t)i, frame);
+    for (size_t i = 0; i < B; ++i) kz_accumulate_item(sc, st, (uint32_t)i, frame, sc.filter.table);
     e->total.paths += tot.paths; e->total.rays_ext += tot.rays_ext; e->total.rays_shadow += tot.rays_shadow; e->total.vertices += tot.vertices;
     return KZ_OK;
 }
