@@ -25,18 +25,27 @@ enum { CAT_TRACE = 0, CAT_SHADE = 1, CAT_TOTAL = 2 };
 
 struct EvPair { cudaEvent_t a, b; int cat; };
 
+struct Lane {
+    cudaStream_t stream = nullptr;   /* lane 1 only; lane 0 runs on the caller's stream */
+    cudaEvent_t done = nullptr;
+    uint32_t pool_cap = 0;
+    KzPathState st{};
+    KzQueues q{};
+    KzControl *ctl = nullptr;
+    std::vector<void *> allocs;
+};
+
 struct Device {
     int id = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
-    std::vector<void *> scene_allocs, accel_allocs, pool_allocs;
+    std::vector<void *> scene_allocs, accel_allocs;
     KzScene sc;                      /* device pointers */
     bool has_accel = false;
-    /* wavefront pool */
-    uint32_t pool_cap = 0;
-    KzPathState st;
-    KzQueues q;
-    KzControl *ctl = nullptr;
+    /* wavefront pools: the chunks of a render alternate between two lanes (own stream, path state, queues and control block), so
+     * the ramp-up and the tail of one chunk's persistent kernels are filled by the other chunk's work */
+    Lane lane[2];
+    KzControl *ctl = nullptr;        /* = lane[0].ctl: counters of the batch entry points */
     uint32_t *cursor = nullptr;      /* batch-trace fetch cursor */
     KzF4 *frame = nullptr;
     size_t frame_texels = 0;
@@ -59,7 +68,8 @@ struct kzgpu_ctx {
     std::unique_ptr<KzHostScene> hs;
     bool class_present[KZ_NUM_CLASSES] = {true, false, false, false, false};
     bool uploaded = false, built = false;
-    uint32_t pool_cap = 1u << 23;     /* path slots per chunk (192 B each = 1.5 GiB): every launch costs ~18 us of ramp + tail, so few big chunks win */
+    uint32_t pool_cap = 1u << 23;     /* path slots per chunk and lane (160 B each = 1.25 GiB): every launch costs ~18 us of ramp + tail, so few big chunks win */
+    int lanes = 2;                    /* concurrent chunks per device (KZGPU_LANES=1: strictly serial chunks) */
     kz_stats totals{};
     double ms_build = 0;
     uint64_t bvh_nodes = 0, bvh_bytes = 0;
@@ -180,17 +190,17 @@ int upload_scene(kzgpu_ctx *ctx, Device &d) {
     return KZ_OK;
 }
 
-int ensure_pool(kzgpu_ctx *ctx, Device &d, uint32_t cap) {
-    if (d.pool_cap >= cap) return KZ_OK;
-    free_all(d.pool_allocs);
-    d.pool_cap = 0;
+int ensure_pool(kzgpu_ctx *ctx, Lane &L, uint32_t cap) {
+    if (L.pool_cap >= cap) return KZ_OK;
+    free_all(L.allocs);
+    L.pool_cap = 0;
     int rc;
-#define AL(ptr) if ((rc = dev_alloc(ctx, d.pool_allocs, (size_t)cap, &(ptr)))) return rc
-    AL(d.st.a); AL(d.st.b); AL(d.st.c);
-    AL(d.q.ext[0]); AL(d.q.ext[1]); AL(d.q.shadow);
-    for (int c = 0; c < KZ_NUM_CLASSES; ++c) AL(d.q.cls[c]);
+#define AL(ptr) if ((rc = dev_alloc(ctx, L.allocs, (size_t)cap, &(ptr)))) return rc
+    AL(L.st.a); AL(L.st.b); AL(L.st.c);
+    AL(L.q.ext[0]); AL(L.q.ext[1]); AL(L.q.shadow);
+    for (int c = 0; c < KZ_NUM_CLASSES; ++c) AL(L.q.cls[c]);
 #undef AL
-    d.pool_cap = cap;
+    L.pool_cap = cap;
     return KZ_OK;
 }
 
@@ -207,7 +217,89 @@ int upload_accel(kzgpu_ctx *ctx, Device &d, const kzbvh::Built &b) {
     return KZ_OK;
 }
 
-/* Enqueues the whole wavefront for one request on `s`; never synchronises. */
+/* One chunk of path slots through the whole wavefront on stream `s` with the pool of lane `L`; never synchronises (except the
+ * unbounded whitted / path_mats loops, which poll a queue count). */
+int enqueue_chunk(kzgpu_ctx *ctx, Device &d, Lane &L, const KzChunk &ch, unsigned long long new_paths, cudaStream_t s) {
+    const KzScene &sc = d.sc;
+    const int max_depth = sc.integrator.max_depth;
+    /* the pass after the last vertex only resolves "miss -> background" (integrator.cpp:315-318) */
+    const int last_pass = sc.background >= 0 ? max_depth : max_depth - 1;
+    const bool alt = sc.integrator.type != KZ_INTEGRATOR_PATH_MIS;
+    if (d.pending.size() > 8192) fold_events(d);       /* very long renders: bound the number of live timing events */
+    {
+        Timed t(d, s, CAT_SHADE);
+        k_chunk_reset<<<1, 32, 0, s>>>(L.ctl, ch.count, new_paths);
+        k_raygen<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, L.st, L.q.ext[0], ch);
+        d.launches += 2;
+    }
+    if (alt) {
+        /* normals / ao: one pass; whitted / path_mats: unbounded loops ended by Russian roulette -- the only place the host
+         * looks at a queue count (every 8 passes), because these loops have no a-priori length */
+        const int passes = (sc.integrator.type == KZ_INTEGRATOR_NORMALS || sc.integrator.type == KZ_INTEGRATOR_AO) ? 1 : 4096;
+        for (int b = 0; b < passes; ++b) {
+            const int cur = b & 1, nxt = cur ^ 1;
+            {
+                Timed t(d, s, CAT_TRACE);
+                k_bounce_reset<<<1, 32, 0, s>>>(L.ctl, nxt);
+                if (b == 0) k_extend<true><<<d.grid_extend0, KZ_TRACE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, cur);
+                else k_extend<false><<<d.grid_extend, KZ_TRACE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, cur);
+                d.launches += 2;
+            }
+            {
+                Timed t(d, s, CAT_SHADE);
+                k_shade<KZ_CLASS_GENERIC><<<d.grid_shade[4], KZ_SHADE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, nxt, b);
+                ++d.launches;
+            }
+            if (sc.integrator.type == KZ_INTEGRATOR_AO || sc.integrator.type == KZ_INTEGRATOR_WHITTED) {
+                Timed t(d, s, CAT_TRACE);
+                k_shadow<<<d.grid_shadow, KZ_TRACE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, nxt);
+                ++d.launches;
+            }
+            if (passes > 1 && (b & 7) == 7) {
+                unsigned long long left = 0;
+                KZ_CUDA(ctx, cudaMemcpyAsync(&left, &L.ctl->ext_shadow[nxt], sizeof(left), cudaMemcpyDeviceToHost, s));
+                KZ_CUDA(ctx, cudaStreamSynchronize(s));
+                if ((left & 0xFFFFFFFFull) == 0ull) break;
+            }
+        }
+    } else
+    for (int b = 0; b <= last_pass; ++b) {
+        const int cur = b & 1, nxt = cur ^ 1;
+        {
+            Timed t(d, s, CAT_TRACE);
+            k_bounce_reset<<<1, 32, 0, s>>>(L.ctl, nxt);
+            if (b == 0) k_extend<true><<<d.grid_extend0, KZ_TRACE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, cur);
+            else k_extend<false><<<d.grid_extend, KZ_TRACE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, cur);
+            d.launches += 2;
+        }
+        {
+            Timed t(d, s, CAT_SHADE);
+            k_shade<KZ_CLASS_TERMINAL><<<d.grid_shade[0], KZ_SHADE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, nxt, b);
+            ++d.launches;
+            if (b < max_depth) {
+                if (ctx->class_present[KZ_CLASS_DIFFUSE]) { k_shade<KZ_CLASS_DIFFUSE><<<d.grid_shade[1], KZ_SHADE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, nxt, b); ++d.launches; }
+                if (ctx->class_present[KZ_CLASS_KISS]) { k_shade<KZ_CLASS_KISS><<<d.grid_shade[2], KZ_SHADE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, nxt, b); ++d.launches; }
+                if (ctx->class_present[KZ_CLASS_NORMALMAP]) { k_shade<KZ_CLASS_NORMALMAP><<<d.grid_shade[3], KZ_SHADE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, nxt, b); ++d.launches; }
+                if (ctx->class_present[KZ_CLASS_GENERIC]) { k_shade<KZ_CLASS_GENERIC><<<d.grid_shade[4], KZ_SHADE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, nxt, b); ++d.launches; }
+            }
+        }
+        if (b < max_depth && sc.n_light_meshes > 0) {
+            Timed t(d, s, CAT_TRACE);
+            k_shadow<<<d.grid_shadow, KZ_TRACE_THREADS, 0, s>>>(sc, L.st, L.ctl, L.q, nxt);
+            ++d.launches;
+        }
+    }
+    {
+        Timed t(d, s, CAT_SHADE);
+        /* (a tiled variant that pre-sums the taps of 256 neighbouring paths in shared memory was 10 % slower end to end:
+         * shared-memory float atomics are compare-and-swap loops, the 128-bit global reductions are not) */
+        k_accumulate<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, L.st, ch.count, d.frame);
+        ++d.launches;
+    }
+    return KZ_OK;
+}
+
+/* Enqueues the whole wavefront for one request; work is ordered after everything already on `s`, and `s` waits for it. */
 int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStream_t s) {
     const KzScene &sc = d.sc;
     const int w = req.x1 - req.x0, h = req.y1 - req.y0, nS = req.spp_end - req.spp_begin;
@@ -219,88 +311,29 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
     ch.npx_padded = ch.tiles_x * tiles_y * 32u;
     ch.spp_begin = req.spp_begin;
     const unsigned long long total = (unsigned long long)ch.npx_padded * (unsigned long long)nS;
-    const uint32_t cap = (uint32_t)std::min<unsigned long long>(ctx->pool_cap, (total + 31ull) & ~31ull);
-    int rc = ensure_pool(ctx, d, cap);
-    if (rc) return rc;
-    const int max_depth = sc.integrator.max_depth;
-    /* the pass after the last vertex only resolves "miss -> background" (integrator.cpp:315-318) */
-    const int last_pass = sc.background >= 0 ? max_depth : max_depth - 1;
+    /* two lanes once there is enough work for two chunks (the unbounded loops of whitted / path_mats poll the host: one lane) */
     const bool alt = sc.integrator.type != KZ_INTEGRATOR_PATH_MIS;
+    const int lanes = (!alt && ctx->lanes > 1 && total >= (1ull << 21)) ? 2 : 1;
+    const unsigned long long per_lane = (((total + lanes - 1) / lanes) + 31ull) & ~31ull;
+    const uint32_t cap = (uint32_t)std::min<unsigned long long>(ctx->pool_cap, per_lane);
+    int rc;
+    for (int l = 0; l < lanes; ++l) if ((rc = ensure_pool(ctx, d.lane[l], cap))) return rc;
     Timed total_t(d, s, CAT_TOTAL);
-    for (unsigned long long first = 0; first < total; first += d.pool_cap) {
+    if (lanes > 1) {       /* lane 1 starts after what is already queued on s (frame clear, earlier requests) */
+        KZ_CUDA(ctx, cudaEventRecord(d.lane[0].done, s));
+        KZ_CUDA(ctx, cudaStreamWaitEvent(d.lane[1].stream, d.lane[0].done, 0));
+    }
+    int k = 0;
+    for (unsigned long long first = 0; first < total; first += cap, ++k) {
+        Lane &L = d.lane[k % lanes];
         ch.first = first;
-        ch.count = (uint32_t)std::min<unsigned long long>(d.pool_cap, total - first);
-        if (d.pending.size() > 8192) fold_events(d);       /* very long renders: bound the number of live timing events */
-        {
-            Timed t(d, s, CAT_SHADE);
-            k_chunk_reset<<<1, 32, 0, s>>>(d.ctl, ch.count, first == 0 ? (unsigned long long)w * (unsigned long long)h * (unsigned long long)nS : 0ull);
-            k_raygen<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.q.ext[0], ch);
-            d.launches += 2;
-        }
-        if (alt) {
-            /* normals / ao: one pass; whitted / path_mats: unbounded loops ended by Russian roulette -- the only place the host
-             * looks at a queue count (every 8 passes), because these loops have no a-priori length */
-            const int passes = (sc.integrator.type == KZ_INTEGRATOR_NORMALS || sc.integrator.type == KZ_INTEGRATOR_AO) ? 1 : 4096;
-            for (int b = 0; b < passes; ++b) {
-                const int cur = b & 1, nxt = cur ^ 1;
-                {
-                    Timed t(d, s, CAT_TRACE);
-                    k_bounce_reset<<<1, 32, 0, s>>>(d.ctl, nxt);
-                    if (b == 0) k_extend<true><<<d.grid_extend0, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur);
-                    else k_extend<false><<<d.grid_extend, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur);
-                    d.launches += 2;
-                }
-                {
-                    Timed t(d, s, CAT_SHADE);
-                    k_shade<KZ_CLASS_GENERIC><<<d.grid_shade[4], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b);
-                    ++d.launches;
-                }
-                if (sc.integrator.type == KZ_INTEGRATOR_AO || sc.integrator.type == KZ_INTEGRATOR_WHITTED) {
-                    Timed t(d, s, CAT_TRACE);
-                    k_shadow<<<d.grid_shadow, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt);
-                    ++d.launches;
-                }
-                if (passes > 1 && (b & 7) == 7) {
-                    unsigned long long left = 0;
-                    KZ_CUDA(ctx, cudaMemcpyAsync(&left, &d.ctl->ext_shadow[nxt], sizeof(left), cudaMemcpyDeviceToHost, s));
-                    KZ_CUDA(ctx, cudaStreamSynchronize(s));
-                    if ((left & 0xFFFFFFFFull) == 0ull) break;
-                }
-            }
-        } else
-        for (int b = 0; b <= last_pass; ++b) {
-            const int cur = b & 1, nxt = cur ^ 1;
-            {
-                Timed t(d, s, CAT_TRACE);
-                k_bounce_reset<<<1, 32, 0, s>>>(d.ctl, nxt);
-                if (b == 0) k_extend<true><<<d.grid_extend0, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur);
-                else k_extend<false><<<d.grid_extend, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, cur);
-                d.launches += 2;
-            }
-            {
-                Timed t(d, s, CAT_SHADE);
-                k_shade<KZ_CLASS_TERMINAL><<<d.grid_shade[0], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b);
-                ++d.launches;
-                if (b < max_depth) {
-                    if (ctx->class_present[KZ_CLASS_DIFFUSE]) { k_shade<KZ_CLASS_DIFFUSE><<<d.grid_shade[1], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
-                    if (ctx->class_present[KZ_CLASS_KISS]) { k_shade<KZ_CLASS_KISS><<<d.grid_shade[2], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
-                    if (ctx->class_present[KZ_CLASS_NORMALMAP]) { k_shade<KZ_CLASS_NORMALMAP><<<d.grid_shade[3], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
-                    if (ctx->class_present[KZ_CLASS_GENERIC]) { k_shade<KZ_CLASS_GENERIC><<<d.grid_shade[4], KZ_SHADE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt, b); ++d.launches; }
-                }
-            }
-            if (b < max_depth && sc.n_light_meshes > 0) {
-                Timed t(d, s, CAT_TRACE);
-                k_shadow<<<d.grid_shadow, KZ_TRACE_THREADS, 0, s>>>(sc, d.st, d.ctl, d.q, nxt);
-                ++d.launches;
-            }
-        }
-        {
-            Timed t(d, s, CAT_SHADE);
-            /* (a tiled variant that pre-sums the taps of 256 neighbouring paths in shared memory was 10 % slower end to end:
-             * shared-memory float atomics are compare-and-swap loops, the 128-bit global reductions are not) */
-            k_accumulate<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, d.st, ch.count, d.frame);
-            ++d.launches;
-        }
+        ch.count = (uint32_t)std::min<unsigned long long>(cap, total - first);
+        const unsigned long long new_paths = first == 0 ? (unsigned long long)w * (unsigned long long)h * (unsigned long long)nS : 0ull;
+        if ((rc = enqueue_chunk(ctx, d, L, ch, new_paths, (k % lanes) == 0 ? s : L.stream))) return rc;
+    }
+    if (lanes > 1) {
+        KZ_CUDA(ctx, cudaEventRecord(d.lane[1].done, d.lane[1].stream));
+        KZ_CUDA(ctx, cudaStreamWaitEvent(s, d.lane[1].done, 0));
     }
     KZ_CUDA(ctx, cudaGetLastError());
     return KZ_OK;
@@ -332,6 +365,7 @@ int kzgpu_create(const int *device_ids, int n_devices, kzgpu_ctx **out) {
     else ids.assign(device_ids, device_ids + n_devices);
     std::unique_ptr<kzgpu_ctx> ctx(new kzgpu_ctx());
     if (const char *p = getenv("KZGPU_POOL_LOG2")) { int l = atoi(p); if (l >= 10 && l <= 26) ctx->pool_cap = 1u << l; }
+    if (const char *p = getenv("KZGPU_LANES")) { int l = atoi(p); if (l >= 1 && l <= 2) ctx->lanes = l; }
     for (int id : ids) {
         if (id < 0 || id >= count) return fail(nullptr, KZ_ERR_NO_DEVICE, "device id " + std::to_string(id) + " out of range");
         cudaDeviceProp prop;
@@ -340,11 +374,16 @@ int kzgpu_create(const int *device_ids, int n_devices, kzgpu_ctx **out) {
                                                                        "; this library is built for sm_100a only");
         Device d;
         d.id = id; d.sm_count = prop.multiProcessorCount;
-        memset(&d.sc, 0, sizeof(d.sc)); memset(&d.st, 0, sizeof(d.st)); memset(&d.q, 0, sizeof(d.q));
+        memset(&d.sc, 0, sizeof(d.sc));
         KZ_CUDA(nullptr, cudaSetDevice(id));
         KZ_CUDA(nullptr, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-        KZ_CUDA(nullptr, cudaMalloc(&d.ctl, sizeof(KzControl)));
-        KZ_CUDA(nullptr, cudaMemset(d.ctl, 0, sizeof(KzControl)));
+        for (Lane &L : d.lane) {
+            KZ_CUDA(nullptr, cudaMalloc(&L.ctl, sizeof(KzControl)));
+            KZ_CUDA(nullptr, cudaMemset(L.ctl, 0, sizeof(KzControl)));
+            KZ_CUDA(nullptr, cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+        }
+        KZ_CUDA(nullptr, cudaStreamCreateWithFlags(&d.lane[1].stream, cudaStreamNonBlocking));
+        d.ctl = d.lane[0].ctl;
         KZ_CUDA(nullptr, cudaMalloc(&d.cursor, 64));
         d.grid_extend0 = persistent_grid(d, k_extend<true>, KZ_TRACE_THREADS);
         d.grid_extend = persistent_grid(d, k_extend<false>, KZ_TRACE_THREADS);
@@ -370,9 +409,10 @@ void kzgpu_destroy(kzgpu_ctx *ctx) {
         cudaDeviceSynchronize();
         fold_events(d);
         for (cudaEvent_t e : d.free_events) cudaEventDestroy(e);
-        free_all(d.scene_allocs); free_all(d.accel_allocs); free_all(d.pool_allocs);
+        free_all(d.scene_allocs); free_all(d.accel_allocs);
+        for (Lane &L : d.lane) { free_all(L.allocs); cudaFree(L.ctl); if (L.done) cudaEventDestroy(L.done); if (L.stream) cudaStreamDestroy(L.stream); }
         for (int k = 0; k < 3; ++k) if (d.scratch[k]) cudaFree(d.scratch[k]);
-        cudaFree(d.ctl); cudaFree(d.cursor);
+        cudaFree(d.cursor);
         cudaStreamDestroy(d.stream);
         if (d.copy_in) cudaStreamDestroy(d.copy_in);
         if (d.copy_out) cudaStreamDestroy(d.copy_out);
@@ -721,9 +761,11 @@ int kzgpu_stats(kzgpu_ctx *ctx, kz_stats *out) {
         KZ_CUDA(ctx, cudaSetDevice(d.id));
         KZ_CUDA(ctx, cudaDeviceSynchronize());
         fold_events(d);
-        KzControl c;
-        KZ_CUDA(ctx, cudaMemcpy(&c, d.ctl, sizeof(c), cudaMemcpyDeviceToHost));
-        out->paths += c.paths; out->rays_extension += c.rays_ext; out->rays_shadow += c.rays_shadow; out->vertices += c.vertices;
+        for (Lane &L : d.lane) {
+            KzControl c;
+            KZ_CUDA(ctx, cudaMemcpy(&c, L.ctl, sizeof(c), cudaMemcpyDeviceToHost));
+            out->paths += c.paths; out->rays_extension += c.rays_ext; out->rays_shadow += c.rays_shadow; out->vertices += c.vertices;
+        }
         out->kernel_launches += d.launches;
         out->ms_trace = std::max(out->ms_trace, d.ms[CAT_TRACE]);
         out->ms_shade = std::max(out->ms_shade, d.ms[CAT_SHADE]);
@@ -741,7 +783,7 @@ int kzgpu_stats_reset(kzgpu_ctx *ctx) {
         fold_events(d);
         d.ms[0] = d.ms[1] = d.ms[2] = 0; d.launches = 0;
         /* keep queue state, zero the counters */
-        KZ_CUDA(ctx, cudaMemset(reinterpret_cast<char *>(d.ctl) + offsetof(KzControl, paths), 0, 4 * sizeof(unsigned long long)));
+        for (Lane &L : d.lane) KZ_CUDA(ctx, cudaMemset(reinterpret_cast<char *>(L.ctl) + offsetof(KzControl, paths), 0, 4 * sizeof(unsigned long long)));
     }
     return KZ_OK;
 }
