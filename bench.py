@@ -291,7 +291,9 @@ def main():
         out = {"value": npaths / (pms * 1e-3) / 1e6, "unit": "Mpaths/s", "mrays_per_s": rays_total / (pms * 1e-3) / 1e6, "ms_per_frame": pms,
                "scene": label + f", {W}x{H}, {spp} spp, stratified, path_mis maxDepth 5",
                "rays_per_path": rays_total / npaths, "scaling": "strong (sample-index shards + one NCCL reduce)",
-               "ms_trace": ps["ms_trace"] / psteps, "ms_shade": ps["ms_shade"] / psteps, "mean_rgb": None}
+               "ms_trace": ps["ms_trace"] / psteps, "ms_shade": ps["ms_shade"] / psteps,
+               "ms_note": "ms_trace / ms_shade are summed over the two concurrent lanes of a device (chunks overlap), so they exceed ms_per_frame",
+               "mean_rgb": None}
         if rank == 0:
             rgb, _ = GP.resolve(frame.cpu().numpy())
             out["mean_rgb"] = float(rgb.mean())

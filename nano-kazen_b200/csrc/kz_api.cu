@@ -25,6 +25,7 @@ enum { CAT_TRACE = 0, CAT_SHADE = 1, CAT_TOTAL = 2 };
 
 struct EvPair { cudaEvent_t a, b; int cat; };
 
+#define KZ_MAX_LANES 4
 struct Lane {
     cudaStream_t stream = nullptr;   /* lane 1 only; lane 0 runs on the caller's stream */
     cudaEvent_t done = nullptr;
@@ -44,7 +45,7 @@ struct Device {
     bool has_accel = false;
     /* wavefront pools: the chunks of a render alternate between two lanes (own stream, path state, queues and control block), so
      * the ramp-up and the tail of one chunk's persistent kernels are filled by the other chunk's work */
-    Lane lane[2];
+    Lane lane[KZ_MAX_LANES];
     KzControl *ctl = nullptr;        /* = lane[0].ctl: counters of the batch entry points */
     uint32_t *cursor = nullptr;      /* batch-trace fetch cursor */
     KzF4 *frame = nullptr;
@@ -69,7 +70,7 @@ struct kzgpu_ctx {
     bool class_present[KZ_NUM_CLASSES] = {true, false, false, false, false};
     bool uploaded = false, built = false;
     uint32_t pool_cap = 1u << 23;     /* path slots per chunk and lane (160 B each = 1.25 GiB): every launch costs ~18 us of ramp + tail, so few big chunks win */
-    int lanes = 2;                    /* concurrent chunks per device (KZGPU_LANES=1: strictly serial chunks) */
+    int lanes = 2;                    /* concurrent chunks per device, 1..4 (KZGPU_LANES=1: strictly serial chunks) */
     kz_stats totals{};
     double ms_build = 0;
     uint64_t bvh_nodes = 0, bvh_bytes = 0;
@@ -313,15 +314,15 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
     const unsigned long long total = (unsigned long long)ch.npx_padded * (unsigned long long)nS;
     /* two lanes once there is enough work for two chunks (the unbounded loops of whitted / path_mats poll the host: one lane) */
     const bool alt = sc.integrator.type != KZ_INTEGRATOR_PATH_MIS;
-    const int lanes = (!alt && ctx->lanes > 1 && total >= (1ull << 21)) ? 2 : 1;
+    const int lanes = (!alt && total >= (1ull << 21)) ? ctx->lanes : 1;
     const unsigned long long per_lane = (((total + lanes - 1) / lanes) + 31ull) & ~31ull;
     const uint32_t cap = (uint32_t)std::min<unsigned long long>(ctx->pool_cap, per_lane);
     int rc;
     for (int l = 0; l < lanes; ++l) if ((rc = ensure_pool(ctx, d.lane[l], cap))) return rc;
     Timed total_t(d, s, CAT_TOTAL);
-    if (lanes > 1) {       /* lane 1 starts after what is already queued on s (frame clear, earlier requests) */
+    if (lanes > 1) {       /* the other lanes start after what is already queued on s (frame clear, earlier requests) */
         KZ_CUDA(ctx, cudaEventRecord(d.lane[0].done, s));
-        KZ_CUDA(ctx, cudaStreamWaitEvent(d.lane[1].stream, d.lane[0].done, 0));
+        for (int l = 1; l < lanes; ++l) KZ_CUDA(ctx, cudaStreamWaitEvent(d.lane[l].stream, d.lane[0].done, 0));
     }
     int k = 0;
     for (unsigned long long first = 0; first < total; first += cap, ++k) {
@@ -331,9 +332,9 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
         const unsigned long long new_paths = first == 0 ? (unsigned long long)w * (unsigned long long)h * (unsigned long long)nS : 0ull;
         if ((rc = enqueue_chunk(ctx, d, L, ch, new_paths, (k % lanes) == 0 ? s : L.stream))) return rc;
     }
-    if (lanes > 1) {
-        KZ_CUDA(ctx, cudaEventRecord(d.lane[1].done, d.lane[1].stream));
-        KZ_CUDA(ctx, cudaStreamWaitEvent(s, d.lane[1].done, 0));
+    for (int l = 1; l < lanes; ++l) {
+        KZ_CUDA(ctx, cudaEventRecord(d.lane[l].done, d.lane[l].stream));
+        KZ_CUDA(ctx, cudaStreamWaitEvent(s, d.lane[l].done, 0));
     }
     KZ_CUDA(ctx, cudaGetLastError());
     return KZ_OK;
@@ -365,7 +366,7 @@ int kzgpu_create(const int *device_ids, int n_devices, kzgpu_ctx **out) {
     else ids.assign(device_ids, device_ids + n_devices);
     std::unique_ptr<kzgpu_ctx> ctx(new kzgpu_ctx());
     if (const char *p = getenv("KZGPU_POOL_LOG2")) { int l = atoi(p); if (l >= 10 && l <= 26) ctx->pool_cap = 1u << l; }
-    if (const char *p = getenv("KZGPU_LANES")) { int l = atoi(p); if (l >= 1 && l <= 2) ctx->lanes = l; }
+    if (const char *p = getenv("KZGPU_LANES")) { int l = atoi(p); if (l >= 1 && l <= KZ_MAX_LANES) ctx->lanes = l; }
     for (int id : ids) {
         if (id < 0 || id >= count) return fail(nullptr, KZ_ERR_NO_DEVICE, "device id " + std::to_string(id) + " out of range");
         cudaDeviceProp prop;
@@ -382,7 +383,7 @@ int kzgpu_create(const int *device_ids, int n_devices, kzgpu_ctx **out) {
             KZ_CUDA(nullptr, cudaMemset(L.ctl, 0, sizeof(KzControl)));
             KZ_CUDA(nullptr, cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
         }
-        KZ_CUDA(nullptr, cudaStreamCreateWithFlags(&d.lane[1].stream, cudaStreamNonBlocking));
+        for (int l = 1; l < KZ_MAX_LANES; ++l) KZ_CUDA(nullptr, cudaStreamCreateWithFlags(&d.lane[l].stream, cudaStreamNonBlocking));
         d.ctl = d.lane[0].ctl;
         KZ_CUDA(nullptr, cudaMalloc(&d.cursor, 64));
         d.grid_extend0 = persistent_grid(d, k_extend<true>, KZ_TRACE_THREADS);
