@@ -336,11 +336,17 @@ __global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_exten
 #ifndef KZ_SHADE_BLOCK_PUSH
 #define KZ_SHADE_BLOCK_PUSH 1
 #endif
+#ifndef KZ_SHADE_MIN_BLOCKS_DIFFUSE
+#define KZ_SHADE_MIN_BLOCKS_DIFFUSE 8       /* 64 registers: measured 4 -> 1038, 5 -> 1060, 6 -> 1056, 8 -> 1077 Mpaths/s */
+#endif
+#ifndef KZ_SHADE_MIN_BLOCKS_TERMINAL
+#define KZ_SHADE_MIN_BLOCKS_TERMINAL 4
+#endif
 #ifndef KZ_SHADE_MIN_BLOCKS
 #define KZ_SHADE_MIN_BLOCKS 4
 #endif
 template <int CLS>
-__global__ void __launch_bounds__(KZ_SHADE_THREADS, KZ_SHADE_MIN_BLOCKS) k_shade(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int nxt, int bounce) {
+__global__ void __launch_bounds__(KZ_SHADE_THREADS, (CLS == KZ_CLASS_DIFFUSE ? KZ_SHADE_MIN_BLOCKS_DIFFUSE : (CLS == KZ_CLASS_TERMINAL ? KZ_SHADE_MIN_BLOCKS_TERMINAL : KZ_SHADE_MIN_BLOCKS))) k_shade(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int nxt, int bounce) {
     const uint32_t n = ctl->n_class[CLS];
     const uint32_t *queue = q.cls[CLS];
     const uint32_t stride = gridDim.x * blockDim.x;
