@@ -25,7 +25,7 @@
 #define KZ_TRACE_THREADS 128
 #endif
 #ifndef KZ_TRACE_MIN_BLOCKS
-#define KZ_TRACE_MIN_BLOCKS 0       /* k_extend / k_shadow: 0 = let ptxas choose (72-80 registers, no spills) */
+#define KZ_TRACE_MIN_BLOCKS 8       /* k_extend / k_shadow: 64 registers (a few spilled words); with two lanes in flight 8 CTAs/SM beat ptxas' 72-80 registers: 1074 -> 1093 Mpaths/s */
 #endif
 #ifndef KZ_BATCH_MIN_BLOCKS
 #define KZ_BATCH_MIN_BLOCKS 8       /* k_trace / k_occluded: 8 CTAs of 128 threads = 64 registers, no spills (measured best) */
