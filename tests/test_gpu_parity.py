@@ -512,3 +512,22 @@ def test_full_size_properties(gpu_lib, n_tris):
     occ, seg = G.occluded(rays[: 1 << 20], 1e-4)
     assert np.array_equal(occ.astype(bool), hit[: 1 << 20]) and np.all(seg == 1)
     G.close()
+
+
+def test_lanes_and_pool_sizes_agree(gpu_lib, monkeypatch):
+    """One lane, two lanes, four lanes and small pools walk the same paths: identical counters, images equal up to the order of the
+    float reductions into the frame."""
+    sb = scenes.cornell_scene(160, 120, 144, "stratified")          # 2.8 M paths: enough for the lanes to engage
+    d = sb.desc()
+    out = []
+    for lanes, pool in (("1", "23"), ("2", "23"), ("4", "19"), ("2", "17")):
+        monkeypatch.setenv("KZGPU_LANES", lanes); monkeypatch.setenv("KZGPU_POOL_LOG2", pool)
+        G = pk.Gpu(d)
+        f = G.render()
+        rgb, _ = G.resolve(f)
+        st = G.stats()
+        out.append((rgb, st["paths"], st["rays_extension"], st["rays_shadow"], st["vertices"]))
+        G.close()
+    for o in out[1:]:
+        assert o[1:] == out[0][1:]
+        assert scenes.rel_mse(o[0], out[0][0]).max() < 1e-9
