@@ -518,7 +518,8 @@ int kzgpu_trace(kzgpu_ctx *ctx, int device, const kz_ray *rays, size_t n, int sh
      * concurrently (PCIe is full duplex; with pinned host buffers the call costs max(copy, trace), not the sum). */
     if (!d->copy_in) KZ_CUDA(ctx, cudaStreamCreateWithFlags(&d->copy_in, cudaStreamNonBlocking));
     if (!d->copy_out) KZ_CUDA(ctx, cudaStreamCreateWithFlags(&d->copy_out, cudaStreamNonBlocking));
-    const size_t chunk = std::min<size_t>(n, std::max<size_t>(1u << 20, (n + 15) / 16));
+    static const size_t n_chunks = [] { const char *e = getenv("KZGPU_TRACE_CHUNKS"); const int k = e ? atoi(e) : 16; return (size_t)(k < 1 ? 1 : (k > 256 ? 256 : k)); }();
+    const size_t chunk = std::min<size_t>(n, std::max<size_t>(1u << 20, (n + n_chunks - 1) / n_chunks));
     std::vector<cudaEvent_t> evs;
     char *d_rays = reinterpret_cast<char *>(d->scratch[0]), *d_hits = reinterpret_cast<char *>(d->scratch[1]);
     for (size_t first = 0; first < n && rc == KZ_OK; first += chunk) {
