@@ -153,6 +153,10 @@ public:
     /* builds (once) the POD tables the C ABI consumes */
     const kz_scene_desc &flatten();
     int gpus = 1;                                   /* devices the GPU integrator may use (CLI --gpus) */
+    /* progressive / resumable accumulation: render only the sample indices [sppBegin, sppEnd) of the sampler's sampleCount
+     * (sppEnd < 0: all) and start from a previously saved raw frame instead of an empty one (CLI --spp-range, --resume) */
+    int sppBegin = 0, sppEnd = -1;
+    std::string resumeFrame;
 private:
     std::vector<Mesh *> m_meshes;
     Camera *m_camera = nullptr;

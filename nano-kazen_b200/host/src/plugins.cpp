@@ -692,7 +692,20 @@ public:
         kzgpu_frame_dims(m_ctx, &w, &h, &b);
         result.width = w; result.height = h; result.border = b;
         result.data.assign((size_t)(w + 2 * b) * (h + 2 * b) * 4, 0.f);
-        kz_render_req req{0, 0, w, h, 0, (int32_t)scene->getSampler()->getSampleCount(), 1};
+        const int32_t total = (int32_t)scene->getSampler()->getSampleCount();
+        const int32_t s0 = std::max(0, scene->sppBegin), s1 = scene->sppEnd < 0 ? total : std::min(total, scene->sppEnd);
+        if (s0 >= s1) throw Exception("GPU integrator: empty sample range");
+        int32_t clear = 1;
+        if (!scene->resumeFrame.empty()) {      /* the frame is a sum over sample indices: keep adding to a saved one */
+            std::ifstream f(scene->resumeFrame, std::ios::binary);
+            int32_t hdr[3] = {0, 0, 0};
+            f.read((char *)hdr, sizeof(hdr));
+            if (!f || hdr[0] != w || hdr[1] != h || hdr[2] != b) throw Exception("resume frame \"" + scene->resumeFrame + "\" does not match this camera / filter");
+            f.read((char *)result.data.data(), (std::streamsize)(result.data.size() * sizeof(float)));
+            if (!f) throw Exception("resume frame \"" + scene->resumeFrame + "\" is truncated");
+            clear = 0;
+        }
+        kz_render_req req{0, 0, w, h, s0, s1, clear};
         if (kzgpu_render(m_ctx, &req, result.data.data()) != KZ_OK) throw Exception(std::string("GPU integrator: render failed: ") + kzgpu_last_error(m_ctx));
         return true;
     }
@@ -726,7 +739,8 @@ void render(Scene *scene, const std::string &outputName, bool writeRaw) {
     const auto t2 = std::chrono::steady_clock::now();
     std::cout << "Scene upload + accel build took " << std::chrono::duration<double, std::milli>(t1 - t0).count() << " ms" << std::endl;
     const double ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
-    const double paths = (double)result.width * result.height * scene->getSampler()->getSampleCount();
+    const int sppTotal = (int)scene->getSampler()->getSampleCount();
+    const double paths = (double)result.width * result.height * ((scene->sppEnd < 0 ? sppTotal : std::min(sppTotal, scene->sppEnd)) - std::max(0, scene->sppBegin));
     std::cout << "Render ready. (took " << ms << " ms, " << paths / ms / 1e3 << " Mpaths/s)" << std::endl;
     GpuPathMisIntegrator *g = dynamic_cast<GpuPathMisIntegrator *>(integrator);
     std::vector<uint8_t> srgb((size_t)result.width * result.height * 3);

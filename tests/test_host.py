@@ -243,6 +243,25 @@ def test_kazen_cli_on_gpu(host, kzo, tmp_path):
     O.close(); hs.close()
 
 
+@pytest.mark.gpu
+def test_kazen_cli_resumes_a_render(host, tmp_path):
+    """Progressive / resumable accumulation: sample indices [0, A) saved as a raw frame, [A, N) added to it by a second
+    process; the sum is the one-shot render up to the order of the float additions."""
+    def load(stem):
+        raw = np.fromfile(stem + ".rgbw", np.uint8)
+        w, h, b = np.frombuffer(raw[:12].tobytes(), np.int32)
+        return np.frombuffer(raw[12:].tobytes(), np.float32).reshape(h + 2 * b, w + 2 * b, 4)
+    full, part, rest = (str(tmp_path / n) for n in ("full", "part", "rest"))
+    for args in (["-o", full, "--raw"], ["-o", part, "--raw", "--spp-range", "0:5"], ["-o", rest, "--raw", "--spp-range", "5:9999", "--resume", part + ".rgbw"]):
+        r = subprocess.run([KAZEN, BOX] + args, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    a, c = load(full), load(rest)
+    assert not np.array_equal(load(part), a)
+    assert np.allclose(a, c, rtol=1e-4, atol=1e-5)
+    r = subprocess.run([KAZEN, BOX, "-o", rest, "--size", "33x17", "--resume", part + ".rgbw"], capture_output=True, text=True)
+    assert r.returncode != 0 and "does not match" in r.stderr
+
+
 @pytest.mark.skipif(not os.path.isdir(REF_SCENES), reason="reference scenes are only mounted in the build container")
 def test_kiss_parameter_sweeps_follow_the_golden_images(host, kzo):
     """The reference ships one golden PNG per parameter-sweep scene (kiss metallic / roughness / specular / specularTint / clearcoat /
