@@ -175,7 +175,8 @@ void render(Scene *scene, const std::string &outputName, bool writeRaw = false);
 /* image I/O used by imagetexture and the PNG writer (bitmap.cpp:38-64) */
 void writePNG(const std::string &path, int w, int h, const uint8_t *rgb8);
 void writeEXR(const std::string &path, int w, int h, const float *rgb);        /* linear float RGB, bitmap.cpp:23-36 */
-bool readImage(const std::string &path, int &w, int &h, std::vector<float> &rgb, std::string &err);   /* PNG (8/16 bit) / PFM */
+bool readImage(const std::string &path, int &w, int &h, std::vector<float> &rgb, std::string &err);   /* PNG (8/16 bit) / JPEG / PFM / HDR / EXR */
+bool readJPEG(const std::string &path, int &w, int &h, std::vector<float> &rgb, std::string &err);    /* baseline / sequential Huffman, jpeg.cpp */
 
 /* Stand-in pmj02bn / blue-noise tables (the reference's table sources are missing from its
  * public tree): Owen-scrambled Sobol' (0,2) point sets + hashed dither.  NOT pbrt's tables. */

@@ -285,9 +285,10 @@ bool readImage(const std::string &path, int &w, int &h, std::vector<float> &rgb,
     char m[4] = {0, 0, 0, 0}; probe.read(m, 4);
     if (m[0] == 'P' && (m[1] == 'F' || m[1] == 'f')) return readPFM(path, w, h, rgb, err);
     if ((uint8_t)m[0] == 0x89 && m[1] == 'P') return readPNG(path, w, h, rgb, err);
+    if ((uint8_t)m[0] == 0xFF && (uint8_t)m[1] == 0xD8) return readJPEG(path, w, h, rgb, err);
     if (m[0] == '#' && m[1] == '?') return readHDR(path, w, h, rgb, err);
     if ((uint8_t)m[0] == 0x76 && (uint8_t)m[1] == 0x2f && (uint8_t)m[2] == 0x31 && (uint8_t)m[3] == 0x01) return readEXR(path, w, h, rgb, err);
-    err = "unsupported image format (this build decodes PNG, PFM, Radiance HDR and scanline OpenEXR; the reference used OpenImageIO)";
+    err = "unsupported image format (this build decodes PNG, JPEG, PFM, Radiance HDR and scanline OpenEXR; the reference used OpenImageIO)";
     return false;
 }
 

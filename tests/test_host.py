@@ -243,6 +243,45 @@ def test_kazen_cli_on_gpu(host, kzo, tmp_path):
     O.close(); hs.close()
 
 
+def test_jpeg_decoder_matches_libjpeg(host, tmp_path):
+    """imagetexture's JPEG path (the reference's look-dev material uses .jpg textures through OpenImageIO = libjpeg): baseline
+    Huffman decode with libjpeg's default arithmetic (slow-integer IDCT, fancy upsampling, fixed-point YCbCr) -- bit identical to
+    Pillow's libjpeg-turbo decode for 4:4:4 / 4:2:2 / 4:2:0 / grayscale, odd sizes, restart intervals, optimised tables."""
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:83, 0:131]
+    base = np.stack([127 + 120 * np.sin(xx / 9.0) * np.cos(yy / 7.0), 255 * (xx % 32 < 16) * (yy % 24 < 12), 2 * yy + 0.5 * xx], -1)
+    img = np.clip(base + rng.normal(0, 12, base.shape), 0, 255).astype(np.uint8)           # smooth + hard edges + noise
+    cases = [dict(quality=90, subsampling=0), dict(quality=75, subsampling=1), dict(quality=60, subsampling=2), dict(quality=95, subsampling=2, optimize=True),
+             dict(quality=30, subsampling=2), dict(quality=85, subsampling=2, restart_marker_blocks=3), dict(quality=85, subsampling=1, restart_marker_rows=1)]
+    n = 0
+    for k, kw in enumerate(cases):
+        for size in ((131, 83), (16, 16), (3, 5), (1, 1), (2, 9), (64, 48)):
+            p = str(tmp_path / f"t{k}_{size[0]}x{size[1]}.jpg")
+            try:
+                Image.fromarray(img[:size[1], :size[0]]).save(p, **kw)
+            except (TypeError, ValueError):
+                continue                                                                 # an older Pillow without restart markers
+            want = np.asarray(Image.open(p).convert("RGB"))
+            got = host.host_read_image(p)
+            assert got.shape == want.shape
+            assert np.array_equal(np.rint(got * 255).astype(np.uint8), want), (kw, size)
+            n += 1
+    assert n >= 30
+    p = str(tmp_path / "g.jpg")
+    Image.fromarray(img[..., 0]).save(p, quality=80)
+    want = np.asarray(Image.open(p))
+    got = host.host_read_image(p)
+    assert np.array_equal(np.rint(got[..., 0] * 255).astype(np.uint8), want) and np.array_equal(got[..., 0], got[..., 2])
+    p = str(tmp_path / "prog.jpg")
+    Image.fromarray(img).save(p, progressive=True)
+    with pytest.raises(RuntimeError, match="progressive"):
+        host.host_read_image(p)
+    (tmp_path / "bad.jpg").write_bytes(open(str(tmp_path / "t0_131x83.jpg"), "rb").read()[:900])
+    with pytest.raises(RuntimeError):
+        host.host_read_image(str(tmp_path / "bad.jpg"))
+
+
 @pytest.mark.gpu
 def test_kazen_cli_resumes_a_render(host, tmp_path):
     """Progressive / resumable accumulation: sample indices [0, A) saved as a raw frame, [A, N) added to it by a second
@@ -316,7 +355,7 @@ def test_image_readers(host, tmp_path):
         f.write(b"PF\n37 19\n-1.0\n"); f.write(img[::-1].tobytes())
     assert np.array_equal(host.host_read_image(p), img)
     with pytest.raises(RuntimeError, match="unsupported image format"):
-        (tmp_path / "x.jpg").write_bytes(b"\xff\xd8\xff\xe0junk"); host.host_read_image(str(tmp_path / "x.jpg"))
+        (tmp_path / "x.tif").write_bytes(b"II*\x00junk"); host.host_read_image(str(tmp_path / "x.tif"))
     # the host's own EXR writer (bitmap.cpp:23-36): read back by our reader and by an independent one (OpenCV)
     p = str(tmp_path / "w.exr")
     host.host_write_exr(p, img)
