@@ -603,3 +603,45 @@ extern "C" int kzo_bsdf_query(kzo_scene *s, int bsdf, int mode, const float wi[3
     else out[0] = bsdfPdf(s->sc, bsdf, bRec);
     return KZ_OK;
 }
+
+/* ------------------------------------------------------------------ math probe (tests/golden/math_kat.json) */
+/* One shading-math helper by name on raw floats: lets the CPU suite check the restatements against vectors produced by the
+ * reference's own function bodies (oracle/ref_math_kat.cpp) on machines where the reference is not mounted. */
+extern "C" int kzo_math_probe(const char *fn, const float *in, int n_in, float *out, int *n_out) {
+    if (!fn || !in || !out || !n_out) return fail(KZ_ERR_INVALID, "null argument");
+    const std::string f(fn);
+    auto v3 = [&](int o) { return V3(in[o], in[o + 1], in[o + 2]); };
+    auto v2 = [&](int o) { return V2{in[o], in[o + 1]}; };
+    auto put3 = [&](V3 v) { out[0] = v.x; out[1] = v.y; out[2] = v.z; *n_out = 3; };
+    auto put1 = [&](float v) { out[0] = v; *n_out = 1; };
+    auto need = [&](int n) { return n_in >= n; };
+    if (f == "roughnessToAlpha" && need(2)) { V2 a = roughnessToAlpha(in[0], in[1]); out[0] = a.x; out[1] = a.y; *n_out = 2; }
+    else if (f == "lambda" && need(5)) put1(ggxLambda(v3(0), v2(3)));
+    else if (f == "smithG1" && need(8)) put1(smithG1(v3(0), v3(3), v2(6)));
+    else if (f == "smithG2" && need(11)) put1(smithG2(v3(0), v3(3), v3(6), v2(9)));
+    else if (f == "ggxNDF" && need(5)) put1(ggxNDF(v3(0), v2(3)));
+    else if (f == "ggxVNDF" && need(8)) put1(ggxVNDF(v3(0), v3(3), v2(6)));
+    else if (f == "sampleVNDF" && need(7)) put3(sampleGGXVNDF(v3(0), v2(3), v2(5)));
+    else if (f == "schlick" && need(4)) put3(schlickFresnel(v3(0), in[3]));
+    else if (f == "ggxSmithBRDF" && need(11)) put3(ggxSmithBRDF(v3(0), v3(3), v3(6), in[9], in[10]));
+    else if (f == "coordinateSystem" && need(3)) { V3 b, c; coordinateSystem(v3(0), b, c); out[0] = b.x; out[1] = b.y; out[2] = b.z; out[3] = c.x; out[4] = c.y; out[5] = c.z; *n_out = 6; }
+    else if (f == "frameToLocal" && need(6)) put3(Frame(v3(0)).toLocal(v3(3)));
+    else if (f == "frameToWorld" && need(6)) put3(Frame(v3(0)).toWorld(v3(3)));
+    else if (f == "reflect" && need(6)) put3(reflect(v3(0), v3(3)));
+    else if (f == "refract" && need(7)) put3(refractDir(v3(0), v3(3), in[6]));
+    else if (f == "fresnel" && need(3)) put1(fresnelExtInt(in[0], in[1], in[2]));
+    else if (f == "fresnelDielectric" && need(2)) { float t = 0.f; out[0] = fresnelDielectric(in[0], in[1], t); out[1] = t; *n_out = 2; }
+    else if (f == "squareToUniformDisk" && need(2)) { V2 d = squareToUniformDisk(v2(0)); out[0] = d.x; out[1] = d.y; *n_out = 2; }
+    else if (f == "squareToCosineHemisphere" && need(2)) put3(squareToCosineHemisphere(v2(0)));
+    else if (f == "squareToBeckmann" && need(3)) put3(squareToBeckmann(v2(0), in[2]));
+    else if (f == "squareToBeckmannPdf" && need(4)) put1(squareToBeckmannPdf(v3(0), in[3]));
+    else if (f == "dpdfSample" && need(2)) {            /* in = weights..., sample value (dpdf.h:35-104 append / normalize / sample) */
+        std::vector<float> cdf(1, 0.f);
+        for (int i = 0; i + 1 < n_in; ++i) cdf.push_back(cdf.back() + in[i]);
+        const float norm = 1.0f / cdf.back();
+        for (size_t i = 1; i < cdf.size(); ++i) cdf[i] *= norm;
+        cdf.back() = 1.0f;
+        put1((float)cdfSample(cdf, in[n_in - 1]));
+    } else return fail(KZ_ERR_INVALID, "unknown probe or too few inputs: " + f);
+    return KZ_OK;
+}
