@@ -642,6 +642,41 @@ extern "C" int kzo_math_probe(const char *fn, const float *in, int n_in, float *
         for (size_t i = 1; i < cdf.size(); ++i) cdf[i] *= norm;
         cdf.back() = 1.0f;
         put1((float)cdfSample(cdf, in[n_in - 1]));
-    } else return fail(KZ_ERR_INVALID, "unknown probe or too few inputs: " + f);
+    } else if ((f == "kissEval" || f == "kissPdf" || f == "kissSample") && need(22)) {
+        /* in = base rgb, roughness, metallic, anisotropy, specular, specularTint, sheen, sheenTint, clearcoat, clearcoatRoughness,
+         *      wi, wo, accumulatedRoughness, sample1, sample2 -- constant textures (bsdf.cpp:1175-1371) */
+        SceneData sc;
+        kz_texture_desc t; memset(&t, 0, sizeof(t)); t.type = KZ_TEX_CONSTANT; t.child[0] = t.child[1] = t.child[2] = -1;
+        t.color[0] = in[0]; t.color[1] = in[1]; t.color[2] = in[2]; sc.textures.push_back(t);
+        t.color[0] = t.color[1] = t.color[2] = in[3]; sc.textures.push_back(t);
+        t.color[0] = t.color[1] = t.color[2] = in[4]; sc.textures.push_back(t);
+        kz_bsdf_desc m; memset(&m, 0, sizeof(m)); m.type = KZ_BSDF_KISS; m.base_color = 0; m.roughness = 1; m.metallic = 2;
+        m.anisotropy = in[5]; m.specular = in[6]; m.specular_tint = in[7]; m.sheen = in[8]; m.sheen_tint = in[9]; m.clearcoat = in[10]; m.clearcoat_roughness = in[11];
+        if (f == "kissSample") {
+            BSDFQueryRecord r(v3(12)); r.its.accumulatedRoughness = in[18];
+            const V3 w = kissSample(sc, m, r, in[19], v2(20));
+            const bool z = iszero(w);
+            out[0] = w.x; out[1] = w.y; out[2] = w.z; out[3] = z ? 0.f : r.wo.x; out[4] = z ? 0.f : r.wo.y; out[5] = z ? 0.f : r.wo.z; *n_out = 6;
+        } else {
+            BSDFQueryRecord r(v3(12), v3(15), ESolidAngle); r.its.accumulatedRoughness = in[18];
+            if (f == "kissEval") put3(kissEval(sc, m, r)); else put1(kissPdf(sc, m, r));
+        }
+    } else if ((f == "diffuseEval" || f == "diffusePdf" || f == "diffuseSample") && need(11)) {     /* in = albedo, wi, wo, sample2 (bsdf.cpp:27-75) */
+        SceneData sc;
+        kz_bsdf_desc m; memset(&m, 0, sizeof(m)); m.type = KZ_BSDF_DIFFUSE; m.albedo[0] = in[0]; m.albedo[1] = in[1]; m.albedo[2] = in[2];
+        sc.bsdfs.push_back(m);
+        if (f == "diffuseSample") {
+            BSDFQueryRecord r(v3(3));
+            const V3 w = bsdfSample(sc, 0, r, 0.5f, v2(9));
+            const bool z = iszero(w);
+            out[0] = w.x; out[1] = w.y; out[2] = w.z; out[3] = z ? 0.f : r.wo.x; out[4] = z ? 0.f : r.wo.y; out[5] = z ? 0.f : r.wo.z; *n_out = 6;
+        } else {
+            BSDFQueryRecord r(v3(3), v3(6), ESolidAngle);
+            if (f == "diffuseEval") put3(bsdfEval(sc, 0, r)); else put1(bsdfPdf(sc, 0, r));
+        }
+    } else if (f == "toSRGB" && need(3)) put3(toSRGB(v3(0)));
+    else if (f == "toLinearRGB" && need(3)) put3(toLinearRGB(v3(0)));
+    else if (f == "luminance" && need(3)) put1(luminance(v3(0)));
+    else return fail(KZ_ERR_INVALID, "unknown probe or too few inputs: " + f);
     return KZ_OK;
 }

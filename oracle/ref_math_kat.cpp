@@ -39,6 +39,30 @@ struct Warp {            /* declarations as in include/kazen/warp.h:24-51 (that 
 #include <kazen/ggx_brdf.h>
 #include <kazen/dpdf.h>
 
+/* ---- the BSDF classes: method bodies of src/kazen/bsdf.cpp extracted by line range (oracle/Makefile), hosted in stand-in classes
+ *      that only declare what the bodies touch (the real base classes drag in the plugin system, PropertyList and OpenImageIO) ---- */
+namespace kazen {
+/* EMeasure comes from the reference's common.h */
+struct ShimIntersection { float accumulatedRoughness = 0.f; };
+struct BSDFQueryRecord {                 /* fields of include/kazen/bsdf.h:20-53 that the bodies use */
+    ShimIntersection its; Vector3f wi, wo; float eta; EMeasure measure; float pdf; Point2f uv;
+    BSDFQueryRecord(const Vector3f &wi) : wi(wi), eta(1.f), measure(EUnknownMeasure) {}
+    BSDFQueryRecord(const Vector3f &wi, const Vector3f &wo, EMeasure measure) : wi(wi), wo(wo), eta(1.f), measure(measure) {}
+};
+template <typename T> struct Texture { T value; T eval(const Point2f &) const { return value; } };     /* constant textures */
+#define override
+struct KissBodies {                      /* KazenStandardSurface, bsdf.cpp:1175-1371: schlickWeight ... sample */
+    Texture<Color3f> *m_baseColor = nullptr, *m_roughness = nullptr, *m_metallic = nullptr;
+    float m_anisotropy, m_specular, m_specularTint, m_sheen, m_sheenTint, m_clearcoat, m_clearcoatRoughness;
+#include "_ref/kiss_extract.inc"
+};
+struct DiffuseBodies {                   /* Diffuse, bsdf.cpp:27-75: eval / pdf / sample */
+    Color3f m_albedo;
+#include "_ref/diffuse_extract.inc"
+};
+#undef override
+}
+
 #include "kzo_shading.h"
 
 static uint64_t g_rng = 0x9E3779B97F4A7C15ull;
@@ -102,6 +126,55 @@ int main() {
         rec("squareToBeckmann", {u.x, u.y, alpha}, f3(kazen::Warp::squareToBeckmann(kazen::Point2f(u.x, u.y), alpha)), f3(kzo::squareToBeckmann(u, alpha)), keep);
         rec("squareToBeckmannPdf", {V.x, V.y, V.z, alpha}, {kazen::Warp::squareToBeckmannPdf(K(V), alpha)}, {kzo::squareToBeckmannPdf(V, alpha)}, keep);
     }
+    /* kiss (KazenStandardSurface) and Diffuse: eval / pdf / sample with constant textures, incl. the accumulated-roughness bias */
+    for (int i = 0; i < N; ++i) {
+        const bool keep = i < KEEP;
+        kazen::Texture<kazen::Color3f> tb, tr, tm;
+        const kzo::V3 base(rnd(), rnd(), rnd());
+        const float rough = i % 9 == 0 ? 0.f : rnd(), metal = i % 4 == 0 ? 0.f : (i % 4 == 1 ? 1.f : rnd());
+        tb.value = KC(base); tr.value = kazen::Color3f(rough); tm.value = kazen::Color3f(metal);
+        kazen::KissBodies kb; kb.m_baseColor = &tb; kb.m_roughness = &tr; kb.m_metallic = &tm;
+        kb.m_anisotropy = i % 3 == 0 ? 0.f : rnd(-0.8f, 0.8f); kb.m_specular = rnd(); kb.m_specularTint = rnd();
+        kb.m_sheen = i % 2 ? rnd() : 0.f; kb.m_sheenTint = rnd(); kb.m_clearcoat = i % 2 ? 0.f : rnd(); kb.m_clearcoatRoughness = rnd();
+        kzo::SceneData sc;
+        kz_texture_desc t; memset(&t, 0, sizeof(t)); t.type = KZ_TEX_CONSTANT; t.child[0] = t.child[1] = t.child[2] = -1;
+        t.color[0] = base.x; t.color[1] = base.y; t.color[2] = base.z; sc.textures.push_back(t);
+        t.color[0] = t.color[1] = t.color[2] = rough; sc.textures.push_back(t);
+        t.color[0] = t.color[1] = t.color[2] = metal; sc.textures.push_back(t);
+        kz_bsdf_desc m; memset(&m, 0, sizeof(m)); m.type = KZ_BSDF_KISS; m.base_color = 0; m.roughness = 1; m.metallic = 2;
+        m.anisotropy = kb.m_anisotropy; m.specular = kb.m_specular; m.specular_tint = kb.m_specularTint; m.sheen = kb.m_sheen; m.sheen_tint = kb.m_sheenTint;
+        m.clearcoat = kb.m_clearcoat; m.clearcoat_roughness = kb.m_clearcoatRoughness;
+        const kzo::V3 wi = rdir(i % 11 != 0), wo = rdir(i % 13 != 0);
+        const float acc = i % 3 == 1 ? rnd(0.f, 0.6f) : 0.f, s1 = rnd(); const kzo::V2 s2{rnd(), rnd()};
+        std::vector<float> in = {base.x, base.y, base.z, rough, metal, m.anisotropy, m.specular, m.specular_tint, m.sheen, m.sheen_tint, m.clearcoat, m.clearcoat_roughness,
+                                 wi.x, wi.y, wi.z, wo.x, wo.y, wo.z, acc, s1, s2.x, s2.y};
+        kazen::BSDFQueryRecord kr(K(wi), K(wo), kazen::ESolidAngle); kr.its.accumulatedRoughness = acc; kr.uv = kazen::Point2f(0.5f, 0.5f);
+        kzo::BSDFQueryRecord orr(wi, wo, kzo::ESolidAngle); orr.its.accumulatedRoughness = acc;
+        rec("kissEval", in, f3(kb.eval(kr)), f3(kzo::kissEval(sc, m, orr)), keep);
+        rec("kissPdf", in, {kb.pdf(kr)}, {kzo::kissPdf(sc, m, orr)}, keep);
+        kazen::BSDFQueryRecord ks(K(wi)); ks.its.accumulatedRoughness = acc; ks.uv = kazen::Point2f(0.5f, 0.5f);
+        kzo::BSDFQueryRecord os(wi); os.its.accumulatedRoughness = acc;
+        const kazen::Color3f kw = kb.sample(ks, s1, kazen::Point2f(s2.x, s2.y)); const kzo::V3 ow = kzo::kissSample(sc, m, os, s1, s2);
+        const bool kz0 = kw.x() == 0.f && kw.y() == 0.f && kw.z() == 0.f;      /* wo is only meaningful for a non-zero weight */
+        rec("kissSample", in, {kw.x(), kw.y(), kw.z(), kz0 ? 0.f : ks.wo.x(), kz0 ? 0.f : ks.wo.y(), kz0 ? 0.f : ks.wo.z()},
+            {ow.x, ow.y, ow.z, kz0 ? 0.f : os.wo.x, kz0 ? 0.f : os.wo.y, kz0 ? 0.f : os.wo.z}, keep);
+        kazen::DiffuseBodies db; db.m_albedo = KC(base);
+        kz_bsdf_desc dm; memset(&dm, 0, sizeof(dm)); dm.type = KZ_BSDF_DIFFUSE; dm.albedo[0] = base.x; dm.albedo[1] = base.y; dm.albedo[2] = base.z;
+        sc.bsdfs.push_back(dm);
+        std::vector<float> din = {base.x, base.y, base.z, wi.x, wi.y, wi.z, wo.x, wo.y, wo.z, s2.x, s2.y};
+        rec("diffuseEval", din, f3(db.eval(kr)), f3(kzo::bsdfEval(sc, 0, orr)), keep);
+        rec("diffusePdf", din, {db.pdf(kr)}, {kzo::bsdfPdf(sc, 0, orr)}, keep);
+        kazen::BSDFQueryRecord kd(K(wi)); kzo::BSDFQueryRecord od(wi);
+        const kazen::Color3f dw = db.sample(kd, s1, kazen::Point2f(s2.x, s2.y)); const kzo::V3 odw = kzo::bsdfSample(sc, 0, od, s1, s2);
+        const bool dz0 = dw.x() == 0.f && dw.y() == 0.f && dw.z() == 0.f;
+        rec("diffuseSample", din, {dw.x(), dw.y(), dw.z(), dz0 ? 0.f : kd.wo.x(), dz0 ? 0.f : kd.wo.y(), dz0 ? 0.f : kd.wo.z()},
+            {odw.x, odw.y, odw.z, dz0 ? 0.f : od.wo.x, dz0 ? 0.f : od.wo.y, dz0 ? 0.f : od.wo.z}, keep);
+        /* Color3f helpers, common.cpp:352-395 */
+        const kzo::V3 c(rnd(0.f, 1.4f), rnd(0.f, 0.01f), rnd());
+        rec("toSRGB", f3(c), f3(KC(c).toSRGB()), f3(kzo::toSRGB(c)), keep);
+        rec("toLinearRGB", f3(c), f3(KC(c).toLinearRGB()), f3(kzo::toLinearRGB(c)), keep);
+        rec("luminance", f3(c), {KC(c).getLuminance()}, {kzo::luminance(c)}, keep);
+    }
     /* DiscretePDF (dpdf.h:35-104): append / normalize / sample against the oracle's CDF sampling (kzo_shading.h cdfSample) */
     for (int t = 0; t < 200; ++t) {
         const int m = 1 + (int)(rnd() * 40);
@@ -119,7 +192,7 @@ int main() {
             rec("dpdfSample", in, {(float)pdf.sample(v)}, {(float)kzo::cdfSample(cdf, v)}, t < 4 && k < 5);
         }
     }
-    printf("{\n \"generator\": \"oracle/ref_math_kat.cpp: the reference's own function bodies (ggx_brdf.h, frame.h, dpdf.h, common.cpp:436-540, warp.cpp:41-130) compiled against oracle/ref_shim; floats as uint32 bit patterns\",\n \"cases_checked\": %ld,\n \"mismatches\": %ld,\n \"kat\": [\n%s\n ]\n}\n", g.cases, g.bad, g.json.c_str());
+    printf("{\n \"generator\": \"oracle/ref_math_kat.cpp: the reference's own function bodies (ggx_brdf.h, frame.h, dpdf.h, common.cpp:352-395,436-540, warp.cpp:41-130, bsdf.cpp:27-75 Diffuse, bsdf.cpp:1175-1371 KazenStandardSurface) compiled against oracle/ref_shim; floats as uint32 bit patterns\",\n \"cases_checked\": %ld,\n \"mismatches\": %ld,\n \"kat\": [\n%s\n ]\n}\n", g.cases, g.bad, g.json.c_str());
     fprintf(stderr, "ref_math_kat: %ld cases, %ld mismatches\n", g.cases, g.bad);
     return g.bad ? 1 : 0;
 }
