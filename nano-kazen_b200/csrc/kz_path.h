@@ -51,6 +51,17 @@ struct KzCounters {
 #define KZ_SHADE_CONTINUE 1u   /* extension ray written, path goes to the next extend pass */
 #define KZ_SHADE_SHADOW 2u     /* shadow ray + pending contribution written               */
 
+/* `bsdf->sample(bRec, sampler->next1D(), sampler->next2D())` (integrator.cpp:122,168,307): GCC evaluates the two draws right to left
+ * (next2D first), see oracle/kzo.cpp; KZ_ARG_ORDER_LTR=1 restores the textual order. */
+#ifndef KZ_ARG_ORDER_LTR
+#define KZ_ARG_ORDER_LTR 0
+#endif
+#if KZ_ARG_ORDER_LTR
+#define KZ_DRAW_BSDF_SAMPLES(sc, sm, s1, s2) const float s1 = kz_next1d(sc, sm); const kz2 s2 = kz_next2d(sc, sm)
+#else
+#define KZ_DRAW_BSDF_SAMPLES(sc, sm, s1, s2) const kz2 s2 = kz_next2d(sc, sm); const float s1 = kz_next1d(sc, sm)
+#endif
+
 KZ_HD float power_heuristic(float a, float b) { a *= a; b *= b; return a > 0.f ? a / (a + b) : 0.f; }
 
 KZ_HD kz3 xform_point(const float *M, kz3 p) {
@@ -261,8 +272,7 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     if (I.regularization) its.acc_rough += bsdf_regularize(bc) * I.accumulated_roughness;
 
     /* ---- BSDF sampling, integrator.cpp:304-314 ---- */
-    const float s1 = kz_next1d(sc, sm);
-    const kz2 s2 = kz_next2d(sc, sm);
+    KZ_DRAW_BSDF_SAMPLES(sc, sm, s1, s2);
     kz3 wo; float bsdfPdf, sampledEta; int measure;
     const kz3 weight = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &bsdfPdf, &measure, &sampledEta);
     throughput *= weight;
@@ -365,8 +375,7 @@ KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &
             st.b[slot].rad.L = mkf4(L.x, L.y, L.z, 1.f);
             return flags;
         }
-        const float s1 = kz_next1d(sc, sm);
-        const kz2 s2 = kz_next2d(sc, sm);
+        KZ_DRAW_BSDF_SAMPLES(sc, sm, s1, s2);
         kz3 wo; float p; int measure; float e;
         const kz3 refl = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &p, &measure, &e);
         if (!(kz_next1d(sc, sm) < 0.95f)) { st.b[slot].rad.L = mkf4(0.f, 0.f, 0.f, 1.f); return 0u; }      /* the whole recursion returns 0 */
@@ -387,8 +396,7 @@ KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &
     weight = weight / probability;
     cnt.vertices += 1;
     const KzBsdfCtx bc = bsdf_ctx(sc, its);
-    const float s1 = kz_next1d(sc, sm);
-    const kz2 s2 = kz_next2d(sc, sm);
+    KZ_DRAW_BSDF_SAMPLES(sc, sm, s1, s2);
     kz3 wo; float p; int measure; float e;
     const kz3 f = bsdf_sample(bc, its, wiLocal, s1, s2, &wo, &p, &measure, &e);
     weight *= f;

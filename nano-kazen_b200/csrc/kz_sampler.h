@@ -167,10 +167,10 @@ KZ_HD float kz_next1d(const KzScene &sc, KzSampler &s) {
 
 KZ_HD kz2 kz_next2d(const KzScene &sc, KzSampler &s) {
     switch (sc.sampler_type) {
-        case KZ_SAMPLER_INDEPENDENT: {
-            float a = kz_pcg_float(s);
-            float b = kz_pcg_float(s);
-            return mk2(a, b);
+        case KZ_SAMPLER_INDEPENDENT: {      /* sampler.cpp:52-57 as GCC evaluates it: x is the second draw (see oracle/kzo_sampler.h) */
+            float second = kz_pcg_float(s);
+            float first = kz_pcg_float(s);
+            return mk2(first, second);
         }
         case KZ_SAMPLER_STRATIFIED: {
             uint64_t h = kz_hash_pixel_dim_seed(s.px, s.py, s.dim, sc.seed);

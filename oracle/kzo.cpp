@@ -11,6 +11,20 @@
 
 using namespace kzo;
 
+/* `bsdf->sample(bRec, sampler->next1D(), sampler->next2D())` (integrator.cpp:122,168,307): the two draws are indeterminately
+ * sequenced call arguments; GCC -- the toolchain the reference is built with on Linux and the only one available here -- evaluates
+ * them RIGHT TO LEFT, so next2D() takes the lower dimensions and next1D() the one after them.  KZO_ARG_ORDER_LTR=1 restores the
+ * textual order (what clang would do). */
+#ifndef KZO_ARG_ORDER_LTR
+#define KZO_ARG_ORDER_LTR 0
+#endif
+#if KZO_ARG_ORDER_LTR
+#define KZO_DRAW_BSDF_SAMPLES(sampler, s1, s2) float s1 = (sampler).next1D(); V2 s2 = (sampler).next2D()
+#else
+#define KZO_DRAW_BSDF_SAMPLES(sampler, s1, s2) V2 s2 = (sampler).next2D(); float s1 = (sampler).next1D()
+#endif
+
+
 struct kzo_scene {
     SceneData sc;
     std::atomic<uint64_t> paths{0}, raysExt{0}, raysShadow{0}, vertices{0};
@@ -335,8 +349,7 @@ static V3 Li(kzo_scene *s, Sampler &sampler, const kz_ray &ray_, PathCounters &p
         BSDFQueryRecord bRec(its.shFrame.toLocal(-rayD));
         bRec.uv = its.uv;
         bRec.its = its;
-        float s1 = sampler.next1D();
-        V2 s2 = sampler.next2D();
+        KZO_DRAW_BSDF_SAMPLES(sampler, s1, s2);
         V3 bsdfColor = bsdfSample(sc, mesh.bsdf, bRec, s1, s2);
         throughput *= bsdfColor;
         eta *= bRec.eta;
@@ -423,7 +436,7 @@ static V3 LiAlt(kzo_scene *s, Sampler &sampler, const kz_ray &ray_, PathCounters
             }
             BSDFQueryRecord bRec(its.toLocal(-rayD));
             bRec.its = its; bRec.uv = its.uv;          /* the reference leaves bRec.its/uv default here; every BSDF that reads them would see zeros */
-            float s1 = sampler.next1D(); V2 s2 = sampler.next2D();
+            KZO_DRAW_BSDF_SAMPLES(sampler, s1, s2);
             V3 refl = bsdfSample(sc, mesh.bsdf, bRec, s1, s2);
             if (!(sampler.next1D() < 0.95f)) return V3(0.f);
             weight = weight * refl / 0.95f;
@@ -447,7 +460,7 @@ static V3 LiAlt(kzo_scene *s, Sampler &sampler, const kz_ray &ray_, PathCounters
         BSDFQueryRecord bRec(its.shFrame.toLocal(-rayD));
         bRec.uv = its.uv; bRec.its = its;
         bRec.its.accumulatedRoughness = 0.f;
-        float s1 = sampler.next1D(); V2 s2 = sampler.next2D();
+        KZO_DRAW_BSDF_SAMPLES(sampler, s1, s2);
         V3 f = bsdfSample(sc, mesh.bsdf, bRec, s1, s2);
         t *= f;
         if (iszero(t)) return color;               /* dead path, as in Li above */
@@ -674,6 +687,25 @@ extern "C" int kzo_math_probe(const char *fn, const float *in, int n_in, float *
             BSDFQueryRecord r(v3(3), v3(6), ESolidAngle);
             if (f == "diffuseEval") put3(bsdfEval(sc, 0, r)); else put1(bsdfPdf(sc, 0, r));
         }
+    } else if ((f == "samplerIndependent" || f == "samplerStratified" || f == "samplerCorrelated") && need(6)) {
+        /* in = px, py, sample index, requested sampleCount, seed & 0xFFFFFF, seed >> 24; out = nextPixel2D, next2D, then 4 x (5 x next1D, next2D) */
+        SamplerCfg cfg; memset(&cfg.d, 0, sizeof(cfg.d));
+        const uint32_t requested = (uint32_t)in[3];
+        cfg.d.seed = (uint64_t)in[4] | ((uint64_t)in[5] << 24);
+        cfg.d.sample_count = requested;
+        if (f == "samplerStratified") {               /* sampler.cpp:83-93 */
+            int res = 4; while ((uint32_t)(res * res) < requested) res++;
+            cfg.d.type = KZ_SAMPLER_STRATIFIED; cfg.d.res_x = cfg.d.res_y = res; cfg.d.sample_count = (uint32_t)(res * res);
+        } else if (f == "samplerCorrelated") {        /* sampler.cpp:178-189 */
+            const int ry = (int)std::sqrt((double)requested), rx = (int)((requested + ry - 1) / ry);
+            cfg.d.type = KZ_SAMPLER_CORRELATED; cfg.d.res_x = rx; cfg.d.res_y = ry; cfg.d.sample_count = (uint32_t)(rx * ry);
+        } else cfg.d.type = KZ_SAMPLER_INDEPENDENT;
+        Sampler sm; sm.cfg = &cfg; sm.generateSample((int32_t)in[0], (int32_t)in[1], (int)in[2]);
+        int k = 0;
+        V2 a = sm.nextPixel2D(); out[k++] = a.x; out[k++] = a.y;
+        a = sm.next2D(); out[k++] = a.x; out[k++] = a.y;
+        for (int v = 0; v < 4; ++v) { for (int j = 0; j < 5; ++j) out[k++] = sm.next1D(); a = sm.next2D(); out[k++] = a.x; out[k++] = a.y; }
+        *n_out = k;
     } else if (f == "toSRGB" && need(3)) put3(toSRGB(v3(0)));
     else if (f == "toLinearRGB" && need(3)) put3(toLinearRGB(v3(0)));
     else if (f == "luminance" && need(3)) put1(luminance(v3(0)));

@@ -46,7 +46,7 @@ def math_probe(fn, values):
     import numpy as np
     L = lib()
     a = np.ascontiguousarray(values, np.float32)
-    out = np.zeros(8, np.float32); n = C.c_int(0)
+    out = np.zeros(64, np.float32); n = C.c_int(0)
     rc = L.kzo_math_probe(fn.encode(), a.ctypes.data_as(C.c_void_p), C.c_int(a.size), out.ctypes.data_as(C.c_void_p), C.byref(n))
     if rc != 0:
         raise RuntimeError(f"kzo_math_probe({fn}) failed ({rc}): {L.kzo_last_error().decode()}")

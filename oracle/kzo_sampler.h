@@ -213,9 +213,13 @@ struct Sampler {
         const kz_sampler_desc &d = cfg->d;
         switch (d.type) {
             case KZ_SAMPLER_INDEPENDENT: {                                  /* sampler.cpp:52-57 */
-                float a = rng.nextFloat();
-                float b = rng.nextFloat();
-                return V2{a, b};
+                /* `Point2f(m_random.nextFloat(), m_random.nextFloat())`: the two calls are indeterminately sequenced constructor
+                 * arguments; GCC (the reference's toolchain) evaluates them right to left, so x receives the SECOND draw
+                 * (observed by running the reference's own body, oracle/ref_math_kat.cpp).  Stratified / Correlated return a
+                 * braced list, which is left to right by the standard. */
+                float second = rng.nextFloat();
+                float first = rng.nextFloat();
+                return V2{first, second};
             }
             case KZ_SAMPLER_STRATIFIED: {                                   /* sampler.cpp:129-139 */
                 uint64_t h = hashPixelDimSeed(px, py, dim, d.seed);

@@ -63,6 +63,26 @@ struct DiffuseBodies {                   /* Diffuse, bsdf.cpp:27-75: eval / pdf 
 #undef override
 }
 
+/* ---- the sampler classes: generateSample / next1D / next2D / nextPixel2D bodies of src/kazen/sampler.cpp, hosted with the members
+ *      of include/kazen/sampler.h:100-106 and of each class; Hash (hash.h), pcg32 (pcg32.h) and random::permute are the real ones ---- */
+#include <kazen/hash.h>
+#include <kazen/pcg32.h>
+namespace kazen {
+namespace random {
+#include "_ref/permute_extract.inc"
+}
+struct SamplerMembers { uint64_t m_seed; uint32_t m_sampleCount, m_sampleIndex, m_dimensionIndex; };
+struct IndependentBodies : SamplerMembers { pcg32 m_random;
+#include "_ref/independent_extract.inc"
+};
+struct StratifiedBodies : SamplerMembers { pcg32 m_random; int m_resolution; Point2i m_pixel;
+#include "_ref/stratified_extract.inc"
+};
+struct CorrelatedBodies : SamplerMembers { pcg32 m_random; Point2i m_resolution; Point2i m_pixel; uint32_t m_permutationSeed;
+#include "_ref/correlated_extract.inc"
+};
+}
+
 #include "kzo_shading.h"
 
 static uint64_t g_rng = 0x9E3779B97F4A7C15ull;
@@ -175,6 +195,41 @@ int main() {
         rec("toLinearRGB", f3(c), f3(KC(c).toLinearRGB()), f3(kzo::toLinearRGB(c)), keep);
         rec("luminance", f3(c), {KC(c).getLuminance()}, {kzo::luminance(c)}, keep);
     }
+    /* samplers: the draw pattern of one path (pixel 2D, aperture 2D, then per vertex 1D x5 + 2D) for random pixels / sample indices */
+    for (int t = 0; t < 3000; ++t) {
+        const int type = t % 3;                          /* 0 independent, 1 stratified, 2 correlated */
+        const uint32_t requested = (uint32_t[]){1, 4, 9, 16, 24, 64, 100, 256, 1024}[(t / 3) % 9];
+        const uint64_t seed = t % 5 == 0 ? 1ull : (uint64_t)(rnd() * 4e9f) + 1ull;
+        const int px = (int)(rnd() * 4096), py = (int)(rnd() * 2160);
+        kzo::SamplerCfg cfg; memset(&cfg.d, 0, sizeof(cfg.d));
+        cfg.d.seed = seed;
+        kazen::IndependentBodies ki; kazen::StratifiedBodies ks; kazen::CorrelatedBodies kc;
+        uint32_t count = requested;
+        if (type == 1) {                                 /* Stratified ctor, sampler.cpp:83-93 */
+            int res = 4; while ((uint32_t)(res * res) < requested) res++;
+            count = (uint32_t)(res * res); ks.m_resolution = res; ks.m_seed = seed; ks.m_sampleCount = count;
+            cfg.d.type = KZ_SAMPLER_STRATIFIED; cfg.d.res_x = cfg.d.res_y = res;
+        } else if (type == 2) {                          /* Correlated ctor, sampler.cpp:178-189 */
+            int ry = (int)sqrt((double)requested), rx = (int)((requested + ry - 1) / ry);
+            count = (uint32_t)(rx * ry); kc.m_resolution = kazen::Point2i(rx, ry); kc.m_seed = seed; kc.m_sampleCount = count;
+            cfg.d.type = KZ_SAMPLER_CORRELATED; cfg.d.res_x = rx; cfg.d.res_y = ry;
+        } else { ki.m_seed = seed; ki.m_sampleCount = count; cfg.d.type = KZ_SAMPLER_INDEPENDENT; }
+        cfg.d.sample_count = count;
+        const int sidx = (int)(rnd() * count) % (int)count;
+        kzo::Sampler os; os.cfg = &cfg; os.generateSample(px, py, sidx);
+        std::vector<float> ref, ours;
+        auto draw = [&](int kind) {                      /* 0: next1D, 1: next2D, 2: nextPixel2D */
+            if (kind == 0) { ref.push_back(type == 0 ? ki.next1D() : (type == 1 ? ks.next1D() : kc.next1D())); ours.push_back(os.next1D()); return; }
+            kazen::Point2f r = type == 0 ? (kind == 2 ? ki.nextPixel2D() : ki.next2D()) : (type == 1 ? (kind == 2 ? ks.nextPixel2D() : ks.next2D()) : (kind == 2 ? kc.nextPixel2D() : kc.next2D()));
+            const kzo::V2 o = kind == 2 ? os.nextPixel2D() : os.next2D();
+            ref.push_back(r.x()); ref.push_back(r.y()); ours.push_back(o.x); ours.push_back(o.y);
+        };
+        if (type == 0) ki.generateSample(kazen::Point2i(px, py), sidx); else if (type == 1) ks.generateSample(kazen::Point2i(px, py), sidx); else kc.generateSample(kazen::Point2i(px, py), sidx);
+        draw(2); draw(1);
+        for (int v = 0; v < 4; ++v) { for (int k = 0; k < 5; ++k) draw(0); draw(1); }
+        const char *names[3] = {"samplerIndependent", "samplerStratified", "samplerCorrelated"};
+        rec(names[type], {(float)px, (float)py, (float)sidx, (float)requested, (float)(seed & 0xFFFFFF), (float)(seed >> 24)}, ref, ours, t < 60);
+    }
     /* DiscretePDF (dpdf.h:35-104): append / normalize / sample against the oracle's CDF sampling (kzo_shading.h cdfSample) */
     for (int t = 0; t < 200; ++t) {
         const int m = 1 + (int)(rnd() * 40);
@@ -192,7 +247,7 @@ int main() {
             rec("dpdfSample", in, {(float)pdf.sample(v)}, {(float)kzo::cdfSample(cdf, v)}, t < 4 && k < 5);
         }
     }
-    printf("{\n \"generator\": \"oracle/ref_math_kat.cpp: the reference's own function bodies (ggx_brdf.h, frame.h, dpdf.h, common.cpp:352-395,436-540, warp.cpp:41-130, bsdf.cpp:27-75 Diffuse, bsdf.cpp:1175-1371 KazenStandardSurface) compiled against oracle/ref_shim; floats as uint32 bit patterns\",\n \"cases_checked\": %ld,\n \"mismatches\": %ld,\n \"kat\": [\n%s\n ]\n}\n", g.cases, g.bad, g.json.c_str());
+    printf("{\n \"generator\": \"oracle/ref_math_kat.cpp: the reference's own function bodies (ggx_brdf.h, frame.h, dpdf.h, common.cpp:352-395,436-540, warp.cpp:41-130, bsdf.cpp:27-75 Diffuse, bsdf.cpp:1175-1371 KazenStandardSurface, sampler.cpp:43-61,111-143,207-255 Independent / Stratified / Correlated with the real hash.h + pcg32.h) compiled against oracle/ref_shim; floats as uint32 bit patterns\",\n \"cases_checked\": %ld,\n \"mismatches\": %ld,\n \"kat\": [\n%s\n ]\n}\n", g.cases, g.bad, g.json.c_str());
     fprintf(stderr, "ref_math_kat: %ld cases, %ld mismatches\n", g.cases, g.bad);
     return g.bad ? 1 : 0;
 }
