@@ -63,6 +63,42 @@ struct DiffuseBodies {                   /* Diffuse, bsdf.cpp:27-75: eval / pdf 
 #undef override
 }
 
+/* ---- mesh sampling, area light and post-intersection: Mesh::surfaceArea / Mesh::sample (mesh.cpp:47-53,108-133), AreaLight
+ *      eval / sample / pdf (light.cpp:16-51) and the post-intersection block of Accel::rayIntersect (accel.cpp:113-236), hosted in
+ *      stand-ins that declare the members / records the bodies use (mesh.h:165-183, light.h:10-40, mesh.h:18-56) ---- */
+#include <kazen/ray.h>
+namespace kazen {
+class Sampler { public: std::vector<float> q; size_t k = 0; float next1D() { return q[k++]; } };      /* replays pre-drawn numbers */
+class Mesh {
+public:
+    MatrixXf m_V, m_N, m_UV; MatrixXu m_F; DiscretePDF *m_dpdf = nullptr;
+    const MatrixXf &getVertexPositions() const { return m_V; }
+    const MatrixXf &getVertexNormals() const { return m_N; }
+    const MatrixXf &getVertexTexCoords() const { return m_UV; }
+    const MatrixXu &getIndices() const { return m_F; }
+    float pdf() const { return m_dpdf->getNormalization(); }                                          /* mesh.h:165-168 */
+    void sample(Sampler *sampler, Point3f &p, Normal3f &n) const;
+    float surfaceArea(uint32_t index) const;
+};
+#include "_ref/mesh_extract.inc"
+struct LightQueryRecord {                /* light.h:10-40 */
+    Point3f ref; Point2f uv; Vector3f wi; Point3f p; Normal3f n; Ray3f shadowRay; EMeasure measure; float pdf;
+    LightQueryRecord(const Point3f &ref) : ref(ref) {}
+    LightQueryRecord(const Point3f &ref, const Point3f &p, const Normal3f &n) : ref(ref), p(p), n(n) { wi = (p - ref).normalized(); }
+};
+#define override
+struct AreaLightBodies { Color3f m_radiance; bool m_lightPrimaryVisibility = false;
+#include "_ref/light_extract.inc"
+};
+#undef override
+struct Intersection { Point3f p; float t; Point2f uv; Frame shFrame, geoFrame; const Mesh *mesh; Vector3f dpdu, dpdv, dndu, dndv; };
+inline bool refPostIntersection(Intersection &its, uint32_t f) {
+    bool foundIntersection = true;
+#include "_ref/accel_extract.inc"
+    return foundIntersection;
+}
+}
+
 /* ---- the sampler classes: generateSample / next1D / next2D / nextPixel2D bodies of src/kazen/sampler.cpp, hosted with the members
  *      of include/kazen/sampler.h:100-106 and of each class; Hash (hash.h), pcg32 (pcg32.h) and random::permute are the real ones ---- */
 #include <kazen/hash.h>
@@ -195,6 +231,61 @@ int main() {
         rec("toLinearRGB", f3(c), f3(KC(c).toLinearRGB()), f3(kzo::toLinearRGB(c)), keep);
         rec("luminance", f3(c), {KC(c).getLuminance()}, {kzo::luminance(c)}, keep);
     }
+    /* meshes: random small meshes with / without normals and texture coordinates; post-intersection at random barycentrics,
+     * Mesh::sample + AreaLight::sample / pdf / eval with the same three random numbers on both sides */
+    for (int t = 0; t < 1500; ++t) {
+        const int nV = 3 + (int)(rnd() * 9), nF = 1 + (int)(rnd() * 8);
+        const bool hasN = t % 3 != 2, hasUV = t % 3 == 0, degenerateUV = hasUV && t % 12 == 0;
+        kazen::Mesh km; kzo::SceneData sc; sc.meshes.emplace_back(); kzo::MeshData &om = sc.meshes[0];
+        km.m_V.resize(3, nV); if (hasN) km.m_N.resize(3, nV); if (hasUV) km.m_UV.resize(2, nV); km.m_F.resize(3, nF);
+        om.nV = (uint32_t)nV; om.nF = (uint32_t)nF;
+        for (int i = 0; i < nV; ++i) {
+            const kzo::V3 pp(rnd(-2, 2), rnd(-2, 2), rnd(-2, 2)); kzo::V3 nn = rdir(false); if (t % 5 == 0) nn = nn * rnd(0.5f, 1.5f);      /* also unnormalised normals */
+            const kzo::V2 uv{degenerateUV ? 0.25f : rnd(), degenerateUV ? 0.5f : rnd()};
+            km.m_V(0, i) = pp.x; km.m_V(1, i) = pp.y; km.m_V(2, i) = pp.z; om.P.insert(om.P.end(), {pp.x, pp.y, pp.z});
+            if (hasN) { km.m_N(0, i) = nn.x; km.m_N(1, i) = nn.y; km.m_N(2, i) = nn.z; om.N.insert(om.N.end(), {nn.x, nn.y, nn.z}); }
+            if (hasUV) { km.m_UV(0, i) = uv.x; km.m_UV(1, i) = uv.y; om.UV.insert(om.UV.end(), {uv.x, uv.y}); }
+        }
+        for (int f = 0; f < nF; ++f) for (int k = 0; k < 3; ++k) { const uint32_t idx = (uint32_t)((f + k * (1 + f % 2) + (int)(rnd() * nV)) % nV); km.m_F(k, f) = idx; om.F.push_back(idx); }
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t f = (uint32_t)(rnd() * nF) % (uint32_t)nF; float bu = rnd(), bv = rnd(); if (bu + bv > 1) { bu = 1 - bu; bv = 1 - bv; }
+            kazen::Intersection ki; ki.mesh = &km; ki.uv = kazen::Point2f(bu, bv); ki.t = 1.f;
+            ki.dpdu = kazen::Vector3f(0.f); ki.dpdv = kazen::Vector3f(0.f);
+            kazen::refPostIntersection(ki, f);
+            kzo::Intersection oi; kzo::HitRec h{1.f, bu, bv, f, 0u};
+            kzo::fillIntersection(sc, h, oi);
+            std::vector<float> in = {(float)t, (float)f, bu, bv};
+            rec("postIntersection", in, {ki.p.x(), ki.p.y(), ki.p.z(), ki.uv.x(), ki.uv.y(), ki.geoFrame.n.x(), ki.geoFrame.n.y(), ki.geoFrame.n.z(),
+                                          ki.shFrame.s.x(), ki.shFrame.s.y(), ki.shFrame.s.z(), ki.shFrame.t.x(), ki.shFrame.t.y(), ki.shFrame.t.z(), ki.shFrame.n.x(), ki.shFrame.n.y(), ki.shFrame.n.z()},
+                {oi.p.x, oi.p.y, oi.p.z, oi.uv.x, oi.uv.y, oi.geoFrame.n.x, oi.geoFrame.n.y, oi.geoFrame.n.z,
+                 oi.shFrame.s.x, oi.shFrame.s.y, oi.shFrame.s.z, oi.shFrame.t.x, oi.shFrame.t.y, oi.shFrame.t.z, oi.shFrame.n.x, oi.shFrame.n.y, oi.shFrame.n.z}, false);
+        }
+        /* the mesh as an emitter: Mesh::activate (mesh.cpp:31-43) builds the area CDF */
+        kazen::DiscretePDF dp((size_t)nF); dp.reserve((size_t)nF);
+        float area = 0.f;
+        for (int i = 0; i < nF; ++i) { const float a = km.surfaceArea((uint32_t)i); dp.append(a); area += a; }
+        dp.normalize(); km.m_dpdf = &dp;
+        kzo::buildLightCdf(om);
+        rec("lightCdfNormalization", {(float)t}, {km.pdf()}, {om.normalization}, false);
+        if (!(area > 0.f)) continue;
+        kazen::AreaLightBodies kl; kl.m_radiance = kazen::Color3f(3.f, 2.f, 1.f);
+        kz_light_desc ol; ol.radiance[0] = 3.f; ol.radiance[1] = 2.f; ol.radiance[2] = 1.f; ol.primary_visibility = 0;
+        for (int q = 0; q < 6; ++q) {
+            const kzo::V3 ref(rnd(-3, 3), rnd(-3, 3), rnd(-3, 3));
+            kazen::Sampler ks; ks.q = {rnd(), rnd(), rnd()};
+            kzo::SamplerCfg cfg; memset(&cfg.d, 0, sizeof(cfg.d)); cfg.d.type = KZ_SAMPLER_INDEPENDENT; cfg.d.sample_count = 1; cfg.d.seed = (uint64_t)(t * 8 + q + 1);
+            kzo::Sampler osm; osm.cfg = &cfg; osm.generateSample(t, q, 0);
+            { kzo::Sampler peek = osm; ks.q = {peek.next1D(), peek.next1D(), peek.next1D()}; }
+            kazen::LightQueryRecord klr(kazen::Point3f(ref.x, ref.y, ref.z)); kzo::LightQueryRecord olr(ref);
+            const kazen::Color3f kw = kl.sample(klr, &ks, &km); const kzo::V3 ow = kzo::lightSample(ol, om, olr, osm);
+            rec("areaLightSample", {(float)t, ref.x, ref.y, ref.z, ks.q[0], ks.q[1], ks.q[2]},
+                {kw.x(), kw.y(), kw.z(), klr.p.x(), klr.p.y(), klr.p.z(), klr.n.x(), klr.n.y(), klr.n.z(), klr.wi.x(), klr.wi.y(), klr.wi.z(), klr.pdf, klr.shadowRay.maxt},
+                {ow.x, ow.y, ow.z, olr.p.x, olr.p.y, olr.p.z, olr.n.x, olr.n.y, olr.n.z, olr.wi.x, olr.wi.y, olr.wi.z, olr.pdf, olr.shadowRay.tmax}, false);
+            const kazen::LightQueryRecord k2(kazen::Point3f(ref.x, ref.y, ref.z), klr.p, klr.n); const kzo::LightQueryRecord o2(ref, olr.p, olr.n);
+            rec("areaLightPdfEval", {(float)t, ref.x, ref.y, ref.z}, {kl.pdf(k2, &km), kl.eval(k2).x(), kl.eval(k2).y(), kl.eval(k2).z()},
+                {kzo::lightPdf(om, o2), kzo::lightEval(ol, o2).x, kzo::lightEval(ol, o2).y, kzo::lightEval(ol, o2).z}, false);
+        }
+    }
     /* samplers: the draw pattern of one path (pixel 2D, aperture 2D, then per vertex 1D x5 + 2D) for random pixels / sample indices */
     for (int t = 0; t < 3000; ++t) {
         const int type = t % 3;                          /* 0 independent, 1 stratified, 2 correlated */
@@ -247,7 +338,7 @@ int main() {
             rec("dpdfSample", in, {(float)pdf.sample(v)}, {(float)kzo::cdfSample(cdf, v)}, t < 4 && k < 5);
         }
     }
-    printf("{\n \"generator\": \"oracle/ref_math_kat.cpp: the reference's own function bodies (ggx_brdf.h, frame.h, dpdf.h, common.cpp:352-395,436-540, warp.cpp:41-130, bsdf.cpp:27-75 Diffuse, bsdf.cpp:1175-1371 KazenStandardSurface, sampler.cpp:43-61,111-143,207-255 Independent / Stratified / Correlated with the real hash.h + pcg32.h) compiled against oracle/ref_shim; floats as uint32 bit patterns\",\n \"cases_checked\": %ld,\n \"mismatches\": %ld,\n \"kat\": [\n%s\n ]\n}\n", g.cases, g.bad, g.json.c_str());
+    printf("{\n \"generator\": \"oracle/ref_math_kat.cpp: the reference's own function bodies (ggx_brdf.h, frame.h, dpdf.h, common.cpp:352-395,436-540, warp.cpp:41-130, bsdf.cpp:27-75 Diffuse, bsdf.cpp:1175-1371 KazenStandardSurface, sampler.cpp:43-61,111-143,207-255 Independent / Stratified / Correlated with the real hash.h + pcg32.h, mesh.cpp:47-53,108-133 Mesh::surfaceArea / sample, light.cpp:16-51 AreaLight, accel.cpp:113-236 post-intersection; mesh-based cases are checked here but not kept in the golden list) compiled against oracle/ref_shim; floats as uint32 bit patterns\",\n \"cases_checked\": %ld,\n \"mismatches\": %ld,\n \"kat\": [\n%s\n ]\n}\n", g.cases, g.bad, g.json.c_str());
     fprintf(stderr, "ref_math_kat: %ld cases, %ld mismatches\n", g.cases, g.bad);
     return g.bad ? 1 : 0;
 }
