@@ -39,75 +39,20 @@ struct Warp {            /* declarations as in include/kazen/warp.h:24-51 (that 
 #include <kazen/ggx_brdf.h>
 #include <kazen/dpdf.h>
 
-/* ---- the BSDF classes: method bodies of src/kazen/bsdf.cpp extracted by line range (oracle/Makefile), hosted in stand-in classes
- *      that only declare what the bodies touch (the real base classes drag in the plugin system, PropertyList and OpenImageIO) ---- */
-namespace kazen {
-/* EMeasure comes from the reference's common.h */
-struct ShimIntersection { float accumulatedRoughness = 0.f; };
-struct BSDFQueryRecord {                 /* fields of include/kazen/bsdf.h:20-53 that the bodies use */
-    ShimIntersection its; Vector3f wi, wo; float eta; EMeasure measure; float pdf; Point2f uv;
-    BSDFQueryRecord(const Vector3f &wi) : wi(wi), eta(1.f), measure(EUnknownMeasure) {}
-    BSDFQueryRecord(const Vector3f &wi, const Vector3f &wo, EMeasure measure) : wi(wi), wo(wo), eta(1.f), measure(measure) {}
-};
-template <typename T> struct Texture { T value; T eval(const Point2f &) const { return value; } };     /* constant textures */
-#define override
-struct KissBodies {                      /* KazenStandardSurface, bsdf.cpp:1175-1371: schlickWeight ... sample */
-    Texture<Color3f> *m_baseColor = nullptr, *m_roughness = nullptr, *m_metallic = nullptr;
-    float m_anisotropy, m_specular, m_specularTint, m_sheen, m_sheenTint, m_clearcoat, m_clearcoatRoughness;
-#include "_ref/kiss_extract.inc"
-};
-struct DiffuseBodies {                   /* Diffuse, bsdf.cpp:27-75: eval / pdf / sample */
-    Color3f m_albedo;
-#include "_ref/diffuse_extract.inc"
-};
-#undef override
-}
-
-/* ---- mesh sampling, area light and post-intersection: Mesh::surfaceArea / Mesh::sample (mesh.cpp:47-53,108-133), AreaLight
- *      eval / sample / pdf (light.cpp:16-51) and the post-intersection block of Accel::rayIntersect (accel.cpp:113-236), hosted in
- *      stand-ins that declare the members / records the bodies use (mesh.h:165-183, light.h:10-40, mesh.h:18-56) ---- */
+/* ---- stand-in hosts for the reference's method bodies --------------------------------------------------------------------------
+ * The real classes hang off the plugin system (Object, PropertyList, OpenImageIO, Embree); the hosts below declare only the
+ * members / records / virtual interfaces those bodies touch (include/kazen/{sampler,mesh,light,bsdf,scene}.h), and every
+ * function BODY is #included from a line range of the reference's sources extracted at build time (oracle/Makefile). */
 #include <kazen/ray.h>
-namespace kazen {
-class Sampler { public: std::vector<float> q; size_t k = 0; float next1D() { return q[k++]; } };      /* replays pre-drawn numbers */
-class Mesh {
-public:
-    MatrixXf m_V, m_N, m_UV; MatrixXu m_F; DiscretePDF *m_dpdf = nullptr;
-    const MatrixXf &getVertexPositions() const { return m_V; }
-    const MatrixXf &getVertexNormals() const { return m_N; }
-    const MatrixXf &getVertexTexCoords() const { return m_UV; }
-    const MatrixXu &getIndices() const { return m_F; }
-    float pdf() const { return m_dpdf->getNormalization(); }                                          /* mesh.h:165-168 */
-    void sample(Sampler *sampler, Point3f &p, Normal3f &n) const;
-    float surfaceArea(uint32_t index) const;
-};
-#include "_ref/mesh_extract.inc"
-struct LightQueryRecord {                /* light.h:10-40 */
-    Point3f ref; Point2f uv; Vector3f wi; Point3f p; Normal3f n; Ray3f shadowRay; EMeasure measure; float pdf;
-    LightQueryRecord(const Point3f &ref) : ref(ref) {}
-    LightQueryRecord(const Point3f &ref, const Point3f &p, const Normal3f &n) : ref(ref), p(p), n(n) { wi = (p - ref).normalized(); }
-};
-#define override
-struct AreaLightBodies { Color3f m_radiance; bool m_lightPrimaryVisibility = false;
-#include "_ref/light_extract.inc"
-};
-#undef override
-struct Intersection { Point3f p; float t; Point2f uv; Frame shFrame, geoFrame; const Mesh *mesh; Vector3f dpdu, dpdv, dndu, dndv; };
-inline bool refPostIntersection(Intersection &its, uint32_t f) {
-    bool foundIntersection = true;
-#include "_ref/accel_extract.inc"
-    return foundIntersection;
-}
-}
-
-/* ---- the sampler classes: generateSample / next1D / next2D / nextPixel2D bodies of src/kazen/sampler.cpp, hosted with the members
- *      of include/kazen/sampler.h:100-106 and of each class; Hash (hash.h), pcg32 (pcg32.h) and random::permute are the real ones ---- */
 #include <kazen/hash.h>
 #include <kazen/pcg32.h>
 namespace kazen {
 namespace random {
 #include "_ref/permute_extract.inc"
 }
-struct SamplerMembers { uint64_t m_seed; uint32_t m_sampleCount, m_sampleIndex, m_dimensionIndex; };
+class Sampler { public: virtual ~Sampler() {} virtual float next1D() = 0; virtual Point2f next2D() = 0; };                  /* sampler.h:44-107 */
+struct ReplaySampler : Sampler { std::vector<float> q; size_t k = 0; float next1D() { return q[k++]; } Point2f next2D() { const float a = q[k++], b = q[k++]; return Point2f(a, b); } };
+struct SamplerMembers : Sampler { uint64_t m_seed; uint32_t m_sampleCount, m_sampleIndex, m_dimensionIndex; };               /* sampler.h:100-106 */
 struct IndependentBodies : SamplerMembers { pcg32 m_random;
 #include "_ref/independent_extract.inc"
 };
@@ -117,9 +62,103 @@ struct StratifiedBodies : SamplerMembers { pcg32 m_random; int m_resolution; Poi
 struct CorrelatedBodies : SamplerMembers { pcg32 m_random; Point2i m_resolution; Point2i m_pixel; uint32_t m_permutationSeed;
 #include "_ref/correlated_extract.inc"
 };
+
+class Mesh; struct LightQueryRecord; struct BSDFQueryRecord;
+struct Light {                                                                                                              /* light.h:46-66 */
+    virtual ~Light() {}
+    virtual Color3f eval(const LightQueryRecord &lRec) const = 0;
+    virtual Color3f sample(LightQueryRecord &lRec, Sampler *sampler, const Mesh *mesh) const = 0;
+    virtual float pdf(const LightQueryRecord &lRec, const Mesh *mesh) const = 0;
+    virtual bool getPrimaryVisibility() const = 0;
+};
+struct BSDF {                                                                                                               /* bsdf.h:58-127 */
+    virtual ~BSDF() {}
+    virtual Color3f eval(const BSDFQueryRecord &bRec) const = 0;
+    virtual float pdf(const BSDFQueryRecord &bRec) const = 0;
+    virtual Color3f sample(BSDFQueryRecord &bRec, float sample1, const Point2f &sample2) const = 0;
+    virtual float regularize(const Point2f &uv) const { return 0.f; }                                                       /* bsdf.h:125 */
+};
+class Mesh {                                                                                                                /* mesh.h:60-187 */
+public:
+    MatrixXf m_V, m_N, m_UV; MatrixXu m_F; DiscretePDF *m_dpdf = nullptr; BSDF *m_bsdf = nullptr; Light *m_light = nullptr;
+    const MatrixXf &getVertexPositions() const { return m_V; }
+    const MatrixXf &getVertexNormals() const { return m_N; }
+    const MatrixXf &getVertexTexCoords() const { return m_UV; }
+    const MatrixXu &getIndices() const { return m_F; }
+    bool isLight() const { return m_light != nullptr; }                                                                     /* mesh.h:133 */
+    const Light *getLight() const { return m_light; }
+    const BSDF *getBSDF() const { return m_bsdf; }
+    float pdf() const { return m_dpdf->getNormalization(); }                                                                /* mesh.h:165-168 */
+    void sample(Sampler *sampler, Point3f &p, Normal3f &n) const;
+    float surfaceArea(uint32_t index) const;
+};
+#include "_ref/mesh_extract.inc"
+struct LightQueryRecord {                                                                                                   /* light.h:10-40 */
+    Point3f ref; Point2f uv; Vector3f wi; Point3f p; Normal3f n; Ray3f shadowRay; EMeasure measure; float pdf;
+    LightQueryRecord(const Point3f &ref) : ref(ref) {}
+    LightQueryRecord(const Point3f &ref, const Point3f &p, const Normal3f &n) : ref(ref), p(p), n(n) { wi = (p - ref).normalized(); }
+};
+struct AreaLightBodies : Light { Color3f m_radiance; bool m_lightPrimaryVisibility = false;
+#include "_ref/light_extract.inc"
+};
+struct Intersection {                                                                                                       /* mesh.h:18-57 */
+    Point3f p; float t; Point2f uv; Frame shFrame, geoFrame; const Mesh *mesh; Vector3f dpdu, dpdv, dndu, dndv; float accumulatedRoughness = 0.f;
+    Intersection() : mesh(nullptr) {}
+    Vector3f toLocal(const Vector3f &d) const { return shFrame.toLocal(d); }
+    Vector3f toWorld(const Vector3f &d) const { return shFrame.toWorld(d); }
+};
+inline bool refPostIntersection(Intersection &its, uint32_t f) {                 /* accel.cpp:113-236 */
+    bool foundIntersection = true;
+#include "_ref/accel_extract.inc"
+    return foundIntersection;
+}
+struct BSDFQueryRecord {                                                                                                    /* bsdf.h:20-53 */
+    Intersection its; Vector3f wi, wo; float eta; EMeasure measure; float pdf; Point2f uv;
+    BSDFQueryRecord(const Vector3f &wi) : wi(wi), eta(1.f), measure(EUnknownMeasure) {}
+    BSDFQueryRecord(const Vector3f &wi, const Vector3f &wo, EMeasure measure) : wi(wi), wo(wo), eta(1.f), measure(measure) {}
+};
+template <typename T> struct Texture { T value; T eval(const Point2f &) const { return value; } };     /* constant textures */
+struct KissBodies : BSDF {               /* KazenStandardSurface, bsdf.cpp:1175-1371 (schlickWeight ... sample) and :1397-1399 (regularize) */
+    Texture<Color3f> *m_baseColor = nullptr, *m_roughness = nullptr, *m_metallic = nullptr;
+    float m_anisotropy, m_specular, m_specularTint, m_sheen, m_sheenTint, m_clearcoat, m_clearcoatRoughness;
+#include "_ref/kiss_extract.inc"
+};
+struct DiffuseBodies : BSDF {            /* Diffuse, bsdf.cpp:27-75: eval / pdf / sample */
+    Color3f m_albedo;
+#include "_ref/diffuse_extract.inc"
+};
+}
+struct RefAccel;                          /* closest hit through the oracle's intersector (Embree's stand-in), defined after kzo.cpp */
+namespace kazen {
+class Scene {                                                                                                               /* scene.h:15-138 */
+public:
+    std::vector<Mesh *> m_meshes, m_lights; const RefAccel *m_accel = nullptr; Color3f m_background;
+#include "_ref/scene_extract.inc"
+    bool rayIntersect(const Ray3f &ray, Intersection &its) const;                 /* scene.h:79-81  -> Accel::rayIntersect(ray, its, false) */
+    bool rayOccluded(const Ray3f &ray, Intersection &its) const;                  /* scene.h:103-105 -> Accel::rayIntersect(ray, its, true) */
+    Color3f getBackgroundColor(const Vector3f &) const { return m_background; }   /* constant background */
+};
+struct PathMisBodies {                   /* PathMisIntegrator, integrator.cpp:195-344: Li and powerHeuristic */
+    int m_maxDepth; float m_rayEpsilon; bool m_regularization; float m_accumulatedRoughness;
+#include "_ref/integrator_extract.inc"
+};
 }
 
-#include "kzo_shading.h"
+#include "kzo.cpp"          /* the oracle itself: SceneData, Sampler, the restated Li (file-static) */
+
+/* Accel::rayIntersect (accel.cpp:63-110) with rtcIntersect1 replaced by the oracle's closest-hit query over the same triangles;
+ * the bookkeeping around it follows :99-110, the post-intersection is the reference's own block. */
+struct RefAccel { const kzo::Accel *accel; const std::vector<kazen::Mesh *> *meshes; };
+static bool refAccelIntersect(const RefAccel &a, const kazen::Ray3f &ray, kazen::Intersection &its, bool shadowRay) {
+    const kz_ray r{{ray.o.x(), ray.o.y(), ray.o.z()}, ray.mint, {ray.d.x(), ray.d.y(), ray.d.z()}, ray.maxt};
+    const kzo::HitRec h = a.accel->traceBvh(r);
+    if (h.geom == KZ_INVALID_ID) return false;
+    if (shadowRay) { its.t = h.t; its.mesh = (*a.meshes)[h.geom]; return true; }
+    its.t = h.t; its.uv = kazen::Point2f(h.u, h.v); its.mesh = (*a.meshes)[h.geom];
+    return kazen::refPostIntersection(its, h.prim);
+}
+bool kazen::Scene::rayIntersect(const Ray3f &ray, Intersection &its) const { return refAccelIntersect(*m_accel, ray, its, false); }
+bool kazen::Scene::rayOccluded(const Ray3f &ray, Intersection &its) const { return refAccelIntersect(*m_accel, ray, its, true); }
 
 static uint64_t g_rng = 0x9E3779B97F4A7C15ull;
 static float rnd() { g_rng ^= g_rng << 13; g_rng ^= g_rng >> 7; g_rng ^= g_rng << 17; return (float)((g_rng >> 40) * (1.0 / 16777216.0)); }
@@ -272,7 +311,7 @@ int main() {
         kz_light_desc ol; ol.radiance[0] = 3.f; ol.radiance[1] = 2.f; ol.radiance[2] = 1.f; ol.primary_visibility = 0;
         for (int q = 0; q < 6; ++q) {
             const kzo::V3 ref(rnd(-3, 3), rnd(-3, 3), rnd(-3, 3));
-            kazen::Sampler ks; ks.q = {rnd(), rnd(), rnd()};
+            kazen::ReplaySampler ks; ks.q = {rnd(), rnd(), rnd()};
             kzo::SamplerCfg cfg; memset(&cfg.d, 0, sizeof(cfg.d)); cfg.d.type = KZ_SAMPLER_INDEPENDENT; cfg.d.sample_count = 1; cfg.d.seed = (uint64_t)(t * 8 + q + 1);
             kzo::Sampler osm; osm.cfg = &cfg; osm.generateSample(t, q, 0);
             { kzo::Sampler peek = osm; ks.q = {peek.next1D(), peek.next1D(), peek.next1D()}; }
@@ -286,6 +325,119 @@ int main() {
                 {kzo::lightPdf(om, o2), kzo::lightEval(ol, o2).x, kzo::lightEval(ol, o2).y, kzo::lightEval(ol, o2).z}, false);
         }
     }
+    /* ---- the integrator loop itself: PathMisIntegrator::Li (integrator.cpp:195-338) on random small scenes.  Reference side:
+     *      the Li body over the hosted Scene / Mesh / AreaLight / kiss / diffuse / Stratified bodies; oracle side: the restated Li of
+     *      kzo.cpp over SceneData.  Both see the same triangles (closest hits come from the oracle's intersector on both sides, as
+     *      Embree's stand-in), the same sampler configuration and the same camera rays; the radiance must agree bit for bit. ---- */
+    long liPaths = 0, liLit = 0;
+    for (int scn = 0; scn < 24; ++scn) {
+        struct Spec { std::vector<kzo::V3> P, N; std::vector<kzo::V2> UV; std::vector<uint32_t> F; int kind; /* 0 diffuse, 1 kiss */ int light; bool visible; };
+        std::vector<Spec> specs;
+        auto quad = [&](kzo::V3 a, kzo::V3 b, kzo::V3 c, kzo::V3 d, bool withN, bool withUV, int kind, int light, bool visible) {
+            Spec m; m.P = {a, b, c, d}; m.F = {0, 1, 2, 0, 2, 3}; m.kind = kind; m.light = light; m.visible = visible;
+            if (withN) { const kzo::V3 n = kzo::normalized(kzo::cross(b - a, c - a)); m.N = {n, n, n, n}; }
+            if (withUV) m.UV = {kzo::V2{0, 0}, kzo::V2{1, 0}, kzo::V2{1, 1}, kzo::V2{0, 1}};
+            specs.push_back(m);
+        };
+        quad(kzo::V3(-3, 0, 3), kzo::V3(3, 0, 3), kzo::V3(3, 0, -3), kzo::V3(-3, 0, -3), true, true, scn % 2, -1, false);                 /* floor */
+        quad(kzo::V3(-3, 0, -3), kzo::V3(3, 0, -3), kzo::V3(3, 4, -3), kzo::V3(-3, 4, -3), scn % 3 != 0, scn % 3 == 1, 1, -1, false);      /* back wall */
+        for (int k = 0; k < 2; ++k) {                                                                                                      /* two triangle clusters */
+            Spec m; m.kind = k == 0 ? 1 : 0; m.light = -1; m.visible = false;
+            const bool withN = k == 0 || scn % 4 == 0, withUV = k == 0 && scn % 2 == 0;
+            for (int t = 0; t < 6; ++t) {
+                const kzo::V3 c(rnd(-2, 2), rnd(0.3f, 2.2f), rnd(-2, 1.5f));
+                kzo::V3 p[3]; for (int v = 0; v < 3; ++v) p[v] = c + kzo::V3(rnd(-0.7f, 0.7f), rnd(-0.5f, 0.5f), rnd(-0.7f, 0.7f));
+                const kzo::V3 gn = kzo::normalized(kzo::cross(p[1] - p[0], p[2] - p[0]));
+                for (int v = 0; v < 3; ++v) {
+                    m.F.push_back((uint32_t)m.P.size()); m.P.push_back(p[v]);
+                    if (withN) m.N.push_back(kzo::normalized(gn + kzo::V3(rnd(-0.35f, 0.35f), rnd(-0.35f, 0.35f), rnd(-0.35f, 0.35f))));   /* smooth-shading normals */
+                    if (withUV) m.UV.push_back(kzo::V2{rnd(), rnd()});
+                }
+            }
+            specs.push_back(m);
+        }
+        quad(kzo::V3(-1, 3.6f, -1), kzo::V3(1, 3.6f, -1), kzo::V3(1, 3.6f, 1), kzo::V3(-1, 3.6f, 1), scn % 2 == 0, false, 0, 0, false);     /* ceiling light, invisible, faces down */
+        quad(kzo::V3(2.9f, 0.5f, 1), kzo::V3(2.9f, 0.5f, -1), kzo::V3(2.9f, 1.5f, -1), kzo::V3(2.9f, 1.5f, 1), false, false, 0, 1, scn % 3 == 0);   /* side light, faces -x */
+        if (scn % 4 == 1) quad(kzo::V3(-0.6f, 1.0f, 2.0f), kzo::V3(0.6f, 1.0f, 2.0f), kzo::V3(0.6f, 2.0f, 2.0f), kzo::V3(-0.6f, 2.0f, 2.0f), false, false, 0, 2, false);   /* invisible panel in front of the camera */
+
+        const bool regularize = scn % 2 == 1; const int maxDepth = scn % 5 == 0 ? 8 : 5; const float eps = 1e-3f;
+        const kzo::V3 bg = scn % 3 == 2 ? kzo::V3(0.f) : kzo::V3(0.2f, 0.3f, 0.4f);
+        /* oracle scene */
+        kzo_scene os; kzo::SceneData &sc = os.sc;
+        sc.integrator.max_depth = maxDepth; sc.integrator.trace_bias = eps; sc.integrator.regularization = regularize; sc.integrator.accumulated_roughness = 0.5f; sc.integrator.type = KZ_INTEGRATOR_PATH_MIS;
+        memset(&sc.sampler.d, 0, sizeof(sc.sampler.d)); sc.sampler.d.type = KZ_SAMPLER_STRATIFIED; sc.sampler.d.sample_count = 16; sc.sampler.d.seed = (uint64_t)(scn + 1); sc.sampler.d.res_x = sc.sampler.d.res_y = 4;
+        { kz_texture_desc t; memset(&t, 0, sizeof(t)); t.type = KZ_TEX_CONSTANT; t.child[0] = t.child[1] = t.child[2] = -1; t.color[0] = bg.x; t.color[1] = bg.y; t.color[2] = bg.z; sc.textures.push_back(t); }
+        sc.background = scn % 3 == 2 ? -1 : 0;
+        /* reference scene */
+        std::vector<kazen::Mesh> kmeshes(specs.size()); std::vector<kazen::Mesh *> kptr;
+        std::vector<kazen::KissBodies> kkiss(specs.size()); std::vector<kazen::DiffuseBodies> kdiff(specs.size()); std::vector<kazen::AreaLightBodies> klights(specs.size());
+        std::vector<std::vector<kazen::Texture<kazen::Color3f>>> ktex(specs.size(), std::vector<kazen::Texture<kazen::Color3f>>(3));
+        std::vector<kazen::DiscretePDF> kdpdf(specs.size());
+        kazen::Scene kscene; kscene.m_background = KC(bg);
+        for (size_t g = 0; g < specs.size(); ++g) {
+            const Spec &m = specs[g]; kazen::Mesh &km = kmeshes[g]; kzo::MeshData om;
+            const int nV = (int)m.P.size(), nF = (int)m.F.size() / 3;
+            km.m_V.resize(3, nV); if (!m.N.empty()) km.m_N.resize(3, nV); if (!m.UV.empty()) km.m_UV.resize(2, nV); km.m_F.resize(3, nF);
+            om.nV = (uint32_t)nV; om.nF = (uint32_t)nF;
+            for (int i = 0; i < nV; ++i) {
+                km.m_V(0, i) = m.P[i].x; km.m_V(1, i) = m.P[i].y; km.m_V(2, i) = m.P[i].z; om.P.insert(om.P.end(), {m.P[i].x, m.P[i].y, m.P[i].z});
+                if (!m.N.empty()) { km.m_N(0, i) = m.N[i].x; km.m_N(1, i) = m.N[i].y; km.m_N(2, i) = m.N[i].z; om.N.insert(om.N.end(), {m.N[i].x, m.N[i].y, m.N[i].z}); }
+                if (!m.UV.empty()) { km.m_UV(0, i) = m.UV[i].x; km.m_UV(1, i) = m.UV[i].y; om.UV.insert(om.UV.end(), {m.UV[i].x, m.UV[i].y}); }
+            }
+            for (int f = 0; f < nF; ++f) for (int k = 0; k < 3; ++k) { km.m_F(k, f) = m.F[3 * f + k]; om.F.push_back(m.F[3 * f + k]); }
+            /* material */
+            kz_bsdf_desc bd; memset(&bd, 0, sizeof(bd));
+            if (m.kind == 1) {
+                const kzo::V3 base(rnd(0.1f, 0.9f), rnd(0.1f, 0.9f), rnd(0.1f, 0.9f)); const float rough = rnd(0.05f, 0.9f), metal = g % 2 ? rnd() : 0.f;
+                ktex[g][0].value = KC(base); ktex[g][1].value = kazen::Color3f(rough); ktex[g][2].value = kazen::Color3f(metal);
+                kazen::KissBodies &kb = kkiss[g]; kb.m_baseColor = &ktex[g][0]; kb.m_roughness = &ktex[g][1]; kb.m_metallic = &ktex[g][2];
+                kb.m_anisotropy = 0.f; kb.m_specular = rnd(); kb.m_specularTint = rnd(); kb.m_sheen = g % 3 ? 0.f : rnd(); kb.m_sheenTint = rnd(); kb.m_clearcoat = g % 2 ? 0.f : rnd(); kb.m_clearcoatRoughness = rnd();
+                km.m_bsdf = &kb;
+                kz_texture_desc t; memset(&t, 0, sizeof(t)); t.type = KZ_TEX_CONSTANT; t.child[0] = t.child[1] = t.child[2] = -1;
+                bd.type = KZ_BSDF_KISS; bd.base_color = (int)sc.textures.size(); t.color[0] = base.x; t.color[1] = base.y; t.color[2] = base.z; sc.textures.push_back(t);
+                bd.roughness = (int)sc.textures.size(); t.color[0] = t.color[1] = t.color[2] = rough; sc.textures.push_back(t);
+                bd.metallic = (int)sc.textures.size(); t.color[0] = t.color[1] = t.color[2] = metal; sc.textures.push_back(t);
+                bd.anisotropy = 0.f; bd.specular = kb.m_specular; bd.specular_tint = kb.m_specularTint; bd.sheen = kb.m_sheen; bd.sheen_tint = kb.m_sheenTint; bd.clearcoat = kb.m_clearcoat; bd.clearcoat_roughness = kb.m_clearcoatRoughness;
+            } else {
+                const kzo::V3 alb(rnd(0.2f, 0.8f), rnd(0.2f, 0.8f), rnd(0.2f, 0.8f));
+                kdiff[g].m_albedo = KC(alb); km.m_bsdf = &kdiff[g];
+                bd.type = KZ_BSDF_DIFFUSE; bd.albedo[0] = alb.x; bd.albedo[1] = alb.y; bd.albedo[2] = alb.z;
+            }
+            om.bsdf = (int)sc.bsdfs.size(); sc.bsdfs.push_back(bd);
+            /* emitter: Mesh::activate (mesh.cpp:31-43) */
+            om.light = -1;
+            if (m.light >= 0) {
+                const kzo::V3 rad(rnd(4, 12), rnd(4, 12), rnd(4, 12));
+                klights[g].m_radiance = KC(rad); klights[g].m_lightPrimaryVisibility = m.visible; km.m_light = &klights[g];
+                kdpdf[g] = kazen::DiscretePDF((size_t)nF); kdpdf[g].reserve((size_t)nF);
+                for (int i = 0; i < nF; ++i) kdpdf[g].append(km.surfaceArea((uint32_t)i));
+                kdpdf[g].normalize(); km.m_dpdf = &kdpdf[g];
+                kz_light_desc ld; ld.radiance[0] = rad.x; ld.radiance[1] = rad.y; ld.radiance[2] = rad.z; ld.primary_visibility = m.visible ? 1 : 0;
+                om.light = (int)sc.lights.size(); sc.lights.push_back(ld);
+                kzo::buildLightCdf(om); sc.lightMeshes.push_back((int)g);
+            }
+            for (uint32_t f = 0; f < om.nF; ++f) { kzo::Tri t; t.p0 = om.pos(om.F[3 * f]); t.p1 = om.pos(om.F[3 * f + 1]); t.p2 = om.pos(om.F[3 * f + 2]); t.geom = (uint32_t)g; t.prim = f; sc.accel.tris.push_back(t); }
+            sc.meshes.push_back(std::move(om));
+        }
+        sc.accel.build();
+        for (kazen::Mesh &km : kmeshes) { kptr.push_back(&km); if (km.isLight()) kscene.m_lights.push_back(&km); }
+        kscene.m_meshes = kptr;
+        RefAccel ra{&sc.accel, &kscene.m_meshes}; kscene.m_accel = &ra;
+        kazen::PathMisBodies ki; ki.m_maxDepth = maxDepth; ki.m_rayEpsilon = eps; ki.m_regularization = regularize; ki.m_accumulatedRoughness = 0.5f;
+        for (int pth = 0; pth < 1500; ++pth) {
+            const int px = (int)(rnd() * 640), py = (int)(rnd() * 480), sidx = (int)(rnd() * 16) % 16;
+            const kzo::V3 o(rnd(-0.5f, 0.5f), rnd(0.8f, 1.6f), 4.f), target(rnd(-2.5f, 2.5f), rnd(0.f, 3.8f), rnd(-2.5f, 1.f)), d = kzo::normalized(target - o);
+            kazen::StratifiedBodies ks; ks.m_seed = sc.sampler.d.seed; ks.m_sampleCount = 16; ks.m_resolution = 4;
+            ks.generateSample(kazen::Point2i(px, py), sidx); ks.nextPixel2D(); ks.next2D();                                             /* renderer.cpp:25-28 */
+            const kazen::Color3f kL = ki.Li(&kscene, &ks, kazen::Ray3f(kazen::Point3f(o.x, o.y, o.z), K(d), 1e-4f, 1e4f));
+            kzo::Sampler osm; osm.cfg = &sc.sampler; osm.generateSample(px, py, sidx); osm.nextPixel2D(); osm.next2D();
+            PathCounters pc; const kz_ray kr{{o.x, o.y, o.z}, 1e-4f, {d.x, d.y, d.z}, 1e4f};
+            const kzo::V3 oL = Li(&os, osm, kr, pc);
+            rec("pathMisLi", {(float)scn, (float)px, (float)py, (float)sidx, o.x, o.y, d.x, d.y, d.z}, f3(kL), f3(oL), false);
+            ++liPaths; if (oL.x > 0.f || oL.y > 0.f || oL.z > 0.f) ++liLit;
+        }
+    }
+    fprintf(stderr, "pathMisLi: %ld paths, %ld with non-zero radiance\n", liPaths, liLit);
     /* samplers: the draw pattern of one path (pixel 2D, aperture 2D, then per vertex 1D x5 + 2D) for random pixels / sample indices */
     for (int t = 0; t < 3000; ++t) {
         const int type = t % 3;                          /* 0 independent, 1 stratified, 2 correlated */
