@@ -123,6 +123,10 @@ struct KissBodies : BSDF {               /* KazenStandardSurface, bsdf.cpp:1175-
     float m_anisotropy, m_specular, m_specularTint, m_sheen, m_sheenTint, m_clearcoat, m_clearcoatRoughness;
 #include "_ref/kiss_extract.inc"
 };
+struct NormalMapBodies : BSDF {          /* NormalMap, bsdf.cpp:290-392 (eval / pdf / sample / getFrame) and :412 (regularize) */
+    Texture<Color3f> *m_normalMap = nullptr; BSDF *m_nested = nullptr;
+#include "_ref/normalmap_extract.inc"
+};
 struct DiffuseBodies : BSDF {            /* Diffuse, bsdf.cpp:27-75: eval / pdf / sample */
     Color3f m_albedo;
 #include "_ref/diffuse_extract.inc"
@@ -264,6 +268,30 @@ int main() {
         const bool dz0 = dw.x() == 0.f && dw.y() == 0.f && dw.z() == 0.f;
         rec("diffuseSample", din, {dw.x(), dw.y(), dw.z(), dz0 ? 0.f : kd.wo.x(), dz0 ? 0.f : kd.wo.y(), dz0 ? 0.f : kd.wo.z()},
             {odw.x, odw.y, odw.z, dz0 ? 0.f : od.wo.x, dz0 ? 0.f : od.wo.y, dz0 ? 0.f : od.wo.z}, keep);
+        /* normal map over the kiss material: random shading frame + dpdu, random tangent-space normal (bsdf.cpp:290-392) */
+        {
+            kazen::Texture<kazen::Color3f> tn; const kzo::V3 nrgb = i % 6 == 0 ? kzo::V3(0.5f, 0.5f, 1.f) : kzo::V3(rnd(0.2f, 0.8f), rnd(0.2f, 0.8f), rnd(0.55f, 1.f));
+            tn.value = KC(nrgb);
+            kazen::NormalMapBodies nb; nb.m_normalMap = &tn; nb.m_nested = &kb;
+            kz_texture_desc t2; memset(&t2, 0, sizeof(t2)); t2.type = KZ_TEX_CONSTANT; t2.child[0] = t2.child[1] = t2.child[2] = -1; t2.color[0] = nrgb.x; t2.color[1] = nrgb.y; t2.color[2] = nrgb.z;
+            sc.textures.push_back(t2);
+            sc.bsdfs.clear(); sc.bsdfs.push_back(m);
+            kz_bsdf_desc nm; memset(&nm, 0, sizeof(nm)); nm.type = KZ_BSDF_NORMALMAP; nm.normal_map = 3; nm.nested = 0; sc.bsdfs.push_back(nm);
+            const kzo::V3 shn = rdir(false), dpdu = rdir(false) * rnd(0.3f, 2.f);
+            kazen::Intersection kit; kit.shFrame = kazen::Frame((kazen::Normal3f)K(shn)); kit.geoFrame = kit.shFrame; kit.dpdu = K(dpdu); kit.uv = kazen::Point2f(0.5f, 0.5f); kit.accumulatedRoughness = acc;
+            kzo::Intersection oit; oit.shFrame = kzo::Frame(shn); oit.geoFrame = oit.shFrame; oit.dpdu = dpdu; oit.uv = kzo::V2{0.5f, 0.5f}; oit.accumulatedRoughness = acc;
+            std::vector<float> nin = in; nin.insert(nin.end(), {nrgb.x, nrgb.y, nrgb.z, shn.x, shn.y, shn.z, dpdu.x, dpdu.y, dpdu.z});
+            kazen::BSDFQueryRecord nr(K(wi), K(wo), kazen::ESolidAngle); nr.its = kit; nr.uv = kit.uv;
+            kzo::BSDFQueryRecord onr(wi, wo, kzo::ESolidAngle); onr.its = oit; onr.uv = oit.uv;
+            rec("normalMapEval", nin, f3(nb.eval(nr)), f3(kzo::bsdfEval(sc, 1, onr)), false);
+            rec("normalMapPdf", nin, {nb.pdf(nr)}, {kzo::bsdfPdf(sc, 1, onr)}, false);
+            kazen::BSDFQueryRecord ns(K(wi)); ns.its = kit; ns.uv = kit.uv; kzo::BSDFQueryRecord ons(wi); ons.its = oit; ons.uv = oit.uv;
+            const kazen::Color3f nw = nb.sample(ns, s1, kazen::Point2f(s2.x, s2.y)); const kzo::V3 onw = kzo::bsdfSample(sc, 1, ons, s1, s2);
+            const bool nz0 = nw.x() == 0.f && nw.y() == 0.f && nw.z() == 0.f;
+            rec("normalMapSample", nin, {nw.x(), nw.y(), nw.z(), nz0 ? 0.f : ns.wo.x(), nz0 ? 0.f : ns.wo.y(), nz0 ? 0.f : ns.wo.z()},
+                {onw.x, onw.y, onw.z, nz0 ? 0.f : ons.wo.x, nz0 ? 0.f : ons.wo.y, nz0 ? 0.f : ons.wo.z}, false);
+            sc.bsdfs.clear(); sc.textures.pop_back();
+        }
         /* Color3f helpers, common.cpp:352-395 */
         const kzo::V3 c(rnd(0.f, 1.4f), rnd(0.f, 0.01f), rnd());
         rec("toSRGB", f3(c), f3(KC(c).toSRGB()), f3(kzo::toSRGB(c)), keep);
@@ -331,7 +359,7 @@ int main() {
      *      Embree's stand-in), the same sampler configuration and the same camera rays; the radiance must agree bit for bit. ---- */
     long liPaths = 0, liLit = 0;
     for (int scn = 0; scn < 24; ++scn) {
-        struct Spec { std::vector<kzo::V3> P, N; std::vector<kzo::V2> UV; std::vector<uint32_t> F; int kind; /* 0 diffuse, 1 kiss */ int light; bool visible; };
+        struct Spec { std::vector<kzo::V3> P, N; std::vector<kzo::V2> UV; std::vector<uint32_t> F; int kind; /* 0 diffuse, 1 kiss, 2 normal map over kiss */ int light; bool visible; };
         std::vector<Spec> specs;
         auto quad = [&](kzo::V3 a, kzo::V3 b, kzo::V3 c, kzo::V3 d, bool withN, bool withUV, int kind, int light, bool visible) {
             Spec m; m.P = {a, b, c, d}; m.F = {0, 1, 2, 0, 2, 3}; m.kind = kind; m.light = light; m.visible = visible;
@@ -340,7 +368,7 @@ int main() {
             specs.push_back(m);
         };
         quad(kzo::V3(-3, 0, 3), kzo::V3(3, 0, 3), kzo::V3(3, 0, -3), kzo::V3(-3, 0, -3), true, true, scn % 2, -1, false);                 /* floor */
-        quad(kzo::V3(-3, 0, -3), kzo::V3(3, 0, -3), kzo::V3(3, 4, -3), kzo::V3(-3, 4, -3), scn % 3 != 0, scn % 3 == 1, 1, -1, false);      /* back wall */
+        quad(kzo::V3(-3, 0, -3), kzo::V3(3, 0, -3), kzo::V3(3, 4, -3), kzo::V3(-3, 4, -3), scn % 3 != 0, scn % 3 == 1, scn % 3 == 1 ? 2 : 1, -1, false);      /* back wall; kind 2 = normal map over kiss */
         for (int k = 0; k < 2; ++k) {                                                                                                      /* two triangle clusters */
             Spec m; m.kind = k == 0 ? 1 : 0; m.light = -1; m.visible = false;
             const bool withN = k == 0 || scn % 4 == 0, withUV = k == 0 && scn % 2 == 0;
@@ -371,7 +399,8 @@ int main() {
         /* reference scene */
         std::vector<kazen::Mesh> kmeshes(specs.size()); std::vector<kazen::Mesh *> kptr;
         std::vector<kazen::KissBodies> kkiss(specs.size()); std::vector<kazen::DiffuseBodies> kdiff(specs.size()); std::vector<kazen::AreaLightBodies> klights(specs.size());
-        std::vector<std::vector<kazen::Texture<kazen::Color3f>>> ktex(specs.size(), std::vector<kazen::Texture<kazen::Color3f>>(3));
+        std::vector<std::vector<kazen::Texture<kazen::Color3f>>> ktex(specs.size(), std::vector<kazen::Texture<kazen::Color3f>>(4));
+        std::vector<kazen::NormalMapBodies> knmap(specs.size());
         std::vector<kazen::DiscretePDF> kdpdf(specs.size());
         kazen::Scene kscene; kscene.m_background = KC(bg);
         for (size_t g = 0; g < specs.size(); ++g) {
@@ -387,7 +416,7 @@ int main() {
             for (int f = 0; f < nF; ++f) for (int k = 0; k < 3; ++k) { km.m_F(k, f) = m.F[3 * f + k]; om.F.push_back(m.F[3 * f + k]); }
             /* material */
             kz_bsdf_desc bd; memset(&bd, 0, sizeof(bd));
-            if (m.kind == 1) {
+            if (m.kind >= 1) {
                 const kzo::V3 base(rnd(0.1f, 0.9f), rnd(0.1f, 0.9f), rnd(0.1f, 0.9f)); const float rough = rnd(0.05f, 0.9f), metal = g % 2 ? rnd() : 0.f;
                 ktex[g][0].value = KC(base); ktex[g][1].value = kazen::Color3f(rough); ktex[g][2].value = kazen::Color3f(metal);
                 kazen::KissBodies &kb = kkiss[g]; kb.m_baseColor = &ktex[g][0]; kb.m_roughness = &ktex[g][1]; kb.m_metallic = &ktex[g][2];
@@ -398,6 +427,14 @@ int main() {
                 bd.roughness = (int)sc.textures.size(); t.color[0] = t.color[1] = t.color[2] = rough; sc.textures.push_back(t);
                 bd.metallic = (int)sc.textures.size(); t.color[0] = t.color[1] = t.color[2] = metal; sc.textures.push_back(t);
                 bd.anisotropy = 0.f; bd.specular = kb.m_specular; bd.specular_tint = kb.m_specularTint; bd.sheen = kb.m_sheen; bd.sheen_tint = kb.m_sheenTint; bd.clearcoat = kb.m_clearcoat; bd.clearcoat_roughness = kb.m_clearcoatRoughness;
+                if (m.kind == 2) {            /* the kiss material becomes the nested BSDF of a normal map */
+                    const kzo::V3 nrgb(rnd(0.3f, 0.7f), rnd(0.3f, 0.7f), rnd(0.7f, 1.f));
+                    ktex[g][3].value = KC(nrgb); knmap[g].m_normalMap = &ktex[g][3]; knmap[g].m_nested = &kb; km.m_bsdf = &knmap[g];
+                    sc.bsdfs.push_back(bd);
+                    t.color[0] = nrgb.x; t.color[1] = nrgb.y; t.color[2] = nrgb.z;
+                    kz_bsdf_desc nd; memset(&nd, 0, sizeof(nd)); nd.type = KZ_BSDF_NORMALMAP; nd.nested = (int)sc.bsdfs.size() - 1; nd.normal_map = (int)sc.textures.size(); sc.textures.push_back(t);
+                    bd = nd;
+                }
             } else {
                 const kzo::V3 alb(rnd(0.2f, 0.8f), rnd(0.2f, 0.8f), rnd(0.2f, 0.8f));
                 kdiff[g].m_albedo = KC(alb); km.m_bsdf = &kdiff[g];
