@@ -99,7 +99,7 @@ KZ_HD kz3 operator/(kz3 a, kz3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z);
 KZ_HD kz3 &operator+=(kz3 &a, kz3 b) { a = a + b; return a; }
 KZ_HD kz3 &operator-=(kz3 &a, kz3 b) { a = a - b; return a; }
 KZ_HD kz3 &operator*=(kz3 &a, kz3 b) { a = a * b; return a; }
-KZ_HD float dot(kz3 a, kz3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+KZ_HD float dot(kz3 a, kz3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }     /* Eigen's unrolled reduction order, see oracle/kzo_math.h */
 KZ_HD kz3 cross(kz3 a, kz3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 KZ_HD float sqnorm(kz3 a) { return dot(a, a); }
 KZ_HD float norm(kz3 a) { return sqrtf(sqnorm(a)); }

@@ -72,7 +72,7 @@ KZ_HD kz3 xform_point(const float *M, kz3 p) {
     return mk3(r0 / r3, r1 / r3, r2 / r3);
 }
 KZ_HD kz3 xform_vector(const float *M, kz3 v) {
-    return mk3(M[0] * v.x + M[1] * v.y + M[2] * v.z, M[4] * v.x + M[5] * v.y + M[6] * v.z, M[8] * v.x + M[9] * v.y + M[10] * v.z);
+    return mk3(M[0] * v.x + (M[1] * v.y + M[2] * v.z), M[4] * v.x + (M[5] * v.y + M[6] * v.z), M[8] * v.x + (M[9] * v.y + M[10] * v.z));
 }
 
 /* camera.cpp:70-91 / 191-223 */

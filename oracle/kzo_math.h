@@ -37,7 +37,9 @@ inline V3 &operator-=(V3 &a, V3 b) { a = a - b; return a; }
 inline V3 &operator*=(V3 &a, V3 b) { a = a * b; return a; }
 inline V3 &operator/=(V3 &a, float s) { a = a / s; return a; }
 /* Eigen dot of a fixed 3-vector: ((x*x' + y*y') + z*z') */
-inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+/* Eigen evaluates a fixed-size dot product as a fully unrolled reduction that splits the range in halves (Redux.h,
+ * redux_novec_unroller): three terms sum as a0 + (a1 + a2). */
+inline float dot(V3 a, V3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
 inline V3 cross(V3 a, V3 b) {
     return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
@@ -114,9 +116,10 @@ inline V3 xformPoint(const M44 &M, V3 p) {
     return V3(r[0] / r[3], r[1] / r[3], r[2] / r[3]);
 }
 inline V3 xformVector(const M44 &M, V3 v) {
-    return V3(M.m[0] * v.x + M.m[1] * v.y + M.m[2] * v.z,
-              M.m[4] * v.x + M.m[5] * v.y + M.m[6] * v.z,
-              M.m[8] * v.x + M.m[9] * v.y + M.m[10] * v.z);
+    /* topLeftCorner<3,3>() * v: each coefficient is the same unrolled reduction as dot() */
+    return V3(M.m[0] * v.x + (M.m[1] * v.y + M.m[2] * v.z),
+              M.m[4] * v.x + (M.m[5] * v.y + M.m[6] * v.z),
+              M.m[8] * v.x + (M.m[9] * v.y + M.m[10] * v.z));
 }
 
 /* warp.cpp:41-50 (math::sincosf -> sinf/cosf, common.h:231) */
