@@ -132,6 +132,17 @@ struct DiffuseBodies : BSDF {            /* Diffuse, bsdf.cpp:27-75: eval / pdf 
 #include "_ref/diffuse_extract.inc"
 };
 }
+#include <kazen/transform.h>
+namespace kazen {
+struct PerspectiveBodies {               /* PerspectiveCamera::sampleRay, camera.cpp:70-91; members of camera.cpp:93-103 */
+    Vector2f m_invOutputSize; Transform m_sampleToCamera, m_cameraToWorld; float m_nearClip, m_farClip;
+#include "_ref/perspective_extract.inc"
+};
+struct ThinlensBodies {                  /* ThinlensCamera::sampleRay, camera.cpp:191-223 */
+    Vector2f m_invOutputSize; Transform m_sampleToCamera, m_cameraToWorld; float m_nearClip, m_farClip, m_apertureRadius, m_focusDistance;
+#include "_ref/thinlens_extract.inc"
+};
+}
 struct RefAccel;                          /* closest hit through the oracle's intersector (Embree's stand-in), defined after kzo.cpp */
 namespace kazen {
 class Scene {                                                                                                               /* scene.h:15-138 */
@@ -475,6 +486,28 @@ int main() {
         }
     }
     fprintf(stderr, "pathMisLi: %ld paths, %ld with non-zero radiance\n", liPaths, liLit);
+    /* cameras: sampleRay of both camera models with random (invertible-looking) matrices; the matrices themselves come from
+     * Camera::activate, which uses Eigen's 4x4 inverse and is not restated here */
+    for (int t = 0; t < 4000; ++t) {
+        kz_camera_desc c; memset(&c, 0, sizeof(c));
+        c.type = t % 2 ? KZ_CAM_THINLENS : KZ_CAM_PERSPECTIVE; c.width = 64 + (int)(rnd() * 4000); c.height = 64 + (int)(rnd() * 2200);
+        c.near_clip = rnd(1e-4f, 0.5f); c.far_clip = rnd(50.f, 1e4f); c.aperture_radius = rnd(0.f, 0.3f); c.focus_distance = rnd(0.5f, 20.f);
+        Eigen::Matrix4f s2c, c2w;
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+            const float a = (i == j ? rnd(0.5f, 2.f) : rnd(-0.4f, 0.4f)) * (i == 3 && j < 3 ? 0.1f : 1.f), b = i == 3 ? (j == 3 ? 1.f : 0.f) : rnd(-1.f, 1.f) * (j == 3 ? 5.f : 1.f);
+            s2c(i, j) = a; c.sample_to_camera[4 * i + j] = a; c2w(i, j) = b; c.camera_to_world[4 * i + j] = b;
+        }
+        const kzo::V2 sp{rnd() * c.width, rnd() * c.height}, ap{rnd(), rnd()};
+        kazen::Ray3f kr;
+        if (t % 2) { kazen::ThinlensBodies cam; cam.m_invOutputSize = kazen::Vector2f(1.0f / c.width, 1.0f / c.height); cam.m_sampleToCamera = kazen::Transform(s2c, s2c); cam.m_cameraToWorld = kazen::Transform(c2w, c2w);
+                     cam.m_nearClip = c.near_clip; cam.m_farClip = c.far_clip; cam.m_apertureRadius = c.aperture_radius; cam.m_focusDistance = c.focus_distance;
+                     cam.sampleRay(kr, kazen::Point2f(sp.x, sp.y), kazen::Point2f(ap.x, ap.y)); }
+        else { kazen::PerspectiveBodies cam; cam.m_invOutputSize = kazen::Vector2f(1.0f / c.width, 1.0f / c.height); cam.m_sampleToCamera = kazen::Transform(s2c, s2c); cam.m_cameraToWorld = kazen::Transform(c2w, c2w);
+               cam.m_nearClip = c.near_clip; cam.m_farClip = c.far_clip; cam.sampleRay(kr, kazen::Point2f(sp.x, sp.y), kazen::Point2f(ap.x, ap.y)); }
+        const kz_ray orr = cameraRay(c, sp, ap);
+        rec(t % 2 ? "thinlensSampleRay" : "perspectiveSampleRay", {sp.x, sp.y, ap.x, ap.y, (float)c.width, (float)c.height},
+            {kr.o.x(), kr.o.y(), kr.o.z(), kr.d.x(), kr.d.y(), kr.d.z(), kr.mint, kr.maxt}, {orr.o[0], orr.o[1], orr.o[2], orr.d[0], orr.d[1], orr.d[2], orr.tmin, orr.tmax}, false);
+    }
     /* samplers: the draw pattern of one path (pixel 2D, aperture 2D, then per vertex 1D x5 + 2D) for random pixels / sample indices */
     for (int t = 0; t < 3000; ++t) {
         const int type = t % 3;                          /* 0 independent, 1 stratified, 2 correlated */
