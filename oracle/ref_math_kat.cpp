@@ -143,6 +143,36 @@ struct ThinlensBodies {                  /* ThinlensCamera::sampleRay, camera.cp
 #include "_ref/thinlens_extract.inc"
 };
 }
+#include <kazen/bbox.h>
+#ifndef KAZEN_FILTER_RESOLUTION
+#define KAZEN_FILTER_RESOLUTION 32       /* rfilter.h:6 */
+#endif
+namespace kazen {
+class ReconstructionFilter { public: virtual ~ReconstructionFilter() {} float getRadius() const { return m_radius; } virtual float eval(float x) const = 0; float m_radius; };   /* rfilter.h */
+struct GaussianBodies : ReconstructionFilter { float m_stddev;
+#include "_ref/rfilter_gaussian.inc"
+};
+struct MitchellBodies : ReconstructionFilter { float m_B, m_C;
+#include "_ref/rfilter_mitchell.inc"
+};
+struct TentBodies : ReconstructionFilter {
+#include "_ref/rfilter_tent.inc"
+};
+struct BoxBodies : ReconstructionFilter {
+#include "_ref/rfilter_box.inc"
+};
+class ImageBlock {                       /* block.h; the constructor (block.cpp:9-31) and put (block.cpp:56-85) are the reference's */
+public:
+    ImageBlock(const Vector2i &size, const ReconstructionFilter *filter);
+    void put(const Point2f &_pos, const Color3f &value);
+    void resize(int rows, int cols) { m_rows = rows; m_cols = cols; m_px.assign((size_t)rows * cols, Color4f()); }
+    Color4f &coeffRef(int y, int x) { return m_px[(size_t)y * m_cols + x]; }
+    int cols() const { return m_cols; } int rows() const { return m_rows; }
+    Point2i m_offset; Vector2i m_size; int m_borderSize = 0; float *m_filter = nullptr; float m_filterRadius = 0; float *m_weightsX = nullptr, *m_weightsY = nullptr; float m_lookupFactor = 0;
+    std::vector<Color4f> m_px; int m_rows = 0, m_cols = 0;
+};
+#include "_ref/block_extract.inc"
+}
 struct RefAccel;                          /* closest hit through the oracle's intersector (Embree's stand-in), defined after kzo.cpp */
 namespace kazen {
 class Scene {                                                                                                               /* scene.h:15-138 */
@@ -486,6 +516,36 @@ int main() {
         }
     }
     fprintf(stderr, "pathMisLi: %ld paths, %ld with non-zero radiance\n", liPaths, liLit);
+    /* film: filter evaluation + ImageBlock's tabulation (block.cpp:9-31) + put (block.cpp:56-85) against the oracle's filmPut fed with
+     * the reference's own table; the tables go to the golden file so that pykazen.filter_table and the C++ host's rfilter plugins are
+     * checked against them too */
+    for (int fk = 0; fk < 6; ++fk) {
+        kazen::GaussianBodies fg; kazen::MitchellBodies fm; kazen::TentBodies ft; kazen::BoxBodies fb; const kazen::ReconstructionFilter *rf = nullptr;
+        float p1 = 0, p2 = 0;
+        if (fk == 0) { fg.m_radius = 2.f; fg.m_stddev = 0.5f; rf = &fg; p1 = 0.5f; }
+        else if (fk == 1) { fg.m_radius = 3.f; fg.m_stddev = 1.0f; rf = &fg; p1 = 1.0f; }
+        else if (fk == 2) { fm.m_radius = 2.f; fm.m_B = 1.0f / 3.0f; fm.m_C = 1.0f / 3.0f; rf = &fm; p1 = fm.m_B; p2 = fm.m_C; }
+        else if (fk == 3) { fm.m_radius = 3.f; fm.m_B = 0.2f; fm.m_C = 0.4f; rf = &fm; p1 = fm.m_B; p2 = fm.m_C; }
+        else if (fk == 4) { ft.m_radius = 1.f; rf = &ft; }
+        else { fb.m_radius = 0.5f; rf = &fb; }
+        const int W = 37, H = 29;
+        kazen::ImageBlock blk(kazen::Vector2i(W, H), rf);
+        kzo::SceneData sc; memset(&sc.camera, 0, sizeof(sc.camera)); sc.camera.width = W; sc.camera.height = H;
+        sc.filter.radius = rf->getRadius(); for (int i = 0; i <= 32; ++i) sc.filter.table[i] = blk.m_filter[i];
+        rec(fk < 2 ? "filterTableGaussian" : (fk < 4 ? "filterTableMitchell" : (fk == 4 ? "filterTableTent" : "filterTableBox")), {rf->getRadius(), p1, p2},
+            std::vector<float>(blk.m_filter, blk.m_filter + 33), std::vector<float>(sc.filter.table, sc.filter.table + 33), true);
+        const int border = (int)std::ceil(sc.filter.radius - 0.5f);
+        std::vector<float> frame((size_t)(W + 2 * border) * (H + 2 * border) * 4, 0.f);
+        for (int k = 0; k < 600; ++k) {
+            const kzo::V2 pos{rnd(-0.2f, W + 0.2f), rnd(-0.2f, H + 0.2f)};
+            kzo::V3 val(rnd(0, 5), rnd(0, 5), rnd(0, 5));
+            if (k % 37 == 5) val.x = -0.1f; if (k % 41 == 7) val.y = NAN; if (k % 43 == 9) val.z = INFINITY;
+            blk.put(kazen::Point2f(pos.x, pos.y), KC(val));
+            filmPut(sc, border, frame.data(), pos, val);
+        }
+        std::vector<float> ref; for (const kazen::Color4f &c : blk.m_px) { ref.push_back(c.x()); ref.push_back(c.y()); ref.push_back(c.z()); ref.push_back(c.w()); }
+        rec("imageBlockPut", {(float)fk}, ref, frame, false);
+    }
     /* cameras: sampleRay of both camera models with random (invertible-looking) matrices; the matrices themselves come from
      * Camera::activate, which uses Eigen's 4x4 inverse and is not restated here */
     for (int t = 0; t < 4000; ++t) {
