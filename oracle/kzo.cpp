@@ -411,9 +411,14 @@ static V3 LiAlt(kzo_scene *s, Sampler &sampler, const kz_ray &ray_, PathCounters
         return V3(0.f);
     }
     if (type == KZ_INTEGRATOR_WHITTED) {                                               /* integrator.cpp:80-128, recursion unrolled */
+        /* The reference recurses: Li = reflect * Li(next) / 0.95, so the factors are applied from the LEAF upwards, one multiply and
+         * one divide per level.  `chain` keeps the per-level factors and `unwind` folds them in that order (a running product from the
+         * top would round differently); `weight` only serves the dead-path test. */
         V3 weight(1.f);
+        std::vector<V3> chain;
+        auto unwind = [&](V3 leaf) { for (size_t k = chain.size(); k-- > 0;) leaf = chain[k] * leaf / 0.95f; return leaf; };
         for (int depth = 0; depth < 4096; ++depth) {
-            if (!rayIntersect(sc, ray, its, pc)) return V3(0.f);
+            if (!rayIntersect(sc, ray, its, pc)) return unwind(V3(0.f));
             const MeshData &mesh = sc.meshes[its.mesh];
             V3 rayO(ray.o[0], ray.o[1], ray.o[2]), rayD(ray.d[0], ray.d[1], ray.d[2]);
             V3 Le(0.f);
@@ -421,7 +426,7 @@ static V3 LiAlt(kzo_scene *s, Sampler &sampler, const kz_ray &ray_, PathCounters
             if (sc.bsdfs[mesh.bsdf].type == KZ_BSDF_DIFFUSE) {                         /* the only BSDF with isDiffuse() == true, bsdf.cpp:77 */
                 float rnd = sampler.next1D();
                 size_t nl = sc.lightMeshes.size();
-                if (nl == 0) return weight * Le;
+                if (nl == 0) return unwind(Le);
                 size_t index = std::min((size_t)std::floor(nl * rnd), nl - 1);
                 const MeshData &lm = sc.meshes[sc.lightMeshes[index]];
                 LightQueryRecord rec(its.p);
@@ -432,13 +437,14 @@ static V3 LiAlt(kzo_scene *s, Sampler &sampler, const kz_ray &ray_, PathCounters
                 BSDFQueryRecord bRec(its.toLocal(-rayD), its.toLocal(rec.wi), ESolidAngle);
                 V3 f = bsdfEval(sc, mesh.bsdf, bRec);
                 V3 Lr = f * Ls * cosTheta;
-                return weight * (Le + Lr / (1.0f / nl));
+                return unwind(Le + Lr / (1.0f / nl));
             }
             BSDFQueryRecord bRec(its.toLocal(-rayD));
             bRec.its = its; bRec.uv = its.uv;          /* the reference leaves bRec.its/uv default here; every BSDF that reads them would see zeros */
             KZO_DRAW_BSDF_SAMPLES(sampler, s1, s2);
             V3 refl = bsdfSample(sc, mesh.bsdf, bRec, s1, s2);
-            if (!(sampler.next1D() < 0.95f)) return V3(0.f);
+            if (!((double)sampler.next1D() < 0.95)) return unwind(V3(0.f));            /* `next1D() < 0.95`: a double comparison upstream */
+            chain.push_back(refl);
             weight = weight * refl / 0.95f;
             if (iszero(weight)) return V3(0.f);
             V3 wo = its.toWorld(bRec.wo);

@@ -77,6 +77,7 @@ struct BSDF {                                                                   
     virtual float pdf(const BSDFQueryRecord &bRec) const = 0;
     virtual Color3f sample(BSDFQueryRecord &bRec, float sample1, const Point2f &sample2) const = 0;
     virtual float regularize(const Point2f &uv) const { return 0.f; }                                                       /* bsdf.h:125 */
+    virtual bool isDiffuse() const { return false; }                                                                        /* bsdf.h:121 */
 };
 class Mesh {                                                                                                                /* mesh.h:60-187 */
 public:
@@ -127,7 +128,7 @@ struct NormalMapBodies : BSDF {          /* NormalMap, bsdf.cpp:290-392 (eval / 
     Texture<Color3f> *m_normalMap = nullptr; BSDF *m_nested = nullptr;
 #include "_ref/normalmap_extract.inc"
 };
-struct DiffuseBodies : BSDF {            /* Diffuse, bsdf.cpp:27-75: eval / pdf / sample */
+struct DiffuseBodies : BSDF {            /* Diffuse, bsdf.cpp:27-79: eval / pdf / sample / isDiffuse */
     Color3f m_albedo;
 #include "_ref/diffuse_extract.inc"
 };
@@ -181,8 +182,23 @@ public:
 #include "_ref/scene_extract.inc"
     bool rayIntersect(const Ray3f &ray, Intersection &its) const;                 /* scene.h:79-81  -> Accel::rayIntersect(ray, its, false) */
     bool rayOccluded(const Ray3f &ray, Intersection &its) const;                  /* scene.h:103-105 -> Accel::rayIntersect(ray, its, true) */
+    bool rayIntersect(const Ray3f &ray) const { Intersection its; return rayOccluded(ray, its); }                           /* scene.h:92-95 */
     Color3f getBackgroundColor(const Vector3f &) const { return m_background; }   /* constant background */
 };
+struct NormalIntegratorBodies {          /* integrator.cpp:18-29 */
+#include "_ref/integ_normals.inc"
+};
+struct AoIntegratorBodies {              /* integrator.cpp:43-62 */
+#include "_ref/integ_ao.inc"
+};
+struct WhittedIntegratorBodies {         /* integrator.cpp:78-129 (recursive) */
+#include "_ref/integ_whitted.inc"
+};
+#define override
+struct PathMatsIntegratorBodies {        /* integrator.cpp:141-175 */
+#include "_ref/integ_pathmats.inc"
+};
+#undef override
 struct PathMisBodies {                   /* PathMisIntegrator, integrator.cpp:195-344: Li and powerHeuristic */
     int m_maxDepth; float m_rayEpsilon; bool m_regularization; float m_accumulatedRoughness;
 #include "_ref/integrator_extract.inc"
@@ -513,6 +529,26 @@ int main() {
             const kzo::V3 oL = Li(&os, osm, kr, pc);
             rec("pathMisLi", {(float)scn, (float)px, (float)py, (float)sidx, o.x, o.y, d.x, d.y, d.z}, f3(kL), f3(oL), false);
             ++liPaths; if (oL.x > 0.f || oL.y > 0.f || oL.z > 0.f) ++liLit;
+        }
+        /* the other four integrators on the same scene (not on the normal-mapped ones: they build the BSDF record without `its`) */
+        if (scn % 3 != 1) {
+            kazen::NormalIntegratorBodies kin; kazen::AoIntegratorBodies kia; kazen::WhittedIntegratorBodies kiw; kazen::PathMatsIntegratorBodies kip;
+            for (int pth = 0; pth < 400; ++pth) {
+                const int type = 1 + pth % 4;            /* kz_integrator_type: normals, ao, whitted, path_mats */
+                const int px = (int)(rnd() * 640), py = (int)(rnd() * 480), sidx = (int)(rnd() * 16) % 16;
+                const kzo::V3 o(rnd(-0.5f, 0.5f), rnd(0.8f, 1.6f), 4.f), target(rnd(-2.5f, 2.5f), rnd(0.f, 3.8f), rnd(-2.5f, 1.f)), d = kzo::normalized(target - o);
+                kazen::StratifiedBodies ks; ks.m_seed = sc.sampler.d.seed; ks.m_sampleCount = 16; ks.m_resolution = 4;
+                ks.generateSample(kazen::Point2i(px, py), sidx); ks.nextPixel2D(); ks.next2D();
+                const kazen::Ray3f kray(kazen::Point3f(o.x, o.y, o.z), K(d), 1e-4f, 1e4f);
+                const kazen::Color3f kL = type == 1 ? kin.Li(&kscene, &ks, kray) : (type == 2 ? kia.Li(&kscene, &ks, kray) : (type == 3 ? kiw.Li(&kscene, &ks, kray) : kip.Li(&kscene, &ks, kray)));
+                kzo::Sampler osm; osm.cfg = &sc.sampler; osm.generateSample(px, py, sidx); osm.nextPixel2D(); osm.next2D();
+                PathCounters pc; const kz_ray kr{{o.x, o.y, o.z}, 1e-4f, {d.x, d.y, d.z}, 1e4f};
+                sc.integrator.type = type;
+                const kzo::V3 oL = LiAlt(&os, osm, kr, pc);
+                sc.integrator.type = KZ_INTEGRATOR_PATH_MIS;
+                const char *names[5] = {"", "normalsLi", "aoLi", "whittedLi", "pathMatsLi"};
+                rec(names[type], {(float)scn, (float)px, (float)py, (float)sidx, o.x, o.y, d.x, d.y, d.z}, f3(kL), f3(oL), false);
+            }
         }
     }
     fprintf(stderr, "pathMisLi: %ld paths, %ld with non-zero radiance\n", liPaths, liLit);
