@@ -294,10 +294,36 @@ def main():
                "ms_trace": ps["ms_trace"] / psteps, "ms_shade": ps["ms_shade"] / psteps,
                "ms_note": "ms_trace / ms_shade are summed over the two concurrent lanes of a device (chunks overlap), so they exceed ms_per_frame",
                "mean_rgb": None}
+        # B_path = n_ext*B_ray + n_sh*(B_ray - 12) + n_vtx*512 + 256, with the MEASURED per-path counts
+        n_tris = sum(int(m.n_triangles) for m in sbp.meshes)
+        n_ext = sum_over_ranks(ps["rays_extension"]) / psteps / npaths
+        n_sh = sum_over_ranks(ps["rays_shadow"]) / psteps / npaths
+        n_vtx = sum_over_ranks(ps["vertices"]) / psteps / npaths
+        br = b_ray(n_tris)
+        b_path = n_ext * br + n_sh * (br - 12) + n_vtx * 512 + 256
+        peak, _kind = measured_peaks()
+        ach = npaths * b_path / (pms * 1e-3) / 1e9 / world       # per GPU, against one GPU's HBM
+        out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                           "bytes_per_path": b_path, "bytes_per_ray": br, "tris": n_tris, "n_ext": n_ext, "n_sh": n_sh, "n_vtx": n_vtx,
+                           "note": "whole wavefront (all stages), per GPU; the accel of this scene is L2 resident, so HBM does not bind (DESIGN 7)"}
         if rank == 0:
             rgb, _ = GP.resolve(frame.cpu().numpy())
             out["mean_rgb"] = float(rgb.mean())
         GP.close()
+        # time-to-image beside it: the CPU port renders a bounded sample range of the SAME frame on all host cores
+        if rank == 0 and world == 1 and not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import kzo_py
+            OP = kzo_py.Oracle(sbp.desc())
+            cs = 2                                                 # 2 of the 64 sample indices of every pixel
+            t0 = time.perf_counter()
+            cf = OP.render(0, cs)
+            dt = time.perf_counter() - t0
+            OP.close()
+            cmp_ = cs * W * H / dt / 1e6
+            out["cpu_baseline"] = {"value": cmp_, "unit": "Mpaths/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": f"sample indices 0..{cs - 1} of all {W}x{H} pixels of the same frame ({cs * W * H} paths)",
+                                   "time_to_image_s": {"cpu_extrapolated": npaths / (cmp_ * 1e6), "gpu": pms * 1e-3}}
         return out
 
     paths = paths_cornell = None
