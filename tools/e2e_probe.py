@@ -18,6 +18,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     for _ in range(5): step()
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
     print(f"chunks {os.environ.get('KZGPU_TRACE_CHUNKS', 'default')}: {dt*1e3:.2f} ms/step, {sum(b[0] for b in batches)/dt/1e6:.1f} Mrays/s end to end", flush=True)
+    for graded in ("0", "1", "0", "1"):        # chunk sizes graded at both ends of a call (KZGPU_TRACE_GRADED), A/B/A/B in one process
+        os.environ["KZGPU_TRACE_GRADED"] = graded
+        step(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5): step()
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
+        print(f"   graded={graded}: {dt*1e3:.2f} ms/step, {sum(b[0] for b in batches)/dt/1e6:.1f} Mrays/s", flush=True)
 else:
     for k in sys.argv[1:] or ["16", "32", "64"]:
         subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, KZGPU_TRACE_CHUNKS=k))
