@@ -169,6 +169,27 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
+    affinity = None
+    if world > 1:
+        # one process per GPU: run on (and first-touch the pinned ray / hit buffers from) the CPUs next to this GPU, when the
+        # platform exposes a proper subset of them; the end-to-end leg is host-memory / PCIe bound with 8 ranks copying at once
+        try:
+            prop = torch.cuda.get_device_properties(local)
+            bus, dom, dev = getattr(prop, "pci_bus_id", None), getattr(prop, "pci_domain_id", 0), getattr(prop, "pci_device_id", 0)
+            if bus is not None:
+                with open(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist") as f:
+                    cpus = set()
+                    for part in f.read().strip().split(","):
+                        if part:
+                            a, _, b = part.partition("-")
+                            cpus.update(range(int(a), int(b or a) + 1))
+                allowed = os.sched_getaffinity(0)
+                near = cpus & allowed
+                if near and near != allowed:
+                    os.sched_setaffinity(0, near)
+                    affinity = f"{len(near)} of {len(allowed)} cpus (local to GPU {local})"
+        except Exception:
+            affinity = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -358,7 +379,8 @@ def main():
                 "config": {"workload": f"triangle-soup intersection microbench, {args.tris} tris, primary + shadow rays (BASELINE configs[1])",
                            "tris": args.tris, "rays_per_step_per_gpu": rays_per_step, "primary": batches[0]["n"], "incoherent_shadow": batches[1]["n"],
                            "builder": args.builder, "accel_build_ms": build_ms, "primary_hit_fraction": hit_frac,
-                           "l2": "inputs larger than L2 (512 MiB of rays + 320 MiB of hits per batch)", "parallelism": f"replicas x{world}"},
+                           "l2": "inputs larger than L2 (512 MiB of rays + 320 MiB of hits per batch)", "parallelism": f"replicas x{world}",
+                           "cpu_affinity": affinity},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_matches_device": same, "gpu_launches": launches, "clocks": clk, "paths": paths, "paths_cornell": paths_cornell}
         emit(line)
     G.close()

@@ -298,9 +298,76 @@ inline void makeRefs(const std::vector<Tri> &tris, std::vector<Ref> &refs, float
     max_abs = m;
 }
 
+/* ---------------- reference pre-splitting (KZ_SAH_PRESPLIT = max references per triangle, default 1 = off) ----------------
+ * A triangle that is large against its neighbours has a mostly empty box; it is given several references, each bounding the part
+ * of the triangle inside one half (quarter, ...) of its box, cut at the spatial median of the longest axis.  The same triangle
+ * may then sit in several leaves: the traversal tests it more than once and the (t, geomID, primID) rule keeps one answer.
+ * Boxes are computed in double, rounded outwards to float and clamped to the triangle's own box, so culling stays conservative. */
+inline int presplitLimit() { static int v = [] { const char *e = getenv("KZ_SAH_PRESPLIT"); int k = e ? atoi(e) : 1; return k < 1 ? 1 : (k > 64 ? 64 : k); }(); return v; }
+struct Poly { double v[10][3]; int n; };
+inline void clipPoly(const Poly &in, int axis, double plane, bool keep_low, Poly &out) {
+    out.n = 0;
+    for (int i = 0; i < in.n; ++i) {
+        const double *a = in.v[i], *b = in.v[(i + 1) % in.n];
+        const double da = keep_low ? plane - a[axis] : a[axis] - plane, db = keep_low ? plane - b[axis] : b[axis] - plane;
+        if (da >= 0.0 && out.n < 10) { for (int k = 0; k < 3; ++k) out.v[out.n][k] = a[k]; ++out.n; }
+        if ((da > 0.0 && db < 0.0) || (da < 0.0 && db > 0.0)) {
+            const double t = da / (da - db);
+            if (out.n < 10) { for (int k = 0; k < 3; ++k) out.v[out.n][k] = a[k] + t * (b[k] - a[k]); out.v[out.n][axis] = plane; ++out.n; }
+        }
+    }
+}
+inline void emitSplitRefs(const Poly &poly, const Box &triBox, uint32_t tri, int budget, float minExtent, std::vector<Ref> &refs) {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int i = 0; i < poly.n; ++i) for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], poly.v[i][a]); hi[a] = std::max(hi[a], poly.v[i][a]); }
+    int axis = 0;
+    for (int a = 1; a < 3; ++a) if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;
+    if (budget >= 2 && hi[axis] - lo[axis] > (double)minExtent) {
+        const double plane = 0.5 * (lo[axis] + hi[axis]);
+        Poly l, r;
+        clipPoly(poly, axis, plane, true, l); clipPoly(poly, axis, plane, false, r);
+        if (l.n >= 3 && r.n >= 3) {
+            emitSplitRefs(l, triBox, tri, budget / 2, minExtent, refs);
+            emitSplitRefs(r, triBox, tri, budget - budget / 2, minExtent, refs);
+            return;
+        }
+    }
+    Ref ref; ref.tri = tri;
+    for (int a = 0; a < 3; ++a) {
+        float flo = (float)lo[a], fhi = (float)hi[a];
+        if ((double)flo > lo[a]) flo = std::nextafter(flo, -FLT_MAX);
+        if ((double)fhi < hi[a]) fhi = std::nextafter(fhi, FLT_MAX);
+        flo = std::nextafter(flo, -FLT_MAX); fhi = std::nextafter(fhi, FLT_MAX);          /* one more ulp for the clip arithmetic */
+        ref.box.lo[a] = std::max(flo, triBox.lo[a]); ref.box.hi[a] = std::min(fhi, triBox.hi[a]);
+        ref.c[a] = 0.5f * (ref.box.lo[a] + ref.box.hi[a]);
+    }
+    refs.push_back(ref);
+}
+inline void makeSplitRefs(const std::vector<Tri> &tris, int limit, std::vector<Ref> &refs, float &max_abs) {
+    std::vector<Ref> whole;
+    makeRefs(tris, whole, max_abs);
+    /* only triangles whose box is large against the average box are worth more than one reference */
+    double mean = 0.0;
+    for (const Ref &r : whole) mean += (double)r.box.area();
+    mean /= (double)std::max<size_t>(1, whole.size());
+    refs.clear(); refs.reserve(whole.size() * 2);
+    const float minExtent = 1e-6f * std::max(max_abs, 1e-30f);
+    for (const Ref &w : whole) {
+        const double rel = mean > 0.0 ? (double)w.box.area() / mean : 0.0;
+        int budget = 1;
+        while (budget < limit && rel > 0.5 * (double)budget) budget *= 2;        /* average-sized boxes get 2, 4x the average 8, ... */
+        budget = std::min(budget, limit);
+        if (budget < 2) { refs.push_back(w); continue; }
+        Poly p; p.n = 3;
+        for (int v = 0; v < 3; ++v) for (int a = 0; a < 3; ++a) p.v[v][a] = (double)tris[w.tri].p[v][a];
+        emitSplitRefs(p, w.box, w.tri, budget, minExtent, refs);
+    }
+}
+
 inline void buildHostSah(const std::vector<Tri> &tris, int threads, Built &out) {
     std::vector<Ref> refs;
-    makeRefs(tris, refs, out.max_abs);
+    if (presplitLimit() > 1) makeSplitRefs(tris, presplitLimit(), refs, out.max_abs);
+    else makeRefs(tris, refs, out.max_abs);
     Sah sah(refs);
     sah.run(threads);
     collapse(sah.nodes(), refs, tris, out);

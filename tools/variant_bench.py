@@ -22,5 +22,7 @@ for lib in sys.argv[1:] or [pk.LIB_GPU]:
         out.append((rays.shape[0] * 5 / e0.elapsed_time(e1) / 1e3, dh.cpu().view(torch.int32)))
     if ref is None: ref = [o[1] for o in out]
     ok = all(torch.equal(a, o[1]) for a, o in zip(ref, out))
+    crc = [int(o[1].to(torch.int64).sum().item()) & 0xFFFFFFFFFFFF for o in out]       # compare across processes (builder knobs are read once per process)
+    print(f"hit checksums {crc[0]:012x} {crc[1]:012x}  bvh {G.stats()['bvh_nodes']} nodes {G.stats()['bvh_bytes'] / 2**20:.0f} MiB  build {G.stats()['ms_build']:.0f} ms")
     print(f"{os.path.basename(lib):22s} primary {out[0][0]:8.1f} Mrays/s   incoherent {out[1][0]:8.1f} Mrays/s   same_hits={ok}", flush=True)
     G.close()
