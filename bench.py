@@ -250,7 +250,7 @@ def main():
 
     # roofline of the dominant kernel (k_trace): CUDA events inside the library around every launch
     peak, peak_kind = measured_peaks()
-    trace_launches = args.steps * len(batches)               # one k_trace per batch; the reordering kernels of an incoherent batch are counted in gpu_launches and timed as reorder_ms
+    trace_launches = args.steps * len(batches)               # one k_trace per batch
     kernel_ms = st["ms_trace"] / max(1, trace_launches)
     bytes_per_launch = 0.5 * (batches[0]["n"] * b_ray(args.tris) + batches[1]["n"] * b_ray(args.tris))   # both batches return 20-byte hits
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
@@ -264,7 +264,7 @@ def main():
         traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
-                "kernel": "k_trace", "kernel_ms": kernel_ms, "reorder_ms_per_step": st["ms_shade"] / args.steps, "bytes_per_ray": b_ray(args.tris), "peak_kind": peak_kind}
+                "kernel": "k_trace", "kernel_ms": kernel_ms, "bytes_per_ray": b_ray(args.tris), "peak_kind": peak_kind}
 
     # ------------------------------------------------------------------ e2e through the host-buffer C ABI
     def e2e_step():

@@ -29,7 +29,7 @@ def test_soup_trace_bit_exact(kzo, emu, n):
     a, b = O.trace(rays, brute=(n <= 5000)), E.trace(rays)
     assert a.tobytes() == b.tobytes()
     nodes, tris, depth = E.bvh_info()
-    assert tris == n and nodes >= 1
+    assert n <= tris <= 2 * n and nodes >= 1          # stored references: the SAH builder may split a triangle in two (KZ_SAH_PRESPLIT)
     O.close(); E.close()
 
 
