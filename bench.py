@@ -256,7 +256,7 @@ def main():
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this workload, if there is one
-        with open(os.path.join(ROOT, "profiles", "r3_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r4_traffic.json")) as f:
             for tj in json.load(f)["workloads"]:
                 if tj["tris"] == args.tris and tj["builder"] == args.builder and tj["rays_per_launch"] == batches[0]["n"] == batches[1]["n"]:
                     traffic = tj["dram_bytes_per_launch_mean"]
