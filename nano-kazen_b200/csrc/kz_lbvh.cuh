@@ -37,7 +37,8 @@ struct Box6 { float lo[3], hi[3]; };
 
 struct BuildState {
     const kzbvh::Tri *tris;      /* scene order */
-    uint32_t n;
+    const float4 *rlo, *rhi;     /* pre-split references (nullptr: one reference per triangle): box lo | triangle index, box hi */
+    uint32_t n;                  /* references */
     const uint32_t *order;       /* sorted position -> triangle */
     const unsigned long long *keys;
     int32_t *left, *right;       /* >= 0 internal node, < 0: ~leaf (sorted position) */
@@ -92,14 +93,21 @@ __device__ __forceinline__ unsigned long long expand21(unsigned long long v) {
     return v;
 }
 
-__global__ void k_morton(const kzbvh::Tri *tris, uint32_t n, const uint32_t *bounds, unsigned long long *keys, uint32_t *vals) {
+__global__ void k_morton(const kzbvh::Tri *tris, const float4 *rlo, const float4 *rhi, uint32_t n, const uint32_t *bounds, unsigned long long *keys, uint32_t *vals) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const kzbvh::Tri t = tris[i];
+    float blo[3], bhi[3];
+    if (rlo) {
+        const float4 l = rlo[i], h = rhi[i];
+        blo[0] = l.x; blo[1] = l.y; blo[2] = l.z; bhi[0] = h.x; bhi[1] = h.y; bhi[2] = h.z;
+    } else {
+        const kzbvh::Tri t = tris[i];
+        for (int a = 0; a < 3; ++a) { blo[a] = fminf(t.p[0][a], fminf(t.p[1][a], t.p[2][a])); bhi[a] = fmaxf(t.p[0][a], fmaxf(t.p[1][a], t.p[2][a])); }
+    }
     unsigned long long code = 0ull;
     for (int a = 0; a < 3; ++a) {
         const float lo = ord2f(bounds[a]), hi = ord2f(bounds[3 + a]);
-        const float mn = fminf(t.p[0][a], fminf(t.p[1][a], t.p[2][a])), mx = fmaxf(t.p[0][a], fmaxf(t.p[1][a], t.p[2][a]));
+        const float mn = blo[a], mx = bhi[a];
         const float c = 0.5f * (mn + mx);
         const float ext = hi - lo;
         float u = ext > 0.f ? (c - lo) / ext : 0.f;
@@ -157,8 +165,15 @@ __device__ __forceinline__ Box6 tri_box(const kzbvh::Tri &t) {
     }
     return r;
 }
+__device__ __forceinline__ uint32_t ref_tri(const BuildState &b, uint32_t ref) { return b.rlo ? __float_as_uint(b.rlo[ref].w) : ref; }
 __device__ __forceinline__ Box6 child_box(const BuildState &b, int c) {
-    if (c < 0) return tri_box(b.tris[b.order[~c]]);
+    if (c < 0) {
+        const uint32_t ref = b.order[~c];
+        if (!b.rlo) return tri_box(b.tris[ref]);
+        const float4 l = b.rlo[ref], h = b.rhi[ref];
+        Box6 r; r.lo[0] = l.x; r.lo[1] = l.y; r.lo[2] = l.z; r.hi[0] = h.x; r.hi[1] = h.y; r.hi[2] = h.z;
+        return r;
+    }
     /* ld.cg: boxes are produced by other SMs in the same launch (k_fit); never trust L1 here */
     const float4 lo = __ldcg(reinterpret_cast<const float4 *>(b.blo) + c), hi = __ldcg(reinterpret_cast<const float4 *>(b.bhi) + c);
     Box6 r; r.lo[0] = lo.x; r.lo[1] = lo.y; r.lo[2] = lo.z; r.hi[0] = hi.x; r.hi[1] = hi.y; r.hi[2] = hi.z;
@@ -306,7 +321,7 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
             nd.meta[s] = (uint8_t)((unary << 5) | triOff);
             const uint32_t first = c < 0 ? (uint32_t)~c : b.first[c];
             for (uint32_t k = 0; k < cnt; ++k) {
-                const kzbvh::Tri t = b.tris[b.order[first + k]];
+                const kzbvh::Tri t = b.tris[ref_tri(b, b.order[first + k])];
                 KzF4 *o = cs.tris + 3 * (size_t)(tri_base + triOff + k);
                 KzF4 v;
                 v.x = t.p[0][0]; v.y = t.p[0][1]; v.z = t.p[0][2]; v.w = __uint_as_float(t.geom); o[0] = v;
@@ -319,6 +334,64 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
     nd.imask = imask;
     cs.nodes[it.wnode] = nd;
 }
+
+/* Reference pre-splitting (as in the host SAH builder, kz_bvh_build.h): a triangle whose box is expected to hold other primitives,
+ * volume(box) * N / volume(centroid bounds) >= need, gets two references, each bounding the part of the triangle on one side of the
+ * spatial median of the box's longest axis.  Clipping is done in float; every reference box is padded by a few ulps of the triangle's
+ * largest coordinate and clamped to the triangle's own box, so it contains its part of the triangle and culling stays conservative. */
+__global__ void k_make_refs(const kzbvh::Tri *tris, uint32_t n, const uint32_t *bounds, float need, float4 *rlo, float4 *rhi, uint32_t *counter) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const kzbvh::Tri t = tris[i];
+    float lo[3], hi[3], ext[3], sext[3], longest = 0.f, mabs = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = fminf(t.p[0][a], fminf(t.p[1][a], t.p[2][a])); hi[a] = fmaxf(t.p[0][a], fmaxf(t.p[1][a], t.p[2][a]));
+        ext[a] = hi[a] - lo[a];
+        sext[a] = ord2f(bounds[3 + a]) - ord2f(bounds[a]);
+        longest = fmaxf(longest, sext[a]);
+        mabs = fmaxf(mabs, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+    }
+    double volume = 1.0;
+    for (int a = 0; a < 3; ++a) volume *= (double)fmaxf(sext[a], 1e-3f * longest);
+    const double inside = volume > 0.0 ? (double)ext[0] * (double)ext[1] * (double)ext[2] * (double)n / volume : 0.0;
+    int axis = 0;
+    for (int a = 1; a < 3; ++a) if (ext[a] > ext[axis]) axis = a;
+    const float plane = 0.5f * (lo[axis] + hi[axis]);
+    const bool split = inside >= (double)need && plane > lo[axis] && plane < hi[axis];
+    const uint32_t tri_bits = i;
+    if (!split) {
+        const uint32_t o = atomicAdd(counter, 1u);
+        rlo[o] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(tri_bits)); rhi[o] = make_float4(hi[0], hi[1], hi[2], 0.f);
+        return;
+    }
+    float llo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, lhi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    float hlo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hhi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int v = 0; v < 3; ++v) {
+        const float *a = t.p[v], *b = t.p[(v + 1) % 3];
+        if (a[axis] <= plane) for (int k = 0; k < 3; ++k) { llo[k] = fminf(llo[k], a[k]); lhi[k] = fmaxf(lhi[k], a[k]); }
+        if (a[axis] >= plane) for (int k = 0; k < 3; ++k) { hlo[k] = fminf(hlo[k], a[k]); hhi[k] = fmaxf(hhi[k], a[k]); }
+        if ((a[axis] < plane && b[axis] > plane) || (a[axis] > plane && b[axis] < plane)) {
+            const float tt = (plane - a[axis]) / (b[axis] - a[axis]);
+            for (int k = 0; k < 3; ++k) {
+                const float q = k == axis ? plane : a[k] + tt * (b[k] - a[k]);
+                llo[k] = fminf(llo[k], q); lhi[k] = fmaxf(lhi[k], q);
+                hlo[k] = fminf(hlo[k], q); hhi[k] = fmaxf(hhi[k], q);
+            }
+        }
+    }
+    const float pad = 8.f * 1.1920929e-7f * mabs;
+    const uint32_t o = atomicAdd(counter, 2u);
+    float4 l, h;
+    l = make_float4(fmaxf(llo[0] - pad, lo[0]), fmaxf(llo[1] - pad, lo[1]), fmaxf(llo[2] - pad, lo[2]), __uint_as_float(tri_bits));
+    h = make_float4(fminf(lhi[0] + pad, hi[0]), fminf(lhi[1] + pad, hi[1]), fminf(lhi[2] + pad, hi[2]), 0.f);
+    rlo[o] = l; rhi[o] = h;
+    l = make_float4(fmaxf(hlo[0] - pad, lo[0]), fmaxf(hlo[1] - pad, lo[1]), fmaxf(hlo[2] - pad, lo[2]), __uint_as_float(tri_bits));
+    h = make_float4(fminf(hhi[0] + pad, hi[0]), fminf(hhi[1] + pad, hi[1]), fminf(hhi[2] + pad, hi[2]), 0.f);
+    rlo[o + 1] = l; rhi[o + 1] = h;
+}
+#ifndef KZ_LBVH_PRESPLIT_DEFAULT
+#define KZ_LBVH_PRESPLIT_DEFAULT 1       /* KZ_LBVH_PRESPLIT=0 turns it off */
+#endif
 
 #define KZL_CUDA(call)                                                                                   \
     do {                                                                                                 \
@@ -334,22 +407,44 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
  * `owner` (freed by the caller), temporaries are released before returning. */
 inline int build(const std::vector<kzbvh::Tri> &tris, cudaStream_t s, std::vector<void *> &owner, Result &r, std::string &err) {
     std::vector<void *> temp;
-    const uint32_t n = (uint32_t)tris.size();
+    const uint32_t n_tris_in = (uint32_t)tris.size();
+    uint32_t n = n_tris_in;                  /* references: == triangles unless pre-splitting adds some */
     r = Result();
     if (n == 0) return KZ_OK;
     auto talloc = [&](size_t bytes, void **p) { cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16)); if (e == cudaSuccess) temp.push_back(*p); return e; };
     kzbvh::Tri *d_tris; unsigned long long *k0, *k1; uint32_t *v0, *v1, *bounds;
     KZL_CUDA(talloc((size_t)n * sizeof(kzbvh::Tri), (void **)&d_tris));
-    KZL_CUDA(talloc((size_t)n * 8, (void **)&k0)); KZL_CUDA(talloc((size_t)n * 8, (void **)&k1));
-    KZL_CUDA(talloc((size_t)n * 4, (void **)&v0)); KZL_CUDA(talloc((size_t)n * 4, (void **)&v1));
     KZL_CUDA(talloc(64, (void **)&bounds));
     KZL_CUDA(cudaMemcpyAsync(d_tris, tris.data(), (size_t)n * sizeof(kzbvh::Tri), cudaMemcpyHostToDevice, s));
     const uint32_t init[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
     KZL_CUDA(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    k_scene_bounds<<<std::min((n + 255u) / 256u, 148u * 8u), 256, 0, s>>>(d_tris, n, bounds);
+    ++r.launches;
+    float4 *rlo = nullptr, *rhi = nullptr;
+    {
+        const char *e = getenv("KZ_LBVH_PRESPLIT");
+        const bool presplit = e ? atoi(e) != 0 : KZ_LBVH_PRESPLIT_DEFAULT != 0;
+        if (presplit && n_tris_in >= 64u && n_tris_in < 0x3FFFFFFFu) {
+            const char *ne = getenv("KZ_SAH_PRESPLIT_NEED");
+            const float need = ne ? (float)atof(ne) : 0.25f;
+            KZL_CUDA(talloc((size_t)n * 2 * sizeof(float4), (void **)&rlo)); KZL_CUDA(talloc((size_t)n * 2 * sizeof(float4), (void **)&rhi));
+            KZL_CUDA(cudaMemsetAsync(bounds + 8, 0, 4, s));
+            k_make_refs<<<(n + 255u) / 256u, 256, 0, s>>>(d_tris, n, bounds, need, rlo, rhi, bounds + 8);
+            ++r.launches;
+            uint32_t nref = 0;
+            KZL_CUDA(cudaMemcpyAsync(&nref, bounds + 8, 4, cudaMemcpyDeviceToHost, s));
+            KZL_CUDA(cudaStreamSynchronize(s));
+            /* kept only when at least a quarter of the triangles qualified: a soup (86 % on the 2^20-triangle one: +5-7 % rays/s) profits,
+             * a surface mesh with a few outsized triangles does not (the host builder's cost arbitration drops those trees, item 22) */
+            if ((unsigned long long)(nref - n_tris_in) * 4ull >= (unsigned long long)n_tris_in) n = nref;
+            else { rlo = nullptr; rhi = nullptr; }
+        }
+    }
+    KZL_CUDA(talloc((size_t)n * 8, (void **)&k0)); KZL_CUDA(talloc((size_t)n * 8, (void **)&k1));
+    KZL_CUDA(talloc((size_t)n * 4, (void **)&v0)); KZL_CUDA(talloc((size_t)n * 4, (void **)&v1));
     const unsigned blocks = (n + 255u) / 256u;
-    k_scene_bounds<<<std::min(blocks, 148u * 8u), 256, 0, s>>>(d_tris, n, bounds);
-    k_morton<<<blocks, 256, 0, s>>>(d_tris, n, bounds, k0, v0);
-    r.launches += 2;
+    k_morton<<<blocks, 256, 0, s>>>(d_tris, rlo, rhi, n, bounds, k0, v0);
+    ++r.launches;
     cub::DoubleBuffer<unsigned long long> dk(k0, k1);
     cub::DoubleBuffer<uint32_t> dv(v0, v1);
     size_t sort_bytes = 0;
@@ -360,7 +455,7 @@ inline int build(const std::vector<kzbvh::Tri> &tris, cudaStream_t s, std::vecto
     r.launches += 8;
 
     BuildState b;
-    b.tris = d_tris; b.n = n; b.order = dv.Current(); b.keys = dk.Current();
+    b.tris = d_tris; b.rlo = rlo; b.rhi = rhi; b.n = n; b.order = dv.Current(); b.keys = dk.Current();
     const size_t ni = n > 1 ? n - 1 : 1;
     KZL_CUDA(talloc(ni * 4, (void **)&b.left)); KZL_CUDA(talloc(ni * 4, (void **)&b.right));
     KZL_CUDA(talloc((size_t)(2 * (size_t)n) * 4, (void **)&b.parent));
