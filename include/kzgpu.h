@@ -68,7 +68,10 @@ typedef struct kz_hit {
 
 /* --------------------------------------------------------------- scene POD */
 /* Mesh buffers exactly as Mesh holds them (mesh.h:175-178): column-major
- * Eigen matrices == packed xyz / uv / index triples. normals/uvs may be NULL. */
+ * Eigen matrices == packed xyz / uv / index triples. normals/uvs may be NULL.
+ * The arrays are copied to HBM as they are and turned into the renderer's records
+ * there; each pointer may be a host pointer or a CUDA device pointer (arrays that
+ * were produced on a GPU are read in place). */
 typedef struct kz_mesh_desc {
     const float    *positions;   /* 3 * n_vertices  */
     const float    *normals;     /* 3 * n_vertices or NULL */
@@ -214,7 +217,8 @@ typedef struct kz_scene_desc {
 /* --------------------------------------------------------------- rendering */
 /* One call renders sample indices [spp_begin, spp_end) of every pixel of the
  * rectangle [x0,x1) x [y0,y1) and ADDS the filtered splats into the bordered
- * frame (block.cpp:56-85).  Frame layout: (H+2b) rows of (W+2b) float4
+ * frame (block.cpp:56-85).  With the pmj02bn sampler spp_end must not exceed the
+ * sampler's sample_count (its per-pixel tables hold sample_count entries).  Frame layout: (H+2b) rows of (W+2b) float4
  * (r*w, g*w, b*w, w), b = ceil(radius - 0.5).  Sharding across GPUs = disjoint
  * spp ranges / rectangles followed by a sum of the frames. */
 typedef struct kz_render_req {
@@ -231,10 +235,12 @@ typedef struct kz_stats {
     uint64_t kernel_launches;  /* CUDA kernels launched by this context since reset  */
     double   ms_trace;         /* device time in traversal kernels                   */
     double   ms_shade;         /* device time in raygen/shade/accumulate kernels     */
-    double   ms_total;         /* device time of the last render/trace call          */
+    double   ms_total;         /* device time of the render calls since reset (accumulates) */
     uint64_t bvh_nodes;        /* wide nodes                                         */
     uint64_t bvh_bytes;        /* nodes + leaf triangles                             */
-    double   ms_build;         /* accel build time (host + device)                   */
+    double   ms_build;         /* wall time of the last kzgpu_accel_build (host + device) */
+    double   ms_upload;        /* wall time of the last kzgpu_scene_upload           */
+    double   ms_merge;         /* device time in the multi-device frame merge since reset */
 } kz_stats;
 
 #define KZ_BUILD_HOST_SAH 0    /* binned SAH on the host, collapsed to 8-wide, uploaded */
@@ -252,7 +258,8 @@ int  kzgpu_accel_build(kzgpu_ctx *ctx, int builder);
 /* Closest-hit queries on host buffers (H2D + trace + D2H), shadow=1 uses the
  * shadow-ray variant of accel.cpp:100-104 (same closest-hit, u/v/prim still filled). */
 int  kzgpu_trace(kzgpu_ctx *ctx, int device, const kz_ray *rays, size_t n, int shadow, kz_hit *hits);
-/* Same on device-resident buffers of `device`; runs on `stream` (cudaStream_t as void*, NULL = default). */
+/* Same on device-resident buffers of `device`; runs on `stream` (cudaStream_t as void*, NULL = default).
+ * d_rays must be 16-byte aligned (rays are read as two 128-bit loads), d_hits 4-byte aligned. */
 int  kzgpu_trace_device(kzgpu_ctx *ctx, int device, const void *d_rays, size_t n, int shadow,
                         void *d_hits, void *stream);
 /* Shadow-ray visibility with kazen's invisible-light stepping (integrator.cpp:259-278):
@@ -281,7 +288,10 @@ int  kzgpu_bsdf_query(kzgpu_ctx *ctx, int bsdf, int mode, const float wi[3], con
 int  kzgpu_image_lookup(kzgpu_ctx *ctx, int image, int level, const float *st, size_t n, float *rgb);
 
 /* Whole-frame render into a host frame ((H+2b)*(W+2b)*4 floats). Multi-device contexts
- * shard [spp_begin,spp_end) by sample index across their devices and sum the frames. */
+ * shard [spp_begin,spp_end) by sample index across their devices and merge the frames on
+ * the devices (ImageBlock::put(ImageBlock&), block.cpp:87-96): every device sums its slice
+ * of all frames through NVLink peer loads into the first device's frame, which is then
+ * copied out once.  clear_frame = 0 adds to the frame passed in. */
 int  kzgpu_render(kzgpu_ctx *ctx, const kz_render_req *req, float *frame_rgbw);
 /* Single-device variant leaving the frame in HBM (for an NCCL reduce by the caller), enqueued on
  * `stream` without synchronising.  *d_frame_inout != NULL on entry: splat into that caller-owned
@@ -293,6 +303,17 @@ int  kzgpu_frame_dims(const kzgpu_ctx *ctx, int32_t *width, int32_t *height, int
 /* frame -> rgb/w -> sRGB 8-bit (truncating, bitmap.cpp:49-51). Host in, host out. */
 int  kzgpu_resolve(kzgpu_ctx *ctx, const float *frame_rgbw, float *rgb_linear /* W*H*3 or NULL */,
                    uint8_t *srgb8 /* W*H*3 or NULL */);
+
+/* Post-intersection parity probe (Accel::rayIntersect's second half, accel.cpp:113-236): for each ray, trace it and fill the
+ * Intersection of the closest hit.  24 floats per ray: t, mesh (as float, -1 = miss), p[3], uv[2], geoFrame.n[3],
+ * shFrame.s[3], shFrame.t[3], shFrame.n[3], dpdu[3], 2 x 0. */
+int  kzgpu_intersection_dump(kzgpu_ctx *ctx, const kz_ray *rays, size_t n, float *out24);
+
+/* Emitter sampling parity probe (Scene::getRandomLight scene.h:45-56, Mesh::sample mesh.cpp:108-133, AreaLight::sample /
+ * pdf / eval light.cpp:16-51): for reference point ref[i] and the five random numbers u5[i] = (light pick, triangle pick,
+ * barycentric 1, barycentric 2, unused) in the order Li draws them.  16 floats per query: mesh, p[3], n[3], wi[3], dist, pdf (solid
+ * angle, without the light-pick probability), Le/pdf [3], 0. */
+int  kzgpu_light_sample_dump(kzgpu_ctx *ctx, const float *ref3, const float *u5, size_t n, float *out16);
 
 int  kzgpu_stats(kzgpu_ctx *ctx, kz_stats *out);
 int  kzgpu_stats_reset(kzgpu_ctx *ctx);

@@ -8,6 +8,7 @@
 #include "kz_kernels.cuh"
 #include "kz_host_scene.h"
 #include "kz_lbvh.cuh"
+#include "kz_ingest.cuh"
 #include <cuda_runtime.h>
 #include <chrono>
 #include <cstdio>
@@ -21,7 +22,7 @@ namespace {
 
 thread_local std::string g_error;
 
-enum { CAT_TRACE = 0, CAT_SHADE = 1, CAT_TOTAL = 2 };
+enum { CAT_TRACE = 0, CAT_SHADE = 1, CAT_TOTAL = 2, CAT_MERGE = 3, CAT_COUNT = 4 };
 
 struct EvPair { cudaEvent_t a, b; int cat; };
 
@@ -50,6 +51,7 @@ struct Device {
     uint32_t *cursor = nullptr;      /* batch-trace fetch cursor */
     KzF4 *frame = nullptr;
     size_t frame_texels = 0;
+    cudaEvent_t splat_done = nullptr, merge_done = nullptr;   /* multi-device frame merge (k_frame_reduce) */
     /* scratch for host-pointer entry points */
     void *scratch[3] = {nullptr, nullptr, nullptr};
     size_t scratch_bytes[3] = {0, 0, 0};
@@ -58,7 +60,7 @@ struct Device {
     /* timing */
     std::vector<EvPair> pending;
     std::vector<cudaEvent_t> free_events;
-    double ms[3] = {0, 0, 0};
+    double ms[CAT_COUNT] = {0, 0, 0, 0};
     uint64_t launches = 0;
 };
 
@@ -75,6 +77,7 @@ struct kzgpu_ctx {
     double ms_build = 0;
     uint64_t bvh_nodes = 0, bvh_bytes = 0;
     double last_total_ms = 0;
+    double ms_upload = 0;             /* wall time of the last kzgpu_scene_upload */
     std::string error;
 };
 
@@ -125,12 +128,21 @@ int ensure_scratch(kzgpu_ctx *ctx, Device &d, int k, size_t bytes) {
 
 cudaEvent_t get_event(Device &d) {
     if (!d.free_events.empty()) { cudaEvent_t e = d.free_events.back(); d.free_events.pop_back(); return e; }
-    cudaEvent_t e; cudaEventCreate(&e); return e;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return e;
 }
-struct Timed {   /* records an event pair around a group of launches on `s` */
-    Device &d; cudaStream_t s; EvPair p;
-    Timed(Device &dev, cudaStream_t st, int cat) : d(dev), s(st) { p.a = get_event(d); p.b = get_event(d); p.cat = cat; cudaEventRecord(p.a, s); }
-    ~Timed() { cudaEventRecord(p.b, s); d.pending.push_back(p); }
+struct Timed {   /* records an event pair around a group of launches on `s`; timing is dropped (never the work) if events run out */
+    Device &d; cudaStream_t s; EvPair p; bool ok;
+    Timed(Device &dev, cudaStream_t st, int cat) : d(dev), s(st) {
+        p.a = get_event(d); p.b = get_event(d); p.cat = cat;
+        ok = p.a && p.b && cudaEventRecord(p.a, s) == cudaSuccess;
+    }
+    ~Timed() {
+        if (ok && cudaEventRecord(p.b, s) == cudaSuccess) { d.pending.push_back(p); return; }
+        if (p.a) d.free_events.push_back(p.a);
+        if (p.b) d.free_events.push_back(p.b);
+    }
 };
 /* Folds finished event pairs into the per-category totals (synchronises on them). */
 void fold_events(Device &d) {
@@ -158,36 +170,110 @@ int select(kzgpu_ctx *ctx, int device, Device **out) {
     return KZ_OK;
 }
 
-int upload_scene(kzgpu_ctx *ctx, Device &d) {
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice;
+}
+
+int grid_for(size_t n, int threads, int sm_count) {
+    const size_t blocks = (n + (size_t)threads - 1) / (size_t)threads;
+    return (int)std::max<size_t>(1, std::min<size_t>(blocks, (size_t)sm_count * 16));
+}
+
+/* Small tables + frame of one device; the bulk arrays (vertex / index records, texels) are filled by ingest_geometry on the
+ * first device and copied to the others over NVLink (replicate_geometry). */
+int upload_tables(kzgpu_ctx *ctx, Device &d) {
     const KzHostScene &h = *ctx->hs;
     free_all(d.scene_allocs);
     d.sc = h.sc;
     d.sc.nodes = nullptr; d.sc.tris = nullptr; d.sc.n_nodes = 0; d.sc.n_tris = 0;
     int rc;
 #define UP(field, vec) if ((rc = dev_upload(ctx, d, d.scene_allocs, (vec).data(), (vec).size(), &d.sc.field))) return rc
-    UP(meshes, h.meshes); UP(vertices, h.vertices); UP(indices, h.indices);
+    UP(meshes, h.meshes);
     UP(light_cdf, h.light_cdf); UP(light_meshes, h.light_meshes); UP(bsdfs, h.bsdfs); UP(textures, h.textures);
-    UP(images, h.images); UP(texels, h.texels); UP(lights, h.lights); UP(blue_noise, h.blue_noise); UP(pmj02bn, h.pmj);
+    UP(images, h.images); UP(lights, h.lights); UP(blue_noise, h.blue_noise); UP(pmj02bn, h.pmj);
     UP(pmj_pixel_samples, h.pmj_pixel_samples);
 #undef UP
-    /* mip pyramids: level l from level l-1, on the device */
-    for (const KzImageRec &im : h.images) {
-        size_t src = im.texel_offset; int sw = im.width, sh = im.height;
-        for (int l = 1; l <= im.n_levels; ++l) {
-            const int dw = sw > 1 ? sw >> 1 : 1, dh = sh > 1 ? sh >> 1 : 1;
-            const size_t dst = src + (size_t)sw * sh;
-            dim3 blk(32, 8), grd((unsigned)(dw + 31) / 32, (unsigned)(dh + 7) / 8);
-            k_mip_level<<<grd, blk, 0, d.stream>>>(const_cast<KzF4 *>(d.sc.texels), src, sw, sh, dst, dw, dh);
-            ++d.launches;
-            src = dst; sw = dw; sh = dh;
-        }
-    }
+    KzVertex *v = nullptr; KzU4 *ix = nullptr; KzF4 *tx = nullptr;
+    if ((rc = dev_alloc(ctx, d.scene_allocs, (size_t)h.total_vertices, &v))) return rc;
+    if ((rc = dev_alloc(ctx, d.scene_allocs, (size_t)h.total_triangles, &ix))) return rc;
+    if ((rc = dev_alloc(ctx, d.scene_allocs, h.total_texels, &tx))) return rc;
+    d.sc.vertices = v; d.sc.indices = ix; d.sc.texels = tx;
     /* frame */
     const size_t texels = (size_t)(h.sc.camera.width + 2 * h.sc.border) * (size_t)(h.sc.camera.height + 2 * h.sc.border);
     if ((rc = dev_alloc(ctx, d.scene_allocs, texels, &d.frame))) return rc;
     d.frame_texels = texels;
     KZ_CUDA(ctx, cudaMemsetAsync(d.frame, 0, texels * sizeof(KzF4), d.stream));
-    KZ_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    return KZ_OK;
+}
+
+/* Mesh and image arrays -> HBM records on device `d` (kz_ingest.cuh).  Host arrays are copied into a staging buffer with one
+ * cudaMemcpyAsync each; arrays that already live on a device are read where they are. */
+int ingest_geometry(kzgpu_ctx *ctx, Device &d, const kz_scene_desc *scene) {
+    const KzHostScene &h = *ctx->hs;
+    size_t stage_bytes = 0;
+    for (uint32_t g = 0; g < scene->n_meshes; ++g) {
+        const kz_mesh_desc &m = scene->meshes[g];
+        stage_bytes = std::max(stage_bytes, (size_t)m.n_vertices * 32 + (size_t)m.n_triangles * 12 + 64);
+    }
+    for (uint32_t i = 0; i < scene->n_images; ++i) stage_bytes = std::max(stage_bytes, (size_t)scene->images[i].width * scene->images[i].height * 12);
+    std::vector<void *> temp;
+    char *stage = nullptr; uint32_t *bad = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, temp, stage_bytes, &stage))) { free_all(temp); return rc; }
+    if ((rc = dev_alloc(ctx, temp, 4, &bad))) { free_all(temp); return rc; }
+    cudaError_t e = cudaMemsetAsync(bad, 0, 4, d.stream);
+    auto fetch = [&](const void *src, size_t bytes, size_t &cursor) -> const void * {      /* device-visible view of a caller array */
+        if (!src || e != cudaSuccess) return nullptr;
+        if (is_device_ptr(src)) return src;
+        char *dst = stage + cursor;
+        cursor += (bytes + 15) & ~(size_t)15;
+        e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.stream);
+        return dst;
+    };
+    KzVertex *vertices = const_cast<KzVertex *>(d.sc.vertices);
+    KzU4 *indices = const_cast<KzU4 *>(d.sc.indices);
+    KzF4 *texels = const_cast<KzF4 *>(d.sc.texels);
+    for (uint32_t g = 0; g < scene->n_meshes && e == cudaSuccess; ++g) {
+        const kz_mesh_desc &m = scene->meshes[g];
+        const KzMeshRec &r = h.meshes[g];
+        size_t cur = 0;
+        const float *pos = (const float *)fetch(m.positions, (size_t)m.n_vertices * 12, cur);
+        const float *nrm = (const float *)fetch(m.normals, (size_t)m.n_vertices * 12, cur);
+        const float *uv = (const float *)fetch(m.uvs, (size_t)m.n_vertices * 8, cur);
+        const uint32_t *idx = (const uint32_t *)fetch(m.indices, (size_t)m.n_triangles * 12, cur);
+        if (e != cudaSuccess) break;
+        if (m.n_vertices) { k_ingest_vertices<<<grid_for(m.n_vertices, 256, d.sm_count), 256, 0, d.stream>>>(pos, nrm, uv, m.n_vertices, vertices + r.vertex_offset); ++d.launches; }
+        if (m.n_triangles) { k_ingest_indices<<<grid_for(m.n_triangles, 256, d.sm_count), 256, 0, d.stream>>>(idx, m.n_triangles, m.n_vertices, indices + r.index_offset, bad); ++d.launches; }
+    }
+    for (uint32_t i = 0; i < scene->n_images && e == cudaSuccess; ++i) {
+        const kz_image_desc &im = scene->images[i];
+        const size_t n = (size_t)im.width * im.height;
+        size_t cur = 0;
+        const float *rgb = (const float *)fetch(im.rgb, n * 12, cur);
+        if (e != cudaSuccess) break;
+        k_ingest_texels<<<grid_for(n, 256, d.sm_count), 256, 0, d.stream>>>(rgb, n, texels + h.images[i].texel_offset);
+        ++d.launches;
+    }
+    uint32_t h_bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    free_all(temp);
+    if (e != cudaSuccess) return fail(ctx, KZ_ERR_CUDA, std::string("scene ingest: ") + cudaGetErrorString(e));
+    if (h_bad) return fail(ctx, KZ_ERR_INVALID, "vertex index out of range");
+    return KZ_OK;
+}
+
+/* Copies the ingested records of `src` into the (already allocated) arrays of `dst`: peer copies over NVLink. */
+int replicate_geometry(kzgpu_ctx *ctx, Device &dst, const Device &src) {
+    const KzHostScene &h = *ctx->hs;
+    KZ_CUDA(ctx, cudaMemcpyPeerAsync(const_cast<KzVertex *>(dst.sc.vertices), dst.id, src.sc.vertices, src.id, (size_t)h.total_vertices * sizeof(KzVertex), dst.stream));
+    KZ_CUDA(ctx, cudaMemcpyPeerAsync(const_cast<KzU4 *>(dst.sc.indices), dst.id, src.sc.indices, src.id, (size_t)h.total_triangles * sizeof(KzU4), dst.stream));
+    KZ_CUDA(ctx, cudaMemcpyPeerAsync(const_cast<KzF4 *>(dst.sc.texels), dst.id, src.sc.texels, src.id, h.total_texels * sizeof(KzF4), dst.stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(dst.stream));
     return KZ_OK;
 }
 
@@ -218,9 +304,25 @@ int upload_accel(kzgpu_ctx *ctx, Device &d, const kzbvh::Built &b) {
     return KZ_OK;
 }
 
+/* Copies the accel that device `src` built into fresh arrays of `dst` (peer copies over NVLink). */
+int replicate_accel(kzgpu_ctx *ctx, Device &dst, const Device &src) {
+    free_all(dst.accel_allocs);
+    KzNode8 *nodes = nullptr; KzF4 *tris = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, dst.accel_allocs, (size_t)src.sc.n_nodes, &nodes))) return rc;
+    if ((rc = dev_alloc(ctx, dst.accel_allocs, (size_t)src.sc.n_tris * 3, &tris))) return rc;
+    KZ_CUDA(ctx, cudaMemcpyPeerAsync(nodes, dst.id, src.sc.nodes, src.id, (size_t)src.sc.n_nodes * sizeof(KzNode8), dst.stream));
+    KZ_CUDA(ctx, cudaMemcpyPeerAsync(tris, dst.id, src.sc.tris, src.id, (size_t)src.sc.n_tris * 3 * sizeof(KzF4), dst.stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(dst.stream));
+    dst.sc.nodes = nodes; dst.sc.tris = tris; dst.sc.n_nodes = src.sc.n_nodes; dst.sc.n_tris = src.sc.n_tris; dst.sc.scene_max_abs = src.sc.scene_max_abs;
+    dst.has_accel = true;
+    return KZ_OK;
+}
+
 /* One chunk of path slots through the whole wavefront on stream `s` with the pool of lane `L`; never synchronises (except the
  * unbounded whitted / path_mats loops, which poll a queue count). */
-int enqueue_chunk(kzgpu_ctx *ctx, Device &d, Lane &L, const KzChunk &ch, unsigned long long new_paths, cudaStream_t s) {
+/* `ectx` receives error messages (nullptr inside the per-device worker threads of kzgpu_render, which report through g_error). */
+int enqueue_chunk(const kzgpu_ctx *ctx, kzgpu_ctx *ectx, Device &d, Lane &L, const KzChunk &ch, unsigned long long new_paths, cudaStream_t s) {
     const KzScene &sc = d.sc;
     const int max_depth = sc.integrator.max_depth;
     /* the pass after the last vertex only resolves "miss -> background" (integrator.cpp:315-318) */
@@ -258,8 +360,8 @@ int enqueue_chunk(kzgpu_ctx *ctx, Device &d, Lane &L, const KzChunk &ch, unsigne
             }
             if (passes > 1 && (b & 7) == 7) {
                 unsigned long long left = 0;
-                KZ_CUDA(ctx, cudaMemcpyAsync(&left, &L.ctl->ext_shadow[nxt], sizeof(left), cudaMemcpyDeviceToHost, s));
-                KZ_CUDA(ctx, cudaStreamSynchronize(s));
+                KZ_CUDA(ectx, cudaMemcpyAsync(&left, &L.ctl->ext_shadow[nxt], sizeof(left), cudaMemcpyDeviceToHost, s));
+                KZ_CUDA(ectx, cudaStreamSynchronize(s));
                 if ((left & 0xFFFFFFFFull) == 0ull) break;
             }
         }
@@ -301,7 +403,7 @@ int enqueue_chunk(kzgpu_ctx *ctx, Device &d, Lane &L, const KzChunk &ch, unsigne
 }
 
 /* Enqueues the whole wavefront for one request; work is ordered after everything already on `s`, and `s` waits for it. */
-int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStream_t s) {
+int enqueue_render(const kzgpu_ctx *ctx, kzgpu_ctx *ectx, Device &d, const kz_render_req &req, cudaStream_t s) {
     const KzScene &sc = d.sc;
     const int w = req.x1 - req.x0, h = req.y1 - req.y0, nS = req.spp_end - req.spp_begin;
     if (w <= 0 || h <= 0 || nS <= 0) return KZ_OK;
@@ -318,11 +420,11 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
     const unsigned long long per_lane = (((total + lanes - 1) / lanes) + 31ull) & ~31ull;
     const uint32_t cap = (uint32_t)std::min<unsigned long long>(ctx->pool_cap, per_lane);
     int rc;
-    for (int l = 0; l < lanes; ++l) if ((rc = ensure_pool(ctx, d.lane[l], cap))) return rc;
+    for (int l = 0; l < lanes; ++l) if ((rc = ensure_pool(ectx, d.lane[l], cap))) return rc;
     Timed total_t(d, s, CAT_TOTAL);
     if (lanes > 1) {       /* the other lanes start after what is already queued on s (frame clear, earlier requests) */
-        KZ_CUDA(ctx, cudaEventRecord(d.lane[0].done, s));
-        for (int l = 1; l < lanes; ++l) KZ_CUDA(ctx, cudaStreamWaitEvent(d.lane[l].stream, d.lane[0].done, 0));
+        KZ_CUDA(ectx, cudaEventRecord(d.lane[0].done, s));
+        for (int l = 1; l < lanes; ++l) KZ_CUDA(ectx, cudaStreamWaitEvent(d.lane[l].stream, d.lane[0].done, 0));
     }
     int k = 0;
     for (unsigned long long first = 0; first < total; first += cap, ++k) {
@@ -330,13 +432,13 @@ int enqueue_render(kzgpu_ctx *ctx, Device &d, const kz_render_req &req, cudaStre
         ch.first = first;
         ch.count = (uint32_t)std::min<unsigned long long>(cap, total - first);
         const unsigned long long new_paths = first == 0 ? (unsigned long long)w * (unsigned long long)h * (unsigned long long)nS : 0ull;
-        if ((rc = enqueue_chunk(ctx, d, L, ch, new_paths, (k % lanes) == 0 ? s : L.stream))) return rc;
+        if ((rc = enqueue_chunk(ctx, ectx, d, L, ch, new_paths, (k % lanes) == 0 ? s : L.stream))) return rc;
     }
     for (int l = 1; l < lanes; ++l) {
-        KZ_CUDA(ctx, cudaEventRecord(d.lane[l].done, d.lane[l].stream));
-        KZ_CUDA(ctx, cudaStreamWaitEvent(s, d.lane[l].done, 0));
+        KZ_CUDA(ectx, cudaEventRecord(d.lane[l].done, d.lane[l].stream));
+        KZ_CUDA(ectx, cudaStreamWaitEvent(s, d.lane[l].done, 0));
     }
-    KZ_CUDA(ctx, cudaGetLastError());
+    KZ_CUDA(ectx, cudaGetLastError());
     return KZ_OK;
 }
 
@@ -385,6 +487,8 @@ int kzgpu_create(const int *device_ids, int n_devices, kzgpu_ctx **out) {
         }
         for (int l = 1; l < KZ_MAX_LANES; ++l) KZ_CUDA(nullptr, cudaStreamCreateWithFlags(&d.lane[l].stream, cudaStreamNonBlocking));
         d.ctl = d.lane[0].ctl;
+        KZ_CUDA(nullptr, cudaEventCreateWithFlags(&d.splat_done, cudaEventDisableTiming));
+        KZ_CUDA(nullptr, cudaEventCreateWithFlags(&d.merge_done, cudaEventDisableTiming));
         KZ_CUDA(nullptr, cudaMalloc(&d.cursor, 64));
         d.grid_extend0 = persistent_grid(d, k_extend<true>, KZ_TRACE_THREADS);
         d.grid_extend = persistent_grid(d, k_extend<false>, KZ_TRACE_THREADS);
@@ -399,6 +503,20 @@ int kzgpu_create(const int *device_ids, int n_devices, kzgpu_ctx **out) {
         d.grid_shade[4] = persistent_grid(d, k_shade<KZ_CLASS_GENERIC>, KZ_SHADE_THREADS);
         ctx->devs.push_back(d);
     }
+    /* a multi-device context replicates the scene and merges the frames through peer memory (NVLink / NVSwitch): every pair of its
+     * devices must be able to map each other's HBM */
+    if (ctx->devs.size() > KZ_MAX_DEVICES) return fail(nullptr, KZ_ERR_INVALID, "more than " + std::to_string(KZ_MAX_DEVICES) + " devices in one context");
+    for (const Device &a : ctx->devs)
+        for (const Device &b : ctx->devs) {
+            if (a.id == b.id) { if (&a != &b) return fail(nullptr, KZ_ERR_INVALID, "device listed twice"); continue; }
+            int ok = 0;
+            KZ_CUDA(nullptr, cudaDeviceCanAccessPeer(&ok, a.id, b.id));
+            if (!ok) return fail(nullptr, KZ_ERR_UNSUPPORTED, "devices " + std::to_string(a.id) + " and " + std::to_string(b.id) + " have no peer access; multi-device contexts need NVLink/PCIe P2P");
+            KZ_CUDA(nullptr, cudaSetDevice(a.id));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(b.id, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else KZ_CUDA(nullptr, e);
+        }
     *out = ctx.release();
     return KZ_OK;
 }
@@ -414,6 +532,8 @@ void kzgpu_destroy(kzgpu_ctx *ctx) {
         for (Lane &L : d.lane) { free_all(L.allocs); cudaFree(L.ctl); if (L.done) cudaEventDestroy(L.done); if (L.stream) cudaStreamDestroy(L.stream); }
         for (int k = 0; k < 3; ++k) if (d.scratch[k]) cudaFree(d.scratch[k]);
         cudaFree(d.cursor);
+        if (d.splat_done) cudaEventDestroy(d.splat_done);
+        if (d.merge_done) cudaEventDestroy(d.merge_done);
         cudaStreamDestroy(d.stream);
         if (d.copy_in) cudaStreamDestroy(d.copy_in);
         if (d.copy_out) cudaStreamDestroy(d.copy_out);
@@ -423,8 +543,29 @@ void kzgpu_destroy(kzgpu_ctx *ctx) {
 
 int kzgpu_scene_upload(kzgpu_ctx *ctx, const kz_scene_desc *scene) {
     if (!ctx) return fail(nullptr, KZ_ERR_INVALID, "null context");
+    if (!scene) return fail(ctx, KZ_ERR_INVALID, "null scene");
+    const auto t0 = std::chrono::steady_clock::now();
+    /* emitters need their positions / indices on the host for the area CDF (Mesh::activate, mesh.cpp:24-45): if such a mesh was
+     * handed over as device arrays, read them back (emitters are small) */
+    std::vector<kz_mesh_desc> meshes(scene->meshes, scene->meshes + (scene->meshes ? scene->n_meshes : 0));
+    std::vector<std::vector<float>> host_pos; std::vector<std::vector<uint32_t>> host_idx;
+    for (kz_mesh_desc &m : meshes) {
+        if (m.light < 0 || !m.positions || !m.indices) continue;
+        if (is_device_ptr(m.positions)) {
+            host_pos.emplace_back((size_t)m.n_vertices * 3);
+            KZ_CUDA(ctx, cudaMemcpy(host_pos.back().data(), m.positions, (size_t)m.n_vertices * 12, cudaMemcpyDeviceToHost));
+            m.positions = host_pos.back().data();
+        }
+        if (is_device_ptr(m.indices)) {
+            host_idx.emplace_back((size_t)m.n_triangles * 3);
+            KZ_CUDA(ctx, cudaMemcpy(host_idx.back().data(), m.indices, (size_t)m.n_triangles * 12, cudaMemcpyDeviceToHost));
+            m.indices = host_idx.back().data();
+        }
+    }
+    kz_scene_desc tables = *scene;
+    tables.meshes = meshes.data();
     std::unique_ptr<KzHostScene> hs(new KzHostScene());
-    if (!hs->flatten(scene)) {
+    if (!hs->flatten(&tables, /*geometry=*/false)) {
         const bool unsupported = hs->error.find("outside the hot-path scope") != std::string::npos || hs->error.find("unsupported") != std::string::npos;
         return fail(ctx, unsupported ? KZ_ERR_UNSUPPORTED : KZ_ERR_INVALID, hs->error);
     }
@@ -440,20 +581,44 @@ int kzgpu_scene_upload(kzgpu_ctx *ctx, const kz_scene_desc *scene) {
         KZ_CUDA(ctx, cudaSetDevice(d.id));
         d.has_accel = false;
         free_all(d.accel_allocs);
-        int rc = upload_scene(ctx, d);
+        int rc = upload_tables(ctx, d);
+        if (rc) return rc;
+        /* the first device ingests the caller's arrays, the others get its records over NVLink */
+        if (&d == &ctx->devs[0]) rc = ingest_geometry(ctx, d, scene);
+        else rc = replicate_geometry(ctx, d, ctx->devs[0]);
         if (rc) return rc;
     }
+    KZ_CUDA(ctx, cudaSetDevice(ctx->devs[0].id));
     ctx->uploaded = true;
+    ctx->ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return KZ_OK;
 }
 
 int kzgpu_accel_build(kzgpu_ctx *ctx, int builder) {
     int rc = check_ready(ctx, false);
     if (rc) return rc;
+    if (builder != KZ_BUILD_HOST_SAH && builder != KZ_BUILD_LBVH) return fail(ctx, KZ_ERR_INVALID, "unknown builder");
     const auto t0 = std::chrono::steady_clock::now();
+    Device &d0 = ctx->devs[0];
+    KZ_CUDA(ctx, cudaSetDevice(d0.id));
+    /* the builders' input: the triangle list in scene order, gathered on the device from the ingested records */
+    const uint32_t n_tris = (uint32_t)ctx->hs->total_triangles;
+    std::vector<void *> temp;
+    kzbvh::Tri *d_tris = nullptr;
+    if ((rc = dev_alloc(ctx, temp, (size_t)n_tris, &d_tris))) { free_all(temp); return rc; }
+    if (n_tris) {
+        k_gather_tris<<<grid_for(n_tris, 256, d0.sm_count), 256, 0, d0.stream>>>(d0.sc.meshes, d0.sc.n_meshes, d0.sc.vertices, d0.sc.indices, n_tris, d_tris);
+        ++d0.launches;
+    }
     if (builder == KZ_BUILD_HOST_SAH) {
+        std::vector<kzbvh::Tri> tris((size_t)n_tris);
+        cudaError_t e = cudaSuccess;
+        if (n_tris) e = cudaMemcpyAsync(tris.data(), d_tris, (size_t)n_tris * sizeof(kzbvh::Tri), cudaMemcpyDeviceToHost, d0.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d0.stream);
+        free_all(temp);
+        KZ_CUDA(ctx, e);
         kzbvh::Built built;
-        kzbvh::buildHostSah(ctx->hs->tris, 0, built);
+        kzbvh::buildHostSah(tris, 0, built);
         if (2 * built.depth + 2 > KZ_SHORT_STACK + KZ_LOCAL_STACK) return fail(ctx, KZ_ERR_UNSUPPORTED, "accel deeper than the traversal stack allows");
         for (Device &d : ctx->devs) {
             KZ_CUDA(ctx, cudaSetDevice(d.id));
@@ -461,23 +626,25 @@ int kzgpu_accel_build(kzgpu_ctx *ctx, int builder) {
         }
         ctx->bvh_nodes = built.nodes.size();
         ctx->bvh_bytes = built.nodes.size() * sizeof(KzNode8) + built.tris.size() * sizeof(KzF4);
-    } else if (builder == KZ_BUILD_LBVH) {
-        for (Device &d : ctx->devs) {
-            KZ_CUDA(ctx, cudaSetDevice(d.id));
-            free_all(d.accel_allocs);
-            kzlbvh::Result r;
-            std::string err;
-            rc = kzlbvh::build(ctx->hs->tris, d.stream, d.accel_allocs, r, err);
-            if (rc) return fail(ctx, rc, err);
-            if (2 * r.depth + 2 > KZ_SHORT_STACK + KZ_LOCAL_STACK) return fail(ctx, KZ_ERR_UNSUPPORTED, "accel deeper than the traversal stack allows");
-            d.sc.nodes = r.nodes; d.sc.tris = r.tris; d.sc.n_nodes = r.n_nodes; d.sc.n_tris = r.n_tris; d.sc.scene_max_abs = r.max_abs;
-            d.has_accel = true;
-            d.launches += r.launches;
-            ctx->bvh_nodes = r.n_nodes;
-            ctx->bvh_bytes = (uint64_t)r.n_nodes * sizeof(KzNode8) + (uint64_t)r.n_tris * 3 * sizeof(KzF4);
-        }
     } else {
-        return fail(ctx, KZ_ERR_INVALID, "unknown builder");
+        free_all(d0.accel_allocs);
+        kzlbvh::Result r;
+        std::string err;
+        rc = kzlbvh::build(d_tris, n_tris, d0.stream, d0.accel_allocs, r, err);
+        free_all(temp);
+        if (rc) return fail(ctx, rc, err);
+        if (2 * r.depth + 2 > KZ_SHORT_STACK + KZ_LOCAL_STACK) return fail(ctx, KZ_ERR_UNSUPPORTED, "accel deeper than the traversal stack allows");
+        d0.sc.nodes = r.nodes; d0.sc.tris = r.tris; d0.sc.n_nodes = r.n_nodes; d0.sc.n_tris = r.n_tris; d0.sc.scene_max_abs = r.max_abs;
+        d0.has_accel = true;
+        d0.launches += r.launches;
+        ctx->bvh_nodes = r.n_nodes;
+        ctx->bvh_bytes = (uint64_t)r.n_nodes * sizeof(KzNode8) + (uint64_t)r.n_tris * 3 * sizeof(KzF4);
+        /* built once; the other devices get the arrays over NVLink */
+        for (size_t g = 1; g < ctx->devs.size(); ++g) {
+            KZ_CUDA(ctx, cudaSetDevice(ctx->devs[g].id));
+            if ((rc = replicate_accel(ctx, ctx->devs[g], d0))) return rc;
+        }
+        KZ_CUDA(ctx, cudaSetDevice(d0.id));
     }
     ctx->ms_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     ctx->built = true;
@@ -494,6 +661,7 @@ int kzgpu_trace_device(kzgpu_ctx *ctx, int device, const void *d_rays, size_t n,
     if (n > 0x7FFFFFFFull) return fail(ctx, KZ_ERR_INVALID, "batch larger than 2^31-1 rays");
     if (!d_rays || !d_hits) return fail(ctx, KZ_ERR_INVALID, "null ray/hit buffer");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (d->pending.size() > 8192) fold_events(*d);      /* callers that never poll kzgpu_stats: bound the live timing events */
     KZ_CUDA(ctx, cudaMemsetAsync(d->cursor, 0, 4, s));
     {
         Timed t(*d, s, CAT_TRACE);
@@ -573,6 +741,7 @@ int kzgpu_occluded(kzgpu_ctx *ctx, int device, const kz_ray *rays, size_t n, flo
     if ((rc = ensure_scratch(ctx, *d, 1, 2 * n))) return rc;
     uint8_t *d_occ = reinterpret_cast<uint8_t *>(d->scratch[1]);
     KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], rays, n * sizeof(kz_ray), cudaMemcpyHostToDevice, d->stream));
+    if (d->pending.size() > 8192) fold_events(*d);
     KZ_CUDA(ctx, cudaMemsetAsync(d->cursor, 0, 4, d->stream));
     {
         Timed t(*d, d->stream, CAT_TRACE);
@@ -663,11 +832,81 @@ int kzgpu_image_lookup(kzgpu_ctx *ctx, int image, int level, const float *st, si
     if (!st || !rgb) return fail(ctx, KZ_ERR_INVALID, "null argument");
     if ((rc = ensure_scratch(ctx, *d, 0, n * 8))) return rc;
     if ((rc = ensure_scratch(ctx, *d, 1, n * 12))) return rc;
-    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], st, n * 8, cudaMemcpyHostToDevice, d->stream));
-    k_image_lookup<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(d->sc, image, level, reinterpret_cast<const float *>(d->scratch[0]), (uint32_t)n,
-                                                                       reinterpret_cast<float *>(d->scratch[1]));
+    KzScene sc = d->sc;
+    int lookup_image = image;
+    std::vector<void *> temp;
+    if (level > 0) {
+        /* the renderer only reads level 0 (ImageTexture::eval passes zero derivatives, texture.cpp:52-57), so the pyramid is not
+         * kept resident: it is built here, for this image, by 2x2 box filtering on the device */
+        const KzImageRec im = ctx->hs->images[(size_t)image];
+        KzImageRec pr = im; pr.texel_offset = 0; pr.n_levels = 0;
+        size_t total = (size_t)im.width * im.height;
+        for (int w = im.width, h = im.height; w > 1 || h > 1;) { w = w > 1 ? w >> 1 : 1; h = h > 1 ? h >> 1 : 1; total += (size_t)w * h; ++pr.n_levels; }
+        KzF4 *pyr = nullptr; KzImageRec *rec = nullptr;
+        if ((rc = dev_alloc(ctx, temp, total, &pyr)) || (rc = dev_alloc(ctx, temp, 1, &rec))) { free_all(temp); return rc; }
+        cudaError_t e = cudaMemcpyAsync(pyr, d->sc.texels + im.texel_offset, (size_t)im.width * im.height * sizeof(KzF4), cudaMemcpyDeviceToDevice, d->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(rec, &pr, sizeof(pr), cudaMemcpyHostToDevice, d->stream);
+        if (e != cudaSuccess) { free_all(temp); KZ_CUDA(ctx, e); }
+        size_t src = 0; int sw = im.width, sh = im.height;
+        for (int l = 1; l <= pr.n_levels; ++l) {
+            const int dw = sw > 1 ? sw >> 1 : 1, dh = sh > 1 ? sh >> 1 : 1;
+            const size_t dst = src + (size_t)sw * sh;
+            dim3 blk(32, 8), grd((unsigned)(dw + 31) / 32, (unsigned)(dh + 7) / 8);
+            k_mip_level<<<grd, blk, 0, d->stream>>>(pyr, src, sw, sh, dst, dw, dh);
+            ++d->launches;
+            src = dst; sw = dw; sh = dh;
+        }
+        sc.texels = pyr; sc.images = rec; lookup_image = 0;
+    }
+    cudaError_t e = cudaMemcpyAsync(d->scratch[0], st, n * 8, cudaMemcpyHostToDevice, d->stream);
+    if (e == cudaSuccess) {
+        k_image_lookup<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(sc, lookup_image, level, reinterpret_cast<const float *>(d->scratch[0]), (uint32_t)n,
+                                                                           reinterpret_cast<float *>(d->scratch[1]));
+        ++d->launches;
+        e = cudaMemcpyAsync(rgb, d->scratch[1], n * 12, cudaMemcpyDeviceToHost, d->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    free_all(temp);
+    KZ_CUDA(ctx, e);
+    return KZ_OK;
+}
+
+int kzgpu_intersection_dump(kzgpu_ctx *ctx, const kz_ray *rays, size_t n, float *out24) {
+    int rc = check_ready(ctx, true);
+    if (rc) return rc;
+    Device *d;
+    if ((rc = select(ctx, 0, &d))) return rc;
+    if (n == 0) return KZ_OK;
+    if (!rays || !out24) return fail(ctx, KZ_ERR_INVALID, "null argument");
+    if (n > 0x7FFFFFFFull) return fail(ctx, KZ_ERR_INVALID, "batch larger than 2^31-1 rays");
+    if ((rc = ensure_scratch(ctx, *d, 0, n * sizeof(kz_ray)))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 1, n * 96))) return rc;
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], rays, n * sizeof(kz_ray), cudaMemcpyHostToDevice, d->stream));
+    k_intersection_dump<<<(unsigned)((n + KZ_TRACE_THREADS - 1) / KZ_TRACE_THREADS), KZ_TRACE_THREADS, 0, d->stream>>>(d->sc, reinterpret_cast<const KzF4 *>(d->scratch[0]), (uint32_t)n,
+                                                                                                                    reinterpret_cast<float *>(d->scratch[1]));
     ++d->launches;
-    KZ_CUDA(ctx, cudaMemcpyAsync(rgb, d->scratch[1], n * 12, cudaMemcpyDeviceToHost, d->stream));
+    KZ_CUDA(ctx, cudaMemcpyAsync(out24, d->scratch[1], n * 96, cudaMemcpyDeviceToHost, d->stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    return KZ_OK;
+}
+
+int kzgpu_light_sample_dump(kzgpu_ctx *ctx, const float *ref3, const float *u5, size_t n, float *out16) {
+    int rc = check_ready(ctx, false);
+    if (rc) return rc;
+    Device *d;
+    if ((rc = select(ctx, 0, &d))) return rc;
+    if (n == 0) return KZ_OK;
+    if (!ref3 || !u5 || !out16) return fail(ctx, KZ_ERR_INVALID, "null argument");
+    if (n > 0x7FFFFFFFull) return fail(ctx, KZ_ERR_INVALID, "batch too large");
+    if ((rc = ensure_scratch(ctx, *d, 0, n * 12))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 1, n * 64))) return rc;
+    if ((rc = ensure_scratch(ctx, *d, 2, n * 20))) return rc;
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[0], ref3, n * 12, cudaMemcpyHostToDevice, d->stream));
+    KZ_CUDA(ctx, cudaMemcpyAsync(d->scratch[2], u5, n * 20, cudaMemcpyHostToDevice, d->stream));
+    k_light_sample_dump<<<(unsigned)((n + 127) / 128), 128, 0, d->stream>>>(d->sc, reinterpret_cast<const float *>(d->scratch[0]), reinterpret_cast<const float *>(d->scratch[2]),
+                                                                            (uint32_t)n, reinterpret_cast<float *>(d->scratch[1]));
+    ++d->launches;
+    KZ_CUDA(ctx, cudaMemcpyAsync(out16, d->scratch[1], n * 64, cudaMemcpyDeviceToHost, d->stream));
     KZ_CUDA(ctx, cudaStreamSynchronize(d->stream));
     return KZ_OK;
 }
@@ -686,6 +925,9 @@ static int check_req(kzgpu_ctx *ctx, const kz_render_req *req) {
     if (req->x0 < 0 || req->y0 < 0 || req->x1 > c.width || req->y1 > c.height || req->x0 > req->x1 || req->y0 > req->y1)
         return fail(ctx, KZ_ERR_INVALID, "render rectangle outside the film");
     if (req->spp_begin < 0 || req->spp_end < req->spp_begin) return fail(ctx, KZ_ERR_INVALID, "bad sample range");
+    /* pmj02bn reads per-pixel sample tables of sample_count entries (sampler.cpp:290-314,333-337): an index beyond is out of bounds */
+    if (ctx->hs->sc.sampler_type == KZ_SAMPLER_PMJ02BN && (uint32_t)req->spp_end > ctx->hs->sc.sample_count)
+        return fail(ctx, KZ_ERR_INVALID, "sample range exceeds the pmj02bn sampler's sample_count");
     return KZ_OK;
 }
 
@@ -703,7 +945,7 @@ int kzgpu_render_device(kzgpu_ctx *ctx, int device, const kz_render_req *req, vo
         cudaError_t e = cudaMemsetAsync(d->frame, 0, d->frame_texels * sizeof(KzF4), s);
         if (e != cudaSuccess) { d->frame = own; return fail(ctx, KZ_ERR_CUDA, std::string("cudaMemsetAsync(frame): ") + cudaGetErrorString(e)); }
     }
-    rc = enqueue_render(ctx, *d, *req, s);
+    rc = enqueue_render(ctx, ctx, *d, *req, s);
     if (d_frame_inout) *d_frame_inout = d->frame;
     d->frame = own;
     return rc;
@@ -719,8 +961,7 @@ int kzgpu_render(kzgpu_ctx *ctx, const kz_render_req *req, float *frame_rgbw) {
     const size_t texels = ctx->devs[0].frame_texels;
     /* shard by sample index: device g takes a contiguous slice of [spp_begin, spp_end).  One host thread per
      * device: a long render is thousands of launches, and a single thread would block on the first device's launch queue
-     * before it ever reaches the second one. */
-    std::vector<std::vector<float>> parts((size_t)nd);
+     * before it ever reaches the second one.  Workers report through their own slot (never through ctx->error). */
     std::vector<int> rcs((size_t)nd, KZ_OK);
     std::vector<std::string> errs((size_t)nd);
     auto work = [&](int g) {
@@ -731,25 +972,50 @@ int kzgpu_render(kzgpu_ctx *ctx, const kz_render_req *req, float *frame_rgbw) {
         kz_render_req r = *req;
         r.spp_begin = req->spp_begin + (int)((long long)nS * g / nd);
         r.spp_end = req->spp_begin + (int)((long long)nS * (g + 1) / nd);
-        if ((e = cudaMemsetAsync(d.frame, 0, texels * sizeof(KzF4), d.stream)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
-        const int rc = enqueue_render(ctx, d, r, d.stream);
+        /* the root's frame starts from the caller's frame when the request accumulates (progressive / resumed renders) */
+        if (g == 0 && !req->clear_frame) e = cudaMemcpyAsync(d.frame, frame_rgbw, texels * sizeof(KzF4), cudaMemcpyHostToDevice, d.stream);
+        else e = cudaMemsetAsync(d.frame, 0, texels * sizeof(KzF4), d.stream);
+        if (e != cudaSuccess) return bail(e, "frame initialisation");
+        const int rc = enqueue_render(ctx, nullptr, d, r, d.stream);
         if (rc != KZ_OK) { rcs[(size_t)g] = rc; errs[(size_t)g] = g_error; return; }
-        float *dst = (g == 0 && req->clear_frame) ? frame_rgbw : (parts[(size_t)g].resize(texels * 4), parts[(size_t)g].data());
-        if ((e = cudaMemcpyAsync(dst, d.frame, texels * sizeof(KzF4), cudaMemcpyDeviceToHost, d.stream)) != cudaSuccess) return bail(e, "cudaMemcpyAsync");
-        if ((e = cudaStreamSynchronize(d.stream)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");
+        if ((e = cudaEventRecord(d.splat_done, d.stream)) != cudaSuccess) return bail(e, "cudaEventRecord");
     };
     std::vector<std::thread> pool;
     for (int g = 1; g < nd; ++g) pool.emplace_back(work, g);
     work(0);
     for (std::thread &t : pool) t.join();
     for (int g = 0; g < nd; ++g)
-        if (rcs[(size_t)g] != KZ_OK) return fail(ctx, rcs[(size_t)g], "device " + std::to_string(g) + ": " + errs[(size_t)g]);
-    for (int g = 0; g < nd; ++g) {
-        if (parts[(size_t)g].empty()) continue;
-        const float *src = parts[(size_t)g].data();
-        for (size_t i = 0; i < texels * 4; ++i) frame_rgbw[i] += src[i];
+        if (rcs[(size_t)g] != KZ_OK) {
+            for (Device &d : ctx->devs) { cudaSetDevice(d.id); cudaStreamSynchronize(d.stream); }
+            return fail(ctx, rcs[(size_t)g], "device " + std::to_string(g) + ": " + errs[(size_t)g]);
+        }
+    Device &root = ctx->devs[0];
+    if (nd > 1) {
+        /* ImageBlock::put(ImageBlock&) (block.cpp:87-96) over NVLink: once every device finished splatting, device g sums slice g of
+         * all frames through peer loads and stores it into the root's frame; the root then holds the merged frame */
+        KzFramePtrs fp;
+        for (int g = 0; g < nd; ++g) fp.f[g] = ctx->devs[(size_t)g].frame;
+        for (int g = 0; g < nd; ++g) {
+            Device &d = ctx->devs[(size_t)g];
+            KZ_CUDA(ctx, cudaSetDevice(d.id));
+            for (int o = 0; o < nd; ++o) if (o != g) KZ_CUDA(ctx, cudaStreamWaitEvent(d.stream, ctx->devs[(size_t)o].splat_done, 0));
+            const size_t begin = texels * (size_t)g / (size_t)nd, end = texels * (size_t)(g + 1) / (size_t)nd;
+            if (end > begin) {
+                Timed t(d, d.stream, CAT_MERGE);
+                k_frame_reduce<<<grid_for(end - begin, 256, d.sm_count), 256, 0, d.stream>>>(fp, nd, begin, end);
+                ++d.launches;
+            }
+            KZ_CUDA(ctx, cudaEventRecord(d.merge_done, d.stream));
+        }
+        KZ_CUDA(ctx, cudaSetDevice(root.id));
+        for (int g = 1; g < nd; ++g) KZ_CUDA(ctx, cudaStreamWaitEvent(root.stream, ctx->devs[(size_t)g].merge_done, 0));
     }
-    KZ_CUDA(ctx, cudaSetDevice(ctx->devs[0].id));
+    KZ_CUDA(ctx, cudaSetDevice(root.id));
+    KZ_CUDA(ctx, cudaMemcpyAsync(frame_rgbw, root.frame, texels * sizeof(KzF4), cudaMemcpyDeviceToHost, root.stream));
+    KZ_CUDA(ctx, cudaStreamSynchronize(root.stream));
+    /* the peers may not start their next request (which clears their frame) before the root has read it */
+    for (int g = 1; g < nd; ++g) { KZ_CUDA(ctx, cudaSetDevice(ctx->devs[(size_t)g].id)); KZ_CUDA(ctx, cudaStreamSynchronize(ctx->devs[(size_t)g].stream)); }
+    KZ_CUDA(ctx, cudaSetDevice(root.id));
     return KZ_OK;
 }
 
@@ -792,8 +1058,9 @@ int kzgpu_stats(kzgpu_ctx *ctx, kz_stats *out) {
         out->ms_trace = std::max(out->ms_trace, d.ms[CAT_TRACE]);
         out->ms_shade = std::max(out->ms_shade, d.ms[CAT_SHADE]);
         out->ms_total = std::max(out->ms_total, d.ms[CAT_TOTAL]);
+        out->ms_merge = std::max(out->ms_merge, d.ms[CAT_MERGE]);
     }
-    out->bvh_nodes = ctx->bvh_nodes; out->bvh_bytes = ctx->bvh_bytes; out->ms_build = ctx->ms_build;
+    out->bvh_nodes = ctx->bvh_nodes; out->bvh_bytes = ctx->bvh_bytes; out->ms_build = ctx->ms_build; out->ms_upload = ctx->ms_upload;
     return KZ_OK;
 }
 
@@ -803,7 +1070,7 @@ int kzgpu_stats_reset(kzgpu_ctx *ctx) {
         KZ_CUDA(ctx, cudaSetDevice(d.id));
         KZ_CUDA(ctx, cudaDeviceSynchronize());
         fold_events(d);
-        d.ms[0] = d.ms[1] = d.ms[2] = 0; d.launches = 0;
+        for (double &m : d.ms) m = 0; d.launches = 0;
         /* keep queue state, zero the counters */
         for (Lane &L : d.lane) KZ_CUDA(ctx, cudaMemset(reinterpret_cast<char *>(L.ctl) + offsetof(KzControl, paths), 0, 4 * sizeof(unsigned long long)));
     }

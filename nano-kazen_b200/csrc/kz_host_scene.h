@@ -26,9 +26,14 @@ struct KzHostScene {
     std::vector<kz2> pmj_pixel_samples;
     std::vector<kzbvh::Tri> tris;       /* scene order, input of the accel build */
     KzScene sc;                         /* pointers into the vectors above once finalize() ran */
+    uint64_t total_vertices = 0, total_triangles = 0;
     std::string error;
 
-    bool flatten(const kz_scene_desc *d) {
+    /* geometry = true: vertex / index records and the triangle list are built here (tests/hostemu runs the device headers on
+     * these vectors).  geometry = false (kz_api.cu): only the small tables are built; the mesh arrays go to HBM as they are and
+     * the records are made there (kz_ingest.cuh), so `vertices`, `indices` and `tris` stay empty and indices are validated on
+     * the device.  Light meshes need host-readable positions / indices in both modes (area CDF, mesh.cpp:24-45). */
+    bool flatten(const kz_scene_desc *d, bool geometry = true) {
         memset(&sc, 0, sizeof(sc));
         if (!d) { error = "null scene"; return false; }
         if (d->n_meshes && !d->meshes) { error = "meshes missing"; return false; }
@@ -50,48 +55,64 @@ struct KzHostScene {
         for (uint32_t i = 0; i < d->n_textures; ++i) {
             const kz_texture_desc &t = d->textures[i];
             if (t.type == KZ_TEX_IMAGE && (t.image < 0 || t.image >= (int)d->n_images)) { error = "image index out of range"; return false; }
-            for (int c = 0; c < 3; ++c) if (t.child[c] >= (int)d->n_textures) { error = "texture child out of range"; return false; }
+            for (int c = 0; c < 3; ++c) if (t.child[c] >= (int)d->n_textures || t.child[c] < -1) { error = "texture child out of range"; return false; }
+        }
+        /* expression trees are evaluated with a fixed-depth stack on the device (kz_tex_eval_tree): reject what it cannot hold */
+        for (uint32_t i = 0; i < d->n_textures; ++i) {
+            const int depth = textureDepth(d, (int)i, 0);
+            if (depth < 0) { error = "texture graph has a cycle"; return false; }
+            if (depth > KZ_TEX_MAX_DEPTH_HOST) { error = "texture tree deeper than " + std::to_string(KZ_TEX_MAX_DEPTH_HOST) + " levels is unsupported"; return false; }
         }
         /* images: level 0 as float4 texels followed by room for the mip pyramid (filled on the GPU by k_mip_level) */
         for (uint32_t i = 0; i < d->n_images; ++i) {
             const kz_image_desc &im = d->images[i];
             if (im.width <= 0 || im.height <= 0 || !im.rgb) { error = "bad image"; return false; }
-            KzImageRec r; r.width = im.width; r.height = im.height; r.texel_offset = (uint32_t)texels.size(); r.n_levels = 0;
-            size_t n = (size_t)im.width * im.height, total = n;
-            for (int w = im.width, h = im.height; w > 1 || h > 1;) { w = w > 1 ? w >> 1 : 1; h = h > 1 ? h >> 1 : 1; total += (size_t)w * h; ++r.n_levels; }
-            if (texels.size() + total > 0xFFFFFFFFull) { error = "texture atlas larger than 2^32 texels"; return false; }
-            texels.resize(texels.size() + total, KzF4{0.f, 0.f, 0.f, 0.f});
-            for (size_t k = 0; k < n; ++k) {
-                KzF4 &t = texels[r.texel_offset + k];
-                t.x = im.rgb[3 * k]; t.y = im.rgb[3 * k + 1]; t.z = im.rgb[3 * k + 2]; t.w = 1.f;
+            if (im.width > 65536 || im.height > 65536) { error = "image larger than 65536 texels per side"; return false; }
+            /* level 0 only: ImageTexture::eval passes zero derivatives to OIIO (texture.cpp:52-57), which resolves to the finest
+             * level; the pyramid is built on demand by kzgpu_image_lookup (n_levels stays 0 for the renderer) */
+            KzImageRec r; r.width = im.width; r.height = im.height; r.texel_offset = (uint32_t)total_texels; r.n_levels = 0;
+            const size_t n = (size_t)im.width * im.height;
+            if (total_texels + n > 0xFFFFFFFFull) { error = "texture atlas larger than 2^32 texels"; return false; }
+            total_texels += n;
+            if (geometry) {
+                texels.resize(total_texels, KzF4{0.f, 0.f, 0.f, 0.f});
+                for (size_t k = 0; k < n; ++k) {
+                    KzF4 &t = texels[r.texel_offset + k];
+                    t.x = im.rgb[3 * k]; t.y = im.rgb[3 * k + 1]; t.z = im.rgb[3 * k + 2]; t.w = 1.f;
+                }
             }
             images.push_back(r);
         }
-        uint32_t voff = 0, foff = 0;
+        uint64_t voff = 0, foff = 0;
         for (uint32_t g = 0; g < d->n_meshes; ++g) {
             const kz_mesh_desc &m = d->meshes[g];
             if (!m.positions || !m.indices) { error = "mesh buffers missing"; return false; }
             if (m.bsdf < 0 || m.bsdf >= (int)d->n_bsdfs) { error = "mesh bsdf index out of range"; return false; }
             if (m.light >= (int)d->n_lights) { error = "mesh light index out of range"; return false; }
             KzMeshRec r; memset(&r, 0, sizeof(r));
-            r.vertex_offset = voff; r.index_offset = foff; r.n_triangles = m.n_triangles;
+            if (voff + m.n_vertices > 0xFFFFFFFFull || foff + m.n_triangles > 0x7FFFFFFFull) { error = "scene larger than 2^32 vertices / 2^31 triangles"; return false; }
+            r.vertex_offset = (uint32_t)voff; r.index_offset = (uint32_t)foff; r.n_triangles = m.n_triangles;
             r.bsdf = m.bsdf; r.light = m.light;
             r.flags = (m.normals ? KZ_MESH_HAS_NORMALS : 0u) | (m.uvs ? KZ_MESH_HAS_UVS : 0u);
-            vertices.reserve(vertices.size() + m.n_vertices);
-            for (uint32_t i = 0; i < m.n_vertices; ++i) {
+            if (geometry) vertices.reserve(vertices.size() + m.n_vertices);
+            for (uint32_t i = 0; geometry && i < m.n_vertices; ++i) {
                 KzVertex v; memset(&v, 0, sizeof(v));
                 v.px = m.positions[3 * (size_t)i]; v.py = m.positions[3 * (size_t)i + 1]; v.pz = m.positions[3 * (size_t)i + 2];
                 if (m.normals) { v.nx = m.normals[3 * (size_t)i]; v.ny = m.normals[3 * (size_t)i + 1]; v.nz = m.normals[3 * (size_t)i + 2]; }
                 if (m.uvs) { v.u = m.uvs[2 * (size_t)i]; v.v = m.uvs[2 * (size_t)i + 1]; }
                 vertices.push_back(v);
             }
-            indices.reserve(indices.size() + m.n_triangles);
-            for (uint32_t f = 0; f < m.n_triangles; ++f) {
+            if (geometry) indices.reserve(indices.size() + m.n_triangles);
+            for (uint32_t f = 0; geometry && f < m.n_triangles; ++f) {
                 KzU4 t; t.x = m.indices[3 * (size_t)f]; t.y = m.indices[3 * (size_t)f + 1]; t.z = m.indices[3 * (size_t)f + 2]; t.w = 0u;
                 if (t.x >= m.n_vertices || t.y >= m.n_vertices || t.z >= m.n_vertices) { error = "vertex index out of range"; return false; }
                 indices.push_back(t);
             }
             if (m.light >= 0) {
+                /* an emitter without triangles cannot be sampled (DiscretePDF over nothing, mesh.cpp:108-133) */
+                if (m.n_triangles == 0) { error = "emissive mesh without triangles"; return false; }
+                for (uint32_t f = 0; !geometry && f < m.n_triangles; ++f)
+                    if (m.indices[3 * (size_t)f] >= m.n_vertices || m.indices[3 * (size_t)f + 1] >= m.n_vertices || m.indices[3 * (size_t)f + 2] >= m.n_vertices) { error = "vertex index out of range"; return false; }
                 r.flags |= KZ_MESH_IS_LIGHT;
                 if (d->lights[m.light].primary_visibility) r.flags |= KZ_MESH_LIGHT_VISIBLE;
                 /* Mesh::activate + DiscretePDF::normalize */
@@ -116,7 +137,7 @@ struct KzHostScene {
                 } else r.inv_area = 0.f;
                 light_meshes.push_back((int32_t)g);
             }
-            for (uint32_t f = 0; f < m.n_triangles; ++f) {
+            for (uint32_t f = 0; geometry && f < m.n_triangles; ++f) {
                 kzbvh::Tri t;
                 for (int k = 0; k < 3; ++k) {
                     const float *p = m.positions + 3 * (size_t)m.indices[3 * f + k];
@@ -128,6 +149,7 @@ struct KzHostScene {
             meshes.push_back(r);
             voff += m.n_vertices; foff += m.n_triangles;
         }
+        total_vertices = voff; total_triangles = foff;
         sc.n_meshes = d->n_meshes;
         sc.n_light_meshes = (int32_t)light_meshes.size();
         sc.background = d->background;
@@ -153,6 +175,22 @@ struct KzHostScene {
         }
         finalize();
         return true;
+    }
+
+    size_t total_texels = 0;
+    enum { KZ_TEX_MAX_DEPTH_HOST = 4 };      /* == KZ_TEX_MAX_DEPTH of kz_shade.h */
+    /* nodes on the longest root-to-leaf chain below `node`, -1 if a cycle is reachable */
+    static int textureDepth(const kz_scene_desc *d, int node, int guard) {
+        if (guard > 64) return -1;
+        int deepest = 0;
+        for (int c = 0; c < 3; ++c) {
+            const int ch = d->textures[node].child[c];
+            if (ch < 0) continue;
+            const int sub = textureDepth(d, ch, guard + 1);
+            if (sub < 0) return -1;
+            deepest = std::max(deepest, sub);
+        }
+        return deepest + 1;
     }
 
     /* sampler.cpp:290-314 */

@@ -594,9 +594,48 @@ __global__ void k_resolve(const KzF4 *frame, int width, int height, int border, 
     }
 }
 
-__global__ void k_frame_add(KzF4 *dst, const KzF4 *src, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { KzF4 a = dst[i]; const KzF4 b = src[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; dst[i] = a; }
+/* ---- parity probes: post-intersection record and emitter sample, field by field --------------------------------------- */
+/* accel.cpp:63-236 for one ray per thread (plain per-ray loop; this is a probe, not a hot path) */
+__global__ void __launch_bounds__(KZ_TRACE_THREADS) k_intersection_dump(KzScene sc, const KzF4 *rays, uint32_t n, float *out24) {
+    __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
+    KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const KzF4 ro = rays[2 * (size_t)i], rd = rays[2 * (size_t)i + 1];
+    const KzHit h = kz_trace(sc, stk, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w, false);
+    float *o = out24 + 24 * (size_t)i;
+    for (int k = 0; k < 24; ++k) o[k] = 0.f;
+    o[0] = h.t; o[1] = -1.f;
+    if (h.geom == KZ_INVALID_ID) return;
+    KzIts its; its.acc_rough = 0.f;
+    fill_intersection(sc, h, its, mk3(0.f));
+    o[1] = (float)its.mesh;
+    o[2] = its.p.x; o[3] = its.p.y; o[4] = its.p.z; o[5] = its.uv.x; o[6] = its.uv.y;
+    o[7] = its.geo_n.x; o[8] = its.geo_n.y; o[9] = its.geo_n.z;
+    o[10] = its.sh.s.x; o[11] = its.sh.s.y; o[12] = its.sh.s.z;
+    o[13] = its.sh.t.x; o[14] = its.sh.t.y; o[15] = its.sh.t.z;
+    o[16] = its.sh.n.x; o[17] = its.sh.n.y; o[18] = its.sh.n.z;
+    o[19] = its.dpdu.x; o[20] = its.dpdu.y; o[21] = its.dpdu.z;
+}
+
+/* scene.h:45-56 + mesh.cpp:108-133 + light.cpp:16-51 */
+__global__ void k_light_sample_dump(KzScene sc, const float *ref3, const float *u5, uint32_t n, float *out16) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float *o = out16 + 16 * (size_t)i;
+    for (int k = 0; k < 16; ++k) o[k] = 0.f;
+    o[0] = -1.f;
+    if (sc.n_light_meshes <= 0) return;
+    const float *u = u5 + 5 * (size_t)i;
+    const KzEmitterSample es = kz_sample_emitter(sc, mk3(ref3[3 * (size_t)i], ref3[3 * (size_t)i + 1], ref3[3 * (size_t)i + 2]), u[0], u[1], u[2], u[3]);
+    o[0] = (float)es.mesh;
+    o[1] = es.p.x; o[2] = es.p.y; o[3] = es.p.z; o[4] = es.n.x; o[5] = es.n.y; o[6] = es.n.z;
+    o[7] = es.wi.x; o[8] = es.wi.y; o[9] = es.wi.z; o[10] = es.dist; o[11] = es.pdf;
+    if (es.pdf > 0.f && !isnan(es.pdf) && !isinf(es.pdf)) {
+        const kz_light_desc l = sc.lights[es.light];
+        const kz3 Ls = mk3(l.radiance[0], l.radiance[1], l.radiance[2]) / es.pdf;
+        o[12] = Ls.x; o[13] = Ls.y; o[14] = Ls.z;
+    }
 }
 
 #endif

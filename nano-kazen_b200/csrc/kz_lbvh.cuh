@@ -210,8 +210,8 @@ struct CollapseState {
     uint32_t *node_counter, *tri_counter;
     const WorkItem *in;
     WorkItem *out;
-    uint32_t *out_count;
-    uint32_t n_in;
+    const uint32_t *in_count;    /* work items of this level (written by the previous level's launch) */
+    uint32_t *out_count;         /* work items of the next level */
 };
 
 __device__ __forceinline__ uint32_t sub_count(const BuildState &b, int c) { return c < 0 ? 1u : b.last[c] - b.first[c] + 1u; }
@@ -220,9 +220,11 @@ __device__ __forceinline__ float box_area(const Box6 &x) {
     return 2.f * (dx * dy + dy * dz + dz * dx);
 }
 
+/* One launch per wide-tree level.  The level's item count lives in HBM (written by the previous launch), so the host enqueues
+ * all levels back to back without reading anything back. */
 __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
-    const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= cs.n_in) return;
+    const uint32_t n_in = *cs.in_count;
+    for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_in; wi += gridDim.x * blockDim.x) {
     const BuildState &b = cs.b;
     const WorkItem it = cs.in[wi];
     int ch[8]; Box6 bx[8]; int nch = 0;
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
     }
     nd.imask = imask;
     cs.nodes[it.wnode] = nd;
+    }
 }
 
 /* Reference pre-splitting (as in the host SAH builder, kz_bvh_build.h): a triangle whose box is expected to hold other primitives,
@@ -403,19 +406,18 @@ __global__ void k_make_refs(const kzbvh::Tri *tris, uint32_t n, const uint32_t *
         }                                                                                                \
     } while (0)
 
-/* Builds the accel of `tris` on the current device; the node/triangle arrays are appended to
- * `owner` (freed by the caller), temporaries are released before returning. */
-inline int build(const std::vector<kzbvh::Tri> &tris, cudaStream_t s, std::vector<void *> &owner, Result &r, std::string &err) {
+#define KZ_LBVH_MAX_LEVELS 31     /* wide-tree levels the traversal stack can hold: 2 * depth + 2 <= 64 entries */
+
+/* Builds the accel of the `n_tris_in` device-resident triangles `d_tris` (scene order) on the current device; the node/triangle
+ * arrays are appended to `owner` (freed by the caller), temporaries are released before returning. */
+inline int build(const kzbvh::Tri *d_tris, uint32_t n_tris_in, cudaStream_t s, std::vector<void *> &owner, Result &r, std::string &err) {
     std::vector<void *> temp;
-    const uint32_t n_tris_in = (uint32_t)tris.size();
     uint32_t n = n_tris_in;                  /* references: == triangles unless pre-splitting adds some */
     r = Result();
     if (n == 0) return KZ_OK;
     auto talloc = [&](size_t bytes, void **p) { cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16)); if (e == cudaSuccess) temp.push_back(*p); return e; };
-    kzbvh::Tri *d_tris; unsigned long long *k0, *k1; uint32_t *v0, *v1, *bounds;
-    KZL_CUDA(talloc((size_t)n * sizeof(kzbvh::Tri), (void **)&d_tris));
+    unsigned long long *k0, *k1; uint32_t *v0, *v1, *bounds;
     KZL_CUDA(talloc(64, (void **)&bounds));
-    KZL_CUDA(cudaMemcpyAsync(d_tris, tris.data(), (size_t)n * sizeof(kzbvh::Tri), cudaMemcpyHostToDevice, s));
     const uint32_t init[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
     KZL_CUDA(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, s));
     k_scene_bounds<<<std::min((n + 255u) / 256u, 148u * 8u), 256, 0, s>>>(d_tris, n, bounds);
@@ -477,33 +479,42 @@ inline int build(const std::vector<kzbvh::Tri> &tris, cudaStream_t s, std::vecto
         KZL_CUDA(cudaMalloc(&p, max_nodes * sizeof(KzNode8))); owner.push_back(p); d_nodes = (KzNode8 *)p;
         KZL_CUDA(cudaMalloc(&p, (size_t)n * 3 * sizeof(KzF4))); owner.push_back(p); d_out_tris = (KzF4 *)p;
     }
-    KZL_CUDA(talloc(64, (void **)&counters));
+    /* counters[0] = wide nodes (root taken), [1] = emitted triangles, [2 + l] = work items of level l */
+    uint32_t cinit[4 + KZ_LBVH_MAX_LEVELS];
+    memset(cinit, 0, sizeof(cinit));
+    cinit[0] = 1u; cinit[2] = 1u;
+    KZL_CUDA(talloc(sizeof(cinit), (void **)&counters));
     KZL_CUDA(talloc(max_nodes * sizeof(WorkItem), (void **)&w0)); KZL_CUDA(talloc(max_nodes * sizeof(WorkItem), (void **)&w1));
-    const uint32_t cinit[4] = {1u, 0u, 0u, 0u};   /* node_counter (root taken), tri_counter, out_count, - */
     KZL_CUDA(cudaMemcpyAsync(counters, cinit, sizeof(cinit), cudaMemcpyHostToDevice, s));
     WorkItem rootItem; rootItem.bnode = n > 1 ? 0 : ~0; rootItem.wnode = 0;
     KZL_CUDA(cudaMemcpyAsync(w0, &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, s));
     CollapseState cs;
-    cs.b = b; cs.nodes = d_nodes; cs.tris = d_out_tris; cs.node_counter = counters; cs.tri_counter = counters + 1; cs.out_count = counters + 2;
-    uint32_t n_in = 1;
+    cs.b = b; cs.nodes = d_nodes; cs.tris = d_out_tris; cs.node_counter = counters; cs.tri_counter = counters + 1;
+    /* level-synchronous, but without a host round trip per level: every launch reads its item count from HBM; the grid is sized
+     * for the widest possible level of its depth (8^l items) and capped at a few waves, with a grid-stride loop inside */
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     WorkItem *in = w0, *out = w1;
-    while (n_in > 0) {
-        cs.in = in; cs.out = out; cs.n_in = n_in;
-        KZL_CUDA(cudaMemsetAsync(cs.out_count, 0, 4, s));
-        k_collapse<<<(n_in + 63u) / 64u, 64, 0, s>>>(cs);
-        ++r.launches; ++r.depth;
-        KZL_CUDA(cudaMemcpyAsync(&n_in, cs.out_count, 4, cudaMemcpyDeviceToHost, s));
-        KZL_CUDA(cudaStreamSynchronize(s));
+    double widest = 1.0;
+    for (int l = 0; l < KZ_LBVH_MAX_LEVELS; ++l) {
+        cs.in = in; cs.out = out; cs.in_count = counters + 2 + l; cs.out_count = counters + 3 + l;
+        const double cap = std::min(widest, (double)max_nodes);
+        const unsigned grid = (unsigned)std::min<double>((cap + 63.0) / 64.0, (double)sms * 32.0);
+        k_collapse<<<std::max(1u, grid), 64, 0, s>>>(cs);
+        ++r.launches;
+        widest *= 8.0;
         std::swap(in, out);
     }
-    uint32_t fin[2]; uint32_t hb[8];
-    KZL_CUDA(cudaMemcpyAsync(fin, counters, 8, cudaMemcpyDeviceToHost, s));
+    uint32_t fin[3 + KZ_LBVH_MAX_LEVELS]; uint32_t hb[8];
+    KZL_CUDA(cudaMemcpyAsync(fin, counters, sizeof(fin), cudaMemcpyDeviceToHost, s));
     KZL_CUDA(cudaMemcpyAsync(hb, bounds, 32, cudaMemcpyDeviceToHost, s));
     KZL_CUDA(cudaStreamSynchronize(s));
     KZL_CUDA(cudaGetLastError());
     r.nodes = d_nodes; r.tris = d_out_tris; r.n_nodes = fin[0]; r.n_tris = fin[1];
     r.max_abs = ord2f(hb[6]);
+    for (int l = 0; l < KZ_LBVH_MAX_LEVELS && fin[2 + l] != 0u; ++l) r.depth = l + 1;
     for (void *p : temp) cudaFree(p);
+    if (fin[2 + KZ_LBVH_MAX_LEVELS] != 0u) { err = "lbvh: accel deeper than the traversal stack allows"; return KZ_ERR_UNSUPPORTED; }
     if (r.n_tris != n) { err = "lbvh: triangle count mismatch after collapse"; return KZ_ERR_CUDA; }
     return KZ_OK;
 }

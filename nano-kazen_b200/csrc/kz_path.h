@@ -157,6 +157,44 @@ KZ_HD int kz_extend_item(const KzScene &sc, const KzStackRef &stk, const KzPathS
     return kz_classify(sc, h.geom);
 }
 
+/* ---- emitter sampling: Scene::getRandomLight (scene.h:45-56) + Mesh::sample (mesh.cpp:108-133) + AreaLight::sample / pdf
+ *      (light.cpp:21-51).  u_pick, u_tri, u_b1, u_b2: the four 1-D draws in the order Li makes them. ------------------------ */
+struct KzEmitterSample {
+    int32_t mesh;        /* scene mesh index of the picked emitter */
+    int32_t light;       /* its kz_light_desc */
+    kz3 p, n, wi;        /* sampled point, its (unnormalised) normal, direction ref -> p */
+    float dist, pdf;     /* |p - ref|, solid-angle density (0: not usable); the pick probability 1/n_lights is NOT included */
+};
+KZ_HD KzEmitterSample kz_sample_emitter(const KzScene &sc, kz3 ref, float u_pick, float u_tri, float u_b1, float u_b2) {
+    KzEmitterSample es;
+    const uint32_t nl = (uint32_t)sc.n_light_meshes;
+    uint32_t index = (uint32_t)floorf((float)nl * u_pick);
+    if (index > nl - 1) index = nl - 1;
+    es.mesh = sc.light_meshes[index];
+    const KzMeshRec lm = sc.meshes[es.mesh];
+    es.light = lm.light;
+    /* Mesh::sample, mesh.cpp:108-133 */
+    const uint32_t tri = cdf_sample(sc.light_cdf + lm.cdf_offset, lm.n_triangles, u_tri);
+    const float su0 = sqrtf(u_b1);
+    const float u = 1 - su0;
+    const float v = u_b2 * su0;
+    const KzU4 F = sc.indices[(size_t)lm.index_offset + tri];
+    const KzVertex lv0 = kz_vertex(sc, lm, F.x), lv1 = kz_vertex(sc, lm, F.y), lv2 = kz_vertex(sc, lm, F.z);
+    const kz3 p0 = kz_vpos(lv0), p1 = kz_vpos(lv1), p2 = kz_vpos(lv2);
+    es.p = p0 + u * (p1 - p0) + v * (p2 - p0);
+    if (lm.flags & KZ_MESH_HAS_NORMALS) {
+        const kz3 n0 = kz_vnrm(lv0), n1 = kz_vnrm(lv1), n2 = kz_vnrm(lv2);
+        es.n = n0 + u * (n1 - n0) + v * (n2 - n0);          /* not normalised, mesh.cpp:128-129 */
+    } else {
+        es.n = normalized(cross(p1 - p0, p2 - p0));
+    }
+    /* AreaLight::sample, light.cpp:21-34 */
+    es.wi = normalized(es.p - ref);
+    es.dist = norm(es.p - ref);
+    es.pdf = light_pdf(lm.inv_area, ref, es.p, es.n, es.wi);
+    return es;
+}
+
 /* ---- shade --------------------------------------------------------------------------------- */
 KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &st, uint32_t slot, int bounce, KzCounters &cnt);
 
@@ -228,31 +266,14 @@ KZ_HD uint32_t kz_shade_item(const KzScene &sc, const KzPathState &st, uint32_t 
     const float rnd = kz_next1d(sc, sm);
     if (sc.n_light_meshes > 0) {
         const uint32_t nl = (uint32_t)sc.n_light_meshes;
-        uint32_t index = (uint32_t)floorf((float)nl * rnd);
-        if (index > nl - 1) index = nl - 1;
-        const KzMeshRec lm = sc.meshes[sc.light_meshes[index]];
-        /* Mesh::sample, mesh.cpp:108-133 */
-        const uint32_t tri = cdf_sample(sc.light_cdf + lm.cdf_offset, lm.n_triangles, kz_next1d(sc, sm));
-        const float su0 = sqrtf(kz_next1d(sc, sm));
-        const float u = 1 - su0;
-        const float v = kz_next1d(sc, sm) * su0;
-        const KzU4 F = sc.indices[(size_t)lm.index_offset + tri];
-        const KzVertex lv0 = kz_vertex(sc, lm, F.x), lv1 = kz_vertex(sc, lm, F.y), lv2 = kz_vertex(sc, lm, F.z);
-        const kz3 p0 = kz_vpos(lv0), p1 = kz_vpos(lv1), p2 = kz_vpos(lv2);
-        const kz3 lp = p0 + u * (p1 - p0) + v * (p2 - p0);
-        kz3 ln;
-        if (lm.flags & KZ_MESH_HAS_NORMALS) {
-            const kz3 n0 = kz_vnrm(lv0), n1 = kz_vnrm(lv1), n2 = kz_vnrm(lv2);
-            ln = n0 + u * (n1 - n0) + v * (n2 - n0);          /* not normalised, mesh.cpp:128-129 */
-        } else {
-            ln = normalized(cross(p1 - p0, p2 - p0));
-        }
-        /* AreaLight::sample, light.cpp:21-34 */
-        const kz3 lwi = normalized(lp - its.p);
-        const float dist = norm(lp - its.p);
-        const float lpdf = light_pdf(lm.inv_area, its.p, lp, ln, lwi);
+        const float u_tri = kz_next1d(sc, sm);
+        const float u_b1 = kz_next1d(sc, sm);
+        const float u_b2 = kz_next1d(sc, sm);
+        const KzEmitterSample es = kz_sample_emitter(sc, its.p, rnd, u_tri, u_b1, u_b2);
+        const kz3 lwi = es.wi;
+        const float dist = es.dist, lpdf = es.pdf;
         if (lpdf > 0.f && !isnan(lpdf) && !isinf(lpdf)) {
-            const kz_light_desc l = sc.lights[lm.light];
+            const kz_light_desc l = sc.lights[es.light];
             /* eval: cosTheta > 0 is implied by lpdf > 0 */
             kz3 Ls = mk3(l.radiance[0], l.radiance[1], l.radiance[2]) / lpdf;
             Ls = Ls / (1.f / (float)nl);
@@ -340,24 +361,14 @@ KZ_HD_NOINLINE uint32_t kz_shade_alt_item(const KzScene &sc, const KzPathState &
             const float rnd = kz_next1d(sc, sm);
             if (sc.n_light_meshes > 0) {
                 const uint32_t nl = (uint32_t)sc.n_light_meshes;
-                uint32_t index = (uint32_t)floorf((float)nl * rnd);
-                if (index > nl - 1) index = nl - 1;
-                const KzMeshRec lm = sc.meshes[sc.light_meshes[index]];
-                const uint32_t tri = cdf_sample(sc.light_cdf + lm.cdf_offset, lm.n_triangles, kz_next1d(sc, sm));
-                const float su0 = sqrtf(kz_next1d(sc, sm));
-                const float u = 1 - su0, v = kz_next1d(sc, sm) * su0;
-                const KzU4 F = sc.indices[(size_t)lm.index_offset + tri];
-                const KzVertex lv0 = kz_vertex(sc, lm, F.x), lv1 = kz_vertex(sc, lm, F.y), lv2 = kz_vertex(sc, lm, F.z);
-                const kz3 p0 = kz_vpos(lv0), p1 = kz_vpos(lv1), p2 = kz_vpos(lv2);
-                const kz3 lp = p0 + u * (p1 - p0) + v * (p2 - p0);
-                kz3 ln;
-                if (lm.flags & KZ_MESH_HAS_NORMALS) { const kz3 n0 = kz_vnrm(lv0), n1 = kz_vnrm(lv1), n2 = kz_vnrm(lv2); ln = n0 + u * (n1 - n0) + v * (n2 - n0); }
-                else ln = normalized(cross(p1 - p0, p2 - p0));
-                const kz3 lwi = normalized(lp - its.p);
-                const float dist = norm(lp - its.p);
-                const float lpdf = light_pdf(lm.inv_area, its.p, lp, ln, lwi);
+                const float u_tri = kz_next1d(sc, sm);
+                const float u_b1 = kz_next1d(sc, sm);
+                const float u_b2 = kz_next1d(sc, sm);
+                const KzEmitterSample es = kz_sample_emitter(sc, its.p, rnd, u_tri, u_b1, u_b2);
+                const kz3 lwi = es.wi;
+                const float dist = es.dist, lpdf = es.pdf;
                 if (lpdf > 0.f && !isnan(lpdf) && !isinf(lpdf)) {
-                    const kz_light_desc l = sc.lights[lm.light];
+                    const kz_light_desc l = sc.lights[es.light];
                     const kz3 Ls = mk3(l.radiance[0], l.radiance[1], l.radiance[2]) / lpdf;
                     float cosTheta = to_local(its.sh, lwi).z;
                     if (cosTheta < 0.f) cosTheta = 0.f;

@@ -97,7 +97,8 @@ class RenderReq(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays_extension", C.c_uint64), ("rays_shadow", C.c_uint64), ("vertices", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("ms_total", C.c_double),
-                ("bvh_nodes", C.c_uint64), ("bvh_bytes", C.c_uint64), ("ms_build", C.c_double)]
+                ("bvh_nodes", C.c_uint64), ("bvh_bytes", C.c_uint64), ("ms_build", C.c_double),
+                ("ms_upload", C.c_double), ("ms_merge", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -358,6 +359,22 @@ class _Backend:
         self._call("resolve", self.h, frame.ctypes.data_as(c_float_p), rgb.ctypes.data_as(c_float_p),
                    srgb.ctypes.data_as(C.POINTER(C.c_uint8)))
         return rgb, srgb
+
+
+    def intersection_dump(self, rays):
+        """closest hit + post-intersection record per ray: (n, 24) float32, layout in include/kzgpu.h"""
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        out = np.zeros((rays.shape[0], 24), np.float32)
+        self._call("intersection_dump", self.h, rays.ctypes.data_as(C.c_void_p), C.c_size_t(rays.shape[0]), out.ctypes.data_as(c_float_p))
+        return out
+
+    def light_sample_dump(self, ref, u5):
+        """emitter sample per (reference point, 5 random numbers): (n, 16) float32, layout in include/kzgpu.h"""
+        ref = np.ascontiguousarray(ref, np.float32).reshape(-1, 3)
+        u5 = np.ascontiguousarray(u5, np.float32).reshape(-1, 5)
+        out = np.zeros((ref.shape[0], 16), np.float32)
+        self._call("light_sample_dump", self.h, ref.ctypes.data_as(c_float_p), u5.ctypes.data_as(c_float_p), C.c_size_t(ref.shape[0]), out.ctypes.data_as(c_float_p))
+        return out
 
 
 class HostScene:

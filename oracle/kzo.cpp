@@ -266,6 +266,56 @@ extern "C" int kzo_light_cdf(kzo_scene *s, int mesh, float *cdf_out, float *norm
     return KZ_OK;
 }
 
+/* ----------------------------------------------------- field-by-field probes */
+/* Accel::rayIntersect, accel.cpp:63-236: closest hit + the Intersection it fills (layout: include/kzgpu.h, kzgpu_intersection_dump) */
+extern "C" int kzo_intersection_dump(kzo_scene *s, const kz_ray *rays, size_t n, float *out24) {
+    if (!s || (!rays && n) || (!out24 && n)) return fail(KZ_ERR_INVALID, "null argument");
+    parallelFor(n, 0, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            float *o = out24 + 24 * i;
+            for (int k = 0; k < 24; ++k) o[k] = 0.f;
+            HitRec h = s->sc.accel.traceBvh(rays[i]);
+            o[0] = h.t; o[1] = -1.f;
+            if (h.geom == KZ_INVALID_ID) continue;
+            Intersection its;
+            fillIntersection(s->sc, h, its);
+            o[1] = (float)its.mesh;
+            o[2] = its.p.x; o[3] = its.p.y; o[4] = its.p.z; o[5] = its.uv.x; o[6] = its.uv.y;
+            o[7] = its.geoFrame.n.x; o[8] = its.geoFrame.n.y; o[9] = its.geoFrame.n.z;
+            o[10] = its.shFrame.s.x; o[11] = its.shFrame.s.y; o[12] = its.shFrame.s.z;
+            o[13] = its.shFrame.t.x; o[14] = its.shFrame.t.y; o[15] = its.shFrame.t.z;
+            o[16] = its.shFrame.n.x; o[17] = its.shFrame.n.y; o[18] = its.shFrame.n.z;
+            o[19] = its.dpdu.x; o[20] = its.dpdu.y; o[21] = its.dpdu.z;
+        }
+    });
+    return KZ_OK;
+}
+
+/* Scene::getRandomLight (scene.h:45-56) + AreaLight::sample (light.cpp:21-34) fed with given random numbers
+ * (layout: include/kzgpu.h, kzgpu_light_sample_dump) */
+extern "C" int kzo_light_sample_dump(kzo_scene *s, const float *ref3, const float *u5, size_t n, float *out16) {
+    if (!s || (n && (!ref3 || !u5 || !out16))) return fail(KZ_ERR_INVALID, "null argument");
+    const SceneData &sc = s->sc;
+    for (size_t i = 0; i < n; ++i) {
+        float *o = out16 + 16 * i;
+        for (int k = 0; k < 16; ++k) o[k] = 0.f;
+        o[0] = -1.f;
+        size_t nl = sc.lightMeshes.size();
+        if (nl == 0) continue;
+        Sampler sm; sm.cfg = &sc.sampler; sm.fixed = u5 + 5 * i;
+        float rnd = sm.next1D();
+        size_t index = std::min((size_t)std::floor(nl * rnd), nl - 1);
+        const MeshData &lm = sc.meshes[sc.lightMeshes[index]];
+        LightQueryRecord lRec(V3(ref3[3 * i], ref3[3 * i + 1], ref3[3 * i + 2]));
+        V3 Ls = lightSample(sc.lights[lm.light], lm, lRec, sm);
+        o[0] = (float)sc.lightMeshes[index];
+        o[1] = lRec.p.x; o[2] = lRec.p.y; o[3] = lRec.p.z; o[4] = lRec.n.x; o[5] = lRec.n.y; o[6] = lRec.n.z;
+        o[7] = lRec.wi.x; o[8] = lRec.wi.y; o[9] = lRec.wi.z; o[10] = lRec.shadowRay.tmax; o[11] = lRec.pdf;
+        o[12] = Ls.x; o[13] = Ls.y; o[14] = Ls.z;
+    }
+    return KZ_OK;
+}
+
 /* -------------------------------------------------------------- integrator */
 static inline float powerHeuristic(float a, float b) {   /* integrator.cpp:340-344 */
     a *= a; b *= b;

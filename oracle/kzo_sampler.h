@@ -170,6 +170,8 @@ struct Sampler {
     Pcg32 rng;
     int32_t px, py;
     uint32_t sampleIndex, dim;
+    /* probe mode (kzo_light_sample_dump): next1D() replays these numbers instead of drawing */
+    const float *fixed = nullptr; int fixedPos = 0;
 
     void generateSample(int32_t x, int32_t y, int sampleIdx, int dimension = 0) {
         const kz_sampler_desc &d = cfg->d;
@@ -183,6 +185,7 @@ struct Sampler {
         rng.advance((uint64_t)sampleIdx * 65536ull + (uint64_t)dimension);
     }
     float next1D() {
+        if (fixed) return fixed[fixedPos++];
         const kz_sampler_desc &d = cfg->d;
         switch (d.type) {
             case KZ_SAMPLER_INDEPENDENT: return rng.nextFloat();           /* sampler.cpp:48-50 */

@@ -203,6 +203,52 @@ int kzemu_render(kzemu *e, const kz_render_req *req, float *frame_rgbw) {
     return KZ_OK;
 }
 
+/* the per-item bodies of k_intersection_dump / k_light_sample_dump (kz_kernels.cuh) */
+int kzemu_intersection_dump(kzemu *e, const kz_ray *rays, size_t n, float *out24) {
+    const KzScene &sc = e->hs.sc;
+    pfor(n, [&](size_t b, size_t en) {
+        KzStackRef stk;
+        for (size_t i = b; i < en; ++i) {
+            const kz_ray &r = rays[i];
+            const KzHit h = kz_trace(sc, stk, r.o[0], r.o[1], r.o[2], r.d[0], r.d[1], r.d[2], r.tmin, r.tmax, false);
+            float *o = out24 + 24 * i;
+            for (int k = 0; k < 24; ++k) o[k] = 0.f;
+            o[0] = h.t; o[1] = -1.f;
+            if (h.geom == KZ_INVALID_ID) continue;
+            KzIts its; its.acc_rough = 0.f;
+            fill_intersection(sc, h, its, mk3(0.f));
+            o[1] = (float)its.mesh;
+            o[2] = its.p.x; o[3] = its.p.y; o[4] = its.p.z; o[5] = its.uv.x; o[6] = its.uv.y;
+            o[7] = its.geo_n.x; o[8] = its.geo_n.y; o[9] = its.geo_n.z;
+            o[10] = its.sh.s.x; o[11] = its.sh.s.y; o[12] = its.sh.s.z;
+            o[13] = its.sh.t.x; o[14] = its.sh.t.y; o[15] = its.sh.t.z;
+            o[16] = its.sh.n.x; o[17] = its.sh.n.y; o[18] = its.sh.n.z;
+            o[19] = its.dpdu.x; o[20] = its.dpdu.y; o[21] = its.dpdu.z;
+        }
+    });
+    return KZ_OK;
+}
+int kzemu_light_sample_dump(kzemu *e, const float *ref3, const float *u5, size_t n, float *out16) {
+    const KzScene &sc = e->hs.sc;
+    for (size_t i = 0; i < n; ++i) {
+        float *o = out16 + 16 * i;
+        for (int k = 0; k < 16; ++k) o[k] = 0.f;
+        o[0] = -1.f;
+        if (sc.n_light_meshes <= 0) continue;
+        const float *u = u5 + 5 * i;
+        const KzEmitterSample es = kz_sample_emitter(sc, mk3(ref3[3 * i], ref3[3 * i + 1], ref3[3 * i + 2]), u[0], u[1], u[2], u[3]);
+        o[0] = (float)es.mesh;
+        o[1] = es.p.x; o[2] = es.p.y; o[3] = es.p.z; o[4] = es.n.x; o[5] = es.n.y; o[6] = es.n.z;
+        o[7] = es.wi.x; o[8] = es.wi.y; o[9] = es.wi.z; o[10] = es.dist; o[11] = es.pdf;
+        if (es.pdf > 0.f && !isnan(es.pdf) && !isinf(es.pdf)) {
+            const kz_light_desc l = sc.lights[es.light];
+            const kz3 Ls = mk3(l.radiance[0], l.radiance[1], l.radiance[2]) / es.pdf;
+            o[12] = Ls.x; o[13] = Ls.y; o[14] = Ls.z;
+        }
+    }
+    return KZ_OK;
+}
+
 int kzemu_stats(kzemu *e, kz_stats *out) {
     memset(out, 0, sizeof(*out));
     out->paths = e->total.paths; out->rays_extension = e->total.rays_ext; out->rays_shadow = e->total.rays_shadow; out->vertices = e->total.vertices;

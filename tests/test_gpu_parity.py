@@ -404,17 +404,22 @@ def test_multi_device_context(kzo, gpu_lib):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
-    sb = scenes.cornell_scene(64, 64, 16, "stratified")
+    sb = scenes.cornell_scene(64, 64, 16, "stratified", with_texture=True)
     d = sb.desc()
-    G1 = pk.Gpu(d, devices=(0,))
-    GN = pk.Gpu(d, devices=tuple(range(n)))
-    f1, fn = G1.render(), GN.render()
-    assert np.allclose(f1, fn, rtol=1e-4, atol=1e-5)
-    st = GN.stats()
-    assert st["paths"] == 64 * 64 * 16
     rays = scenes.incoherent_rays(10000, extent=0.9)
-    assert G1.trace(rays).tobytes() == GN.trace(rays, device=n - 1).tobytes()
-    G1.close(); GN.close()
+    for builder in (pk.BUILD_HOST_SAH, pk.BUILD_LBVH):           # LBVH: built on device 0, replicated over NVLink
+        G1 = pk.Gpu(d, devices=(0,), builder=builder)
+        GN = pk.Gpu(d, devices=tuple(range(n)), builder=builder)
+        f1, fn = G1.render(), GN.render()
+        assert np.allclose(f1, fn, rtol=1e-4, atol=1e-5)
+        st = GN.stats()
+        assert st["paths"] == 64 * 64 * 16 and st["ms_merge"] > 0          # the frames were merged on the devices (k_frame_reduce)
+        assert G1.trace(rays).tobytes() == GN.trace(rays, device=n - 1).tobytes()
+        # progressive: a second request adds to the frame passed in (clear_frame = 0), on one device as on N
+        half = GN.render(0, 8)
+        full = GN.render(8, 16, frame=half.copy())
+        assert np.allclose(full, fn, rtol=1e-4, atol=1e-5)
+        G1.close(); GN.close()
 
 
 def test_nan_rays_are_misses(kzo, gpu_lib):
@@ -511,6 +516,118 @@ def test_full_size_properties(gpu_lib, n_tris):
     # occlusion walk without invisible lights
     occ, seg = G.occluded(rays[: 1 << 20], 1e-4)
     assert np.array_equal(occ.astype(bool), hit[: 1 << 20]) and np.all(seg == 1)
+    G.close()
+
+
+@pytest.mark.parametrize("n_tris", [1 << 20, 10_000_000])
+def test_full_size_sampled_oracle(kzo, gpu_lib, n_tris):
+    """BASELINE configs[1] at full size against the oracle: the GPU-built LBVH accel of the 1 M / 10 M triangle soup and the
+    oracle's BVH2 over the same triangles return identical bytes for 2^18 primary + 2^18 incoherent rays (a sample of the
+    bench batches: same generators, same seeds)."""
+    sb = scenes.soup_scene(n_tris)
+    d = sb.desc()
+    G = pk.Gpu(d, builder=pk.BUILD_LBVH)
+    O = kzo.Oracle(d)
+    rays = np.concatenate([scenes.primary_rays(512), scenes.incoherent_rays(1 << 18)])
+    a, b = O.trace(rays), G.trace(rays)
+    assert a.tobytes() == b.tobytes()
+    assert 0.5 < (a["geom_id"] != 0xFFFFFFFF).mean() < 1.0
+    occ_o, seg_o = O.occluded(rays[-(1 << 16):], 1e-4)
+    occ_g, seg_g = G.occluded(rays[-(1 << 16):], 1e-4)
+    assert np.array_equal(occ_o, occ_g) and np.array_equal(seg_o, seg_g)
+    O.close(); G.close()
+
+
+def test_intersection_record(kzo, gpu_lib):
+    """A3 on the device, field by field (accel.cpp:113-236): all three shading-frame cases, textured and untextured meshes."""
+    from test_hostemu import check_intersection_dump
+    for sb, rays in ((scenes.cornell_scene(16, 16, 4, with_texture=True, normalmap=True),
+                      np.concatenate([scenes.primary_rays(96, 39.0, (0, 0, -3.4)), scenes.incoherent_rays(40000, extent=0.95)])),
+                     (scenes.gallery_scene(16, 12, 4),
+                      np.concatenate([scenes.primary_rays(96, 50.0, (0, 0.1, -3.2)), scenes.incoherent_rays(40000, extent=0.9)]))):
+        for builder in (pk.BUILD_HOST_SAH, pk.BUILD_LBVH):
+            O, G = _pair(kzo, sb, builder)
+            check_intersection_dump(O, G, rays)
+            O.close(); G.close()
+
+
+def test_emitter_sample(kzo, gpu_lib):
+    """S1 / L1 / L2 on the device, field by field (scene.h:45-56, mesh.cpp:108-133, light.cpp:16-51)."""
+    from test_hostemu import check_light_sample_dump
+    O, G = _pair(kzo, scenes.cornell_scene(16, 16, 4))
+    check_light_sample_dump(O, G, n=50000)
+    O.close(); G.close()
+    sb = scenes.studio_scene(16, 16, 4)                    # one emitter of 32 triangles: exercises the area CDF
+    O, G = _pair(kzo, sb)
+    rng = np.random.default_rng(9)
+    ref = rng.uniform(-1.0, 1.0, (20000, 3)).astype(np.float32) + np.array([0, 1, 0], np.float32)
+    u5 = rng.uniform(0, 1, (20000, 5)).astype(np.float32)
+    a, b = O.light_sample_dump(ref, u5), G.light_sample_dump(ref, u5)
+    assert a[:, 0].tobytes() == b[:, 0].tobytes()
+    np.testing.assert_allclose(b[:, 1:11], a[:, 1:11], rtol=2e-5, atol=2e-6)
+    O.close(); G.close()
+
+
+def test_scene_ingest_from_device_arrays(kzo, gpu_lib):
+    """kz_mesh_desc arrays may be CUDA device pointers (read in place by the ingest kernels): same accel, same hits, same image
+    as the host-array upload -- including an emitter, whose arrays are read back for the area CDF."""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+    sb = scenes.cornell_scene(48, 48, 16, with_texture=True)
+    d = sb.desc()
+    keep = []
+    dd = pk.SceneDesc.from_buffer_copy(d)
+    meshes = (pk.MeshDesc * d.n_meshes)()
+    for g in range(d.n_meshes):
+        m = d.meshes[g]
+        C.memmove(C.byref(meshes[g]), C.byref(m), C.sizeof(pk.MeshDesc))
+        for name, per, cnt, ctype in (("positions", 3, m.n_vertices, C.c_float), ("normals", 3, m.n_vertices, C.c_float),
+                                      ("uvs", 2, m.n_vertices, C.c_float), ("indices", 3, m.n_triangles, C.c_uint32)):
+            src = getattr(m, name)
+            if not src:
+                continue
+            host = np.ctypeslib.as_array(src, shape=(cnt * per,)).copy()
+            t = torch.from_numpy(host.view(np.float32 if ctype is C.c_float else np.int32)).cuda()
+            keep.append(t)
+            setattr(meshes[g], name, C.cast(t.data_ptr(), C.POINTER(ctype)))
+    dd.meshes = meshes
+    rays = np.concatenate([scenes.primary_rays(96, 39.0, (0, 0, -3.4)), scenes.incoherent_rays(30000, extent=0.95)])
+    for builder in (pk.BUILD_HOST_SAH, pk.BUILD_LBVH):
+        G1, G2 = pk.Gpu(d, builder=builder), pk.Gpu(dd, builder=builder)
+        assert G1.trace(rays).tobytes() == G2.trace(rays).tobytes()
+        assert G1.render().tobytes() == G2.render().tobytes() or scenes.rel_mse(G2.resolve(G2.render())[0], G1.resolve(G1.render())[0]).max() < 1e-9
+        G1.close(); G2.close()
+
+
+def test_upload_validation(gpu_lib):
+    """kzgpu_scene_upload rejects what the device code cannot hold instead of reading out of bounds."""
+    sb = scenes.cornell_scene(8, 8, 1)
+    P = np.zeros((3, 3), np.float32)
+    sb.mesh(P, np.array([[0, 1, 3]], np.uint32), 0)                       # vertex index out of range (checked on the device)
+    with pytest.raises(RuntimeError, match="vertex index out of range"):
+        pk.Gpu(sb.desc())
+    sb = scenes.cornell_scene(8, 8, 1)
+    sb.mesh(np.zeros((3, 3), np.float32), np.zeros((0, 3), np.uint32), 0, light=sb.light((1, 1, 1)))
+    with pytest.raises(RuntimeError, match="emissive mesh without triangles"):
+        pk.Gpu(sb.desc())
+    sb = scenes.cornell_scene(8, 8, 1)
+    t = sb.tex_constant((1, 1, 1))
+    for _ in range(5):
+        t = sb.tex_colorramp(0.0, 1.0, t)                                    # six levels deep
+    sb.mesh(*scenes.quad((0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0)), sb.bsdf_lambertian(t))
+    with pytest.raises(RuntimeError, match="deeper than"):
+        pk.Gpu(sb.desc())
+    sb = scenes.cornell_scene(8, 8, 1)
+    a = sb.tex_colorramp(0.0, 1.0, 0); b = sb.tex_colorramp(0.0, 1.0, a); sb.textures[a].child[0] = b      # cycle
+    with pytest.raises(RuntimeError, match="cycle"):
+        pk.Gpu(sb.desc())
+    bn, pm = pk.host_fallback_tables()
+    sb = scenes.cornell_scene(8, 8, 4)
+    sb.set_sampler("pmj02bn", 4, tables=(bn, pm))
+    G = pk.Gpu(sb.desc())
+    with pytest.raises(RuntimeError, match="sample_count"):
+        G.render(0, 5)                                                       # pmj02bn tables hold sample_count entries per pixel
+    G.render(0, 4)
     G.close()
 
 

@@ -210,3 +210,56 @@ def test_latlong_environment_map_cpu(kzo, emu):
     ro, _ = O.resolve(O.render()); re, _ = O.resolve(E.render())
     assert ro.mean() > 0.05 and scenes.rel_mse(re, ro).max() < 1e-6
     O.close(); E.close()
+
+
+def _probe_rays(n_primary=48, n_incoherent=6000):
+    return np.concatenate([scenes.primary_rays(n_primary, 39.0, (0, 0, -3.4)), scenes.incoherent_rays(n_incoherent, extent=0.95)])
+
+
+def check_intersection_dump(O, X, rays, rtol=2e-5):
+    """A3 field by field (accel.cpp:113-236): t and the mesh bit-exact, positions / uv / frames / dpdu to rounding."""
+    a, b = O.intersection_dump(rays), X.intersection_dump(rays)
+    assert a[:, :2].tobytes() == b[:, :2].tobytes()
+    hit = a[:, 1] >= 0
+    assert hit.sum() > rays.shape[0] // 2
+    np.testing.assert_allclose(b[hit, 2:7], a[hit, 2:7], rtol=rtol, atol=2e-6)          # p, uv
+    np.testing.assert_allclose(b[hit, 7:19], a[hit, 7:19], rtol=0, atol=3e-5)            # unit vectors of the two frames
+    scale = np.abs(a[hit, 19:22]).max(axis=1, keepdims=True) + 1e-6
+    np.testing.assert_allclose(b[hit, 19:22] / scale, a[hit, 19:22] / scale, rtol=0, atol=1e-4)   # dpdu (any magnitude)
+
+
+def check_light_sample_dump(O, X, n=4000, seed=5, rtol=2e-5):
+    """L1 / L2 / S1 field by field (scene.h:45-56, mesh.cpp:108-133, light.cpp:16-51) on shared random numbers."""
+    rng = np.random.default_rng(seed)
+    ref = rng.uniform(-0.9, 0.9, (n, 3)).astype(np.float32)
+    u5 = rng.uniform(0, 1, (n, 5)).astype(np.float32)
+    u5[:8, 0] = [0.0, 0.49999997, 0.5, 0.99999994, 0.25, 0.75, 0.0, 0.5]            # light-pick edges
+    u5[:4, 1] = [0.0, 0.99999994, 0.5, 0.50000006]                                  # CDF edges
+    a, b = O.light_sample_dump(ref, u5), X.light_sample_dump(ref, u5)
+    assert a[:, 0].tobytes() == b[:, 0].tobytes()                                    # same emitter picked
+    assert (a[:, 0] >= 0).all() and len(np.unique(a[:, 0])) >= 2
+    np.testing.assert_allclose(b[:, 1:11], a[:, 1:11], rtol=rtol, atol=2e-6)         # p, n, wi, dist
+    usable = a[:, 11] > 0
+    assert usable.sum() > n // 4 and ((b[:, 11] > 0) == usable).all()
+    np.testing.assert_allclose(b[usable, 11:15], a[usable, 11:15], rtol=1e-4)        # pdf, Le / pdf
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(with_texture=True, normalmap=True)])
+def test_intersection_record_cpu(kzo, emu, kw):
+    O, E = _pair(kzo, emu, scenes.cornell_scene(16, 16, 4, **kw))
+    check_intersection_dump(O, E, _probe_rays())
+    O.close(); E.close()
+
+
+def test_intersection_record_gallery_cpu(kzo, emu):
+    """meshes with uvs + normals, normals only, and neither (all three shading-frame cases of accel.cpp:190-236)"""
+    O, E = _pair(kzo, emu, scenes.gallery_scene(16, 12, 4))
+    rays = np.concatenate([scenes.primary_rays(64, 50.0, (0, 0.1, -3.2)), scenes.incoherent_rays(6000, extent=0.9)])
+    check_intersection_dump(O, E, rays)
+    O.close(); E.close()
+
+
+def test_emitter_sample_cpu(kzo, emu):
+    O, E = _pair(kzo, emu, scenes.cornell_scene(16, 16, 4))
+    check_light_sample_dump(O, E)
+    O.close(); E.close()
