@@ -1042,6 +1042,14 @@ int kzgpu_resolve(kzgpu_ctx *ctx, const float *frame_rgbw, float *rgb_linear, ui
     return KZ_OK;
 }
 
+int kzgpu_configure(kzgpu_ctx *ctx, const char *key, int value) {
+    if (!ctx || !key) return fail(ctx, KZ_ERR_INVALID, "null argument");
+    const std::string k(key);
+    if (k == "lanes") { if (value < 1 || value > KZ_MAX_LANES) return fail(ctx, KZ_ERR_INVALID, "lanes must be 1.." + std::to_string(KZ_MAX_LANES)); ctx->lanes = value; return KZ_OK; }
+    if (k == "pool_log2") { if (value < 10 || value > 26) return fail(ctx, KZ_ERR_INVALID, "pool_log2 must be 10..26"); ctx->pool_cap = 1u << value; return KZ_OK; }
+    return fail(ctx, KZ_ERR_INVALID, "unknown option \"" + k + "\"");
+}
+
 int kzgpu_stats(kzgpu_ctx *ctx, kz_stats *out) {
     if (!ctx || !out) return fail(ctx, KZ_ERR_INVALID, "null argument");
     memset(out, 0, sizeof(*out));

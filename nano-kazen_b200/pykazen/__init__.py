@@ -555,6 +555,16 @@ class Gpu(_Backend):
         self._call("image_lookup", self.h, C.c_int(image), C.c_int(level), st.ctypes.data_as(c_float_p), C.c_size_t(st.shape[0]), out.ctypes.data_as(c_float_p))
         return out
 
+    def configure(self, key, value):
+        self._call("configure", self.h, key.encode(), C.c_int(int(value)))
+
+    def render_host_ptr(self, spp_begin, spp_end, frame_ptr, clear=True, rect=None):
+        """kzgpu_render into a caller-owned (pinned) host frame given by address"""
+        H, W, b = self.frame_shape()
+        x0, y0, x1, y1 = rect if rect else (0, 0, W - 2 * b, H - 2 * b)
+        req = RenderReq(x0, y0, x1, y1, spp_begin, spp_end, int(clear))
+        self._call("render", self.h, C.byref(req), C.c_void_p(frame_ptr))
+
     def stats(self, reset=False):
         s = Stats()
         self._call("stats", self.h, C.byref(s))

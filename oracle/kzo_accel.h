@@ -31,6 +31,9 @@
 #include "../include/kzgpu.h"
 #include <vector>
 #include <cfloat>
+#include <atomic>
+#include <functional>
+#include <thread>
 
 namespace kzo {
 
@@ -140,39 +143,58 @@ inline void Accel::build() {
      * ray origin with one rounding per vertex; the boxes are inflated per ray in traceBvh by
      * an amount that covers both (see there). */
     slack = maxAbs;
-    nodes.reserve(2 * n);
-    nodes.push_back(Bvh2Node());
-    struct Job { int node; size_t b, e; };
-    std::vector<Job> stack;
-    stack.push_back(Job{0, 0, n});
+    /* median split; subtrees are independent, so the upper levels fork a thread per right half (the result -- hit bytes -- does
+     * not depend on node numbering).  Nodes come from a preallocated array through an atomic cursor. */
+    nodes.assign(2 * n + 1, Bvh2Node());
+    std::atomic<int> next{1};
     std::vector<Tri> out(n);
-    while (!stack.empty()) {
-        Job j = stack.back(); stack.pop_back();
-        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        for (size_t i = j.b; i < j.e; ++i)
-            for (int a = 0; a < 3; ++a) {
-                lo[a] = std::min(lo[a], refs[i].lo[a]); hi[a] = std::max(hi[a], refs[i].hi[a]);
-                clo[a] = std::min(clo[a], refs[i].c[a]); chi[a] = std::max(chi[a], refs[i].c[a]);
+    std::function<void(int, size_t, size_t, int)> split = [&](int node, size_t jb, size_t je, int fork_levels) {
+        struct Job { int node; size_t b, e; };
+        std::vector<Job> stack;
+        std::vector<std::thread> forked;
+        stack.push_back(Job{node, jb, je});
+        while (!stack.empty()) {
+            Job j = stack.back(); stack.pop_back();
+            float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (size_t i = j.b; i < j.e; ++i)
+                for (int a = 0; a < 3; ++a) {
+                    lo[a] = std::min(lo[a], refs[i].lo[a]); hi[a] = std::max(hi[a], refs[i].hi[a]);
+                    clo[a] = std::min(clo[a], refs[i].c[a]); chi[a] = std::max(chi[a], refs[i].c[a]);
+                }
+            Bvh2Node &nd = nodes[j.node];
+            for (int a = 0; a < 3; ++a) { nd.lo[a] = lo[a]; nd.hi[a] = hi[a]; }
+            size_t cnt = j.e - j.b;
+            int axis = 0;
+            for (int a = 1; a < 3; ++a) if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
+            if (cnt <= 4 || !(chi[axis] > clo[axis])) {
+                nd.left = (int32_t)j.b; nd.count = (int32_t)cnt;
+                continue;
             }
-        Bvh2Node &nd = nodes[j.node];
-        for (int a = 0; a < 3; ++a) { nd.lo[a] = lo[a]; nd.hi[a] = hi[a]; }
-        size_t cnt = j.e - j.b;
-        int axis = 0;
-        for (int a = 1; a < 3; ++a) if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
-        if (cnt <= 4 || !(chi[axis] > clo[axis])) {
-            nd.left = (int32_t)j.b; nd.count = (int32_t)cnt;
-            continue;
+            size_t mid = (j.b + j.e) / 2;
+            std::nth_element(refs.begin() + j.b, refs.begin() + mid, refs.begin() + j.e,
+                             [axis](const Ref &x, const Ref &y) { return x.c[axis] < y.c[axis]; });
+            int l = next.fetch_add(2);
+            nd.left = l; nd.count = 0; nd.axis = axis;
+            if (fork_levels > 0 && cnt > (1u << 16)) {
+                --fork_levels;
+                const int fl = fork_levels;
+                forked.emplace_back([&split, l, mid, j, fl]() { split(l + 1, mid, j.e, fl); });
+                stack.push_back(Job{l, j.b, mid});
+            } else {
+                stack.push_back(Job{l, j.b, mid});
+                stack.push_back(Job{l + 1, mid, j.e});
+            }
         }
-        size_t mid = (j.b + j.e) / 2;
-        std::nth_element(refs.begin() + j.b, refs.begin() + mid, refs.begin() + j.e,
-                         [axis](const Ref &x, const Ref &y) { return x.c[axis] < y.c[axis]; });
-        int l = (int)nodes.size();
-        nodes.push_back(Bvh2Node()); nodes.push_back(Bvh2Node());
-        nodes[j.node].left = l; nodes[j.node].count = 0; nodes[j.node].axis = axis;
-        stack.push_back(Job{l, j.b, mid});
-        stack.push_back(Job{l + 1, mid, j.e});
+        for (std::thread &t : forked) t.join();
+    };
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        int levels = 0;
+        while ((1u << levels) < std::max(1u, hw) && levels < 6) ++levels;
+        split(0, 0, n, levels);
     }
+    nodes.resize((size_t)next.load());
     for (size_t i = 0; i < n; ++i) out[i] = tris[refs[i].idx];
     ordered.swap(out);
 }

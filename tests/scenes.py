@@ -247,3 +247,95 @@ def rel_mse(a, b, eps=1e-2):
     """per-channel relative MSE of image a against reference b"""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return ((a - b) ** 2 / (b ** 2 + eps)).mean(axis=(0, 1))
+
+
+# ------------------------------------------------------------------------------------------------ procedural soup from a seed
+# BASELINE configs[4] (SURVEY 8d-5): a 10^8-triangle procedural soup "generated on device from a seed".  The triangles are a pure
+# function of (triangle index, seed) through a 32-bit integer hash, so the GPU (torch, int64 arithmetic masked to 32 bits) and the
+# CPU (numpy uint32) produce bit-identical float32 coordinates without 3.6 GB of positions ever crossing PCIe.
+# Same distribution as soup_triangles(): centres uniform in [-1,1]^3, three offsets uniform in [-s,s]^3, s = 2 n^(-1/3).
+_HK1, _HK2 = 0x7FEB352D, 0x846CA68B
+
+
+def _lowbias32_np(x):
+    x = x.astype(np.uint32, copy=True)
+    x ^= x >> np.uint32(16); x *= np.uint32(_HK1); x ^= x >> np.uint32(15); x *= np.uint32(_HK2); x ^= x >> np.uint32(16)
+    return x
+
+
+def hash_soup_numpy(n, seed=0x5EED, first=0, count=None, chunk=1 << 20):
+    """positions (3*count, 3) float32 of triangles [first, first+count) of the n-triangle hash soup (chunks on a thread pool: numpy
+    releases the GIL inside its loops, and 10^8 triangles are 3.6 GB of coordinates)"""
+    count = n - first if count is None else count
+    if count > chunk:
+        from concurrent.futures import ThreadPoolExecutor
+        out = np.empty((3 * count, 3), np.float32)
+
+        def work(b):
+            c = min(chunk, count - b)
+            out[3 * b: 3 * (b + c)] = hash_soup_numpy(n, seed, first + b, c, chunk)
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+            list(ex.map(work, range(0, count, chunk)))
+        return out
+    s = np.float32(2.0 * n ** (-1.0 / 3.0))
+    kc = np.uint32((seed * 2654435761 + 0x9E3779B9) & 0xFFFFFFFF); ko = np.uint32((seed * 40503 + 0x85EBCA6B) & 0xFFFFFFFF)
+    t = np.arange(first, first + count, dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        cc = (t[:, None] * np.uint32(3) + np.arange(3, dtype=np.uint32)[None, :])                    # (count, 3)
+        hc = _lowbias32_np(_lowbias32_np(cc) ^ kc)
+        oc = (t[:, None] * np.uint32(9) + np.arange(9, dtype=np.uint32)[None, :])                    # (count, 9)
+        ho = _lowbias32_np(_lowbias32_np(oc) ^ ko)
+    uc = (hc >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    uo = (ho >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    c = uc * np.float32(2) - np.float32(1)
+    off = (uo * np.float32(2) - np.float32(1)) * s
+    return (c[:, None, :] + off.reshape(count, 3, 3)).reshape(-1, 3)
+
+
+def hash_soup_torch(n, seed=0x5EED, device="cuda", chunk=1 << 24):
+    """the same triangles generated on `device`: (3n, 3) float32 positions and (n, 3) int32 indices (torch tensors)"""
+    import torch
+    s = float(np.float32(2.0 * n ** (-1.0 / 3.0)))
+    kc = (seed * 2654435761 + 0x9E3779B9) & 0xFFFFFFFF; ko = (seed * 40503 + 0x85EBCA6B) & 0xFFFFFFFF
+    M = 0xFFFFFFFF
+
+    def lb(x):
+        x = x ^ (x >> 16); x = (x * _HK1) & M; x = x ^ (x >> 15); x = (x * _HK2) & M; x = x ^ (x >> 16)
+        return x
+    P = torch.empty((3 * n, 3), dtype=torch.float32, device=device)
+    for first in range(0, n, chunk):
+        cnt = min(chunk, n - first)
+        t = torch.arange(first, first + cnt, dtype=torch.int64, device=device)
+        cc = (t[:, None] * 3 + torch.arange(3, dtype=torch.int64, device=device)[None, :]) & M
+        oc = (t[:, None] * 9 + torch.arange(9, dtype=torch.int64, device=device)[None, :]) & M
+        hc = lb(lb(cc) ^ kc); ho = lb(lb(oc) ^ ko)
+        uc = (hc >> 8).to(torch.float32) * (2.0 ** -24); uo = (ho >> 8).to(torch.float32) * (2.0 ** -24)
+        c = uc * 2.0 - 1.0
+        off = (uo * 2.0 - 1.0) * s
+        P[3 * first: 3 * (first + cnt)] = (c[:, None, :] + off.reshape(cnt, 3, 3)).reshape(-1, 3)
+    F = torch.arange(3 * n, dtype=torch.int32, device=device).reshape(-1, 3)
+    return P, F
+
+
+def big_scene(n, width=3840, height=2160, spp=1024, positions=None, indices=None, keep=None):
+    """BASELINE configs[4]: n-triangle hash soup, diffuse, constant environment light as the only emitter (NEE draws
+    are consumed but skipped, integrator.cpp:247-248), pinhole camera, stratified sampler.  positions / indices: numpy arrays or
+    raw device pointers (ints) of arrays that already live on the GPU (kz_mesh_desc accepts both); default: numpy hash soup."""
+    import ctypes as C
+    sb = pk.SceneBuilder()
+    bs = sb.bsdf_diffuse((0.5, 0.5, 0.5))
+    if positions is None:
+        positions = hash_soup_numpy(n); indices = np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)
+    if isinstance(positions, (int, np.integer)):
+        m = pk.MeshDesc()
+        m.positions = C.cast(int(positions), pk.c_float_p); m.indices = C.cast(int(indices), pk.c_u32_p)
+        m.n_vertices, m.n_triangles, m.bsdf, m.light = 3 * n, n, bs, -1
+        sb.meshes.append(m); sb._keep.append(keep)
+    else:
+        sb.mesh(positions, indices, bs)
+    sb.background = sb.tex_background(1.0, sb.tex_constant((0.8, 0.9, 1.0)))
+    sb.set_camera(width, height, 40.0, pk.lookat((0, 0, -3), (0, 0, 0), (0, 1, 0)))
+    sb.set_sampler("stratified", spp)
+    sb.set_filter("gaussian")
+    sb.set_integrator(max_depth=5)
+    return sb
