@@ -118,7 +118,12 @@ struct BSDFQueryRecord {                                                        
     BSDFQueryRecord(const Vector3f &wi) : wi(wi), eta(1.f), measure(EUnknownMeasure) {}
     BSDFQueryRecord(const Vector3f &wi, const Vector3f &wo, EMeasure measure) : wi(wi), wo(wo), eta(1.f), measure(measure) {}
 };
-template <typename T> struct Texture { T value; T eval(const Point2f &) const { return value; } };     /* constant textures */
+template <typename T> struct Texture {                                                                 /* texture.h:9-16; the base doubles as the constant texture */
+    T value;
+    virtual ~Texture() {}
+    virtual T eval(const Point2f &) const { return value; }
+    virtual T eval(const Vector3f &) const { return value; }
+};
 struct KissBodies : BSDF {               /* KazenStandardSurface, bsdf.cpp:1175-1371 (schlickWeight ... sample) and :1397-1399 (regularize) */
     Texture<Color3f> *m_baseColor = nullptr, *m_roughness = nullptr, *m_metallic = nullptr;
     float m_anisotropy, m_specular, m_specularTint, m_sheen, m_sheenTint, m_clearcoat, m_clearcoatRoughness;
@@ -132,7 +137,69 @@ struct DiffuseBodies : BSDF {            /* Diffuse, bsdf.cpp:27-79: eval / pdf 
     Color3f m_albedo;
 #include "_ref/diffuse_extract.inc"
 };
+/* the seven other BSDF plugins, eval / pdf / sample (+ their private helpers) by line range */
+struct DielectricBodies : BSDF {         /* bsdf.cpp:109-143 */
+    float m_intIOR, m_extIOR;
+#include "_ref/dielectric_extract.inc"
+};
+struct MirrorBodies : BSDF {             /* bsdf.cpp:165-191 */
+#include "_ref/mirror_extract.inc"
+};
+struct LambertianBodies : BSDF {         /* bsdf.cpp:210-257 */
+    Texture<Color3f> *m_albedo = nullptr;
+#include "_ref/lambertian_extract.inc"
+};
+struct GGXBodies : BSDF {                /* bsdf.cpp:640-670 over ggx_brdf.h */
+    Texture<Color3f> *m_albedo = nullptr; float m_roughness, m_anisotropy;
+#include "_ref/ggx_extract.inc"
+};
+struct RoughConductorBodies : BSDF {     /* bsdf.cpp:716-799: fresnelCond, evalBeckmann, smithBeckmannG1, eval, pdf, sample */
+    float m_alpha; Color3f m_eta, m_k;
+#include "_ref/roughconductor_extract.inc"
+};
+struct RoughPlasticBodies : BSDF {       /* bsdf.cpp:843-918 */
+    float m_alpha, m_intIOR, m_extIOR, m_ks; Color3f m_kd;
+#include "_ref/roughplastic_extract.inc"
+};
+struct RoughDielectricBodies : BSDF {    /* bsdf.cpp:964-1132 */
+    float m_intIOR, m_extIOR, m_eta, m_invEta, m_alpha;
+#include "_ref/roughdielectric_extract.inc"
+};
+/* texture expression nodes, texture.cpp:114-126 (background), :160-171 (colorramp), :207-231 (blend) */
+struct BackgroundTexBodies : Texture<Color3f> { float m_intensity; Texture<Color3f> *m_nested = nullptr;
+#include "_ref/tex_background.inc"
+};
+struct ColorRampTexBodies : Texture<Color3f> { float m_min = 0.0f, m_max = 1.0f; Texture<Color3f> *m_nested = nullptr;
+#include "_ref/tex_colorramp.inc"
+};
+struct BlendTexBodies : Texture<Color3f> { std::string m_blendmode = "mix"; Texture<Color3f> *m_mask = nullptr, *m_input1 = nullptr, *m_input2 = nullptr;
+#include "_ref/tex_blend.inc"
+};
 }
+/* PMJ02BN (sampler.cpp:273-390) over the reference's own table headers.  The tables themselves (bluenoise.cpp / pmj02table.cpp) are
+ * missing from the public tree, so they are DEFINED here with synthetic contents (a scrambled (0,2)-sequence and hashed blue-noise
+ * values): what is pinned is the class body -- pixel-sample bucketing, index permutation, Cranley-Patterson rotation, clamping --
+ * not pbrt's numbers.  `const` is dropped from the extern declarations so the arrays can be filled at run time. */
+#include <cassert>
+#include <memory>
+#define const
+#include <kazen/pmj02table.h>
+#include <kazen/bluenoise.h>
+#undef const
+namespace kazen {
+uint32_t pmj02bnSamples[nPMJ02bnSets][nPMJ02bnSamples][2];
+uint16_t BlueNoiseTextures[NumBlueNoiseTextures][BlueNoiseResolution][BlueNoiseResolution];
+struct PMJ02BNBodies : SamplerMembers { Point2i m_pixel; int m_pixelTileSize; std::shared_ptr<std::vector<Point2f>> m_pixelSamples;
+    void construct() {                   /* the constructor after the PropertyList reads, sampler.cpp:284-309 */
+#undef assert
+#define assert(x) ((void)0)              /* the synthetic table need not be a perfect (0,2) net for non power-of-4 counts */
+#include "_ref/pmj02bn_ctor.inc"
+    }
+#include "_ref/pmj02bn_extract.inc"
+#undef assert
+};
+}
+#include <cassert>
 #include <kazen/transform.h>
 namespace kazen {
 struct PerspectiveBodies {               /* PerspectiveCamera::sampleRay, camera.cpp:70-91; members of camera.cpp:93-103 */
