@@ -762,6 +762,52 @@ extern "C" int kzo_math_probe(const char *fn, const float *in, int n_in, float *
         a = sm.next2D(); out[k++] = a.x; out[k++] = a.y;
         for (int v = 0; v < 4; ++v) { for (int j = 0; j < 5; ++j) out[k++] = sm.next1D(); a = sm.next2D(); out[k++] = a.x; out[k++] = a.y; }
         *n_out = k;
+    } else if ((f == "extraEval" || f == "extraPdf" || f == "extraSample") && need(18)) {
+        /* in = bsdf type, albedo / kd rgb, roughness, anisotropy, intIOR, extIOR, conductor (0 Au, 1 Cu, 2 Cr), wi, wo, sample1, sample2
+         * (bsdf.cpp:98-276,629-1145: dielectric, mirror, lambertian, ggx, roughconductor, roughplastic, roughdielectric) */
+        SceneData sc;
+        kz_texture_desc t; memset(&t, 0, sizeof(t)); t.type = KZ_TEX_CONSTANT; t.child[0] = t.child[1] = t.child[2] = -1;
+        t.color[0] = in[1]; t.color[1] = in[2]; t.color[2] = in[3]; sc.textures.push_back(t);
+        kz_bsdf_desc m; memset(&m, 0, sizeof(m)); m.type = (int)in[0]; m.base_color = 0; m.roughness = m.metallic = m.normal_map = m.nested = -1;
+        m.int_ior = in[6]; m.ext_ior = in[7]; m.anisotropy = in[5];
+        m.alpha = m.type == KZ_BSDF_GGX ? in[4] : std::max(0.001f, in[4] * in[4]);          /* the constructors' max(MIN_ALPHA, sqr(roughness)) */
+        static const float E[3][3] = {{0.1431189557f, 0.3749570432f, 1.4424785571f}, {0.2004376970f, 0.9240334304f, 1.1022119527f}, {4.3696828663f, 2.9167024892f, 1.6547005413f}};
+        static const float K[3][3] = {{3.9831604247f, 2.3857207478f, 1.6032152899f}, {3.9129485033f, 2.4528477015f, 2.1421879552f}, {5.2064337956f, 4.2313645277f, 3.7549467933f}};
+        const int mat = std::min(2, std::max(0, (int)in[8]));
+        for (int c = 0; c < 3; ++c) { m.eta[c] = E[mat][c]; m.k[c] = K[mat][c]; m.albedo[c] = in[1 + c]; }
+        sc.bsdfs.push_back(m);
+        if (f == "extraSample") {
+            BSDFQueryRecord r(v3(9)); r.uv = V2{0.5f, 0.5f};
+            const V3 w = bsdfSample(sc, 0, r, in[15], v2(16));
+            const bool z = iszero(w);
+            out[0] = w.x; out[1] = w.y; out[2] = w.z; out[3] = z ? 0.f : r.wo.x; out[4] = z ? 0.f : r.wo.y; out[5] = z ? 0.f : r.wo.z;
+            out[6] = z ? 0.f : r.eta; out[7] = z ? 0.f : (float)(r.measure == EDiscrete); *n_out = 8;
+        } else {
+            BSDFQueryRecord r(v3(9), v3(12), ESolidAngle); r.uv = V2{0.5f, 0.5f};
+            if (f == "extraEval") put3(bsdfEval(sc, 0, r)); else put1(bsdfPdf(sc, 0, r));
+        }
+    } else if ((f == "texColorRamp" || f == "texBlend" || f == "texBackgroundUV" || f == "texBackgroundDir") && need(18)) {
+        /* in = three constant colours, ramp min / max, background intensity, blend mode, then five "child missing" flags (mask, input1, ramp's nested,
+         * input2, background's nested): background(blend(mask = colorramp(c0), c1, c2)), texture.cpp:104-270 */
+        SceneData sc;
+        auto constant = [&](int at) { kz_texture_desc t; memset(&t, 0, sizeof(t)); t.type = KZ_TEX_CONSTANT; t.child[0] = t.child[1] = t.child[2] = -1;
+                                      t.color[0] = in[at]; t.color[1] = in[at + 1]; t.color[2] = in[at + 2]; sc.textures.push_back(t); return (int)sc.textures.size() - 1; };
+        const int n0 = constant(0), n1 = constant(3), n2 = constant(6);
+        kz_texture_desc tr; memset(&tr, 0, sizeof(tr)); tr.type = KZ_TEX_COLORRAMP; tr.a = in[9]; tr.b = in[10]; tr.child[0] = in[15] != 0.f ? -1 : n0; tr.child[1] = tr.child[2] = -1;
+        sc.textures.push_back(tr); const int nr = (int)sc.textures.size() - 1;
+        kz_texture_desc tb; memset(&tb, 0, sizeof(tb)); tb.type = KZ_TEX_BLEND; tb.mode = (int)in[12];
+        tb.child[0] = in[13] != 0.f ? -1 : nr; tb.child[1] = in[14] != 0.f ? -1 : n1; tb.child[2] = in[16] != 0.f ? -1 : n2;
+        sc.textures.push_back(tb); const int nb = (int)sc.textures.size() - 1;
+        kz_texture_desc tg; memset(&tg, 0, sizeof(tg)); tg.type = KZ_TEX_BACKGROUND; tg.a = in[11]; tg.child[0] = in[17] != 0.f ? -1 : nb; tg.child[1] = tg.child[2] = -1;
+        sc.textures.push_back(tg); const int ng = (int)sc.textures.size() - 1;
+        const V2 uv{0.25f, 0.75f};                                    /* constant leaves: the lookup position does not matter */
+        if (f == "texColorRamp") put3(evalTextureUV(sc, nr, uv));
+        else if (f == "texBlend") put3(evalTextureUV(sc, nb, uv));
+        else if (f == "texBackgroundUV") put3(evalTextureUV(sc, ng, uv));
+        else { kz_texture_desc td = tg; td.child[0] = n2; sc.textures.push_back(td); put3(evalTextureDir(sc, (int)sc.textures.size() - 1, V3(0.f, 0.f, 1.f))); }
+    } else if (f == "pmj02bnTileSize" && need(1)) {                   /* sampler.cpp:291: tile = 1 << (log4(65536) - log4(roundUpPow4(spp))) */
+        const int spp = (int)in[0];
+        put1((float)(1 << (log2i_int(65536) / 2 - log2i_int(roundUpPow4(spp)) / 2)));
     } else if (f == "toSRGB" && need(3)) put3(toSRGB(v3(0)));
     else if (f == "toLinearRGB" && need(3)) put3(toLinearRGB(v3(0)));
     else if (f == "luminance" && need(3)) put1(luminance(v3(0)));

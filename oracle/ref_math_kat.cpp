@@ -153,11 +153,11 @@ struct GGXBodies : BSDF {                /* bsdf.cpp:640-670 over ggx_brdf.h */
     Texture<Color3f> *m_albedo = nullptr; float m_roughness, m_anisotropy;
 #include "_ref/ggx_extract.inc"
 };
-struct RoughConductorBodies : BSDF {     /* bsdf.cpp:716-799: fresnelCond, evalBeckmann, smithBeckmannG1, eval, pdf, sample */
+struct RoughConductorBodies : BSDF {     /* bsdf.cpp:716-794: fresnelCond, evalBeckmann, smithBeckmannG1, eval, pdf, sample */
     float m_alpha; Color3f m_eta, m_k;
 #include "_ref/roughconductor_extract.inc"
 };
-struct RoughPlasticBodies : BSDF {       /* bsdf.cpp:843-918 */
+struct RoughPlasticBodies : BSDF {       /* bsdf.cpp:843-920 */
     float m_alpha, m_intIOR, m_extIOR, m_ks; Color3f m_kd;
 #include "_ref/roughplastic_extract.inc"
 };
@@ -705,6 +705,136 @@ int main() {
         for (int v = 0; v < 4; ++v) { for (int k = 0; k < 5; ++k) draw(0); draw(1); }
         const char *names[3] = {"samplerIndependent", "samplerStratified", "samplerCorrelated"};
         rec(names[type], {(float)px, (float)py, (float)sidx, (float)requested, (float)(seed & 0xFFFFFF), (float)(seed >> 24)}, ref, ours, t < 60);
+    }
+    /* ---- dielectric / mirror / lambertian / ggx / roughconductor / roughplastic / roughdielectric, eval / pdf / sample ---- */
+    for (int i = 0; i < 6000; ++i) {
+        const bool keep = i < 42;
+        const int type = KZ_BSDF_DIELECTRIC + i % 7;
+        const kzo::V3 base(rnd(), rnd(), rnd());
+        const float rough = i % 11 == 0 ? 0.02f : rnd(0.03f, 0.95f), intIOR = i % 5 == 0 ? 1.5046f : rnd(1.05f, 2.4f), extIOR = i % 5 == 0 ? 1.000277f : rnd(1.f, 1.3f);
+        const float aniso = i % 3 == 0 ? 0.f : rnd(-0.8f, 0.8f);
+        const bool twoSided = type == KZ_BSDF_DIELECTRIC || type == KZ_BSDF_ROUGHDIELECTRIC;
+        const kzo::V3 wi = rdir(twoSided ? (i % 2 == 0) && false : (i % 13 != 0)), wo = rdir(twoSided ? false : (i % 17 != 0));
+        const float s1 = rnd(); const kzo::V2 s2{rnd(), rnd()};
+        kzo::SceneData sc;
+        kz_texture_desc t; memset(&t, 0, sizeof(t)); t.type = KZ_TEX_CONSTANT; t.child[0] = t.child[1] = t.child[2] = -1;
+        t.color[0] = base.x; t.color[1] = base.y; t.color[2] = base.z; sc.textures.push_back(t);
+        kz_bsdf_desc m; memset(&m, 0, sizeof(m)); m.type = type; m.base_color = 0; m.roughness = m.metallic = m.normal_map = m.nested = -1;
+        m.int_ior = intIOR; m.ext_ior = extIOR; m.anisotropy = aniso;
+        kazen::Texture<kazen::Color3f> tb; tb.value = KC(base);
+        kazen::DielectricBodies kd; kazen::MirrorBodies km; kazen::LambertianBodies kl; kazen::GGXBodies kg; kazen::RoughConductorBodies kc; kazen::RoughPlasticBodies kp; kazen::RoughDielectricBodies kr;
+        kazen::BSDF *ref = nullptr;
+        const float alpha = std::max(0.001f, rough * rough);                      /* the constructors' max(MIN_ALPHA, sqr(roughness)), bsdf.cpp:698-700,820-822,958-959 */
+        switch (type) {
+            case KZ_BSDF_DIELECTRIC: kd.m_intIOR = intIOR; kd.m_extIOR = extIOR; ref = &kd; break;
+            case KZ_BSDF_MIRROR: ref = &km; break;
+            case KZ_BSDF_LAMBERTIAN: kl.m_albedo = &tb; ref = &kl; break;
+            case KZ_BSDF_GGX: kg.m_albedo = &tb; kg.m_roughness = rough; kg.m_anisotropy = aniso; m.alpha = rough; ref = &kg; break;
+            case KZ_BSDF_ROUGHCONDUCTOR: {
+                const float e[3][3] = {{0.1431189557f, 0.3749570432f, 1.4424785571f}, {0.2004376970f, 0.9240334304f, 1.1022119527f}, {4.3696828663f, 2.9167024892f, 1.6547005413f}};
+                const float k[3][3] = {{3.9831604247f, 2.3857207478f, 1.6032152899f}, {3.9129485033f, 2.4528477015f, 2.1421879552f}, {5.2064337956f, 4.2313645277f, 3.7549467933f}};
+                const int mat = (i / 7) % 3;                                      /* Au, Cu, Cr: bsdf.cpp:703-714 */
+                kc.m_alpha = alpha; kc.m_eta = kazen::Color3f(e[mat][0], e[mat][1], e[mat][2]); kc.m_k = kazen::Color3f(k[mat][0], k[mat][1], k[mat][2]);
+                m.alpha = alpha; for (int c = 0; c < 3; ++c) { m.eta[c] = e[mat][c]; m.k[c] = k[mat][c]; }
+                ref = &kc; break; }
+            case KZ_BSDF_ROUGHPLASTIC:
+                kp.m_alpha = alpha; kp.m_intIOR = intIOR; kp.m_extIOR = extIOR; kp.m_kd = KC(base); kp.m_ks = 1 - kp.m_kd.maxCoeff();      /* bsdf.cpp:840 */
+                m.alpha = alpha; m.albedo[0] = base.x; m.albedo[1] = base.y; m.albedo[2] = base.z; ref = &kp; break;
+            default:
+                kr.m_intIOR = intIOR; kr.m_extIOR = extIOR; kr.m_alpha = alpha; kr.m_eta = intIOR / extIOR; kr.m_invEta = extIOR / intIOR;    /* bsdf.cpp:961-962 */
+                m.alpha = alpha; ref = &kr; break;
+        }
+        sc.bsdfs.push_back(m);
+        std::vector<float> in = {(float)type, base.x, base.y, base.z, rough, aniso, intIOR, extIOR, (float)((i / 7) % 3), wi.x, wi.y, wi.z, wo.x, wo.y, wo.z, s1, s2.x, s2.y};
+        kazen::BSDFQueryRecord ke(K(wi), K(wo), kazen::ESolidAngle); ke.uv = kazen::Point2f(0.5f, 0.5f);
+        kzo::BSDFQueryRecord oe(wi, wo, kzo::ESolidAngle); oe.uv = kzo::V2{0.5f, 0.5f};
+        rec("extraEval", in, f3(ref->eval(ke)), f3(kzo::bsdfEval(sc, 0, oe)), keep);
+        rec("extraPdf", in, {ref->pdf(ke)}, {kzo::bsdfPdf(sc, 0, oe)}, keep);
+        kazen::BSDFQueryRecord ks(K(wi)); ks.uv = kazen::Point2f(0.5f, 0.5f);
+        kzo::BSDFQueryRecord os(wi); os.uv = kzo::V2{0.5f, 0.5f};
+        const kazen::Color3f kw = ref->sample(ks, s1, kazen::Point2f(s2.x, s2.y)); const kzo::V3 ow = kzo::bsdfSample(sc, 0, os, s1, s2);
+        const bool z0 = kw.x() == 0.f && kw.y() == 0.f && kw.z() == 0.f;          /* wo / eta / measure only matter for a non-zero weight */
+        rec("extraSample", in, {kw.x(), kw.y(), kw.z(), z0 ? 0.f : ks.wo.x(), z0 ? 0.f : ks.wo.y(), z0 ? 0.f : ks.wo.z(), z0 ? 0.f : ks.eta, z0 ? 0.f : (float)(ks.measure == kazen::EDiscrete)},
+            {ow.x, ow.y, ow.z, z0 ? 0.f : os.wo.x, z0 ? 0.f : os.wo.y, z0 ? 0.f : os.wo.z, z0 ? 0.f : os.eta, z0 ? 0.f : (float)(os.measure == kzo::EDiscrete)}, keep);
+    }
+    /* ---- texture expression nodes (texture.cpp:104-270) over constant leaves: background (uv and direction), colorramp, blend mix / multiply / other,
+     *      missing children, nesting two deep ---- */
+    for (int i = 0; i < 3000; ++i) {
+        const bool keep = i < 30;
+        kzo::SceneData sc;
+        auto constant = [&](kzo::V3 c) { kz_texture_desc t; memset(&t, 0, sizeof(t)); t.type = KZ_TEX_CONSTANT; t.child[0] = t.child[1] = t.child[2] = -1;
+                                         t.color[0] = c.x; t.color[1] = c.y; t.color[2] = c.z; sc.textures.push_back(t); return (int)sc.textures.size() - 1; };
+        const kzo::V3 c0(rnd(-0.3f, 1.4f), rnd(-0.3f, 1.4f), rnd(-0.3f, 1.4f)), c1(rnd(), rnd(), rnd()), c2(rnd(0.f, 2.f), rnd(0.f, 2.f), rnd(0.f, 2.f));
+        kazen::Texture<kazen::Color3f> k0, k1, k2; k0.value = KC(c0); k1.value = KC(c1); k2.value = KC(c2);
+        const int n0 = constant(c0), n1 = constant(c1), n2 = constant(c2);
+        const float lo = rnd(-0.5f, 0.5f), hi = rnd(0.2f, 1.5f), intensity = rnd(0.f, 5.f);
+        /* colorramp over c0 */
+        kazen::ColorRampTexBodies kr; kr.m_min = lo; kr.m_max = hi; kr.m_nested = i % 9 == 0 ? nullptr : &k0;
+        kz_texture_desc tr; memset(&tr, 0, sizeof(tr)); tr.type = KZ_TEX_COLORRAMP; tr.a = lo; tr.b = hi; tr.child[0] = i % 9 == 0 ? -1 : n0; tr.child[1] = tr.child[2] = -1;
+        sc.textures.push_back(tr); const int nr = (int)sc.textures.size() - 1;
+        /* blend(mask = ramp, input1 = c1, input2 = c2) */
+        const int mode = i % 4 == 3 ? KZ_BLEND_OTHER : (i % 2 ? KZ_BLEND_MULTIPLY : KZ_BLEND_MIX);
+        kazen::BlendTexBodies kb; kb.m_blendmode = mode == KZ_BLEND_MIX ? "mix" : (mode == KZ_BLEND_MULTIPLY ? "multiply" : "screen");
+        kb.m_mask = i % 5 == 0 ? nullptr : &kr; kb.m_input1 = i % 7 == 0 ? nullptr : &k1; kb.m_input2 = i % 11 == 0 ? nullptr : &k2;
+        kz_texture_desc tb; memset(&tb, 0, sizeof(tb)); tb.type = KZ_TEX_BLEND; tb.mode = mode;
+        tb.child[0] = i % 5 == 0 ? -1 : nr; tb.child[1] = i % 7 == 0 ? -1 : n1; tb.child[2] = i % 11 == 0 ? -1 : n2;
+        sc.textures.push_back(tb); const int nb = (int)sc.textures.size() - 1;
+        /* background(intensity) over the blend */
+        kazen::BackgroundTexBodies kg; kg.m_intensity = intensity; kg.m_nested = i % 13 == 0 ? nullptr : &kb;
+        kz_texture_desc tg; memset(&tg, 0, sizeof(tg)); tg.type = KZ_TEX_BACKGROUND; tg.a = intensity; tg.child[0] = i % 13 == 0 ? -1 : nb; tg.child[1] = tg.child[2] = -1;
+        sc.textures.push_back(tg); const int ng = (int)sc.textures.size() - 1;
+        const kzo::V2 uv{rnd(), rnd()}; const kzo::V3 dir = rdir(false);
+        std::vector<float> in = {c0.x, c0.y, c0.z, c1.x, c1.y, c1.z, c2.x, c2.y, c2.z, lo, hi, intensity, (float)mode, (float)(i % 5 == 0), (float)(i % 7 == 0), (float)(i % 9 == 0), (float)(i % 11 == 0), (float)(i % 13 == 0)};
+        rec("texColorRamp", in, f3(kr.eval(kazen::Point2f(uv.x, uv.y))), f3(kzo::evalTextureUV(sc, nr, uv)), keep);
+        rec("texBlend", in, f3(kb.eval(kazen::Point2f(uv.x, uv.y))), f3(kzo::evalTextureUV(sc, nb, uv)), keep);
+        rec("texBackgroundUV", in, f3(kg.eval(kazen::Point2f(uv.x, uv.y))), f3(kzo::evalTextureUV(sc, ng, uv)), keep);
+        /* eval(dir): only the background node and constants forward a direction (texture.cpp:121-126, texture.h:12); a constant nested directly */
+        kazen::BackgroundTexBodies kd; kd.m_intensity = intensity; kd.m_nested = &k2;
+        kz_texture_desc td = tg; td.child[0] = n2; sc.textures.push_back(td);
+        rec("texBackgroundDir", in, f3(kd.eval(K(dir))), f3(kzo::evalTextureDir(sc, (int)sc.textures.size() - 1, dir)), keep);
+    }
+    /* ---- PMJ02BN (sampler.cpp:273-390): constructor bucketing + generateSample / nextPixel2D / next1D / next2D over synthetic tables ---- */
+    {
+        /* set 0: the 2-D Sobol' (0,2)-sequence (van der Corput x Sobol' dimension 2); sets 1..4: digit-scrambled copies; blue noise: hashed */
+        for (uint32_t i = 0; i < 65536; ++i) {
+            uint32_t x = i; x = (x << 16) | (x >> 16); x = ((x & 0x00ff00ffu) << 8) | ((x & 0xff00ff00u) >> 8); x = ((x & 0x0f0f0f0fu) << 4) | ((x & 0xf0f0f0f0u) >> 4);
+            x = ((x & 0x33333333u) << 2) | ((x & 0xccccccccu) >> 2); x = ((x & 0x55555555u) << 1) | ((x & 0xaaaaaaaau) >> 1);
+            uint32_t y = 0; for (uint32_t v = 1u << 31, k = i; k; k >>= 1, v ^= v >> 1) if (k & 1u) y ^= v;
+            for (int set = 0; set < 5; ++set) { kazen::pmj02bnSamples[set][i][0] = x ^ (set * 0x9E3779B9u); kazen::pmj02bnSamples[set][i][1] = y ^ (set * 0x85EBCA6Bu); }
+        }
+        uint32_t h = 12345u;
+        for (int a = 0; a < 48; ++a) for (int b = 0; b < 128; ++b) for (int c = 0; c < 128; ++c) { h = h * 1664525u + 1013904223u; kazen::BlueNoiseTextures[a][b][c] = (uint16_t)(h >> 16); }
+        const uint32_t counts[] = {1, 4, 16, 64, 256, 1024, 9, 24, 100};
+        for (int t = 0; t < 1800; ++t) {
+            const uint32_t count = counts[t % 9];
+            const uint64_t seed = t % 5 == 0 ? 1ull : (uint64_t)(rnd() * 4e9f) + 1ull;
+            kazen::PMJ02BNBodies kp; kp.m_seed = seed; kp.m_sampleCount = count; kp.construct();
+            kzo::SamplerCfg cfg; memset(&cfg.d, 0, sizeof(cfg.d));
+            cfg.d.type = KZ_SAMPLER_PMJ02BN; cfg.d.seed = seed; cfg.d.sample_count = count;
+            cfg.d.blue_noise = &kazen::BlueNoiseTextures[0][0][0]; cfg.d.pmj02bn = &kazen::pmj02bnSamples[0][0][0];
+            kzo::buildPmjPixelSamples(cfg);
+            if (t < 9) {     /* the whole per-pixel table the constructor builds */
+                std::vector<float> a, b;
+                for (const kazen::Point2f &p : *kp.m_pixelSamples) { a.push_back(p.x()); a.push_back(p.y()); }
+                for (const kzo::V2 &p : cfg.pmjPix.samples) { b.push_back(p.x); b.push_back(p.y); }
+                rec("pmj02bnPixelTable", {(float)count, (float)kp.m_pixelTileSize}, a, b, false);
+                rec("pmj02bnTileSize", {(float)count}, {(float)kp.m_pixelTileSize}, {(float)cfg.pmjPix.tileSize}, true);
+            }
+            for (int q = 0; q < 4; ++q) {
+                const int px = (int)(rnd() * 4096), py = (int)(rnd() * 2160), sidx = (int)(rnd() * count) % (int)count;
+                kp.generateSample(kazen::Point2i(px, py), sidx);
+                kzo::Sampler os; os.cfg = &cfg; os.generateSample(px, py, sidx);
+                std::vector<float> ref, ours;
+                auto draw = [&](int kind) {
+                    if (kind == 0) { ref.push_back(kp.next1D()); ours.push_back(os.next1D()); return; }
+                    const kazen::Point2f r = kind == 2 ? kp.nextPixel2D() : kp.next2D(); const kzo::V2 o = kind == 2 ? os.nextPixel2D() : os.next2D();
+                    ref.push_back(r.x()); ref.push_back(r.y()); ours.push_back(o.x); ours.push_back(o.y);
+                };
+                draw(2); draw(1);
+                for (int v = 0; v < 5; ++v) { for (int k = 0; k < 5; ++k) draw(0); draw(1); }      /* 5 vertices: 2-D dimensions beyond the 5 table sets are permuted */
+                rec("samplerPMJ02BN", {(float)px, (float)py, (float)sidx, (float)count, (float)(seed & 0xFFFFFF), (float)(seed >> 24)}, ref, ours, false);
+            }
+        }
     }
     /* DiscretePDF (dpdf.h:35-104): append / normalize / sample against the oracle's CDF sampling (kzo_shading.h cdfSample) */
     for (int t = 0; t < 200; ++t) {

@@ -181,12 +181,12 @@ def test_render_converges_to_itself(kzo):
 def test_math_helpers_match_the_reference_bodies(kzo):
     """tests/golden/math_kat.json holds inputs and outputs of the reference's OWN function bodies (ggx_brdf.h, frame.h, dpdf.h,
     common.cpp colour helpers / fresnel / refract / reflect / coordinateSystem, warp.cpp, the eval / pdf / sample methods of
-    KazenStandardSurface and Diffuse from bsdf.cpp, and the generateSample / next1D / next2D / nextPixel2D methods of the Independent,
+    KazenStandardSurface, Diffuse and the seven other BSDF plugins from bsdf.cpp, the background / colorramp / blend nodes of texture.cpp, and the generateSample / next1D / next2D / nextPixel2D methods of the Independent,
     Stratified and Correlated samplers from sampler.cpp) run by oracle/ref_math_kat.cpp: the oracle's restatements must reproduce every
     output bit for bit."""
     import json
     g = json.load(open(os.path.join(HERE, "golden", "math_kat.json")))
-    assert g["mismatches"] == 0 and g["cases_checked"] >= 210000 and len(g["kat"]) >= 1200
+    assert g["mismatches"] == 0 and g["cases_checked"] >= 248000 and len(g["kat"]) >= 1450
     seen = set()
     for case in g["kat"]:
         inp = np.array(case["in"], np.uint32).view(np.float32)
@@ -201,13 +201,14 @@ def test_math_helpers_match_the_reference_bodies(kzo):
         got = kzo.math_probe(case["fn"], inp).view(np.uint32)
         assert np.array_equal(got, want), (case["fn"], inp.tolist())
         seen.add(case["fn"])
-    assert len(seen) == 37 and {"kissEval", "kissPdf", "kissSample", "sampleVNDF", "dpdfSample", "samplerStratified", "samplerCorrelated"} <= seen
+    assert len(seen) == 45 and {"kissEval", "kissPdf", "kissSample", "sampleVNDF", "dpdfSample", "samplerStratified", "samplerCorrelated",
+                                "extraEval", "extraPdf", "extraSample", "texColorRamp", "texBlend", "texBackgroundUV", "texBackgroundDir", "pmj02bnTileSize"} <= seen
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/include/kazen"), reason="the reference is only mounted in the build container")
 def test_reference_math_bodies_run_here_agree(kzo):
     """Where the reference is mounted: build oracle/_ref/ref_math_kat from the reference's sources in place and require 0 mismatches
-    over all 188 000 cases (incl. post-intersection, Mesh::sample and AreaLight on random meshes, and 36 000 whole paths through the reference's own PathMisIntegrator::Li body on random scenes) (the golden file keeps about 1 200 of them)."""
+    over all 248 000 cases (incl. the seven other BSDF plugins, the texture expression nodes, the PMJ02BN sampler body over synthetic tables, post-intersection, Mesh::sample and AreaLight on random meshes, and 36 000 whole paths through the reference's own PathMisIntegrator::Li body on random scenes) (the golden file keeps about 1 200 of them)."""
     import subprocess
     root = os.path.dirname(HERE)
     subprocess.check_call(["make", "-s", "-C", os.path.join(root, "oracle"), "_ref/ref_math_kat"])
