@@ -116,6 +116,19 @@ void free_all(std::vector<void *> &v) {
     for (void *p : v) cudaFree(p);
     v.clear();
 }
+/* Short-lived buffers (ingest staging, the builders' triangle list) come from the device's stream-ordered memory pool: a plain
+ * cudaMalloc maps every new block into all peers once peer access is enabled (multi-device contexts, NCCL in the same process). */
+template <typename T> int temp_alloc(kzgpu_ctx *ctx, std::vector<void *> &owner, size_t count, cudaStream_t s, T **out) {
+    void *p = nullptr;
+    KZ_CUDA(ctx, cudaMallocAsync(&p, std::max<size_t>(16, count * sizeof(T)), s));
+    owner.push_back(p);
+    *out = reinterpret_cast<T *>(p);
+    return KZ_OK;
+}
+void temp_free_all(std::vector<void *> &v, cudaStream_t s) {
+    for (void *p : v) cudaFreeAsync(p, s);
+    v.clear();
+}
 
 int ensure_scratch(kzgpu_ctx *ctx, Device &d, int k, size_t bytes) {
     if (d.scratch_bytes[k] >= bytes) return KZ_OK;
@@ -222,8 +235,8 @@ int ingest_geometry(kzgpu_ctx *ctx, Device &d, const kz_scene_desc *scene) {
     std::vector<void *> temp;
     char *stage = nullptr; uint32_t *bad = nullptr;
     int rc;
-    if ((rc = dev_alloc(ctx, temp, stage_bytes, &stage))) { free_all(temp); return rc; }
-    if ((rc = dev_alloc(ctx, temp, 4, &bad))) { free_all(temp); return rc; }
+    if ((rc = temp_alloc(ctx, temp, stage_bytes, d.stream, &stage))) { temp_free_all(temp, d.stream); return rc; }
+    if ((rc = temp_alloc(ctx, temp, 4, d.stream, &bad))) { temp_free_all(temp, d.stream); return rc; }
     cudaError_t e = cudaMemsetAsync(bad, 0, 4, d.stream);
     auto fetch = [&](const void *src, size_t bytes, size_t &cursor) -> const void * {      /* device-visible view of a caller array */
         if (!src || e != cudaSuccess) return nullptr;
@@ -261,7 +274,7 @@ int ingest_geometry(kzgpu_ctx *ctx, Device &d, const kz_scene_desc *scene) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
     if (e == cudaSuccess) e = cudaGetLastError();
-    free_all(temp);
+    temp_free_all(temp, d.stream);
     if (e != cudaSuccess) return fail(ctx, KZ_ERR_CUDA, std::string("scene ingest: ") + cudaGetErrorString(e));
     if (h_bad) return fail(ctx, KZ_ERR_INVALID, "vertex index out of range");
     return KZ_OK;
@@ -605,7 +618,7 @@ int kzgpu_accel_build(kzgpu_ctx *ctx, int builder) {
     const uint32_t n_tris = (uint32_t)ctx->hs->total_triangles;
     std::vector<void *> temp;
     kzbvh::Tri *d_tris = nullptr;
-    if ((rc = dev_alloc(ctx, temp, (size_t)n_tris, &d_tris))) { free_all(temp); return rc; }
+    if ((rc = temp_alloc(ctx, temp, (size_t)n_tris, d0.stream, &d_tris))) { temp_free_all(temp, d0.stream); return rc; }
     if (n_tris) {
         k_gather_tris<<<grid_for(n_tris, 256, d0.sm_count), 256, 0, d0.stream>>>(d0.sc.meshes, d0.sc.n_meshes, d0.sc.vertices, d0.sc.indices, n_tris, d_tris);
         ++d0.launches;
@@ -615,7 +628,7 @@ int kzgpu_accel_build(kzgpu_ctx *ctx, int builder) {
         cudaError_t e = cudaSuccess;
         if (n_tris) e = cudaMemcpyAsync(tris.data(), d_tris, (size_t)n_tris * sizeof(kzbvh::Tri), cudaMemcpyDeviceToHost, d0.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(d0.stream);
-        free_all(temp);
+        temp_free_all(temp, d0.stream);
         KZ_CUDA(ctx, e);
         kzbvh::Built built;
         kzbvh::buildHostSah(tris, 0, built);
@@ -631,7 +644,9 @@ int kzgpu_accel_build(kzgpu_ctx *ctx, int builder) {
         kzlbvh::Result r;
         std::string err;
         rc = kzlbvh::build(d_tris, n_tris, d0.stream, d0.accel_allocs, r, err);
-        free_all(temp);
+        temp_free_all(temp, d0.stream);
+        /* hand the pool's memory back: the path pools and the caller's own allocations need it, the next build allocates afresh */
+        { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, d0.id) == cudaSuccess) { cudaStreamSynchronize(d0.stream); cudaMemPoolTrimTo(pool, 0); } }
         if (rc) return fail(ctx, rc, err);
         if (2 * r.depth + 2 > KZ_SHORT_STACK + KZ_LOCAL_STACK) return fail(ctx, KZ_ERR_UNSUPPORTED, "accel deeper than the traversal stack allows");
         d0.sc.nodes = r.nodes; d0.sc.tris = r.tris; d0.sc.n_nodes = r.n_nodes; d0.sc.n_tris = r.n_tris; d0.sc.scene_max_abs = r.max_abs;

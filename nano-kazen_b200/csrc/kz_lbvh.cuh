@@ -401,7 +401,8 @@ __global__ void k_make_refs(const kzbvh::Tri *tris, uint32_t n, const uint32_t *
         cudaError_t e__ = (call);                                                                        \
         if (e__ != cudaSuccess) {                                                                        \
             err = std::string(#call) + ": " + cudaGetErrorString(e__);                                   \
-            for (void *p__ : temp) cudaFree(p__);                                                        \
+            for (void *p__ : temp) cudaFreeAsync(p__, s);                                                \
+            cudaStreamSynchronize(s);                                                                    \
             return e__ == cudaErrorMemoryAllocation ? KZ_ERR_NOMEM : KZ_ERR_CUDA;                        \
         }                                                                                                \
     } while (0)
@@ -415,7 +416,9 @@ inline int build(const kzbvh::Tri *d_tris, uint32_t n_tris_in, cudaStream_t s, s
     uint32_t n = n_tris_in;                  /* references: == triangles unless pre-splitting adds some */
     r = Result();
     if (n == 0) return KZ_OK;
-    auto talloc = [&](size_t bytes, void **p) { cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16)); if (e == cudaSuccess) temp.push_back(*p); return e; };
+    /* temporaries come from the device's stream-ordered pool: with peer access enabled (multi-device contexts, NCCL) every plain
+     * cudaMalloc maps the new block into all peers, which made this build 12x slower on two GPUs than on one */
+    auto talloc = [&](size_t bytes, void **p) { cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 16), s); if (e == cudaSuccess) temp.push_back(*p); return e; };
     unsigned long long *k0, *k1; uint32_t *v0, *v1, *bounds;
     KZL_CUDA(talloc(64, (void **)&bounds));
     const uint32_t init[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
@@ -513,7 +516,8 @@ inline int build(const kzbvh::Tri *d_tris, uint32_t n_tris_in, cudaStream_t s, s
     r.nodes = d_nodes; r.tris = d_out_tris; r.n_nodes = fin[0]; r.n_tris = fin[1];
     r.max_abs = ord2f(hb[6]);
     for (int l = 0; l < KZ_LBVH_MAX_LEVELS && fin[2 + l] != 0u; ++l) r.depth = l + 1;
-    for (void *p : temp) cudaFree(p);
+    for (void *p : temp) cudaFreeAsync(p, s);
+    cudaStreamSynchronize(s);
     if (fin[2 + KZ_LBVH_MAX_LEVELS] != 0u) { err = "lbvh: accel deeper than the traversal stack allows"; return KZ_ERR_UNSUPPORTED; }
     if (r.n_tris != n) { err = "lbvh: triangle count mismatch after collapse"; return KZ_ERR_CUDA; }
     return KZ_OK;

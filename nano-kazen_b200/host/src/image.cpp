@@ -75,13 +75,17 @@ void writePNG(const std::string &path, int w, int h, const uint8_t *rgb8) {
     f.write((const char *)out.data(), (std::streamsize)out.size());
 }
 
+/* header fields come from untrusted files: positive, at most 65536 per side (kzgpu's texture atlas limit), so that the
+ * w * h * channels products below cannot overflow */
+static bool saneSize(long long w, long long h) { return w > 0 && h > 0 && w <= 65536 && h <= 65536; }
+
 static bool readPFM(const std::string &path, int &w, int &h, std::vector<float> &rgb, std::string &err) {
     std::ifstream f(path, std::ios::binary);
     std::string magic; float scale;
     f >> magic >> w >> h >> scale;
     f.get();
     const int ch = magic == "PF" ? 3 : (magic == "Pf" ? 1 : 0);
-    if (!f || !ch || w <= 0 || h <= 0) { err = "bad PFM header"; return false; }
+    if (!f || !ch || !saneSize(w, h)) { err = "bad PFM header"; return false; }
     std::vector<float> buf((size_t)w * h * ch);
     if (!f.read((char *)buf.data(), (std::streamsize)(buf.size() * 4))) { err = "truncated PFM"; return false; }
     if (scale > 0) { for (float &v : buf) { uint32_t u; memcpy(&u, &v, 4); u = __builtin_bswap32(u); memcpy(&v, &u, 4); } }
@@ -99,16 +103,23 @@ static bool readPNG(const std::string &path, int &w, int &h, std::vector<float> 
     if (d.size() < 33 || memcmp(d.data(), sig, 8) != 0) { err = "not a PNG file"; return false; }
     auto rd32 = [&](size_t o) { return ((uint32_t)d[o] << 24) | ((uint32_t)d[o + 1] << 16) | ((uint32_t)d[o + 2] << 8) | d[o + 3]; };
     int depth = 0, ctype = 0, interlace = 0;
+    bool have_ihdr = false;
     std::vector<uint8_t> idat, plte;
     for (size_t p = 8; p + 12 <= d.size();) {
         const uint32_t len = rd32(p); const std::string type((const char *)&d[p + 4], 4);
         if (p + 12 + len > d.size()) { err = "truncated PNG"; return false; }
-        if (type == "IHDR") { w = (int)rd32(p + 8); h = (int)rd32(p + 12); depth = d[p + 16]; ctype = d[p + 17]; interlace = d[p + 20]; }
+        if (type == "IHDR") {
+            if (len < 13) { err = "bad PNG IHDR"; return false; }
+            const uint32_t uw = rd32(p + 8), uh = rd32(p + 12);
+            if (!saneSize(uw, uh)) { err = "PNG dimensions out of range"; return false; }
+            w = (int)uw; h = (int)uh; depth = d[p + 16]; ctype = d[p + 17]; interlace = d[p + 20]; have_ihdr = true;
+        }
         else if (type == "PLTE") plte.assign(d.begin() + p + 8, d.begin() + p + 8 + len);
         else if (type == "IDAT") idat.insert(idat.end(), d.begin() + p + 8, d.begin() + p + 8 + len);
         else if (type == "IEND") break;
         p += 12 + len;
     }
+    if (!have_ihdr) { err = "PNG without IHDR"; return false; }
     if (interlace) { err = "interlaced PNG is not supported"; return false; }
     if (depth != 8 && depth != 16) { err = "only 8/16-bit PNG is supported"; return false; }
     const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
@@ -151,7 +162,7 @@ static bool readHDR(const std::string &path, int &w, int &h, std::vector<float> 
     bool fmt_ok = false;
     while (std::getline(f, line) && !line.empty() && line != "\r") if (line.find("32-bit_rle_rgbe") != std::string::npos) fmt_ok = true;
     if (!std::getline(f, line)) { err = "truncated HDR header"; return false; }
-    if (!fmt_ok || sscanf(line.c_str(), "-Y %d +X %d", &h, &w) != 2 || w <= 0 || h <= 0) { err = "unsupported HDR variant (need 32-bit_rle_rgbe, -Y H +X W)"; return false; }
+    if (!fmt_ok || sscanf(line.c_str(), "-Y %d +X %d", &h, &w) != 2 || !saneSize(w, h)) { err = "unsupported HDR variant (need 32-bit_rle_rgbe, -Y H +X W)"; return false; }
     std::vector<uint8_t> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     size_t p = 0;
     std::vector<uint8_t> scan((size_t)w * 4);
@@ -209,18 +220,23 @@ static bool readEXR(const std::string &path, int &w, int &h, std::vector<float> 
         const int size = i32(p); p += 4;
         if (size < 0 || p + (size_t)size > d.size()) { err = "truncated EXR header"; return false; }
         if (name == "channels") {
-            size_t q = p;
-            while (q < p + size && d[q]) {
-                Chan c; while (d[q]) c.name += (char)d[q++]; ++q;
+            /* name\0, pixel type (4), pLinear + reserved (4), x / y sampling (8) per channel, a lone \0 ends the list; every read stays
+             * inside the attribute, which lies inside the file (checked above) */
+            size_t q = p; const size_t end = p + (size_t)size;
+            while (q < end && d[q]) {
+                Chan c; while (q < end && d[q]) c.name += (char)d[q++];
+                if (q >= end || q + 1 + 16 > end) { err = "bad EXR channel list"; return false; }
+                ++q;
                 c.type = i32(q); q += 16;
                 chans.push_back(c);
             }
-        } else if (name == "compression") comp = d[p];
-        else if (name == "dataWindow") { xmin = i32(p); ymin = i32(p + 4); xmax = i32(p + 8); ymax = i32(p + 12); }
+        } else if (name == "compression") { if (size < 1) { err = "bad EXR compression attribute"; return false; } comp = d[p]; }
+        else if (name == "dataWindow") { if (size < 16) { err = "bad EXR dataWindow"; return false; } xmin = i32(p); ymin = i32(p + 4); xmax = i32(p + 8); ymax = i32(p + 12); }
         p += (size_t)size;
     }
-    w = xmax - xmin + 1; h = ymax - ymin + 1;
-    if (w <= 0 || h <= 0 || chans.empty()) { err = "bad EXR header"; return false; }
+    const long long lw = (long long)xmax - xmin + 1, lh = (long long)ymax - ymin + 1;
+    if (!saneSize(lw, lh) || chans.empty()) { err = "bad EXR header"; return false; }
+    w = (int)lw; h = (int)lh;
     if (comp < 0 || comp > 3) { err = "EXR compression other than NONE / RLE / ZIPS / ZIP is not supported"; return false; }
     size_t bytesPerLine = 0;
     std::vector<size_t> chanOff;

@@ -750,7 +750,8 @@ void render(Scene *scene, const std::string &outputName, bool writeRaw) {
         kz_stats st;
         if (kzgpu_stats(g->context(), &st) == KZ_OK)
             std::cout << "paths " << st.paths << ", extension rays " << st.rays_extension << ", shadow rays " << st.rays_shadow << ", vertices " << st.vertices
-                      << ", kernel launches " << st.kernel_launches << ", trace " << st.ms_trace << " ms, shade " << st.ms_shade << " ms, accel " << st.bvh_nodes
+                      << ", kernel launches " << st.kernel_launches << ", trace " << st.ms_trace << " ms, shade " << st.ms_shade << " ms, frame merge over NVLink "
+                      << st.ms_merge << " ms, scene upload " << st.ms_upload << " ms, accel build " << st.ms_build << " ms, accel " << st.bvh_nodes
                       << " nodes / " << st.bvh_bytes / 1048576.0 << " MiB" << std::endl;
     }
     writePNG(outputName + ".png", result.width, result.height, srgb.data());

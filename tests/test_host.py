@@ -360,6 +360,34 @@ def test_kazen_cli_on_gpu(host, kzo, tmp_path):
     O.close(); hs.close()
 
 
+def test_image_readers_reject_malformed_headers(host, tmp_path):
+    """header fields of texture files are untrusted: out-of-range sizes, a missing IHDR and a channel list that runs past its
+    attribute are errors, not out-of-bounds reads or huge allocations"""
+    import struct, zlib
+
+    def png(chunks):
+        out = b"\x89PNG\r\n\x1a\n"
+        for t, d in chunks:
+            out += struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+        return out
+    idat = zlib.compress(b"\x00" + bytes(3))
+    cases = {
+        "huge.png": png([(b"IHDR", struct.pack(">IIBBBBB", 0xFFFFFFF0, 7, 8, 2, 0, 0, 0)), (b"IDAT", idat), (b"IEND", b"")]),
+        "zero.png": png([(b"IHDR", struct.pack(">IIBBBBB", 0, 1, 8, 2, 0, 0, 0)), (b"IDAT", idat), (b"IEND", b"")]),
+        "noihdr.png": png([(b"IDAT", idat), (b"IEND", b""), (b"tEXt", b"padding-padding-padding")]),
+        "neg.pfm": b"PF\n-4 4\n-1.0\n" + bytes(64),
+        "big.hdr": b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 2000000 +X 2000000\n",
+    }
+    # EXR: a channel list whose last name has no terminator inside the attribute
+    exr = bytes([0x76, 0x2f, 0x31, 0x01, 2, 0, 0, 0]) + b"channels\0chlist\0" + struct.pack("<i", 3) + b"RGB" + b"compression\0compression\0" + struct.pack("<i", 1) + b"\0" + b"\0"
+    cases["chlist.exr"] = exr + bytes(64)
+    for name, blob in cases.items():
+        p = tmp_path / name
+        p.write_bytes(blob)
+        with pytest.raises(RuntimeError):
+            host.host_read_image(str(p))
+
+
 def test_jpeg_decoder_matches_libjpeg(host, tmp_path):
     """imagetexture's JPEG path (the reference's look-dev material uses .jpg textures through OpenImageIO = libjpeg): baseline
     Huffman decode with libjpeg's default arithmetic (slow-integer IDCT, fancy upsampling, fixed-point YCbCr) -- bit identical to
