@@ -372,6 +372,7 @@ def main():
                        label + f", {d.camera.width}x{d.camera.height}, {spp} spp", st["ms_upload"], st["ms_build"],
                        oracle_desc=d if with_cpu else None, cpu_rect=cpu_rect)
         out["accel"] = {"builder": "sah" if builder == pk.BUILD_HOST_SAH else "lbvh", "nodes": st["bvh_nodes"], "bytes": st["bvh_bytes"]}
+        out["roofline"]["traffic"] = committed_traffic(tris=n_tris, kernel="k_extend+k_shadow")
         G.close(); hs.close()
         return out
 

@@ -63,10 +63,10 @@ def test_reference_arm_prints_one_line_under_torchrun(kzo):
     """bench.py --impl reference: rank 0 alone runs and prints the JSON line, the other rank exits 0"""
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29732", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
-                        "--tris", "20000"], capture_output=True, text=True, timeout=900)
+                        "--tris", "20000", "--width", "256", "--height", "144"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     j = json.loads(lines[0])
-    assert j["impl"] == "reference" and j["metric"] == "Mrays/s" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
+    assert j["impl"] == "reference" and j["metric"] == "Mpaths/s" and j["value"] > 0 and j["cpu_baseline"]["kind"] == "port"
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["n_gpus"] == 2
