@@ -245,10 +245,11 @@ inline void collapse(const std::vector<Node2> &nodes2, const std::vector<Ref> &r
         nd.ex = e[0]; nd.ey = e[1]; nd.ez = e[2];
         nd.child_base = (uint32_t)out.nodes.size();
         nd.tri_base = (uint32_t)(out.tris.size() / 3);
+        nd.magic = KZ_NODE_MAGIC;
         uint32_t triOff = 0; uint8_t imask = 0;
         for (int s = 0; s < 8; ++s) {
             int c = childAt[s];
-            if (c < 0) { nd.meta[s] = 0; continue; }   /* empty: q boxes stay 0, meta 0 never sets a bit */
+            if (c < 0) continue;                        /* empty: q boxes stay 0, neither mask has a bit for the slot */
             const Node2 &cn = nodes2[c];
             double sc[3] = {std::ldexp(1.0, (int)e[0] - 127), std::ldexp(1.0, (int)e[1] - 127), std::ldexp(1.0, (int)e[2] - 127)};
             uint8_t *qlo[3] = {nd.qlox, nd.qloy, nd.qloz}, *qhi[3] = {nd.qhix, nd.qhiy, nd.qhiz};
@@ -260,13 +261,11 @@ inline void collapse(const std::vector<Node2> &nodes2, const std::vector<Ref> &r
             }
             if (cn.count == 0) {
                 imask |= (uint8_t)(1u << s);
-                nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
                 int w = (int)out.nodes.size();
                 out.nodes.push_back(KzNode8());
                 q.push_back(Item{c, w, it.depth + 1});
             } else {
-                static const uint8_t unary[4] = {0, 1, 3, 7};
-                nd.meta[s] = (uint8_t)((unary[cn.count] << 5) | triOff);
+                nd.trimask |= ((1u << cn.count) - 1u) << (3 * s);
                 for (int k = 0; k < cn.count; ++k) {
                     const Tri &t = tris[refs[cn.left + k].tri];
                     KzF4 a, b, c4;

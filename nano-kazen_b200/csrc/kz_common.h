@@ -34,7 +34,7 @@ KZ_HD float kz_sub(float a, float b) { return __fsub_rn(a, b); }
 KZ_HD float kz_rcp(float a) { return __frcp_rn(a); }
 KZ_HD float kz_div(float a, float b) { return __fdiv_rn(a, b); }
 KZ_HD float kz_sqrt(float a) { return __fsqrt_rn(a); }
-KZ_HD uint32_t kz_bfind(uint32_t x) { return 31u - (uint32_t)__clz((int)x); }
+KZ_HD uint32_t kz_bfind(uint32_t x) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x)); return r; }
 KZ_HD uint32_t kz_popc(uint32_t x) { return (uint32_t)__popc(x); }
 /* PTX prmt in its generic mode: selector nibble bit 3 replicates the sign of the selected byte
  * (the __byte_perm intrinsic only honours the low three selector bits, so it cannot be used). */
@@ -45,6 +45,10 @@ KZ_HD uint32_t kz_byte_perm(uint32_t a, uint32_t b, uint32_t s) {
 }
 KZ_HD float kz_u2f(uint32_t u) { return __uint_as_float(u); }
 KZ_HD uint32_t kz_f2u(float f) { return __float_as_uint(f); }
+/* prmt with an immediate selector */
+#define kz_byte_perm_sel(a, b, sel) ([&] { uint32_t r_; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r_) : "r"((uint32_t)(a)), "r"((uint32_t)(b)), "n"(sel)); return r_; }())
+/* (m << 1) | sign bit of f: one funnel shift */
+KZ_HD uint32_t kz_shl1_sign(uint32_t m, float f) { return __funnelshift_l(__float_as_uint(f), m, 1); }
 #else
 /* host emulation: volatile stops g++ from contracting a*b+c behind our back */
 KZ_HD float kz_fma(float a, float b, float c) { return fmaf(a, b, c); }
@@ -69,6 +73,8 @@ KZ_HD uint32_t kz_byte_perm(uint32_t a, uint32_t b, uint32_t s) {
 }
 KZ_HD float kz_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 KZ_HD uint32_t kz_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+KZ_HD uint32_t kz_shl1_sign(uint32_t m, float f) { return (m << 1) | (kz_f2u(f) >> 31); }
+#define kz_byte_perm_sel(a, b, sel) kz_byte_perm((a), (b), (sel))
 #endif
 
 #define KZ_PI 3.14159265358979323846f

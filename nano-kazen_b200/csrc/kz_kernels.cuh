@@ -183,7 +183,6 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
         while (active && !finished) {
             for (;;) {
                 if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
-                else if (t.ng_y != 0u) { t.tg_x = t.ng_x; t.tg_y = t.ng_y; t.ng_x = 0u; t.ng_y = 0u; }
                 if (t.tg_y != 0u) break;
                 if (t.ng_y <= 0x00FFFFFFu) {
                     if (t.sp == 0) break;
@@ -203,12 +202,10 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
 #else
         while (active && !finished) {
             if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
-            else { t.tg_x = t.ng_x; t.tg_y = t.ng_y; t.ng_x = 0u; t.ng_y = 0u; }
             const int total = __popc(__activemask());
             while (t.tg_y != 0u) {
-                if (__popc(__activemask()) * KZ_POSTPONE_DEN < total * KZ_POSTPONE_NUM && t.sp < KZ_SHORT_STACK + KZ_LOCAL_STACK - 1) {   /* too few lanes have triangles: postpone */
-                    kz_trav_push(t, stk, ls, t.tg_x, t.tg_y);
-                    t.tg_y = 0u;
+                if (__popc(__activemask()) * KZ_POSTPONE_DEN < total * KZ_POSTPONE_NUM && t.sp < KZ_SHORT_STACK + KZ_LOCAL_STACK - 2) {   /* too few lanes have triangles: postpone */
+                    kz_trav_postpone(t, stk, ls);
                     break;
                 }
                 kz_trav_tri(sc, t);
@@ -325,8 +322,7 @@ struct KzExtendJob {
 
 template <bool FIRST>
 __global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_extend(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int cur) {
-    __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
-    KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
+    const KzStackRef stk = kz_trav_shared_init();
     KzExtendJob<FIRST> job(sc, st, ctl, q, q.ext[cur]);
     kz_warp_trace(sc, stk, &ctl->head_ext, kz_ext_count(ctl, cur), job);
     kz_flush_counters(ctl, job.cnt);
@@ -446,8 +442,7 @@ struct KzShadowJob {
     }
 };
 __global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_shadow(KzScene sc, KzPathState st, KzControl *ctl, KzQueues q, int nxt) {
-    __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
-    KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
+    const KzStackRef stk = kz_trav_shared_init();
     KzShadowJob job(sc, st, q.shadow);
     kz_warp_trace(sc, stk, &ctl->head_shadow, kz_shadow_count(ctl, nxt), job);
     kz_flush_counters(ctl, job.cnt);
@@ -479,8 +474,7 @@ struct KzTraceJob {
     }
 };
 __global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_BATCH_MIN_BLOCKS) k_trace(KzScene sc, const KzF4 *rays, uint32_t n, float *hits, uint32_t *cursor, KzControl *ctl) {
-    __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
-    KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
+    const KzStackRef stk = kz_trav_shared_init();
     KzTraceJob job; job.rays = rays; job.hits = hits;
     kz_warp_trace(sc, stk, cursor, n, job);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->rays_ext, (unsigned long long)n);
@@ -507,8 +501,7 @@ struct KzOccludedJob {
 };
 __global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_BATCH_MIN_BLOCKS) k_occluded(KzScene sc, const KzF4 *rays, uint32_t n, float eps, uint8_t *occ, uint8_t *segments,
                                                                 uint32_t *cursor, KzControl *ctl) {
-    __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
-    KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
+    const KzStackRef stk = kz_trav_shared_init();
     KzOccludedJob job(sc, rays, eps, occ, segments);
     kz_warp_trace(sc, stk, cursor, n, job);
     kz_flush_counters(ctl, job.cnt);
@@ -597,8 +590,7 @@ __global__ void k_resolve(const KzF4 *frame, int width, int height, int border, 
 /* ---- parity probes: post-intersection record and emitter sample, field by field --------------------------------------- */
 /* accel.cpp:63-236 for one ray per thread (plain per-ray loop; this is a probe, not a hot path) */
 __global__ void __launch_bounds__(KZ_TRACE_THREADS) k_intersection_dump(KzScene sc, const KzF4 *rays, uint32_t n, float *out24) {
-    __shared__ uint2 s_stack[KZ_SHORT_STACK * KZ_TRACE_THREADS];
-    KzStackRef stk; stk.smem = s_stack + threadIdx.x; stk.stride = KZ_TRACE_THREADS;
+    const KzStackRef stk = kz_trav_shared_init();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const KzF4 ro = rays[2 * (size_t)i], rd = rays[2 * (size_t)i + 1];

@@ -297,10 +297,10 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
     memset(&nd, 0, sizeof(nd));
     nd.px = nb.lo[0]; nd.py = nb.lo[1]; nd.pz = nb.lo[2];
     nd.ex = (uint8_t)e[0]; nd.ey = (uint8_t)e[1]; nd.ez = (uint8_t)e[2];
-    nd.child_base = child_base; nd.tri_base = tri_base;
+    nd.child_base = child_base; nd.tri_base = tri_base; nd.magic = KZ_NODE_MAGIC;
     uint32_t triOff = 0, rel = 0; uint8_t imask = 0;
     for (int s = 0; s < 8; ++s) {
-        if (childAt[s] < 0) { nd.meta[s] = 0; continue; }
+        if (childAt[s] < 0) continue;
         const int ci = childAt[s];
         const int c = ch[ci];
         uint8_t *qlo[3] = {nd.qlox, nd.qloy, nd.qloz}, *qhi[3] = {nd.qhix, nd.qhiy, nd.qhiz};
@@ -314,13 +314,12 @@ __global__ void __launch_bounds__(64) k_collapse(CollapseState cs) {
         const uint32_t cnt = sub_count(b, c);
         if (c >= 0 && cnt > KZ_LBVH_MAXLEAF) {
             imask |= (uint8_t)(1u << s);
-            nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
             WorkItem w; w.bnode = c; w.wnode = child_base + rel;
             cs.out[out_base + rel] = w;
             ++rel;
         } else {
             const uint32_t unary = cnt == 1u ? 1u : (cnt == 2u ? 3u : 7u);
-            nd.meta[s] = (uint8_t)((unary << 5) | triOff);
+            nd.trimask |= unary << (3 * s);
             const uint32_t first = c < 0 ? (uint32_t)~c : b.first[c];
             for (uint32_t k = 0; k < cnt; ++k) {
                 const kzbvh::Tri t = b.tris[ref_tri(b, b.order[first + k])];

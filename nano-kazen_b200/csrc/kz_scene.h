@@ -1,8 +1,9 @@
 /* kz_scene.h -- HBM-resident scene layout shared by the kernels (and by tests/hostemu).
  *
  * Accel:
- *   nodes : 80-byte 8-wide compressed nodes (quantised child boxes, Ylitie/Karras/Laine 2017
- *           style layout), read as 5 x 16-byte vector loads.
+ *   nodes : 80-byte 8-wide compressed nodes (quantised child boxes after Ylitie/Karras/Laine 2017; the per-slot meta
+ *           bytes of that layout are replaced by two masks in slot order -- imask and trimask -- so that the traversal
+ *           builds its hit masks with word-parallel bit operations instead of per-child shifts), read as 5 x 16-byte loads.
  *   tris  : 48 bytes per triangle in leaf order = 3 x float4
  *           (p0.xyz | geomID), (p1.xyz | primID), (p2.xyz | 0): raw vertices because the
  *           parity-contracted Pluecker test works on origin-relative vertices.
@@ -21,10 +22,13 @@ struct alignas(16) KzNode8 {
     uint8_t  ex, ey, ez, imask;   /* per-axis exponent (IEEE biased), internal-child mask  */
     uint32_t child_base;          /* index of first internal child                         */
     uint32_t tri_base;            /* index of first triangle referenced by this node       */
-    uint8_t  meta[8];             /* per slot: inner = 0x20|(24+slot); leaf = unary(ntri)<<5 | tri offset; 0 = empty */
+    uint32_t trimask;             /* leaf slot s owns bits [3s, 3s+3): its n <= 3 triangles set the low n of them; the triangle of set bit k
+                                     is tri_base + popc(trimask below k) (triangles are stored in slot order)                       */
+    uint32_t magic;               /* KZ_NODE_MAGIC: operand of the byte->float permutes of the node step (kz_traverse.h)             */
     uint8_t  qlox[8], qloy[8], qloz[8];
     uint8_t  qhix[8], qhiy[8], qhiz[8];
 };
+#define KZ_NODE_MAGIC 0x47000000u
 static_assert(sizeof(KzNode8) == 80, "node must be 80 bytes");
 
 struct KzMeshRec {

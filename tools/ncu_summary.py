@@ -17,6 +17,9 @@ want = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "us"), ("launch__r
         ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "st_short"), ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "st_lg"),
         ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "st_br"), ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "st_noinst"),
         ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "st_math"), ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "st_notsel"),
+        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "pipe_alu%"), ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "pipe_fma%"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "pipe_xu%"), ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "pipe_lsu%"),
+        ("smsp__inst_executed.sum", "warp_inst"),
         ("local_load_bytes", "lld"), ("smsp__inst_executed_op_local_ld.sum", "ld.local"), ("smsp__inst_executed_op_local_st.sum", "st.local")]
 idx = [(col(n), s) for n, s in want]
 units = rows[1]
