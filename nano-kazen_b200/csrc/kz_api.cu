@@ -73,6 +73,9 @@ struct kzgpu_ctx {
     bool uploaded = false, built = false;
     uint32_t pool_cap = 1u << 23;     /* path slots per chunk and lane (160 B each = 1.25 GiB): every launch costs ~18 us of ramp + tail, so few big chunks win */
     int lanes = 2;                    /* concurrent chunks per device, 1..4 (KZGPU_LANES=1: strictly serial chunks) */
+    int spp_group = 8;                /* sample indices of one tile that are neighbours in path order (KZGPU_SPP_GROUP, 1 = sample-major); measured on the
+                                       * 10^8-triangle 4K headline / WarmStudio.xml / configs[2], Mpaths/s: 1 -> 827 / 1213 / 821, 2 -> 835 / 1218 / 830, 4 -> 839 / 1216 / 824,
+                                       * 8 -> 842 / 1213 / 823, 16 -> 838 / 1191 / 816, 64 -> 807 / 1110 / 780 (the splats of neighbouring warps then pile onto the same texels) */
     kz_stats totals{};
     double ms_build = 0;
     uint64_t bvh_nodes = 0, bvh_bytes = 0;
@@ -426,6 +429,8 @@ int enqueue_render(const kzgpu_ctx *ctx, kzgpu_ctx *ectx, Device &d, const kz_re
     const uint32_t tiles_y = (uint32_t)(h + 3) / 4u;
     ch.npx_padded = ch.tiles_x * tiles_y * 32u;
     ch.spp_begin = req.spp_begin;
+    ch.n_spp = (uint32_t)nS;
+    ch.spp_group = (uint32_t)std::min(nS, ctx->spp_group);
     const unsigned long long total = (unsigned long long)ch.npx_padded * (unsigned long long)nS;
     /* two lanes once there is enough work for two chunks (the unbounded loops of whitted / path_mats poll the host: one lane) */
     const bool alt = sc.integrator.type != KZ_INTEGRATOR_PATH_MIS;
@@ -482,6 +487,7 @@ int kzgpu_create(const int *device_ids, int n_devices, kzgpu_ctx **out) {
     std::unique_ptr<kzgpu_ctx> ctx(new kzgpu_ctx());
     if (const char *p = getenv("KZGPU_POOL_LOG2")) { int l = atoi(p); if (l >= 10 && l <= 26) ctx->pool_cap = 1u << l; }
     if (const char *p = getenv("KZGPU_LANES")) { int l = atoi(p); if (l >= 1 && l <= KZ_MAX_LANES) ctx->lanes = l; }
+    if (const char *p = getenv("KZGPU_SPP_GROUP")) { int g = atoi(p); if (g >= 1) ctx->spp_group = g; }
     for (int id : ids) {
         if (id < 0 || id >= count) return fail(nullptr, KZ_ERR_NO_DEVICE, "device id " + std::to_string(id) + " out of range");
         cudaDeviceProp prop;
@@ -632,7 +638,7 @@ int kzgpu_accel_build(kzgpu_ctx *ctx, int builder) {
         KZ_CUDA(ctx, e);
         kzbvh::Built built;
         kzbvh::buildHostSah(tris, 0, built);
-        if (2 * built.depth + 2 > KZ_SHORT_STACK + KZ_LOCAL_STACK) return fail(ctx, KZ_ERR_UNSUPPORTED, "accel deeper than the traversal stack allows");
+        if (built.depth > KZ_MAX_ACCEL_DEPTH) return fail(ctx, KZ_ERR_UNSUPPORTED, "accel deeper than the traversal stack allows");
         for (Device &d : ctx->devs) {
             KZ_CUDA(ctx, cudaSetDevice(d.id));
             if ((rc = upload_accel(ctx, d, built))) return rc;
@@ -648,7 +654,7 @@ int kzgpu_accel_build(kzgpu_ctx *ctx, int builder) {
         /* hand the pool's memory back: the path pools and the caller's own allocations need it, the next build allocates afresh */
         { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, d0.id) == cudaSuccess) { cudaStreamSynchronize(d0.stream); cudaMemPoolTrimTo(pool, 0); } }
         if (rc) return fail(ctx, rc, err);
-        if (2 * r.depth + 2 > KZ_SHORT_STACK + KZ_LOCAL_STACK) return fail(ctx, KZ_ERR_UNSUPPORTED, "accel deeper than the traversal stack allows");
+        if (r.depth > KZ_MAX_ACCEL_DEPTH) return fail(ctx, KZ_ERR_UNSUPPORTED, "accel deeper than the traversal stack allows");
         d0.sc.nodes = r.nodes; d0.sc.tris = r.tris; d0.sc.n_nodes = r.n_nodes; d0.sc.n_tris = r.n_tris; d0.sc.scene_max_abs = r.max_abs;
         d0.has_accel = true;
         d0.launches += r.launches;

@@ -53,6 +53,8 @@ struct KzChunk {
     uint32_t tiles_x;                /* 8x4 pixel tiles per row                             */
     uint32_t npx_padded;             /* tiles_x * tiles_y * 32                              */
     int32_t spp_begin;
+    uint32_t n_spp;                  /* sample indices of the request                       */
+    uint32_t spp_group;              /* consecutive sample indices of one tile that are neighbours in path order (1 = sample-major) */
     unsigned long long first;        /* first global path index of this chunk               */
     uint32_t count;                  /* slots used by this chunk                            */
 };
@@ -204,7 +206,7 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
             if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
             const int total = __popc(__activemask());
             while (t.tg_y != 0u) {
-                if (__popc(__activemask()) * KZ_POSTPONE_DEN < total * KZ_POSTPONE_NUM && t.sp < KZ_SHORT_STACK + KZ_LOCAL_STACK - 2) {   /* too few lanes have triangles: postpone */
+                if (__popc(__activemask()) * KZ_POSTPONE_DEN < total * KZ_POSTPONE_NUM && t.sp < KZ_POSTPONE_SP_LIMIT) {   /* too few lanes have triangles: postpone */
                     kz_trav_postpone(t, stk, ls);
                     break;
                 }
@@ -253,16 +255,23 @@ __global__ void k_bounce_reset(KzControl *ctl, int nxt) {
 }
 
 /* ---- raygen: renderer.cpp:20-33 + camera.cpp:70-91,191-223 ------------------------------- */
-/* Slot i of the chunk = global path index first+i = (sample-major, 8x4-pixel-tile-minor), so a
- * warp is one 8x4 pixel tile of one sample index: coherent primary rays, and the splats of a
- * warp land on neighbouring frame texels instead of piling onto one pixel. */
+/* Slot i of the chunk = global path index first+i; a warp is one 8x4 pixel tile of one sample index: coherent primary rays,
+ * and the splats of a warp land on neighbouring frame texels instead of piling onto one pixel.  Consecutive warps are
+ * consecutive sample indices of the SAME tile (KzChunk::spp_group of them), so the warps resident on an SM walk the same
+ * part of the accel and shade neighbouring surface points. */
 __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_raygen(KzScene sc, KzPathState st, uint32_t *q0, KzChunk ch) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ch.count) return;
-    const unsigned long long g = ch.first + i;
-    const uint32_t s_local = (uint32_t)(g / ch.npx_padded);
-    const uint32_t pix = (uint32_t)(g % ch.npx_padded);
-    const uint32_t tile = pix >> 5, in_tile = pix & 31u;
+    /* path order: (block of spp_group sample indices, tile, sample index in the block, pixel of the tile) */
+    unsigned long long g = ch.first + i;
+    const unsigned long long per_block = (unsigned long long)ch.npx_padded * ch.spp_group;
+    const uint32_t blk = (uint32_t)(g / per_block);
+    g -= (unsigned long long)blk * per_block;
+    const uint32_t left = ch.n_spp - blk * ch.spp_group;
+    const uint32_t grp = left < ch.spp_group ? left : ch.spp_group;        /* the last block may be short */
+    const uint32_t tile = (uint32_t)(g / (32u * grp));
+    const uint32_t r = (uint32_t)(g - (unsigned long long)tile * (32u * grp));
+    const uint32_t s_local = blk * ch.spp_group + (r >> 5), in_tile = r & 31u;
     const int x = ch.x0 + (int)((tile % ch.tiles_x) * 8u + (in_tile & 7u));
     const int y = ch.y0 + (int)((tile / ch.tiles_x) * 4u + (in_tile >> 3));
     if (x < ch.x1 && y < ch.y1) kz_raygen_item(sc, st, i, x, y, (uint32_t)(ch.spp_begin + (int)s_local));

@@ -406,7 +406,7 @@ __global__ void k_make_refs(const kzbvh::Tri *tris, uint32_t n, const uint32_t *
         }                                                                                                \
     } while (0)
 
-#define KZ_LBVH_MAX_LEVELS 31     /* wide-tree levels the traversal stack can hold: 2 * depth + 2 <= 64 entries */
+#define KZ_LBVH_MAX_LEVELS 31     /* levels the collapse walks; the API accepts KZ_MAX_ACCEL_DEPTH = 30 of them (stack budget in kz_traverse.h) */
 
 /* Builds the accel of the `n_tris_in` device-resident triangles `d_tris` (scene order) on the current device; the node/triangle
  * arrays are appended to `owner` (freed by the caller), temporaries are released before returning. */

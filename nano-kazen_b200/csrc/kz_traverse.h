@@ -104,6 +104,11 @@ KZ_HD float kz_rcp_safe(float d) {
 #define KZ_SHORT_STACK 8          /* entries per thread kept in shared memory */
 #endif
 #define KZ_LOCAL_STACK (64 - KZ_SHORT_STACK)   /* overflow entries in local memory */
+/* Stack budget (64 entries): a node step leaves at most one entry (the siblings of the child it descends into), i.e. at most
+ * `depth` entries at any time; a postponed triangle group takes two and is only put aside while fewer than
+ * KZ_POSTPONE_SP_LIMIT entries are stacked.  32 + 2 + KZ_MAX_ACCEL_DEPTH = 64. */
+#define KZ_POSTPONE_SP_LIMIT 32
+#define KZ_MAX_ACCEL_DEPTH (KZ_SHORT_STACK + KZ_LOCAL_STACK - 2 - KZ_POSTPONE_SP_LIMIT)
 
 #ifndef KZ_TRACE_THREADS
 #define KZ_TRACE_THREADS 128      /* threads per CTA of every kernel that traverses (kz_kernels.cuh) */
