@@ -64,7 +64,7 @@ def measured_peaks():
 def committed_traffic(**match):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of the same workload, else None"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r5_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r6_traffic.json")) as f:
             for tj in json.load(f)["workloads"]:
                 if all(tj.get(k) == v for k, v in match.items()):
                     return tj["dram_bytes_per_launch_mean"]
