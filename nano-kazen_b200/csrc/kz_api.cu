@@ -71,8 +71,8 @@ struct kzgpu_ctx {
     std::unique_ptr<KzHostScene> hs;
     bool class_present[KZ_NUM_CLASSES] = {true, false, false, false, false};
     bool uploaded = false, built = false;
-    uint32_t pool_cap = 1u << 23;     /* path slots per chunk and lane (160 B each = 1.25 GiB): every launch costs ~18 us of ramp + tail, so few big chunks win */
-    int lanes = 2;                    /* concurrent chunks per device, 1..4 (KZGPU_LANES=1: strictly serial chunks) */
+    uint32_t pool_cap = 1u << 24;     /* path slots per chunk and lane (160 B each = 2.5 GiB): every launch costs ~18 us of ramp + tail, so few big chunks win */
+    int lanes = 3;                    /* concurrent chunks per device at most, 1..4 (KZGPU_LANES=1: strictly serial chunks); frames below 2^25 paths use two */
     int spp_group = 8;                /* sample indices of one tile that are neighbours in path order (KZGPU_SPP_GROUP, 1 = sample-major); measured on the
                                        * 10^8-triangle 4K headline / WarmStudio.xml / configs[2], Mpaths/s: 1 -> 827 / 1213 / 821, 2 -> 835 / 1218 / 830, 4 -> 839 / 1216 / 824,
                                        * 8 -> 842 / 1213 / 823, 16 -> 838 / 1191 / 816, 64 -> 807 / 1110 / 780 (the splats of neighbouring warps then pile onto the same texels) */
@@ -434,7 +434,9 @@ int enqueue_render(const kzgpu_ctx *ctx, kzgpu_ctx *ectx, Device &d, const kz_re
     const unsigned long long total = (unsigned long long)ch.npx_padded * (unsigned long long)nS;
     /* two lanes once there is enough work for two chunks (the unbounded loops of whitted / path_mats poll the host: one lane) */
     const bool alt = sc.integrator.type != KZ_INTEGRATOR_PATH_MIS;
-    const int lanes = (!alt && total >= (1ull << 21)) ? ctx->lanes : 1;
+    /* measured on B200 (Mpaths/s, pool 2^23 x 2 lanes -> 2^24 x 3): 10^8-triangle 4K headline 848 -> 866, configs[2] 826 -> 840, configs[3] 792 -> 812;
+     * a 2^24-path frame (WarmStudio.xml 512x512x64) is best left on two lanes (1213 vs 1203) */
+    const int lanes = (alt || total < (1ull << 21)) ? 1 : (total >= (1ull << 25) ? ctx->lanes : std::min(ctx->lanes, 2));
     const unsigned long long per_lane = (((total + lanes - 1) / lanes) + 31ull) & ~31ull;
     const uint32_t cap = (uint32_t)std::min<unsigned long long>(ctx->pool_cap, per_lane);
     int rc;
