@@ -64,7 +64,7 @@ def measured_peaks():
 def committed_traffic(**match):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of the same workload, else None"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r6_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r7_traffic.json")) as f:
             for tj in json.load(f)["workloads"]:
                 if all(tj.get(k) == v for k, v in match.items()):
                     return tj["dram_bytes_per_launch_mean"]
@@ -277,11 +277,16 @@ def main():
         clocks = ClockSampler(local) if (rank == 0 and clocks_on) else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        prof = clocks_on and os.environ.get("KZ_PROFILE_STEP") == "1"      # ncu --profile-from-start off: the timed steps of the headline only
+        if prof:
+            torch.cuda.profiler.start()
         e0.record()
         for k in range(steps):
             pstep(k)
         e1.record()
         barrier()
+        if prof:
+            torch.cuda.profiler.stop()
         ms = rmax(e0.elapsed_time(e1)) / steps
         clk = clocks.stop() if clocks else None
         st = G.stats(reset=True)
@@ -305,7 +310,7 @@ def main():
         pstep(0); barrier(); G.stats(reset=True)
         pstep(0); barrier()
         s1 = G.stats(reset=True)
-        G.configure("lanes", 2)
+        G.configure("lanes", int(os.environ.get("KZGPU_LANES", 3)))
         ext_bytes = s1["rays_extension"] * b_ray(n_tris) + s1["rays_shadow"] * b_ray(n_tris, shadow=True)
         tr_ach = ext_bytes / (s1["ms_trace"] * 1e-3) / 1e9 if s1["ms_trace"] > 0 else 0.0
         out["roofline"] = {"bound": "hbm", "kernel": "k_extend + k_shadow (closest-hit traversal inside the wavefront)", "achieved": tr_ach, "peak": peak, "unit": "GB/s",
@@ -335,8 +340,14 @@ def main():
                       "api": "kzgpu_render (request in, host frame out)" if world == 1 else "kzgpu_render_device + NCCL reduce + D2H of the frame on rank 0",
                       "note": "the scene is resident; a step's input is the 28-byte kz_render_req"}
         render_s = n_steps_frame * ms * 1e-3
-        out["time_to_image_s"] = {"scene_upload": upload_ms * 1e-3, "accel_build": build_ms * 1e-3, "render": render_s, "frame_readback": fh * fw * 16 / 50e9,
-                                  "total": upload_ms * 1e-3 + build_ms * 1e-3 + render_s + fh * fw * 16 / 50e9,
+        readback_s = fh * fw * 16 / 50e9
+        if rank == 0:            # the D2H copy of the finished frame into pinned memory, measured
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            host_frame.copy_(frame, non_blocking=True); torch.cuda.synchronize()
+            ev0.record(); host_frame.copy_(frame, non_blocking=True); ev1.record(); torch.cuda.synchronize()
+            readback_s = ev0.elapsed_time(ev1) * 1e-3
+        out["time_to_image_s"] = {"scene_upload": upload_ms * 1e-3, "accel_build": build_ms * 1e-3, "render": render_s, "frame_readback": readback_s,
+                                  "total": upload_ms * 1e-3 + build_ms * 1e-3 + render_s + readback_s,
                                   "spans": f"kzgpu_scene_upload + kzgpu_accel_build + {n_steps_frame} step(s) = {spp_total} spp + D2H (renderer.cpp:72-153 without XML/OBJ parsing)"}
         if rank == 0:
             fr = host_frame.numpy()

@@ -437,8 +437,11 @@ int enqueue_render(const kzgpu_ctx *ctx, kzgpu_ctx *ectx, Device &d, const kz_re
     /* measured on B200 (Mpaths/s, pool 2^23 x 2 lanes -> 2^24 x 3): 10^8-triangle 4K headline 848 -> 866, configs[2] 826 -> 840, configs[3] 792 -> 812;
      * a 2^24-path frame (WarmStudio.xml 512x512x64) is best left on two lanes (1213 vs 1203) */
     const int lanes = (alt || total < (1ull << 21)) ? 1 : (total >= (1ull << 25) ? ctx->lanes : std::min(ctx->lanes, 2));
-    const unsigned long long per_lane = (((total + lanes - 1) / lanes) + 31ull) & ~31ull;
-    const uint32_t cap = (uint32_t)std::min<unsigned long long>(ctx->pool_cap, per_lane);
+    /* equal chunks, a multiple of the lane count of them, none larger than the pool: the lanes finish together (4 chunks on 3 lanes
+     * would leave two lanes idle for the last quarter of the frame) */
+    const unsigned long long rounds = (total + (unsigned long long)lanes * ctx->pool_cap - 1) / ((unsigned long long)lanes * ctx->pool_cap);
+    const unsigned long long n_chunks = rounds * (unsigned long long)lanes;
+    const uint32_t cap = (uint32_t)((((total + n_chunks - 1) / n_chunks) + 31ull) & ~31ull);
     int rc;
     for (int l = 0; l < lanes; ++l) if ((rc = ensure_pool(ectx, d.lane[l], cap))) return rc;
     Timed total_t(d, s, CAT_TOTAL);

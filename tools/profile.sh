@@ -8,9 +8,9 @@ R=${R:-r6}
 NCU="ncu --clock-control none"
 case "${1:-}" in
 launches)
-  # one steady-state step (1664 launches) of the headline at spec: skip the build and the 3 warm-up steps
+  # one steady-state step of the headline at spec (KZ_PROFILE_STEP brackets the timed step with cudaProfilerStart/Stop)
   python bench.py --steps 1 --warmup 3 --no-cpu --legs headline > $O/${R}_bench_plain.json 2> $O/${R}_bench_plain.err &&
-  timeout 900 $NCU --metrics gpu__time_duration.sum -s 5060 -c 1700 --csv --log-file $O/${R}_launches_headline.csv python bench.py --steps 1 --warmup 3 --no-cpu --legs headline > $O/${R}_bench_ncu.log 2>&1
+  KZ_PROFILE_STEP=1 timeout 900 $NCU --metrics gpu__time_duration.sum --profile-from-start off --csv --log-file $O/${R}_launches_headline.csv python bench.py --steps 1 --warmup 3 --no-cpu --legs headline > $O/${R}_bench_ncu.log 2>&1
   # one frame of kazen's WarmStudio.xml at 512x512x64 (second frame of prof_paths.py)
   python tools/prof_paths.py warm > $O/${R}_prof_warm_plain.log 2>&1 &&
   timeout 300 $NCU --metrics gpu__time_duration.sum --profile-from-start off --csv --log-file $O/${R}_launches_warm.csv python tools/prof_paths.py warm > /dev/null 2>&1
