@@ -318,7 +318,8 @@ int  kzgpu_light_sample_dump(kzgpu_ctx *ctx, const float *ref3, const float *u5,
 /* Tuning knobs of the wavefront (defaults: up to 3 lanes -- frames below 2^25 paths use 2 --, 2^24 path slots per lane, runs of 8 sample
  * indices per pixel tile in path order; also read from KZGPU_LANES / KZGPU_POOL_LOG2 / KZGPU_SPP_GROUP at
  * kzgpu_create).  "lanes" = concurrent chunks per device (1 = strictly serial kernels, which is what per-kernel timings in
- * kz_stats need to be meaningful), "pool_log2" = log2 of the path slots per chunk. */
+ * kz_stats need to be meaningful), "pool_log2" = log2 of the path slots per chunk, "spp_group" = consecutive sample indices of a pixel
+ * tile that are neighbours in path order (1 = sample-major).  None of them changes which paths are traced. */
 int  kzgpu_configure(kzgpu_ctx *ctx, const char *key, int value);
 
 int  kzgpu_stats(kzgpu_ctx *ctx, kz_stats *out);

@@ -1073,6 +1073,7 @@ int kzgpu_configure(kzgpu_ctx *ctx, const char *key, int value) {
     const std::string k(key);
     if (k == "lanes") { if (value < 1 || value > KZ_MAX_LANES) return fail(ctx, KZ_ERR_INVALID, "lanes must be 1.." + std::to_string(KZ_MAX_LANES)); ctx->lanes = value; return KZ_OK; }
     if (k == "pool_log2") { if (value < 10 || value > 26) return fail(ctx, KZ_ERR_INVALID, "pool_log2 must be 10..26"); ctx->pool_cap = 1u << value; return KZ_OK; }
+    if (k == "spp_group") { if (value < 1) return fail(ctx, KZ_ERR_INVALID, "spp_group must be >= 1"); ctx->spp_group = value; return KZ_OK; }
     return fail(ctx, KZ_ERR_INVALID, "unknown option \"" + k + "\"");
 }
 

@@ -84,6 +84,8 @@ struct KzHostScene {
             images.push_back(r);
         }
         uint64_t voff = 0, foff = 0;
+        sc.n_invisible_lights = 0;
+        for (int a = 0; a < 3; ++a) { sc.inv_light_lo[a] = kz_u2f(0x7f800000u); sc.inv_light_hi[a] = kz_u2f(0xff800000u); }
         for (uint32_t g = 0; g < d->n_meshes; ++g) {
             const kz_mesh_desc &m = d->meshes[g];
             if (!m.positions || !m.indices) { error = "mesh buffers missing"; return false; }
@@ -115,12 +117,16 @@ struct KzHostScene {
                     if (m.indices[3 * (size_t)f] >= m.n_vertices || m.indices[3 * (size_t)f + 1] >= m.n_vertices || m.indices[3 * (size_t)f + 2] >= m.n_vertices) { error = "vertex index out of range"; return false; }
                 r.flags |= KZ_MESH_IS_LIGHT;
                 if (d->lights[m.light].primary_visibility) r.flags |= KZ_MESH_LIGHT_VISIBLE;
+                else ++sc.n_invisible_lights;
                 /* Mesh::activate + DiscretePDF::normalize */
                 r.cdf_offset = (uint32_t)light_cdf.size();
                 light_cdf.push_back(0.0f);
                 for (uint32_t f = 0; f < m.n_triangles; ++f) {
                     const float *p0 = m.positions + 3 * (size_t)m.indices[3 * f], *p1 = m.positions + 3 * (size_t)m.indices[3 * f + 1],
                                 *p2 = m.positions + 3 * (size_t)m.indices[3 * f + 2];
+                    if (!d->lights[m.light].primary_visibility)        /* bounds of the invisible emitters: shadow rays stop early outside them */
+                        for (const float *q : {p0, p1, p2})
+                            for (int a = 0; a < 3; ++a) { sc.inv_light_lo[a] = fminf(sc.inv_light_lo[a], q[a]); sc.inv_light_hi[a] = fmaxf(sc.inv_light_hi[a], q[a]); }
                     kz3 e1 = mk3(kz_sub(p1[0], p0[0]), kz_sub(p1[1], p0[1]), kz_sub(p1[2], p0[2]));
                     kz3 e2 = mk3(kz_sub(p2[0], p0[0]), kz_sub(p2[1], p0[1]), kz_sub(p2[2], p0[2]));
                     kz3 c = mk3(kz_sub(kz_mul(e1.y, e2.z), kz_mul(e1.z, e2.y)), kz_sub(kz_mul(e1.z, e2.x), kz_mul(e1.x, e2.z)),

@@ -124,7 +124,9 @@ __device__ __forceinline__ void kz_flush_counters(KzControl *ctl, const KzCounte
  * Job: per-lane policy object.
  *   void begin(uint32_t item, KzRayIn &r)                   load the ray of work item `item`
  *   bool end(uint32_t item, const KzHit &h, KzRayIn &r)     consume the closest hit; return true and fill `r`
- *                                                           to continue the same item with a follow-up ray */
+ *                                                           to continue the same item with a follow-up ray
+ *   static constexpr bool kStopsEarly                       the job only asks WHETHER something opaque is hit (shadow rays)
+ *   bool stop(const KzScene &sc, const KzTrav &t)           called after a triangle became the best hit: true ends the ray there */
 struct KzRayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
 #ifndef KZ_FETCH_ND
 #define KZ_FETCH_ND 0
@@ -134,6 +136,9 @@ struct KzRayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
 #endif
 #ifndef KZ_TRAV_MODE
 #define KZ_TRAV_MODE 0          /* 0: one node step + postponed leaf tests per iteration; 1: while-while */
+#endif
+#ifndef KZ_WAIT_IDLE
+#define KZ_WAIT_IDLE 1
 #endif
 #ifndef KZ_POSTPONE_NUM
 #define KZ_POSTPONE_NUM 1       /* postpone leaf tests while active lanes < NUM/DEN of the lanes in the loop */
@@ -203,6 +208,24 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
         }
 #else
         while (active && !finished) {
+#if KZ_WAIT_IDLE
+            /* A lane whose triangles wait (too few lanes hold any) puts them on its stack only if it has a node group in hand to go
+             * on with; otherwise it keeps them in registers and sits out the iteration -- pushing them would only be followed by
+             * popping the same entry again (two entries each way, every iteration, until enough lanes have caught up). */
+            if (t.tg_y == 0u && t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
+            const int total = __popc(__activemask());
+            while (t.tg_y != 0u) {
+                if (__popc(__activemask()) * KZ_POSTPONE_DEN < total * KZ_POSTPONE_NUM) {
+                    if (t.ng_y > 0x00FFFFFFu && t.sp < KZ_POSTPONE_SP_LIMIT) kz_trav_postpone(t, stk, ls);
+                    break;
+                }
+                if (kz_trav_tri(sc, t) && Job::kStopsEarly && job.stop(sc, t)) { t.tg_y = 0u; t.ng_y = 0u; t.sp = 0; }
+            }
+            if (t.tg_y == 0u && t.ng_y <= 0x00FFFFFFu) {
+                if (t.sp == 0) finished = true;
+                else kz_trav_pop(t, stk, ls);
+            }
+#else
             if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
             const int total = __popc(__activemask());
             while (t.tg_y != 0u) {
@@ -210,12 +233,13 @@ __device__ __forceinline__ void kz_warp_trace(const KzScene &sc, const KzStackRe
                     kz_trav_postpone(t, stk, ls);
                     break;
                 }
-                kz_trav_tri(sc, t);
+                if (kz_trav_tri(sc, t) && Job::kStopsEarly && job.stop(sc, t)) { t.tg_y = 0u; t.ng_y = 0u; t.sp = 0; }
             }
             if (t.ng_y <= 0x00FFFFFFu) {
                 if (t.sp == 0) finished = true;
                 else kz_trav_pop(t, stk, ls);
             }
+#endif
             if (!exhausted) {
                 lost += 32 - __popc(__activemask()) - KZ_FETCH_ND;
                 if (lost >= KZ_FETCH_NW) break;
@@ -289,6 +313,8 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_raygen(KzScene sc, KzPathS
 /* ---- extend: Scene::rayIntersect for every queued path, then sort by material class ------- */
 template <bool FIRST>
 struct KzExtendJob {
+    static constexpr bool kStopsEarly = false;
+    __device__ __forceinline__ bool stop(const KzScene &, const KzTrav &) { return false; }
     const KzScene &sc; const KzPathState &st; KzControl *ctl; const KzQueues &q; const uint32_t *queue;
     KzCounters cnt;
     uint32_t slot;
@@ -414,6 +440,15 @@ struct KzWalk {
         o = o_; d = d_; tmax = tmax_; seg = 0;
         r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = tmin; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = tmax;
     }
+    /* The walk only asks whether its ray reaches something opaque.  A hit on an opaque mesh settles that as soon as no invisible
+     * emitter can lie in front of it -- none in the scene, or the ray up to the hit stays outside their bounds: the closest hit of
+     * this segment is then opaque too, whichever triangle it is, and step() answers "occluded" exactly as for the closest one. */
+    __device__ __forceinline__ static bool settles(const KzScene &sc, const KzTrav &t) {
+        if (sc.integrator.type != KZ_INTEGRATOR_PATH_MIS) return true;                      /* ao / whitted: any hit occludes */
+        const uint32_t fl = sc.meshes[t.best.geom].flags;
+        if ((fl & KZ_MESH_IS_LIGHT) && !(fl & KZ_MESH_LIGHT_VISIBLE)) return false;
+        return sc.n_invisible_lights == 0 || kz_trav_misses_box(t, sc.inv_light_lo, sc.inv_light_hi, t.best.t);
+    }
     /* returns 0 = unoccluded, 1 = occluded, 2 = continue with the ray written to r */
     __device__ __forceinline__ int step(const KzScene &sc, const KzHit &h, float eps, KzRayIn &r) {
         ++seg;
@@ -428,6 +463,8 @@ struct KzWalk {
     }
 };
 struct KzShadowJob {
+    static constexpr bool kStopsEarly = true;
+    __device__ __forceinline__ bool stop(const KzScene &s, const KzTrav &t) { return KzWalk::settles(s, t); }
     const KzScene &sc; const KzPathState &st; const uint32_t *queue;
     KzCounters cnt; uint32_t slot; KzWalk walk;
     __device__ KzShadowJob(const KzScene &s, const KzPathState &p, const uint32_t *qu) : sc(s), st(p), queue(qu) { cnt.paths = cnt.rays_ext = cnt.rays_shadow = cnt.vertices = 0ull; }
@@ -470,6 +507,8 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_accumulate(KzScene sc, KzP
 /* ---- batch entry points (parity tests + intersection microbench) -------------------------- */
 /* kzgpu_trace: rays/hits in the C-ABI's AoS layout (32 B in, 20 B out). */
 struct KzTraceJob {
+    static constexpr bool kStopsEarly = false;
+    __device__ __forceinline__ bool stop(const KzScene &, const KzTrav &) { return false; }
     const KzF4 *rays; float *hits;
     __device__ __forceinline__ void begin(uint32_t item, KzRayIn &r) {
         const KzU4 a = kz_load_u4(rays + 2 * (size_t)item), b = kz_load_u4(rays + 2 * (size_t)item + 1);
@@ -490,6 +529,8 @@ __global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_BATCH_MIN_BLOCKS) k_trace
 }
 
 struct KzOccludedJob {
+    static constexpr bool kStopsEarly = true;
+    __device__ __forceinline__ bool stop(const KzScene &s, const KzTrav &t) { return KzWalk::settles(s, t); }
     const KzScene &sc; const KzF4 *rays; float eps; uint8_t *occ, *segments;
     KzCounters cnt; KzWalk walk;
     __device__ KzOccludedJob(const KzScene &s, const KzF4 *r, float e, uint8_t *o, uint8_t *sg) : sc(s), rays(r), eps(e), occ(o), segments(sg) {

@@ -78,6 +78,8 @@ struct KzScene {
     const float    *light_cdf;
     const int32_t  *light_meshes;     /* scene.cpp:42-46 order */
     int32_t         n_light_meshes;
+    int32_t         n_invisible_lights;                  /* emitters a shadow ray passes through (integrator.cpp:259-294) ...  */
+    float           inv_light_lo[3], inv_light_hi[3];    /* ... and the bounds of their vertices                               */
     /* materials */
     const kz_bsdf_desc    *bsdfs;
     const kz_texture_desc *textures;

@@ -311,8 +311,19 @@ KZ_HD void kz_trav_node(const KzScene &sc, KzTrav &t, const KzStackRef &stk, KzL
     t.tg_y = sp7 & n1.z;
 }
 
-/* Tests the next triangle of the current triangle group (tg_y != 0). */
-KZ_HD void kz_trav_tri(const KzScene &sc, KzTrav &t) {
+/* True if the ray cannot touch the box [lo, hi] before `tfar`: the slab test of the node step (same widened origin), on exact bounds. */
+KZ_HD bool kz_trav_misses_box(const KzTrav &t, const float *lo, const float *hi, float tfar) {
+    const bool nx = !(t.oct_inv & 1u), ny = !(t.oct_inv & 2u), nz = !(t.oct_inv & 4u);
+    const float tnx = fmaf(nx ? hi[0] : lo[0], t.rdx, t.cnx), tfx = fmaf(nx ? lo[0] : hi[0], t.rdx, t.cfx);
+    const float tny = fmaf(ny ? hi[1] : lo[1], t.rdy, t.cny), tfy = fmaf(ny ? lo[1] : hi[1], t.rdy, t.cfy);
+    const float tnz = fmaf(nz ? hi[2] : lo[2], t.rdz, t.cnz), tfz = fmaf(nz ? lo[2] : hi[2], t.rdz, t.cfz);
+    const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t.tmin));
+    const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tfar));
+    return cmin > cmax;          /* a NaN says "may touch" */
+}
+
+/* Tests the next triangle of the current triangle group (tg_y != 0); returns true if it became the best hit. */
+KZ_HD bool kz_trav_tri(const KzScene &sc, KzTrav &t) {
     const uint32_t ti = kz_bfind(t.tg_y);
     t.tg_y &= ~(1u << ti);
     const KzF4 *tp = sc.tris + (size_t)(t.tg_x + kz_popc(t.tg_m & ~(0xFFFFFFFFu << ti))) * 3;
@@ -322,7 +333,9 @@ KZ_HD void kz_trav_tri(const KzScene &sc, KzTrav &t) {
         const uint32_t geom = a.w, prim = b.w;
         const bool better = tt < t.best.t || geom < t.best.geom || (geom == t.best.geom && prim < t.best.prim);
         if (better) { t.best.t = tt; t.best.u = u; t.best.v = v; t.best.geom = geom; t.best.prim = prim; }
+        return better;
     }
+    return false;
 }
 
 /* The plain per-ray loop.  `stk` gives the shared-memory short stack on the device; on the host

@@ -632,13 +632,13 @@ def test_upload_validation(gpu_lib):
 
 
 def test_lanes_and_pool_sizes_agree(gpu_lib, monkeypatch):
-    """One lane, two lanes, four lanes and small pools walk the same paths: identical counters, images equal up to the order of the
-    float reductions into the frame."""
+    """One lane, two lanes, four lanes, small pools and every path order (runs of 1 / 5 / 8 / 144 sample indices per pixel tile, 5 not
+    dividing the sample count) walk the same paths: identical counters, images equal up to the order of the float reductions into the frame."""
     sb = scenes.cornell_scene(160, 120, 144, "stratified")          # 2.8 M paths: enough for the lanes to engage
     d = sb.desc()
     out = []
-    for lanes, pool in (("1", "23"), ("2", "23"), ("4", "19"), ("2", "17")):
-        monkeypatch.setenv("KZGPU_LANES", lanes); monkeypatch.setenv("KZGPU_POOL_LOG2", pool)
+    for lanes, pool, group in (("1", "23", "1"), ("2", "23", "8"), ("4", "19", "5"), ("2", "17", "144"), ("3", "24", "8")):
+        monkeypatch.setenv("KZGPU_LANES", lanes); monkeypatch.setenv("KZGPU_POOL_LOG2", pool); monkeypatch.setenv("KZGPU_SPP_GROUP", group)
         G = pk.Gpu(d)
         f = G.render()
         rgb, _ = G.resolve(f)
