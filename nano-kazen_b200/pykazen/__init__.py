@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 PKG = os.path.join(ROOT, "nano-kazen_b200")
-LIB_GPU = os.path.join(PKG, "csrc", "libkzgpu.so")
+LIB_GPU = os.environ.get("KZGPU_LIB") or os.path.join(PKG, "csrc", "libkzgpu.so")      # KZGPU_LIB: another build of the same ABI (tuning experiments)
 LIB_HOST = os.path.join(PKG, "host", "libkazen_host.so")
 
 KZ_INVALID_ID = 0xFFFFFFFF
