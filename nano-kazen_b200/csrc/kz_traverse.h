@@ -89,7 +89,13 @@ KZ_HD bool kz_pluecker(float ox, float oy, float oz, float dx, float dy, float d
 KZ_HD float kz_magic_adjust(float v, float k) { return fmaf(fabsf(v), k, v); }
 KZ_HD float kz_rcp_safe(float d) {
     if (fabsf(d) < 1e-18f) d = (kz_f2u(d) >> 31) ? -1e-18f : 1e-18f;
+#if KZ_DEVICE_CODE
+    /* culling only: the approximate reciprocal (one MUFU instead of the IEEE division's ~8 instructions, three per ray) is within 2 ulp,
+     * i.e. 2^-22 |p - o| in position space, far inside the slack */
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r;
+#else
     return 1.0f / d;
+#endif
 }
 
 #ifndef KZ_PRMT_AXES
