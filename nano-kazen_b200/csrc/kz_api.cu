@@ -73,9 +73,11 @@ struct kzgpu_ctx {
     bool uploaded = false, built = false;
     uint32_t pool_cap = 1u << 24;     /* path slots per chunk and lane (160 B each = 2.5 GiB): every launch costs ~18 us of ramp + tail, so few big chunks win */
     int lanes = 3;                    /* concurrent chunks per device at most, 1..4 (KZGPU_LANES=1: strictly serial chunks); frames below 2^25 paths use two */
-    int spp_group = 8;                /* sample indices of one tile that are neighbours in path order (KZGPU_SPP_GROUP, 1 = sample-major); measured on the
-                                       * 10^8-triangle 4K headline / WarmStudio.xml / configs[2], Mpaths/s: 1 -> 827 / 1213 / 821, 2 -> 835 / 1218 / 830, 4 -> 839 / 1216 / 824,
-                                       * 8 -> 842 / 1213 / 823, 16 -> 838 / 1191 / 816, 64 -> 807 / 1110 / 780 (the splats of neighbouring warps then pile onto the same texels) */
+    int spp_group = 64;               /* sample indices of one tile that are neighbours in path order (KZGPU_SPP_GROUP, 1 = sample-major).  Measured on the
+                                       * 10^8-triangle 4K headline / WarmStudio.xml / configs[2], Mpaths/s, with k_accumulate splatting one 32-path unit per warp at a time
+                                       * (the splats of neighbouring warps then pile onto the same texels): 1 -> 827 / 1213 / 821, 8 -> 842 / 1213 / 823, 64 -> 807 / 1110 / 780;
+                                       * with every warp of k_accumulate walking its own run of units (KZ_ACC_RUNS): 8 -> 892 / 1261 / 860, 16 -> 904 / 1262 / 861,
+                                       * 32 -> 909 / 1264 / 862, 64 -> 918 / 1263 / 866 */
     kz_stats totals{};
     double ms_build = 0;
     uint64_t bvh_nodes = 0, bvh_bytes = 0;
@@ -412,7 +414,11 @@ int enqueue_chunk(const kzgpu_ctx *ctx, kzgpu_ctx *ectx, Device &d, Lane &L, con
         Timed t(d, s, CAT_SHADE);
         /* (a tiled variant that pre-sums the taps of 256 neighbouring paths in shared memory was 10 % slower end to end:
          * shared-memory float atomics are compare-and-swap loops, the 128-bit global reductions are not) */
+#if KZ_ACC_RUNS
+        k_accumulate<<<std::min<uint32_t>((ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, (uint32_t)d.sm_count * 16u), KZ_SHADE_THREADS, 0, s>>>(sc, L.st, ch.count, d.frame);
+#else
         k_accumulate<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, L.st, ch.count, d.frame);
+#endif
         ++d.launches;
     }
     return KZ_OK;

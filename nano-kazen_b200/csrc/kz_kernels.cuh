@@ -137,6 +137,9 @@ struct KzRayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
 #ifndef KZ_TRAV_MODE
 #define KZ_TRAV_MODE 0          /* 0: one node step + postponed leaf tests per iteration; 1: while-while */
 #endif
+#ifndef KZ_ACC_RUNS
+#define KZ_ACC_RUNS 1
+#endif
 #ifndef KZ_WAIT_IDLE
 #define KZ_WAIT_IDLE 1
 #endif
@@ -499,9 +502,21 @@ __global__ void __launch_bounds__(KZ_SHADE_THREADS) k_accumulate(KzScene sc, KzP
     __shared__ float s_table[33];
     if (threadIdx.x < 33) s_table[threadIdx.x] = sc.filter.table[threadIdx.x];
     __syncthreads();
+#if KZ_ACC_RUNS
+    /* Every warp splats its own run of consecutive 32-path units: in path order the next units are the same pixel tile's next sample
+     * indices, whose splats hit the same frame texels -- from one warp they arrive one after the other, from neighbouring warps at once. */
+    const uint32_t n_units = (count + 31u) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, per = (n_units + n_warps - 1u) / n_warps;
+    const uint32_t u1 = min(n_units, (w + 1u) * per);
+    for (uint32_t u = w * per; u < u1; ++u) {
+        const uint32_t i = (u << 5) + (threadIdx.x & 31u);
+        if (i < count && st.b[i].smp.pix != 0xFFFFFFFFu) kz_accumulate_item(sc, st, i, frame, s_table);
+    }
+#else
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count || st.b[i].smp.pix == 0xFFFFFFFFu) return;
     kz_accumulate_item(sc, st, i, frame, s_table);
+#endif
 }
 
 /* ---- batch entry points (parity tests + intersection microbench) -------------------------- */
