@@ -412,13 +412,9 @@ int enqueue_chunk(const kzgpu_ctx *ctx, kzgpu_ctx *ectx, Device &d, Lane &L, con
     }
     {
         Timed t(d, s, CAT_SHADE);
-        /* (a tiled variant that pre-sums the taps of 256 neighbouring paths in shared memory was 10 % slower end to end:
-         * shared-memory float atomics are compare-and-swap loops, the 128-bit global reductions are not) */
-#if KZ_ACC_RUNS
-        k_accumulate<<<std::min<uint32_t>((ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, (uint32_t)d.sm_count * 16u), KZ_SHADE_THREADS, 0, s>>>(sc, L.st, ch.count, d.frame);
-#else
-        k_accumulate<<<(ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, KZ_SHADE_THREADS, 0, s>>>(sc, L.st, ch.count, d.frame);
-#endif
+        /* (an earlier tiled variant pre-summed the taps of 256 neighbouring paths with shared-memory float atomics -- compare-and-swap
+         * loops -- and was 10 % slower end to end; k_accumulate now sums a tile's sample indices conflict-free, see there) */
+        k_accumulate<<<std::min<uint32_t>((ch.count + KZ_SHADE_THREADS - 1) / KZ_SHADE_THREADS, (uint32_t)d.sm_count * 16u), KZ_SHADE_THREADS, 0, s>>>(sc, L.st, ch.count, d.frame, ch.x0, ch.y0);
         ++d.launches;
     }
     return KZ_OK;

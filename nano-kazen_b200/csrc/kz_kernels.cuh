@@ -137,9 +137,6 @@ struct KzRayIn { float ox, oy, oz, tmin, dx, dy, dz, tmax; };
 #ifndef KZ_TRAV_MODE
 #define KZ_TRAV_MODE 0          /* 0: one node step + postponed leaf tests per iteration; 1: while-while */
 #endif
-#ifndef KZ_ACC_RUNS
-#define KZ_ACC_RUNS 1
-#endif
 #ifndef KZ_WAIT_IDLE
 #define KZ_WAIT_IDLE 1
 #endif
@@ -498,25 +495,78 @@ __global__ void __launch_bounds__(KZ_TRACE_THREADS, KZ_TRACE_MIN_BLOCKS) k_shado
 }
 
 /* ---- accumulate: ImageBlock::put over the whole chunk (block.cpp:56-85) ------------------- */
-__global__ void __launch_bounds__(KZ_SHADE_THREADS) k_accumulate(KzScene sc, KzPathState st, uint32_t count, KzF4 *frame) {
+#ifndef KZ_ACC_MAX_TEXELS
+#define KZ_ACC_MAX_TEXELS 160        /* (8 + span) x (4 + span) texels of a tile's footprint region: span 4 (radius 2) -> 96, span 6 -> 140 */
+#endif
+/* Every warp splats its own run of consecutive 32-path units.  In path order the next units are the same 8x4-pixel tile's next sample
+ * indices, whose splats land on the same (8 + span) x (4 + span) frame texels: the warp sums them in shared memory and adds the region
+ * to the frame once per tile -- 3 global reductions per lane and tile instead of 16-25 per path.  No shared-memory atomics are needed:
+ * the taps are walked by their offset from the path's own pixel, and at a given offset the 32 paths of a unit (32 different pixels)
+ * touch 32 different texels.  (rx0, ry0): origin of the request rectangle, which the tiles are aligned to. */
+__global__ void __launch_bounds__(KZ_SHADE_THREADS) k_accumulate(KzScene sc, KzPathState st, uint32_t count, KzF4 *frame, int rx0, int ry0) {
     __shared__ float s_table[33];
+    __shared__ KzF4 s_region[KZ_SHADE_THREADS / 32][KZ_ACC_MAX_TEXELS];
     if (threadIdx.x < 33) s_table[threadIdx.x] = sc.filter.table[threadIdx.x];
+    const uint32_t lane = threadIdx.x & 31u;
+    KzF4 *region = s_region[threadIdx.x >> 5];
+    for (uint32_t e = lane; e < KZ_ACC_MAX_TEXELS; e += 32u) region[e] = mkf4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-#if KZ_ACC_RUNS
-    /* Every warp splats its own run of consecutive 32-path units: in path order the next units are the same pixel tile's next sample
-     * indices, whose splats hit the same frame texels -- from one warp they arrive one after the other, from neighbouring warps at once. */
+    const float radius = sc.filter.radius, lookup = 32 / radius;
+    const int b = sc.border, cols = sc.camera.width + 2 * b, rows = sc.camera.height + 2 * b;
+    const int lo = -(int)floorf(radius + 0.5f), hi = (int)ceilf(radius + 0.5f) - 1;      /* tap offsets from the path's own pixel */
+    const int tw = 8 + hi - lo, th = 4 + hi - lo;
+    const bool tiled = tw * th <= KZ_ACC_MAX_TEXELS;
     const uint32_t n_units = (count + 31u) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, per = (n_units + n_warps - 1u) / n_warps;
     const uint32_t u1 = min(n_units, (w + 1u) * per);
+    int cur_x = 0, cur_y = 0; bool open = false;          /* tile whose sums the region holds */
     for (uint32_t u = w * per; u < u1; ++u) {
-        const uint32_t i = (u << 5) + (threadIdx.x & 31u);
-        if (i < count && st.b[i].smp.pix != 0xFFFFFFFFu) kz_accumulate_item(sc, st, i, frame, s_table);
+        const uint32_t i = (u << 5) + lane;
+        KzSplat sp = {};
+        bool ok = i < count && st.b[i].smp.pix != 0xFFFFFFFFu && kz_splat_of(sc, st, i, sp);
+        if (!tiled) { if (ok) kz_accumulate_item(sc, st, i, frame, s_table); continue; }
+        /* a footprint that does not fit the offsets walked below (it always does for sample positions in [0, 1)) goes the direct way */
+        if (ok && (sp.x0 < sp.ipx + b + lo || sp.x1 > sp.ipx + b + hi || sp.y0 < sp.ipy + b + lo || sp.y1 > sp.ipy + b + hi)) { kz_accumulate_item(sc, st, i, frame, s_table); ok = false; }
+        const uint32_t m = __ballot_sync(KZ_FULL, ok);
+        if (!m) continue;
+        const int leader = __ffs((int)m) - 1;
+        const int tx = __shfl_sync(KZ_FULL, ok ? rx0 + ((sp.ipx - rx0) & ~7) : 0, leader), ty = __shfl_sync(KZ_FULL, ok ? ry0 + ((sp.ipy - ry0) & ~3) : 0, leader);
+        if (open && (tx != cur_x || ty != cur_y)) {       /* next tile: hand the finished one to the frame */
+            for (int e = (int)lane; e < tw * th; e += 32) {
+                const KzF4 v = region[e];
+                const int X = cur_x + b + lo + e % tw, Y = cur_y + b + lo + e / tw;
+                if ((v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) && X >= 0 && X < cols && Y >= 0 && Y < rows) KZ_FRAME_ADD(frame + ((size_t)Y * cols + X), v.x, v.y, v.z, v.w);
+                region[e] = mkf4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+        }
+        cur_x = tx; cur_y = ty; open = true;
+        const int bx = ok ? sp.ipx - tx - lo : 0, by = ok ? sp.ipy - ty - lo : 0;      /* region column / row of the tap at offset (lo, lo) */
+        for (int dy = lo; dy <= hi; ++dy) {
+            const int Y = sp.ipy + b + dy;
+            const bool rowok = ok && Y >= sp.y0 && Y <= sp.y1;
+            const float wy = rowok ? s_table[(int)(fabsf((float)Y - sp.py) * lookup)] : 0.f;
+            for (int dx = lo; dx <= hi; ++dx) {
+                const int X = sp.ipx + b + dx;
+                if (rowok && X >= sp.x0 && X <= sp.x1) {
+                    const float wx = s_table[(int)(fabsf((float)X - sp.px) * lookup)];
+                    KzF4 *p = region + ((by + dy) * tw + (bx + dx));
+                    KzF4 v = *p;
+                    v.x += sp.value.x * wx * wy; v.y += sp.value.y * wx * wy; v.z += sp.value.z * wx * wy; v.w += 1.0f * wx * wy;
+                    *p = v;
+                }
+                __syncwarp();
+            }
+        }
     }
-#else
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count || st.b[i].smp.pix == 0xFFFFFFFFu) return;
-    kz_accumulate_item(sc, st, i, frame, s_table);
-#endif
+    if (tiled && open) {
+        __syncwarp();
+        for (int e = (int)lane; e < tw * th; e += 32) {
+            const KzF4 v = region[e];
+            const int X = cur_x + b + lo + e % tw, Y = cur_y + b + lo + e / tw;
+            if ((v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) && X >= 0 && X < cols && Y >= 0 && Y < rows) KZ_FRAME_ADD(frame + ((size_t)Y * cols + X), v.x, v.y, v.z, v.w);
+        }
+    }
 }
 
 /* ---- batch entry points (parity tests + intersection microbench) -------------------------- */

@@ -461,26 +461,38 @@ KZ_HD void kz_shadow_item(const KzScene &sc, const KzStackRef &stk, const KzPath
 /* ImageBlock::put on the whole bordered frame, block.cpp:56-85 */
 /* `table`: the 33-entry filter table (the kernel reads it from a shared-memory copy: a dynamically indexed kernel parameter
  * serialises divergent lanes in the constant cache). */
-KZ_HD void kz_accumulate_item(const KzScene &sc, const KzPathState &st, uint32_t slot, KzF4 *frame, const float *table) {
+/* What one path puts on the film: its value, its sample position and the texel rectangle of its filter footprint, all in the
+ * coordinates of the bordered frame (block.cpp:56-76).  False if the value is invalid (block.cpp:58-62). */
+struct KzSplat { kz3 value; float px, py; int x0, y0, x1, y1; int ipx, ipy; };
+KZ_HD bool kz_splat_of(const KzScene &sc, const KzPathState &st, uint32_t slot, KzSplat &sp) {
     const KzF4 L = st.b[slot].rad.L;
-    const kz3 value = mk3(L.x, L.y, L.z);
-    if (!color_valid(value)) return;
+    sp.value = mk3(L.x, L.y, L.z);
+    if (!color_valid(sp.value)) return false;
     /* the pixel sample position is not carried with the path: the samplers are addressable by (pixel, sample index), so it is
      * drawn again exactly as in raygen (renderer.cpp:25-26) */
     const KzSmpRec smp = st.b[slot].smp;
     KzSampler sm;
-    const int32_t ipx = (int32_t)(smp.pix & 0xFFFFu), ipy = (int32_t)(smp.pix >> 16);
-    kz_sampler_start(sc, sm, ipx, ipy, smp.sidx);
+    sp.ipx = (int32_t)(smp.pix & 0xFFFFu); sp.ipy = (int32_t)(smp.pix >> 16);
+    kz_sampler_start(sc, sm, sp.ipx, sp.ipy, smp.sidx);
     const kz2 jitter = kz_next_pixel2d(sc, sm);
-    KzF4 misc; misc.z = (float)ipx + jitter.x; misc.w = (float)ipy + jitter.y;
     const int b = sc.border, cols = sc.camera.width + 2 * b, rows = sc.camera.height + 2 * b;
     const float radius = sc.filter.radius;
-    const float px = misc.z - 0.5f - (float)(0 - b), py = misc.w - 0.5f - (float)(0 - b);
-    const float lookup = 32 / radius;
-    int x0 = (int)ceilf(px - radius), y0 = (int)ceilf(py - radius);
-    int x1 = (int)floorf(px + radius), y1 = (int)floorf(py + radius);
-    x0 = x0 < 0 ? 0 : x0; y0 = y0 < 0 ? 0 : y0;
-    x1 = x1 > cols - 1 ? cols - 1 : x1; y1 = y1 > rows - 1 ? rows - 1 : y1;
+    sp.px = ((float)sp.ipx + jitter.x) - 0.5f - (float)(0 - b); sp.py = ((float)sp.ipy + jitter.y) - 0.5f - (float)(0 - b);
+    int x0 = (int)ceilf(sp.px - radius), y0 = (int)ceilf(sp.py - radius);
+    int x1 = (int)floorf(sp.px + radius), y1 = (int)floorf(sp.py + radius);
+    sp.x0 = x0 < 0 ? 0 : x0; sp.y0 = y0 < 0 ? 0 : y0;
+    sp.x1 = x1 > cols - 1 ? cols - 1 : x1; sp.y1 = y1 > rows - 1 ? rows - 1 : y1;
+    return true;
+}
+
+KZ_HD void kz_accumulate_item(const KzScene &sc, const KzPathState &st, uint32_t slot, KzF4 *frame, const float *table) {
+    KzSplat sp;
+    if (!kz_splat_of(sc, st, slot, sp)) return;
+    const kz3 value = sp.value;
+    const float px = sp.px, py = sp.py;
+    const int x0 = sp.x0, y0 = sp.y0, x1 = sp.x1, y1 = sp.y1;
+    const int cols = sc.camera.width + 2 * sc.border;
+    const float lookup = 32 / sc.filter.radius;
     for (int y = y0; y <= y1; ++y) {
         const float wy = table[(int)(fabsf((float)y - py) * lookup)];
         for (int x = x0; x <= x1; ++x) {
