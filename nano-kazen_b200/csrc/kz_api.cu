@@ -76,7 +76,7 @@ struct kzgpu_ctx {
     int spp_group = 64;               /* sample indices of one tile that are neighbours in path order (KZGPU_SPP_GROUP, 1 = sample-major).  Measured on the
                                        * 10^8-triangle 4K headline / WarmStudio.xml / configs[2], Mpaths/s, with k_accumulate splatting one 32-path unit per warp at a time
                                        * (the splats of neighbouring warps then pile onto the same texels): 1 -> 827 / 1213 / 821, 8 -> 842 / 1213 / 823, 64 -> 807 / 1110 / 780;
-                                       * with every warp of k_accumulate walking its own run of units (KZ_ACC_RUNS): 8 -> 892 / 1261 / 860, 16 -> 904 / 1262 / 861,
+                                       * with every warp of k_accumulate walking its own run of units: 8 -> 892 / 1261 / 860, 16 -> 904 / 1262 / 861,
                                        * 32 -> 909 / 1264 / 862, 64 -> 918 / 1263 / 866 */
     kz_stats totals{};
     double ms_build = 0;
