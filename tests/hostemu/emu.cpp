@@ -203,6 +203,91 @@ int kzemu_render(kzemu *e, const kz_render_req *req, float *frame_rgbw) {
     return KZ_OK;
 }
 
+/* The film accumulation of the device, restated lane by lane: k_raygen's path order (kz_kernels.cuh: blocks of `spp_group` sample
+ * indices, 8x4-pixel tiles, 32-path units), every "warp" a run of `units_per_warp` units, the taps of a tile summed in a region by their
+ * offset from the path's own pixel and handed to the frame when the tile changes (k_accumulate).  Every path carries the radiance
+ * L = hash(pixel, sample) instead of a traced one.  Fills `direct` (kz_accumulate_item per path) and `tiled`; returns the number of
+ * (lane, offset) steps in which two lanes of a unit touched the same region texel -- the scheme is race free iff that is 0. */
+int kzemu_splat_orders(kzemu *e, const kz_render_req *req, int spp_group, int units_per_warp, float *direct_rgbw, float *tiled_rgbw, uint64_t *conflicts) {
+    const KzScene &sc = e->hs.sc;
+    const int b = sc.border, cols = sc.camera.width + 2 * b, rows = sc.camera.height + 2 * b;
+    KzF4 *fd = reinterpret_cast<KzF4 *>(direct_rgbw), *ft = reinterpret_cast<KzF4 *>(tiled_rgbw);
+    memset(fd, 0, (size_t)cols * rows * sizeof(KzF4)); memset(ft, 0, (size_t)cols * rows * sizeof(KzF4));
+    const int w = req->x1 - req->x0, h = req->y1 - req->y0, nS = req->spp_end - req->spp_begin;
+    const uint32_t tiles_x = (uint32_t)(w + 7) / 8u, tiles_y = (uint32_t)(h + 3) / 4u, npx = tiles_x * tiles_y * 32u;
+    const uint64_t total = (uint64_t)npx * nS;
+    std::vector<KzBlockA> sa(total); std::vector<KzBlockB> sb(total); std::vector<KzBlockC> scv(total);
+    KzPathState st{sa.data(), sb.data(), scv.data()};
+    const uint32_t G = (uint32_t)std::min(nS, std::max(1, spp_group));
+    for (uint64_t i = 0; i < total; ++i) {                       /* k_raygen's decode of the path index */
+        uint64_t g = i;
+        const uint64_t per_block = (uint64_t)npx * G;
+        const uint32_t blk = (uint32_t)(g / per_block); g -= (uint64_t)blk * per_block;
+        const uint32_t left = (uint32_t)nS - blk * G, grp = left < G ? left : G;
+        const uint32_t tile = (uint32_t)(g / (32u * grp)), r = (uint32_t)(g - (uint64_t)tile * (32u * grp));
+        const uint32_t s_local = blk * G + (r >> 5), in_tile = r & 31u;
+        const int x = req->x0 + (int)((tile % tiles_x) * 8u + (in_tile & 7u)), y = req->y0 + (int)((tile / tiles_x) * 4u + (in_tile >> 3));
+        if (x < req->x1 && y < req->y1) {
+            kz_raygen_item(sc, st, (uint32_t)i, x, y, (uint32_t)(req->spp_begin + (int)s_local));
+            const uint32_t hsh = (uint32_t)x * 73856093u ^ (uint32_t)y * 19349663u ^ (s_local + 1u) * 83492791u;
+            st.b[i].rad.L = mkf4((float)(hsh & 255u) / 64.f, (float)((hsh >> 8) & 255u) / 64.f, (float)((hsh >> 16) & 255u) / 64.f, 1.f);
+            if ((hsh >> 24) == 7u) st.b[i].rad.L.x = -1.f;          /* an invalid value now and then (block.cpp:58-62) */
+        } else st.b[i].smp.pix = 0xFFFFFFFFu;
+    }
+    for (uint64_t i = 0; i < total; ++i) if (st.b[i].smp.pix != 0xFFFFFFFFu) kz_accumulate_item(sc, st, (uint32_t)i, fd, sc.filter.table);
+    /* ---- k_accumulate ---- */
+    const float radius = sc.filter.radius, lookup = 32 / radius;
+    const int lo = -(int)floorf(radius + 0.5f), hi = (int)ceilf(radius + 0.5f) - 1, tw = 8 + hi - lo, th = 4 + hi - lo;
+    std::vector<KzF4> region((size_t)tw * th, KzF4{0.f, 0.f, 0.f, 0.f});
+    std::vector<int> touched((size_t)tw * th);
+    uint64_t bad = 0;
+    const uint64_t n_units = (total + 31u) >> 5;
+    auto flush = [&](int cx, int cy) {
+        for (int k = 0; k < tw * th; ++k) {
+            const KzF4 v = region[k];
+            const int X = cx + b + lo + k % tw, Y = cy + b + lo + k / tw;
+            if ((v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) && X >= 0 && X < cols && Y >= 0 && Y < rows) { KzF4 &p = ft[(size_t)Y * cols + X]; p.x += v.x; p.y += v.y; p.z += v.z; p.w += v.w; }
+            region[k] = KzF4{0.f, 0.f, 0.f, 0.f};
+        }
+    };
+    for (uint64_t u0 = 0; u0 < n_units; u0 += (uint64_t)units_per_warp) {            /* one warp's run */
+        bool open = false; int cur_x = 0, cur_y = 0;
+        for (uint64_t u = u0; u < std::min<uint64_t>(n_units, u0 + units_per_warp); ++u) {
+            KzSplat sp[32]; bool ok[32]; int leader = -1;
+            for (int l = 0; l < 32; ++l) {
+                const uint64_t i = (u << 5) + l;
+                ok[l] = i < total && st.b[i].smp.pix != 0xFFFFFFFFu && kz_splat_of(sc, st, (uint32_t)i, sp[l]);
+                if (ok[l] && (sp[l].x0 < sp[l].ipx + b + lo || sp[l].x1 > sp[l].ipx + b + hi || sp[l].y0 < sp[l].ipy + b + lo || sp[l].y1 > sp[l].ipy + b + hi)) {
+                    kz_accumulate_item(sc, st, (uint32_t)i, ft, sc.filter.table); ok[l] = false;
+                }
+                if (ok[l] && leader < 0) leader = l;
+            }
+            if (leader < 0) continue;
+            const int tx = req->x0 + ((sp[leader].ipx - req->x0) & ~7), ty = req->y0 + ((sp[leader].ipy - req->y0) & ~3);
+            if (open && (tx != cur_x || ty != cur_y)) flush(cur_x, cur_y);
+            cur_x = tx; cur_y = ty; open = true;
+            for (int dy = lo; dy <= hi; ++dy)
+                for (int dx = lo; dx <= hi; ++dx) {
+                    std::fill(touched.begin(), touched.end(), 0);
+                    for (int l = 0; l < 32; ++l) {
+                        if (!ok[l]) continue;
+                        const int X = sp[l].ipx + b + dx, Y = sp[l].ipy + b + dy;
+                        if (Y < sp[l].y0 || Y > sp[l].y1 || X < sp[l].x0 || X > sp[l].x1) continue;
+                        const float wy = sc.filter.table[(int)(fabsf((float)Y - sp[l].py) * lookup)], wx = sc.filter.table[(int)(fabsf((float)X - sp[l].px) * lookup)];
+                        const int ry = sp[l].ipy - ty - lo + dy, rx = sp[l].ipx - tx - lo + dx;
+                        if (ry < 0 || ry >= th || rx < 0 || rx >= tw) { ++bad; continue; }
+                        if (touched[(size_t)ry * tw + rx]++) ++bad;
+                        KzF4 &p = region[(size_t)ry * tw + rx];
+                        p.x += sp[l].value.x * wx * wy; p.y += sp[l].value.y * wx * wy; p.z += sp[l].value.z * wx * wy; p.w += 1.0f * wx * wy;
+                    }
+                }
+        }
+        if (open) flush(cur_x, cur_y);
+    }
+    *conflicts = bad;
+    return KZ_OK;
+}
+
 /* the per-item bodies of k_intersection_dump / k_light_sample_dump (kz_kernels.cuh) */
 int kzemu_intersection_dump(kzemu *e, const kz_ray *rays, size_t n, float *out24) {
     const KzScene &sc = e->hs.sc;

@@ -86,6 +86,15 @@ class Emu(pk._Backend):
         self._call("render", self.h, C.byref(req), frame.ctypes.data_as(pk.c_float_p))
         return frame
 
+    def splat_orders(self, rect, spp, spp_group, units_per_warp):
+        """frames (direct per-path splats, k_accumulate's tile sums) of synthetic radiances + the number of same-texel collisions inside a unit"""
+        H, W, b = self.frame_shape()
+        fd, ft = np.zeros((H, W, 4), np.float32), np.zeros((H, W, 4), np.float32)
+        req = pk.RenderReq(rect[0], rect[1], rect[2], rect[3], 0, spp, 1)
+        bad = C.c_uint64(0)
+        self._call("splat_orders", self.h, C.byref(req), C.c_int(spp_group), C.c_int(units_per_warp), fd.ctypes.data_as(pk.c_float_p), ft.ctypes.data_as(pk.c_float_p), C.byref(bad))
+        return fd, ft, int(bad.value)
+
     def bsdf_query(self, bsdf, mode, wi, wo=(0, 0, 1), uv=(0.5, 0.5), acc_rough=0.0, s1=0.5, s2=(0.5, 0.5)):
         out = (C.c_float * 8)()
         f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])

@@ -263,3 +263,23 @@ def test_emitter_sample_cpu(kzo, emu):
     O, E = _pair(kzo, emu, scenes.cornell_scene(16, 16, 4))
     check_light_sample_dump(O, E)
     O.close(); E.close()
+
+
+@pytest.mark.parametrize("kind,kw", [("gaussian", {}), ("mitchell", {}), ("tent", {}), ("box", {}), ("gaussian", {"radius": 2.5}), ("gaussian", {"radius": 3.0})])
+def test_tiled_film_accumulation_cpu(emu, kind, kw):
+    """k_accumulate's order of summation (kz_kernels.cuh), restated lane by lane in tests/hostemu: the taps of a pixel tile's sample
+    indices summed in a region by their offset from the path's own pixel, the region added to the frame when the tile changes.  For
+    every reconstruction filter, aligned and unaligned request rectangles, runs of sample indices that do and do not divide the
+    sample count and warps whose runs split tiles: the frame equals the path-by-path splats up to the order of the float additions,
+    and no two lanes of a unit ever meet in one texel at one offset (the reason it needs no atomics)."""
+    sb = scenes.cornell_scene(61, 37, 6, "stratified")
+    sb.set_filter(kind, **kw)
+    E = emu.Emu(sb.desc())
+    for rect in ((0, 0, 61, 37), (3, 2, 58, 31), (17, 5, 26, 9)):
+        for spp, group, run in ((6, 64, 53), (6, 4, 3), (5, 2, 1), (1, 1, 7)):
+            fd, ft, bad = E.splat_orders(rect, spp, group, run)
+            assert bad == 0
+            assert fd[..., 3].sum() > 0
+            scale = np.abs(fd).max()
+            assert np.abs(fd - ft).max() <= 2e-5 * scale, (kind, rect, spp, group, run)
+    E.close()
