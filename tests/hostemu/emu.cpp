@@ -63,6 +63,73 @@ int kzemu_trace(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits) {
     return KZ_OK;
 }
 
+/* kz_warp_trace (kz_kernels.cuh), restated lane by lane: 32 lanes share a fetch cursor, every iteration the lanes still at work make one
+ * node step, the lanes that hold triangles test them while at least 1/`den` of the lanes at work hold some -- otherwise a lane with a node
+ * group in hand puts its triangle group on its stack (two entries) and one without waits with it in registers -- and lanes whose groups are
+ * exhausted pop; finished lanes are refilled once `nw` lane-iterations were lost.  This is the only caller of kz_trav_postpone and of the
+ * triangle-group branch of kz_trav_pop on the host.  out_events = {postponed groups, groups waited with, refills}. */
+int kzemu_trace_warp(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits, int den, int nw, uint64_t *out_events) {
+    const KzScene &sc = e->hs.sc;
+    struct Lane { KzTrav t; KzLocalStack ls; bool active = false, finished = false, wait = false; size_t item = 0; };
+    std::vector<Lane> L(32);
+    KzStackRef stk;
+    size_t cursor = 0; bool exhausted = false;
+    uint64_t ev_post = 0, ev_wait = 0, ev_refill = 0;
+    for (Lane &l : L) { l.t.sp = 0; l.t.ng_y = 0u; l.t.tg_y = 0u; }
+    for (;;) {
+        for (Lane &l : L) if (l.finished) {
+            const KzHit &h = l.t.best;
+            hits[l.item].t = h.t; hits[l.item].u = h.u; hits[l.item].v = h.v; hits[l.item].prim_id = h.prim; hits[l.item].geom_id = h.geom;
+            l.active = false; l.finished = false;
+        }
+        if (!exhausted) {
+            int idle = 0; for (Lane &l : L) idle += !l.active;
+            if (idle) {
+                ++ev_refill;
+                for (Lane &l : L) if (!l.active && cursor < n) {
+                    l.item = cursor++;
+                    const kz_ray &r = rays[l.item];
+                    kz_trav_init(sc, l.t, r.o[0], r.o[1], r.o[2], r.d[0], r.d[1], r.d[2], r.tmin, r.tmax);
+                    l.active = true;
+                }
+                exhausted = cursor >= n;
+            }
+        }
+        bool any = false; for (Lane &l : L) any |= l.active;
+        if (!any) break;
+        int lost = 0;
+        for (;;) {
+            std::vector<Lane *> S;
+            for (Lane &l : L) if (l.active && !l.finished) S.push_back(&l);
+            if (S.empty()) break;
+            for (Lane *l : S) if (l->t.tg_y == 0u && l->t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, l->t, stk, l->ls);
+            const int total = (int)S.size();
+            for (;;) {
+                std::vector<Lane *> T;
+                for (Lane *l : S) if (l->t.tg_y != 0u && !l->wait) T.push_back(l);
+                if (T.empty()) break;
+                if ((int)T.size() * den < total) {
+                    for (Lane *l : T) {
+                        if (l->t.ng_y > 0x00FFFFFFu && l->t.sp < KZ_POSTPONE_SP_LIMIT) { kz_trav_postpone(l->t, stk, l->ls); ++ev_post; }
+                        else { l->wait = true; ++ev_wait; }          /* leaves the loop with its group in registers */
+                    }
+                    break;
+                }
+                for (Lane *l : T) kz_trav_tri(sc, l->t);
+            }
+            for (Lane *l : S) {
+                l->wait = false;
+                if (l->t.tg_y == 0u && l->t.ng_y <= 0x00FFFFFFu) {
+                    if (l->t.sp == 0) l->finished = true; else kz_trav_pop(l->t, stk, l->ls);
+                }
+            }
+            if (!exhausted) { lost += 32 - total; if (lost >= nw) break; }
+        }
+    }
+    if (out_events) { out_events[0] = ev_post; out_events[1] = ev_wait; out_events[2] = ev_refill; }
+    return KZ_OK;
+}
+
 /* Traversal statistics of the plain per-ray loop (tuning aid): out = {node steps, triangle tests, triangle groups, accepted hits, max stack}. */
 int kzemu_trace_stats(kzemu *e, const kz_ray *rays, size_t n, uint64_t *out) {
     const KzScene &sc = e->hs.sc;

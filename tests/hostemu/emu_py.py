@@ -53,6 +53,14 @@ class Emu(pk._Backend):
         self._call("trace", self.h, rays.ctypes.data_as(C.c_void_p), C.c_size_t(rays.shape[0]), hits.ctypes.data_as(C.c_void_p))
         return hits
 
+    def trace_warp(self, rays, den=5, nw=8):
+        """the warp-cooperative loop of kz_kernels.cuh restated lane by lane; returns (hits, {postponed, waited, refills})"""
+        rays = np.ascontiguousarray(rays, pk.RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], pk.HIT_DTYPE)
+        ev = (C.c_uint64 * 3)()
+        self._call("trace_warp", self.h, rays.ctypes.data_as(C.c_void_p), C.c_size_t(rays.shape[0]), hits.ctypes.data_as(C.c_void_p), C.c_int(den), C.c_int(nw), ev)
+        return hits, {"postponed": int(ev[0]), "waited": int(ev[1]), "refills": int(ev[2])}
+
     def occluded(self, rays, trace_bias):
         rays = np.ascontiguousarray(rays, pk.RAY_DTYPE)
         occ = np.zeros(rays.shape[0], np.uint8); seg = np.zeros(rays.shape[0], np.uint8)

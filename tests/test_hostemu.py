@@ -283,3 +283,19 @@ def test_tiled_film_accumulation_cpu(emu, kind, kw):
             scale = np.abs(fd).max()
             assert np.abs(fd - ft).max() <= 2e-5 * scale, (kind, rect, spp, group, run)
     E.close()
+
+
+@pytest.mark.parametrize("den,nw", [(5, 8), (1, 8), (32, 4), (3, 64)])
+def test_warp_cooperative_loop_cpu(emu, den, nw):
+    """kz_warp_trace (kz_kernels.cuh) restated lane by lane in tests/hostemu -- lane refill from a cursor, triangle groups postponed to
+    the stack (two entries) or waited with in registers, pops of either kind of entry: whatever the schedule, the hits are those of
+    the plain per-ray loop, bit for bit (ties included: the soup has duplicated references)."""
+    for sb, rays in ((scenes.soup_scene(60000), np.concatenate([scenes.primary_rays(48), scenes.incoherent_rays(6000)])),
+                     (scenes.cornell_scene(16, 16, 4), scenes.incoherent_rays(5000, extent=0.95))):
+        E = emu.Emu(sb.desc())
+        a = E.trace(rays)
+        b, ev = E.trace_warp(rays, den, nw)
+        assert a.tobytes() == b.tobytes()
+        if den < 32:                                               # den 32: a group is never put aside (the plain schedule)
+            assert ev["postponed"] > 0 and ev["waited"] > 0        # both ways of putting a group aside were exercised
+        E.close()
