@@ -67,7 +67,7 @@ int kzemu_trace(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits) {
  * node step, the lanes that hold triangles test them while at least 1/`den` of the lanes at work hold some -- otherwise a lane with a node
  * group in hand puts its triangle group on its stack (two entries) and one without waits with it in registers -- and lanes whose groups are
  * exhausted pop; finished lanes are refilled once `nw` lane-iterations were lost.  This is the only caller of kz_trav_postpone and of the
- * triangle-group branch of kz_trav_pop on the host.  out_events = {postponed groups, groups waited with, refills}. */
+ * triangle-group branch of kz_trav_pop on the host.  out_events[12] = {postponed groups, groups waited with, refills, then warp-level iteration / lane counts}. */
 int kzemu_trace_warp(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits, int den, int nw, uint64_t *out_events) {
     const KzScene &sc = e->hs.sc;
     struct Lane { KzTrav t; KzLocalStack ls; bool active = false, finished = false, wait = false; size_t item = 0; };
@@ -75,6 +75,7 @@ int kzemu_trace_warp(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits, int d
     KzStackRef stk;
     size_t cursor = 0; bool exhausted = false;
     uint64_t ev_post = 0, ev_wait = 0, ev_refill = 0;
+    uint64_t c_node_it = 0, c_node_ln = 0, c_tri_it = 0, c_tri_ln = 0, c_pop_it = 0, c_pop_ln = 0, c_iter = 0, c_iter_ln = 0, c_post_it = 0;
     for (Lane &l : L) { l.t.sp = 0; l.t.ng_y = 0u; l.t.tg_y = 0u; }
     for (;;) {
         for (Lane &l : L) if (l.finished) {
@@ -102,13 +103,16 @@ int kzemu_trace_warp(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits, int d
             std::vector<Lane *> S;
             for (Lane &l : L) if (l.active && !l.finished) S.push_back(&l);
             if (S.empty()) break;
-            for (Lane *l : S) if (l->t.tg_y == 0u && l->t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, l->t, stk, l->ls);
+            { int k = 0; for (Lane *l : S) if (l->t.tg_y == 0u && l->t.ng_y > 0x00FFFFFFu) { kz_trav_node(sc, l->t, stk, l->ls); ++k; }
+              if (k) { ++c_node_it; c_node_ln += (uint64_t)k; } }
+            ++c_iter; c_iter_ln += S.size();
             const int total = (int)S.size();
             for (;;) {
                 std::vector<Lane *> T;
                 for (Lane *l : S) if (l->t.tg_y != 0u && !l->wait) T.push_back(l);
                 if (T.empty()) break;
                 if ((int)T.size() * den < total) {
+                    ++c_post_it;
                     for (Lane *l : T) {
                         if (l->t.ng_y > 0x00FFFFFFu && l->t.sp < KZ_POSTPONE_SP_LIMIT) { kz_trav_postpone(l->t, stk, l->ls); ++ev_post; }
                         else { l->wait = true; ++ev_wait; }          /* leaves the loop with its group in registers */
@@ -116,17 +120,25 @@ int kzemu_trace_warp(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits, int d
                     break;
                 }
                 for (Lane *l : T) kz_trav_tri(sc, l->t);
+                ++c_tri_it; c_tri_ln += T.size();
             }
-            for (Lane *l : S) {
+            { int k = 0;
+              for (Lane *l : S) {
                 l->wait = false;
                 if (l->t.tg_y == 0u && l->t.ng_y <= 0x00FFFFFFu) {
-                    if (l->t.sp == 0) l->finished = true; else kz_trav_pop(l->t, stk, l->ls);
+                    if (l->t.sp == 0) l->finished = true; else { kz_trav_pop(l->t, stk, l->ls); ++k; }
                 }
-            }
+              }
+              if (k) { ++c_pop_it; c_pop_ln += (uint64_t)k; } }
             if (!exhausted) { lost += 32 - total; if (lost >= nw) break; }
         }
     }
-    if (out_events) { out_events[0] = ev_post; out_events[1] = ev_wait; out_events[2] = ev_refill; }
+    if (out_events) {
+        out_events[0] = ev_post; out_events[1] = ev_wait; out_events[2] = ev_refill;
+        /* warp-level iteration counts and the lanes that took part (tools/warp_sim.py) */
+        out_events[3] = c_iter; out_events[4] = c_iter_ln; out_events[5] = c_node_it; out_events[6] = c_node_ln; out_events[7] = c_tri_it; out_events[8] = c_tri_ln;
+        out_events[9] = c_pop_it; out_events[10] = c_pop_ln; out_events[11] = c_post_it;
+    }
     return KZ_OK;
 }
 

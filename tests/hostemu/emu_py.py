@@ -57,9 +57,11 @@ class Emu(pk._Backend):
         """the warp-cooperative loop of kz_kernels.cuh restated lane by lane; returns (hits, {postponed, waited, refills})"""
         rays = np.ascontiguousarray(rays, pk.RAY_DTYPE)
         hits = np.zeros(rays.shape[0], pk.HIT_DTYPE)
-        ev = (C.c_uint64 * 3)()
+        ev = (C.c_uint64 * 12)()
         self._call("trace_warp", self.h, rays.ctypes.data_as(C.c_void_p), C.c_size_t(rays.shape[0]), hits.ctypes.data_as(C.c_void_p), C.c_int(den), C.c_int(nw), ev)
-        return hits, {"postponed": int(ev[0]), "waited": int(ev[1]), "refills": int(ev[2])}
+        names = ("postponed", "waited", "refills", "iterations", "iteration_lanes", "node_iterations", "node_lanes", "tri_iterations", "tri_lanes",
+                 "pop_iterations", "pop_lanes", "postpone_iterations")
+        return hits, {k: int(v) for k, v in zip(names, ev)}
 
     def occluded(self, rays, trace_bias):
         rays = np.ascontiguousarray(rays, pk.RAY_DTYPE)
