@@ -127,7 +127,7 @@ struct KzStackRef {
 };
 
 /* Look-up tables of the node step (2 KB + 1 KB): the octant permutation of an 8-bit child mask (bit j -> bit j ^ c) and the
- * spread of 8 child bits to 3 bits per slot.  On the device they sit in shared memory (filled by KZ_TRAV_SHARED at the top of
+ * spread of 8 child bits to 3 bits per slot.  On the device they sit in shared memory (filled by kz_trav_shared_init at the top of
  * every traversing kernel): two loads replace ~25 bit operations of the issue-bound node step. */
 KZ_HD uint32_t kz_perm8(uint32_t m, uint32_t c) {
     if (c & 1u) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
