@@ -142,6 +142,89 @@ int kzemu_trace_warp(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits, int d
     return KZ_OK;
 }
 
+/* A scheduling policy that is NOT in the product (tools/warp_sim.py evaluates it against kzemu_trace_warp): every lane keeps the triangle
+ * groups it meets in a list of its own and goes on with node steps; the leaf tests run when at least 1/`den` of the lanes at work
+ * have groups listed (or nothing else is left to do), one triangle per lane and iteration, until fewer than 1/`den2` of the lanes still hold
+ * triangles.  Same hits as the plain loop (checked by the caller); out_events as kzemu_trace_warp. */
+int kzemu_trace_warp_lists(kzemu *e, const kz_ray *rays, size_t n, kz_hit *hits, int den, int den2, int nw, uint64_t *out_events) {
+    const KzScene &sc = e->hs.sc;
+    struct Grp { uint32_t x, y, m; };
+    struct Lane { KzTrav t; KzLocalStack ls; bool active = false, finished = false; size_t item = 0; std::vector<Grp> pend; };
+    std::vector<Lane> L(32);
+    KzStackRef stk;
+    size_t cursor = 0; bool exhausted = false;
+    uint64_t ev_refill = 0, c_node_it = 0, c_node_ln = 0, c_tri_it = 0, c_tri_ln = 0, c_pop_it = 0, c_pop_ln = 0, c_iter = 0, c_iter_ln = 0, c_listed = 0, c_fire = 0;
+    for (Lane &l : L) { l.t.sp = 0; l.t.ng_y = 0u; l.t.tg_y = 0u; }
+    for (;;) {
+        for (Lane &l : L) if (l.finished) {
+            const KzHit &h = l.t.best;
+            hits[l.item].t = h.t; hits[l.item].u = h.u; hits[l.item].v = h.v; hits[l.item].prim_id = h.prim; hits[l.item].geom_id = h.geom;
+            l.active = false; l.finished = false;
+        }
+        if (!exhausted) {
+            int idle = 0; for (Lane &l : L) idle += !l.active;
+            if (idle) {
+                ++ev_refill;
+                for (Lane &l : L) if (!l.active && cursor < n) {
+                    l.item = cursor++;
+                    const kz_ray &r = rays[l.item];
+                    kz_trav_init(sc, l.t, r.o[0], r.o[1], r.o[2], r.d[0], r.d[1], r.d[2], r.tmin, r.tmax);
+                    l.active = true;
+                }
+                exhausted = cursor >= n;
+            }
+        }
+        bool any = false; for (Lane &l : L) any |= l.active;
+        if (!any) break;
+        int lost = 0;
+        for (;;) {
+            std::vector<Lane *> S;
+            for (Lane &l : L) if (l.active && !l.finished) S.push_back(&l);
+            if (S.empty()) break;
+            const int total = (int)S.size();
+            ++c_iter; c_iter_ln += S.size();
+            { int k = 0;
+              for (Lane *l : S) if (l->t.ng_y > 0x00FFFFFFu) {
+                  kz_trav_node(sc, l->t, stk, l->ls); ++k;
+                  if (l->t.tg_y != 0u) { l->pend.push_back(Grp{l->t.tg_x, l->t.tg_y, l->t.tg_m}); l->t.tg_y = 0u; ++c_listed; }
+              }
+              if (k) { ++c_node_it; c_node_ln += (uint64_t)k; } }
+            int holders = 0, busy = 0;
+            for (Lane *l : S) { holders += !l->pend.empty(); busy += (l->t.ng_y > 0x00FFFFFFu || l->t.sp > 0); }
+            if (holders && (holders * den >= total || busy == 0)) {
+                ++c_fire;
+                for (;;) {
+                    int k = 0;
+                    for (Lane *l : S) {
+                        if (l->t.tg_y == 0u && !l->pend.empty()) { const Grp g = l->pend.back(); l->pend.pop_back(); l->t.tg_x = g.x; l->t.tg_y = g.y; l->t.tg_m = g.m; }
+                        k += l->t.tg_y != 0u;
+                    }
+                    if (k == 0) break;
+                    if (k * den2 < total && busy > 0) {       /* the tail goes back on the lists */
+                        for (Lane *l : S) if (l->t.tg_y != 0u) { l->pend.push_back(Grp{l->t.tg_x, l->t.tg_y, l->t.tg_m}); l->t.tg_y = 0u; }
+                        break;
+                    }
+                    for (Lane *l : S) if (l->t.tg_y != 0u) kz_trav_tri(sc, l->t);
+                    ++c_tri_it; c_tri_ln += (uint64_t)k;
+                }
+            }
+            { int k = 0;
+              for (Lane *l : S) if (l->t.ng_y <= 0x00FFFFFFu) {
+                  if (l->t.sp > 0) { kz_trav_pop(l->t, stk, l->ls); ++k; }
+                  else if (l->pend.empty()) l->finished = true;
+              }
+              if (k) { ++c_pop_it; c_pop_ln += (uint64_t)k; } }
+            if (!exhausted) { lost += 32 - total; if (lost >= nw) break; }
+        }
+    }
+    if (out_events) {
+        out_events[0] = c_listed; out_events[1] = c_fire; out_events[2] = ev_refill;
+        out_events[3] = c_iter; out_events[4] = c_iter_ln; out_events[5] = c_node_it; out_events[6] = c_node_ln; out_events[7] = c_tri_it; out_events[8] = c_tri_ln;
+        out_events[9] = c_pop_it; out_events[10] = c_pop_ln; out_events[11] = 0;
+    }
+    return KZ_OK;
+}
+
 /* Traversal statistics of the plain per-ray loop (tuning aid): out = {node steps, triangle tests, triangle groups, accepted hits, max stack}. */
 int kzemu_trace_stats(kzemu *e, const kz_ray *rays, size_t n, uint64_t *out) {
     const KzScene &sc = e->hs.sc;

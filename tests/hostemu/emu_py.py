@@ -63,6 +63,15 @@ class Emu(pk._Backend):
                  "pop_iterations", "pop_lanes", "postpone_iterations")
         return hits, {k: int(v) for k, v in zip(names, ev)}
 
+    def trace_warp_lists(self, rays, den=5, den2=8, nw=8):
+        """a policy that is not in the product (per-lane lists of triangle groups), for tools/warp_sim.py"""
+        rays = np.ascontiguousarray(rays, pk.RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], pk.HIT_DTYPE)
+        ev = (C.c_uint64 * 12)()
+        self._call("trace_warp_lists", self.h, rays.ctypes.data_as(C.c_void_p), C.c_size_t(rays.shape[0]), hits.ctypes.data_as(C.c_void_p), C.c_int(den), C.c_int(den2), C.c_int(nw), ev)
+        names = ("listed", "firings", "refills", "iterations", "iteration_lanes", "node_iterations", "node_lanes", "tri_iterations", "tri_lanes", "pop_iterations", "pop_lanes", "unused")
+        return hits, {k: int(v) for k, v in zip(names, ev)}
+
     def occluded(self, rays, trace_bias):
         rays = np.ascontiguousarray(rays, pk.RAY_DTYPE)
         occ = np.zeros(rays.shape[0], np.uint8); seg = np.zeros(rays.shape[0], np.uint8)

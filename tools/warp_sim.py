@@ -23,4 +23,13 @@ for name, rays in (("primary", scenes.primary_rays(res)[: n_rays]), ("incoherent
         print(f"  postpone below 1/{den:<2d} refill after {nw:2d}: per 32 rays {ev['node_iterations']/nr:6.1f} node steps at {ev['node_lanes']/max(1,ev['node_iterations']):4.1f} lanes, "
               f"{ev['tri_iterations']/nr:6.1f} leaf-test iterations at {ev['tri_lanes']/max(1,ev['tri_iterations']):4.1f} lanes, {ev['postponed']/nr:5.1f} postponed, {ev['waited']/nr:5.1f} waited, "
               f"{ev['refills']/nr:4.1f} refills; ~{cost/nr:7.0f} warp instructions")
+    # a policy that is NOT in the product: per-lane lists of triangle groups (profiles/README.md item 41)
+    ref = E.trace(rays)
+    for fire, stop in ((2, 3), (3, 4), (5, 8)):
+        h, ev = E.trace_warp_lists(rays, fire, stop, 8)
+        assert h.tobytes() == ref.tobytes()
+        nr = rays.shape[0] / 32.0
+        cost = 229 * ev["node_iterations"] + 190 * ev["tri_iterations"] + 8 * ev["pop_iterations"] + 25 * ev["iterations"] + 120 * ev["refills"] + 30 * ev["firings"]
+        print(f"  lists, tests from 1/{fire} of the lanes down to 1/{stop}: per 32 rays {ev['node_iterations']/nr:6.1f} node steps at {ev['node_lanes']/max(1,ev['node_iterations']):4.1f} lanes, "
+              f"{ev['tri_iterations']/nr:6.1f} leaf-test iterations at {ev['tri_lanes']/max(1,ev['tri_iterations']):4.1f} lanes, {ev['firings']/nr:5.1f} firings; ~{cost/nr:7.0f} warp instructions")
 E.close()
