@@ -267,6 +267,55 @@ int kzemu_occluded(kzemu *e, const kz_ray *rays, size_t n, float trace_bias, uin
     return KZ_OK;
 }
 
+/* The shadow walk with the early stop of the device's shadow / occlusion jobs (KzWalk::settles in kz_kernels.cuh, restated): a segment
+ * ends at the first OPAQUE hit the traversal comes across once no invisible emitter can lie in front of it.  Must answer exactly as
+ * kzemu_occluded (the closest-hit walk of integrator.cpp:259-294): same flags, same segment counts.  stops[0] counts the early stops. */
+int kzemu_occluded_early(kzemu *e, const kz_ray *rays, size_t n, float trace_bias, uint8_t *occ, uint8_t *segments, uint64_t *stops) {
+    const KzScene &sc = e->hs.sc;
+    std::atomic<uint64_t> n_stop{0};
+    pfor(n, [&](size_t b, size_t en) {
+        KzStackRef stk; uint64_t my_stops = 0;
+        for (size_t i = b; i < en; ++i) {
+            const kz_ray &r = rays[i];
+            kz3 o = mk3(r.o[0], r.o[1], r.o[2]); const kz3 d = mk3(r.d[0], r.d[1], r.d[2]);
+            float tmin = r.tmin, tmax = r.tmax;
+            int seg = 0; bool occluded = false;
+            for (;;) {
+                ++seg;
+                KzTrav t; KzLocalStack ls;
+                kz_trav_init(sc, t, o.x, o.y, o.z, d.x, d.y, d.z, tmin, tmax);
+                bool stopped = false;
+                while (!stopped && sc.n_nodes) {
+                    if (t.ng_y > 0x00FFFFFFu) kz_trav_node(sc, t, stk, ls);
+                    while (t.tg_y != 0u) {
+                        if (!kz_trav_tri(sc, t)) continue;
+                        bool settles = sc.integrator.type != KZ_INTEGRATOR_PATH_MIS;
+                        if (!settles) {
+                            const uint32_t fl = sc.meshes[t.best.geom].flags;
+                            if (!((fl & KZ_MESH_IS_LIGHT) && !(fl & KZ_MESH_LIGHT_VISIBLE)))
+                                settles = sc.n_invisible_lights == 0 || kz_trav_misses_box(t, sc.inv_light_lo, sc.inv_light_hi, t.best.t);
+                        }
+                        if (settles) { stopped = true; ++my_stops; break; }
+                    }
+                    if (stopped) break;
+                    if (t.ng_y <= 0x00FFFFFFu) { if (t.sp == 0) break; kz_trav_pop(t, stk, ls); }
+                }
+                const KzHit h = t.best;
+                if (h.geom == KZ_INVALID_ID) break;
+                const uint32_t fl = sc.meshes[h.geom].flags;
+                if (!(fl & KZ_MESH_IS_LIGHT) || (fl & KZ_MESH_LIGHT_VISIBLE) || sc.integrator.type != KZ_INTEGRATOR_PATH_MIS) { occluded = true; break; }
+                o = o + d * (h.t + trace_bias); tmin = trace_bias; tmax = tmax - h.t;
+                if (seg > 4096) break;
+            }
+            occ[i] = occluded ? 1 : 0;
+            if (segments) segments[i] = (uint8_t)std::min(seg, 255);
+        }
+        n_stop += my_stops;
+    });
+    if (stops) stops[0] = n_stop.load();
+    return KZ_OK;
+}
+
 int kzemu_sample_dump(kzemu *e, const int32_t *triples, size_t n, const char *pattern, float *out) {
     const KzScene &sc = e->hs.sc;
     size_t per = 0;

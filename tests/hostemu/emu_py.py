@@ -79,6 +79,15 @@ class Emu(pk._Backend):
                    occ.ctypes.data_as(C.c_void_p), seg.ctypes.data_as(C.c_void_p))
         return occ, seg
 
+    def occluded_early(self, rays, trace_bias):
+        """the walk with the device's early stop; returns (occluded, segments, early stops)"""
+        rays = np.ascontiguousarray(rays, pk.RAY_DTYPE)
+        occ = np.zeros(rays.shape[0], np.uint8); seg = np.zeros(rays.shape[0], np.uint8)
+        st = (C.c_uint64 * 1)()
+        self._call("occluded_early", self.h, rays.ctypes.data_as(C.c_void_p), C.c_size_t(rays.shape[0]), C.c_float(trace_bias),
+                   occ.ctypes.data_as(C.c_void_p), seg.ctypes.data_as(C.c_void_p), st)
+        return occ, seg, int(st[0])
+
     def sample_dump(self, triples, pattern):
         t = np.ascontiguousarray(triples, np.int32).reshape(-1, 3)
         out = np.zeros((t.shape[0], pk._pattern_floats(pattern)), np.float32)

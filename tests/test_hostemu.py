@@ -299,3 +299,32 @@ def test_warp_cooperative_loop_cpu(emu, den, nw):
         if den < 32:                                               # den 32: a group is never put aside (the plain schedule)
             assert ev["postponed"] > 0 and ev["waited"] > 0        # both ways of putting a group aside were exercised
         E.close()
+
+
+def test_shadow_walk_early_stop_is_exact_cpu(emu):
+    """The device's shadow and occlusion jobs end a segment at the first opaque hit once no invisible emitter can lie in front of it
+    (KzWalk::settles, restated in tests/hostemu with the same kz_trav_misses_box): flags AND segment counts must equal the closest-hit
+    walk of integrator.cpp:259-294 for every ray -- also for rays aimed at, grazing and starting inside the bounds of the invisible
+    emitters, with visible emitters, and for the integrators whose shadow rays take any hit."""
+    rng = np.random.default_rng(11)
+    for kw in ({}, {"visible_light": True}):
+        sb = scenes.cornell_scene(16, 16, 4, **kw)
+        for kind in ("path_mis", "ao"):
+            sb.set_integrator(kind=kind)
+            E = emu.Emu(sb.desc())
+            rays = scenes.incoherent_rays(40000, extent=0.97, seed=5)
+            rays["tmax"] *= 1.5
+            # a third of the rays end on (or just beyond) the ceiling emitters, as the shadow rays of the integrator do
+            k = rays.shape[0] // 3
+            tgt = np.stack([rng.uniform(-0.65, 0.35, k), rng.choice([0.9, 0.98, 1.05], k), rng.uniform(-0.35, 0.95, k)], 1).astype(np.float32)
+            dvec = tgt - rays["o"][:k]
+            ln = np.linalg.norm(dvec, axis=1).astype(np.float32)
+            rays["d"][:k] = dvec / ln[:, None]
+            rays["tmax"][:k] = ln * rng.choice([0.999, 1.0, 1.2], k).astype(np.float32)
+            o0, s0 = E.occluded(rays, 1e-3)
+            o1, s1, stops = E.occluded_early(rays, 1e-3)
+            assert np.array_equal(o0, o1) and np.array_equal(s0, s1), (kw, kind)
+            assert stops > 1000
+            if kind == "path_mis" and not kw:
+                assert s0.max() >= 2          # some rays stepped through an invisible emitter
+            E.close()
