@@ -786,7 +786,7 @@ extern "C" int kzo_math_probe(const char *fn, const float *in, int n_in, float *
             BSDFQueryRecord r(v3(9), v3(12), ESolidAngle); r.uv = V2{0.5f, 0.5f};
             if (f == "extraEval") put3(bsdfEval(sc, 0, r)); else put1(bsdfPdf(sc, 0, r));
         }
-    } else if ((f == "texColorRamp" || f == "texBlend" || f == "texBackgroundUV" || f == "texBackgroundDir") && need(18)) {
+    } else if ((f == "texColorRamp" || f == "texBlend" || f == "texBackgroundUV" || f == "texBackgroundDir" || (f == "sceneBackground" && need(20))) && need(18)) {
         /* in = three constant colours, ramp min / max, background intensity, blend mode, then five "child missing" flags (mask, input1, ramp's nested,
          * input2, background's nested): background(blend(mask = colorramp(c0), c1, c2)), texture.cpp:104-270 */
         SceneData sc;
@@ -804,7 +804,17 @@ extern "C" int kzo_math_probe(const char *fn, const float *in, int n_in, float *
         if (f == "texColorRamp") put3(evalTextureUV(sc, nr, uv));
         else if (f == "texBlend") put3(evalTextureUV(sc, nb, uv));
         else if (f == "texBackgroundUV") put3(evalTextureUV(sc, ng, uv));
-        else { kz_texture_desc td = tg; td.child[0] = n2; sc.textures.push_back(td); put3(evalTextureDir(sc, (int)sc.textures.size() - 1, V3(0.f, 0.f, 1.f))); }
+        else {
+            kz_texture_desc td = tg; td.child[0] = n2; sc.textures.push_back(td);
+            if (f == "texBackgroundDir") put3(evalTextureDir(sc, (int)sc.textures.size() - 1, V3(0.f, 0.f, 1.f)));
+            else {      /* scene.cpp:54-79 over that node: in[18] = no background, in[19] odd = a NaN component in the direction */
+                sc.background = in[18] != 0.f ? -1 : (int)sc.textures.size() - 1;
+                V3 dir(0.f, 0.f, 1.f);
+                const int k = (int)in[19];
+                if (k == 1) dir.x = std::nanf(""); else if (k == 3) dir.y = std::nanf(""); else if (k == 5) dir.z = std::nanf("");
+                put3(backgroundColor(sc, dir));
+            }
+        }
     } else if (f == "pmj02bnTileSize" && need(1)) {                   /* sampler.cpp:291: tile = 1 << (log4(65536) - log4(roundUpPow4(spp))) */
         const int spp = (int)in[0];
         put1((float)(1 << (log2i_int(65536) / 2 - log2i_int(roundUpPow4(spp)) / 2)));

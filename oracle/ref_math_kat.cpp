@@ -176,6 +176,14 @@ struct BlendTexBodies : Texture<Color3f> { std::string m_blendmode = "mix"; Text
 #include "_ref/tex_blend.inc"
 };
 }
+/* Scene::getBackgroundColor (scene.cpp:54-79: null background, NaN guard, m_background->eval(dir)): the out-of-class definition is compiled
+ * as a member of a stand-in class that only holds the background texture */
+namespace kazen {
+struct SceneBackgroundBodies { Texture<Color3f> *m_background = nullptr; const Color3f getBackgroundColor(const Vector3f &dir) const; };
+#define Scene SceneBackgroundBodies
+#include "_ref/scene_background.inc"
+#undef Scene
+}
 /* PMJ02BN (sampler.cpp:273-390) over the reference's own table headers.  The tables themselves (bluenoise.cpp / pmj02table.cpp) are
  * missing from the public tree, so they are DEFINED here with synthetic contents (a scrambled (0,2)-sequence and hashed blue-noise
  * values): what is pinned is the class body -- pixel-sample bucketing, index permutation, Cranley-Patterson rotation, clamping --
@@ -792,6 +800,13 @@ int main() {
         kazen::BackgroundTexBodies kd; kd.m_intensity = intensity; kd.m_nested = &k2;
         kz_texture_desc td = tg; td.child[0] = n2; sc.textures.push_back(td);
         rec("texBackgroundDir", in, f3(kd.eval(K(dir))), f3(kzo::evalTextureDir(sc, (int)sc.textures.size() - 1, dir)), keep);
+        /* Scene::getBackgroundColor over that node: no background at all, a direction with a NaN component, an ordinary direction */
+        kazen::SceneBackgroundBodies ks; ks.m_background = i % 17 == 0 ? nullptr : &kd;
+        sc.background = i % 17 == 0 ? -1 : (int)sc.textures.size() - 1;
+        kzo::V3 bd = dir;
+        if (i % 6 == 1) bd.x = std::nanf(""); else if (i % 6 == 3) bd.y = std::nanf(""); else if (i % 6 == 5) bd.z = std::nanf("");
+        in.push_back((float)(i % 17 == 0)); in.push_back((float)(i % 6));
+        rec("sceneBackground", in, f3(ks.getBackgroundColor(K(bd))), f3(kzo::backgroundColor(sc, bd)), keep);
     }
     /* ---- PMJ02BN (sampler.cpp:273-390): constructor bucketing + generateSample / nextPixel2D / next1D / next2D over synthetic tables ---- */
     {

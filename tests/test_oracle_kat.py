@@ -186,7 +186,7 @@ def test_math_helpers_match_the_reference_bodies(kzo):
     output bit for bit."""
     import json
     g = json.load(open(os.path.join(HERE, "golden", "math_kat.json")))
-    assert g["mismatches"] == 0 and g["cases_checked"] >= 248000 and len(g["kat"]) >= 1450
+    assert g["mismatches"] == 0 and g["cases_checked"] >= 251000 and len(g["kat"]) >= 1480
     seen = set()
     for case in g["kat"]:
         inp = np.array(case["in"], np.uint32).view(np.float32)
@@ -201,14 +201,14 @@ def test_math_helpers_match_the_reference_bodies(kzo):
         got = kzo.math_probe(case["fn"], inp).view(np.uint32)
         assert np.array_equal(got, want), (case["fn"], inp.tolist())
         seen.add(case["fn"])
-    assert len(seen) == 45 and {"kissEval", "kissPdf", "kissSample", "sampleVNDF", "dpdfSample", "samplerStratified", "samplerCorrelated",
-                                "extraEval", "extraPdf", "extraSample", "texColorRamp", "texBlend", "texBackgroundUV", "texBackgroundDir", "pmj02bnTileSize"} <= seen
+    assert len(seen) == 46 and {"kissEval", "kissPdf", "kissSample", "sampleVNDF", "dpdfSample", "samplerStratified", "samplerCorrelated",
+                                "extraEval", "extraPdf", "extraSample", "texColorRamp", "texBlend", "texBackgroundUV", "texBackgroundDir", "sceneBackground", "pmj02bnTileSize"} <= seen
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/include/kazen"), reason="the reference is only mounted in the build container")
 def test_reference_math_bodies_run_here_agree(kzo):
     """Where the reference is mounted: build oracle/_ref/ref_math_kat from the reference's sources in place and require 0 mismatches
-    over all 248 000 cases (incl. the seven other BSDF plugins, the texture expression nodes, the PMJ02BN sampler body over synthetic tables, post-intersection, Mesh::sample and AreaLight on random meshes, and 36 000 whole paths through the reference's own PathMisIntegrator::Li body on random scenes) (the golden file keeps about 1 200 of them)."""
+    over all 251 000 cases (incl. Scene::getBackgroundColor, the seven other BSDF plugins, the texture expression nodes, the PMJ02BN sampler body over synthetic tables, post-intersection, Mesh::sample and AreaLight on random meshes, and 36 000 whole paths through the reference's own PathMisIntegrator::Li body on random scenes) (the golden file keeps about 1 200 of them)."""
     import subprocess
     root = os.path.dirname(HERE)
     subprocess.check_call(["make", "-s", "-C", os.path.join(root, "oracle"), "_ref/ref_math_kat"])
