@@ -530,8 +530,10 @@ public:
             else if (prefix == "vn") {
                 Vec3 n; line >> n.x >> n.y >> n.z;
                 n = trafo.normal(n);
-                const float l = std::sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
-                normals.push_back(Vec3{n.x / l, n.y / l, n.z / l});
+                /* Eigen's normalized() (mesh.cpp:244): v / sqrt(v.v) when v.v > 0, else v itself; the unrolled 3-term reduction adds a0*b0 + (a1*b1 + a2*b2) */
+                const float z = n.x * n.x + (n.y * n.y + n.z * n.z);
+                if (z > 0.f) { const float l = std::sqrt(z); n = Vec3{n.x / l, n.y / l, n.z / l}; }
+                normals.push_back(n);
             } else if (prefix == "f") {
                 std::string v1, v2, v3, v4; line >> v1 >> v2 >> v3 >> v4;
                 Key f[6]; int nv = 3;
