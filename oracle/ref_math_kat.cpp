@@ -50,7 +50,7 @@ namespace kazen {
 namespace random {
 #include "_ref/permute_extract.inc"
 }
-class Sampler { public: virtual ~Sampler() {} virtual float next1D() = 0; virtual Point2f next2D() = 0; };                  /* sampler.h:44-107 */
+class Sampler { public: virtual ~Sampler() {} virtual float next1D() = 0; virtual Point2f next2D() = 0; virtual Point2f nextPixel2D() { return Point2f(0.f, 0.f); } };   /* sampler.h:44-107 */
 struct ReplaySampler : Sampler { std::vector<float> q; size_t k = 0; float next1D() { return q[k++]; } Point2f next2D() { const float a = q[k++], b = q[k++]; return Point2f(a, b); } };
 struct SamplerMembers : Sampler { uint64_t m_seed; uint32_t m_sampleCount, m_sampleIndex, m_dimensionIndex; };               /* sampler.h:100-106 */
 struct IndependentBodies : SamplerMembers { pcg32 m_random;
@@ -251,9 +251,13 @@ public:
 }
 struct RefAccel;                          /* closest hit through the oracle's intersector (Embree's stand-in), defined after kzo.cpp */
 namespace kazen {
+class Integrator; class Camera;
 class Scene {                                                                                                               /* scene.h:15-138 */
 public:
     std::vector<Mesh *> m_meshes, m_lights; const RefAccel *m_accel = nullptr; Color3f m_background;
+    const Integrator *m_integrator = nullptr; const Camera *m_camera = nullptr;
+    const Integrator *getIntegrator() const { return m_integrator; }                  /* scene.h:30 */
+    const Camera *getCamera() const { return m_camera; }                              /* scene.h:39 */
 #include "_ref/scene_extract.inc"
     bool rayIntersect(const Ray3f &ray, Intersection &its) const;                 /* scene.h:79-81  -> Accel::rayIntersect(ray, its, false) */
     bool rayOccluded(const Ray3f &ray, Intersection &its) const;                  /* scene.h:103-105 -> Accel::rayIntersect(ray, its, true) */
@@ -278,6 +282,16 @@ struct PathMisBodies {                   /* PathMisIntegrator, integrator.cpp:19
     int m_maxDepth; float m_rayEpsilon; bool m_regularization; float m_accumulatedRoughness;
 #include "_ref/integrator_extract.inc"
 };
+/* renderer::renderSample (renderer.cpp:18-38): pixel sample, aperture sample, camera ray, Li, ImageBlock::put -- over the interfaces it
+ * calls (integrator.h:26, camera.h:32), implemented by the hosted bodies above */
+class Integrator { public: virtual ~Integrator() {} virtual Color3f Li(const Scene *scene, Sampler *sampler, const Ray3f &ray) const = 0; };
+class Camera { public: virtual ~Camera() {} virtual Color3f sampleRay(Ray3f &ray, const Point2f &samplePosition, const Point2f &apertureSample) const = 0; };
+struct HostedPathMis : Integrator { PathMisBodies b; Color3f Li(const Scene *s, Sampler *sm, const Ray3f &r) const { return b.Li(s, sm, r); } };
+struct HostedPerspective : Camera { PerspectiveBodies b; Color3f sampleRay(Ray3f &r, const Point2f &p, const Point2f &a) const { return b.sampleRay(r, p, a); } };
+struct HostedThinlens : Camera { ThinlensBodies b; Color3f sampleRay(Ray3f &r, const Point2f &p, const Point2f &a) const { return b.sampleRay(r, p, a); } };
+namespace renderer {
+#include "_ref/render_sample.inc"
+}
 }
 
 #include "kzo.cpp"          /* the oracle itself: SceneData, Sampler, the restated Li (file-static) */
@@ -604,6 +618,43 @@ int main() {
             const kzo::V3 oL = Li(&os, osm, kr, pc);
             rec("pathMisLi", {(float)scn, (float)px, (float)py, (float)sidx, o.x, o.y, d.x, d.y, d.z}, f3(kL), f3(oL), false);
             ++liPaths; if (oL.x > 0.f || oL.y > 0.f || oL.z > 0.f) ++liLit;
+        }
+        /* renderer::renderSample on the same scene: a camera (both models), the Stratified sampler, the hosted Li and a whole-frame ImageBlock
+         * against the oracle's render loop body (kzo_render: generateSample, nextPixel2D, next2D, cameraRay, Li, filmPut) */
+        {
+            const int W = 64, H = 48;
+            kz_camera_desc &c = sc.camera; memset(&c, 0, sizeof(c));
+            c.type = scn % 2 ? KZ_CAM_THINLENS : KZ_CAM_PERSPECTIVE; c.width = W; c.height = H; c.near_clip = 1e-4f; c.far_clip = 1e4f; c.aperture_radius = 0.05f; c.focus_distance = 4.5f;
+            Eigen::Matrix4f s2c, c2w;
+            const float m1[16] = {1.3f, 0, 0, -0.65f, 0, -0.98f, 0, 0.49f, 0, 0, 0, 1, 0, 0, 0, 1};               /* (u, v, 0) -> ((2u-1) tx, (1-2v) ty, 1) */
+            const float m2[16] = {-1, 0, 0, rnd(-0.3f, 0.3f), 0, 1, 0, rnd(1.0f, 1.5f), 0, 0, -1, 4.f, 0, 0, 0, 1};  /* camera at (x, y, 4) looking down -z */
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { s2c(i, j) = m1[4 * i + j]; c.sample_to_camera[4 * i + j] = m1[4 * i + j]; c2w(i, j) = m2[4 * i + j]; c.camera_to_world[4 * i + j] = m2[4 * i + j]; }
+            kazen::HostedPerspective kcp; kazen::HostedThinlens kct;
+            kcp.b.m_invOutputSize = kct.b.m_invOutputSize = kazen::Vector2f(1.0f / W, 1.0f / H);
+            kcp.b.m_sampleToCamera = kct.b.m_sampleToCamera = kazen::Transform(s2c, s2c); kcp.b.m_cameraToWorld = kct.b.m_cameraToWorld = kazen::Transform(c2w, c2w);
+            kcp.b.m_nearClip = kct.b.m_nearClip = c.near_clip; kcp.b.m_farClip = kct.b.m_farClip = c.far_clip; kct.b.m_apertureRadius = c.aperture_radius; kct.b.m_focusDistance = c.focus_distance;
+            kazen::HostedPathMis kint; kint.b = ki;
+            kscene.m_integrator = &kint; kscene.m_camera = scn % 2 ? (const kazen::Camera *)&kct : (const kazen::Camera *)&kcp;
+            kazen::GaussianBodies fg; fg.m_radius = 2.f; fg.m_stddev = 0.5f;
+            kazen::ImageBlock blk(kazen::Vector2i(W, H), &fg);
+            sc.filter.radius = fg.getRadius(); for (int i = 0; i <= 32; ++i) sc.filter.table[i] = blk.m_filter[i];
+            const int border = (int)std::ceil(sc.filter.radius - 0.5f);
+            std::vector<float> frame((size_t)(W + 2 * border) * (H + 2 * border) * 4, 0.f);
+            for (int k = 0; k < 400; ++k) {
+                const int px = (int)(rnd() * W) % W, py = (int)(rnd() * H) % H, sidx = (int)(rnd() * 16) % 16;
+                kazen::StratifiedBodies ks; ks.m_seed = sc.sampler.d.seed; ks.m_sampleCount = 16; ks.m_resolution = 4;
+                ks.generateSample(kazen::Point2i(px, py), sidx);
+                kazen::renderer::renderSample(&kscene, &ks, blk, kazen::Point2i(px, py));
+                kzo::Sampler osm; osm.cfg = &sc.sampler; osm.generateSample(px, py, sidx);
+                const kzo::V2 pix = osm.nextPixel2D(); const kzo::V2 pixelSample{float(px) + pix.x, float(py) + pix.y}; const kzo::V2 apertureSample = osm.next2D();
+                const kz_ray ray = cameraRay(sc.camera, pixelSample, apertureSample);
+                PathCounters pc; const kzo::V3 value = kzo::V3(1.0f) * Li(&os, osm, ray, pc);
+                filmPut(sc, border, frame.data(), pixelSample, value);
+            }
+            std::vector<float> ref; for (const kazen::Color4f &cc : blk.m_px) { ref.push_back(cc.x()); ref.push_back(cc.y()); ref.push_back(cc.z()); ref.push_back(cc.w()); }
+            double lit = 0; for (size_t i = 0; i < ref.size(); i += 4) lit += ref[i] + ref[i + 1] + ref[i + 2];
+            rec("renderSample", {(float)scn, (float)(scn % 2)}, ref, frame, false);
+            if (!(lit > 0)) fprintf(stderr, "renderSample: scene %d rendered black\n", scn);
         }
         /* the other four integrators on the same scene (not on the normal-mapped ones: they build the BSDF record without `its`) */
         if (scn % 3 != 1) {
