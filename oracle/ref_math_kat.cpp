@@ -282,6 +282,12 @@ struct PathMisBodies {                   /* PathMisIntegrator, integrator.cpp:19
     int m_maxDepth; float m_rayEpsilon; bool m_regularization; float m_accumulatedRoughness;
 #include "_ref/integrator_extract.inc"
 };
+/* the 8-bit conversion of Bitmap::savePNG (bitmap.cpp:46-54: toSRGB, scale, clamp, truncate), one pixel at a time */
+static void refQuantise(Color3f &cur, uint8_t *dst) {
+    auto coeffRef = [&](int, int) -> Color3f & { return cur; };
+    const int i = 0, j = 0;
+#include "_ref/bitmap_quantise.inc"
+}
 /* renderer::renderSample (renderer.cpp:18-38): pixel sample, aperture sample, camera ray, Li, ImageBlock::put -- over the interfaces it
  * calls (integrator.h:26, camera.h:32), implemented by the hosted bodies above */
 class Integrator { public: virtual ~Integrator() {} virtual Color3f Li(const Scene *scene, Sampler *sampler, const Ray3f &ray) const = 0; };
@@ -707,6 +713,27 @@ int main() {
         }
         std::vector<float> ref; for (const kazen::Color4f &c : blk.m_px) { ref.push_back(c.x()); ref.push_back(c.y()); ref.push_back(c.z()); ref.push_back(c.w()); }
         rec("imageBlockPut", {(float)fk}, ref, frame, false);
+    }
+    /* resolve: ImageBlock::toBitmap's divideByFilterWeight (block.cpp:39-45, color.h:93-98) + savePNG's 8-bit conversion (bitmap.cpp:46-54) against kzo_resolve */
+    {
+        const int N = 4000;
+        kzo_scene os; memset(&os.sc.camera, 0, sizeof(os.sc.camera)); os.sc.camera.width = N; os.sc.camera.height = 1; os.border = 0;
+        std::vector<float> frame((size_t)N * 4), lin((size_t)N * 3), refLin, refQ, ourQ; std::vector<uint8_t> q8((size_t)N * 3);
+        for (int k = 0; k < N; ++k) {
+            const float w = k % 11 == 0 ? 0.f : rnd(0.05f, 40.f), scale = k % 7 == 0 ? 30.f : 1.2f;
+            float *p = &frame[(size_t)4 * k];
+            p[0] = rnd(-0.05f, scale) * w; p[1] = rnd(0.f, scale) * w; p[2] = (k % 13 == 0 ? 1e-4f : rnd(0.f, scale)) * w; p[3] = w;
+            if (k % 97 == 3) p[1] = INFINITY;
+            kazen::Color4f c4(p[0], p[1], p[2], p[3]);
+            kazen::Color3f c = c4.divideByFilterWeight();
+            refLin.push_back(c.x()); refLin.push_back(c.y()); refLin.push_back(c.z());
+            uint8_t d[3]; kazen::refQuantise(c, d);
+            refQ.push_back(d[0]); refQ.push_back(d[1]); refQ.push_back(d[2]);
+        }
+        kzo_resolve(&os, frame.data(), lin.data(), q8.data());
+        for (uint8_t v : q8) ourQ.push_back(v);
+        rec("resolveLinear", {(float)N}, refLin, lin, false);
+        rec("resolveSRGB8", {(float)N}, refQ, ourQ, false);
     }
     /* cameras: sampleRay of both camera models with random (invertible-looking) matrices; the matrices themselves come from
      * Camera::activate, which uses Eigen's 4x4 inverse and is not restated here */

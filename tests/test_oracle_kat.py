@@ -186,7 +186,7 @@ def test_math_helpers_match_the_reference_bodies(kzo):
     output bit for bit."""
     import json
     g = json.load(open(os.path.join(HERE, "golden", "math_kat.json")))
-    assert g["mismatches"] == 0 and g["cases_checked"] >= 251030 and len(g["kat"]) >= 1480
+    assert g["mismatches"] == 0 and g["cases_checked"] >= 251032 and len(g["kat"]) >= 1480
     seen = set()
     for case in g["kat"]:
         inp = np.array(case["in"], np.uint32).view(np.float32)
